@@ -1,0 +1,194 @@
+/*
+ * vaeq.h -- C ABI of libvaeq.so: the B200 (sm_100a) implementation of the VAE blind-equalizer
+ * training hot path of kit-cel/vae-equalizer.
+ *
+ * The reference is pure Python/PyTorch and has no FFI layer: its "plugin API" is
+ * the Python module surface  optical_DP_channel/shared_funcs.py  that the Eval_run_*.py drivers
+ * reach through  func_*_MQAM_shaping.processing().  The entry points below are what a binding for
+ * that surface needs; each one cites the reference function (file:line, relative to the reference
+ * root, sf = optical_DP_channel/shared_funcs.py) it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the name ends in _host;
+ *   - tensors are contiguous float32 with time innermost, exactly the reference layouts:
+ *       rx (2,2,L) [pol][I/Q][sample], q (2,2n,B) [pol][I rows 0..n-1 | Q rows n..2n-1][symbol],
+ *       out (2,2,B), W (2,4,M) [out pol][Re<-p0,Re<-p1,Im<-p0,Im<-p1][tap], h (2,2,2,M) [rx pol][tx pol][Re/Im][tap];
+ *     "ld_*" arguments are the distance in elements between consecutive rows, so a window of a
+ *     longer frame can be passed without a copy (func_VAELE_DP_MQAM_shaping.py:58 copies instead);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host;
+ *   - return value 0 = ok, otherwise a negative VAEQ_E* code or a positive cudaError_t;
+ *     vaeq_last_error() gives the text.  No entry point allocates device memory: scratch comes from
+ *     the caller-provided workspace (size from vaeq_dp_workspace_bytes).
+ *   - sps == 2 and odd M_est only (what every reference driver uses; even M_est breaks the
+ *     reference itself, sf:494 yields B+1 outputs).
+ */
+#ifndef VAEQ_H_
+#define VAEQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAEQ_ABI_VERSION 1
+
+#define VAEQ_OK 0
+#define VAEQ_EINVAL (-1)     /* bad argument (shape, sps, even M, n_lev not in {2,4,8}) */
+#define VAEQ_EWORKSPACE (-2) /* workspace too small */
+#define VAEQ_ENODEV (-3)     /* no sm_100 device / kernel image */
+
+#define VAEQ_MAX_TAPS 63
+#define VAEQ_MAX_LEVELS 8
+
+int vaeq_abi_version(void);
+const char *vaeq_last_error(void);
+/* number of SMs of the current device (persistent grids are sized from it) */
+int vaeq_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * DP VAE-LE / VAE-flex training step
+ *   replaces  twoXtwoFIR.forward (sf:500-527) + loss_function_shaping (sf:92-137) + loss.backward()
+ *   + optim.Adam.step() with two parameter groups (func_VAELE_DP_MQAM_shaping.py:26-31,57-66).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vaeq_dp_desc {
+    /* problem */
+    int32_t B;       /* symbols in this minibatch (batch_len)                                   */
+    int32_t sps;     /* samples per symbol, must be 2                                            */
+    int32_t M;       /* M_est, odd, <= VAEQ_MAX_TAPS                                             */
+    int32_t n_lev;   /* ASK levels per component: 2, 4 or 8 (4/16/64-QAM)                        */
+    float nu_sc;     /* PCS demapper term (sf:570)                                               */
+    int32_t flags;   /* VAEQ_F_* below                                                           */
+    /* inputs */
+    const float *rx; /* (2,2,L=B*sps) window start                                               */
+    int64_t ld_rx;   /* row stride of rx in elements                                             */
+    const float *amp; /* (n_lev) amplitude levels, ascending (sf:568)                            */
+    const float *P;   /* (n_lev) PCS pmf (sf:572)                                                */
+    const float *var; /* (2) demapper noise variance per pol (sf:581)                            */
+    /* trainable state (updated in place by the *_train_* entry points) */
+    float *W;        /* (2,4,M) equalizer taps = twoXtwoFIR.conv_w.weight                        */
+    float *h;        /* (2,2,2,M) channel estimate h_est                                         */
+    float *adam;     /* Adam state, vaeq_adam_state_floats(M) floats, zero-initialised by caller */
+    /* outputs */
+    float *q;        /* (2,2n,B) posteriors of the whole minibatch (needed by the backward pass) */
+    int64_t ld_q;
+    float *out;      /* (2,2,B) equalizer output                                                 */
+    int64_t ld_out;
+    float *q_keep;   /* optional second copy restricted to symbols [keep_lo, keep_lo+keep_n):    */
+    int64_t ld_q_keep; /* what VAE-flex stores (func_VAEflex_DP_MQAM_shaping.py:64-65); may be NULL */
+    float *out_keep;
+    int64_t ld_out_keep;
+    int32_t keep_lo, keep_n;
+    float *loss;     /* (1)  ELBO loss of this minibatch (sf:136)                                */
+    float *var_est;  /* (2)  C/(L-Mh), the estimated noise variance (sf:137)                     */
+    float *gW;       /* optional (2,4,M) gradient of the loss w.r.t. W, may be NULL              */
+    float *gh;       /* optional (2,2,2,M) gradient w.r.t. h, may be NULL                        */
+    /* scratch */
+    void *workspace;
+    size_t workspace_bytes;
+} vaeq_dp_desc;
+
+#define VAEQ_F_AMSGRAD 1 /* Adam amsgrad=True (AWGN driver, func_VAELE_MQAM_shaping.py:283) */
+
+size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev);
+/* floats of Adam state for one run: exp_avg, exp_avg_sq, max_exp_avg_sq for W and h, + step counter */
+size_t vaeq_adam_state_floats(int32_t M);
+
+/* forward only: q, out, loss, var_est  (net(minibatch) + loss_function_shaping, no grad) */
+int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream);
+/* forward + backward: additionally gW, gh (must be non-NULL); parameters are NOT updated */
+int vaeq_dp_forward_backward(const vaeq_dp_desc *d, void *stream);
+/* forward + backward + Adam on both groups: lr_w for W (group 0), lr_h for h (group 1);
+ * betas (0.9,0.999), eps 1e-8, no weight decay (torch defaults used at func_VAELE_DP_MQAM_shaping.py:28) */
+int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stream);
+
+/* A frame of sequential minibatches (func_VAELE_DP_MQAM_shaping.py:57-66 with stride_sym = B,
+ * func_VAEflex_DP_MQAM_shaping.py:59-70 with stride_sym = flex_step): step m trains on symbols
+ * [m*stride_sym, m*stride_sym + B) of the frame.  d->rx / d->q_keep / d->out_keep address the FRAME
+ * (rx_frame (2,2,L_frame), out_train (2,2n,*), out_const (2,2,*)); the kept columns of step m land at
+ * column m*stride_sym (+keep_lo when keep_lo_in_dst != 0) of q_keep/out_keep.  d->q / d->out are
+ * per-minibatch scratch.  loss_steps (n_steps) and var_est_steps (2,n_steps) receive every step's
+ * values (var_est[:,m] at func_VAELE_DP_MQAM_shaping.py:64). */
+int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
+                        float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream);
+
+/* generic Adam update on n floats (torch.optim.Adam single-tensor semantics); state = [m|v|vmax] (3n floats),
+ * step_count is a device int32 incremented by the call when bump_step != 0 */
+int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,
+                     int32_t *step_count, int32_t bump_step, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * soft demapper alone: soft_dec (sf:529-542)
+ * ---------------------------------------------------------------------------------------------- */
+int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var, const float *amp, float nu_sc,
+                  int32_t n_lev, int32_t N, float *q, int64_t ld_q, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * evaluation: shift search and SER estimators (sf:188-338).  tx is the reference's float16
+ * data_tensor (2,2,N) (sf:89), passed as uint16_t bit patterns.
+ * ---------------------------------------------------------------------------------------------- */
+/* find_shift (sf:290-314) when q != NULL (E = sum_l amp_l q_I[l]), find_shift_symb_full (sf:316-338)
+ * when q == NULL (E = out[:,0,:]).  corr_out (2 comp,2 eq-pol,2 tx-pol,n_shift) |correlations|,
+ * shift_out int16 (2) = n_shift/2 - argmax, r_out int32 (1) in {0,1}.  scratch: n_shift*8 doubles. */
+int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, int64_t ld_out, const uint16_t *tx, int64_t ld_tx,
+                    const float *amp, int32_t n_lev, int32_t N, int32_t n_shift, float *corr_out, int16_t *shift_out,
+                    int32_t *r_out, void *scratch, void *stream);
+/* SER_IQflip (sf:188-222): counts int32 (2 flip,2 pol,4 rot) of symbol errors, ser_out float (2) = min/N */
+int vaeq_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, int32_t n_lev, int32_t N,
+                    int32_t *counts_out, float *ser_out, void *stream);
+/* SER_constell_shaping + dec_on_bound (sf:225-287): rescales rx IN PLACE (sf:242) like the reference.
+ * scratch: 4 doubles. */
+int vaeq_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx, const float *amp, const float *var,
+                      float nu_sc, int32_t n_lev, int32_t N, int32_t *counts_out, float *ser_out, void *scratch, void *stream);
+/* extension, not in the reference: achievable-rate estimate H(X)+E[log2 q(x_tx|y)] per pol (bit/2D symbol) */
+int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, const float *P, int32_t n_lev, int32_t N,
+             float *gmi_out, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CMA baselines (sf:341-488) and carrier phase estimation (sf:140-186)
+ * ---------------------------------------------------------------------------------------------- */
+#define VAEQ_CMA_SAMPLE 0 /* CMA      sf:341-379: tap update after every symbol                 */
+#define VAEQ_CMA_BATCH 1  /* CMAbatch sf:381-434: k%batchlen==0 && k!=0, window [k-batchlen,k)  */
+#define VAEQ_CMA_FLEX 2   /* CMAflex  sf:436-488: k%symb_step==0 && k>=batchlen                 */
+/* Rx (2,2,N) samples; h (2,2,2,M) updated in place when train != 0; out (2,2,N/sps); e (N/sps,2).
+ * n_runs independent runs may be batched: every pointer then strides by its tensor size per run
+ * (Rx by 4*ld... see INTEGRATION.md); n_runs == 1 for the reference call.  scratch: vaeq_cma_scratch_bytes. */
+size_t vaeq_cma_scratch_bytes(int32_t N, int32_t M, int32_t n_runs);
+int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float *h, int32_t M, float lr, int32_t batchlen,
+             int32_t symb_step, int32_t sps, int32_t train, float *out, float *e, int32_t n_runs, void *scratch,
+             void *stream);
+/* CPE (sf:140-186): y (2,2,N) -> y_corr (2,2,N); scratch: vaeq_cpe_scratch_bytes(N) */
+size_t vaeq_cpe_scratch_bytes(int32_t N);
+int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AWGN single-polarisation VAE-LE step: twoFIR.forward (AWGN_channel/func_VAELE_MQAM_shaping.py:214-231)
+ * + loss_function (:63-95) + backward + Adam(amsgrad=True) (:283-306)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vaeq_awgn_desc {
+    int32_t B, sps, M, n_lev;
+    float amp_mean; /* :271 */
+    float var;      /* 10^(-SNR/10), :272 */
+    const float *rx; /* (2,L) [I/Q][sample] */
+    const float *amp, *P;
+    float *W;       /* (1,2,M) */
+    float *h;       /* (2,M)   */
+    float *adam;    /* vaeq_adam_state_floats_awgn(M) floats */
+    float *q;       /* (2n,B) */
+    float *out;     /* (2,B)  */
+    float *loss;    /* (1)    */
+    float *gW, *gh; /* optional */
+    void *workspace;
+    size_t workspace_bytes;
+} vaeq_awgn_desc;
+size_t vaeq_awgn_workspace_bytes(int32_t B, int32_t M, int32_t n_lev);
+size_t vaeq_adam_state_floats_awgn(int32_t M);
+int vaeq_awgn_forward(const vaeq_awgn_desc *d, void *stream);
+int vaeq_awgn_forward_backward(const vaeq_awgn_desc *d, void *stream);
+int vaeq_awgn_train_step(const vaeq_awgn_desc *d, float lr_w, float lr_h, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEQ_H_ */

@@ -1,0 +1,146 @@
+"""GPU parity of the fused DP VAE step (through the C ABI) against the CPU oracle and the golden
+vectors produced by the reference.  Tolerances: out abs 2e-6; q abs 3e-5 (1e-7 in out is amplified
+by 1/(2 var) in the logits -- the reference itself moves by 3e-6 with the host thread count);
+loss / var_est / gradients / taps 1e-4 relative (north_star), measured against the float64 closed form."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as CF
+from oracle import vaeq_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+T = torch.from_numpy
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def make_eq(g, M, **kw):
+    from vae_equalizer_b200.dp import DPEqualizer
+    return DPEqualizer(M, 2, g["amp"], g["P"], g["var"], float(g["nu_sc"]), W0=T(g["W0"]), h0=T(g["h0"]), **kw)
+
+
+DP_CASES = ["dp_step_64qam_M25_B100", "dp_step_16qam_M9_B64", "dp_step_4qam_M5_B48", "dp_step_64qam_M25_B1000"]
+
+
+def test_kat_single_step():
+    g = load("kat_64qam_M25_B100")
+    eq = make_eq(g, 25)
+    q, out, loss, ve, gW, gh = eq.forward_backward(T(g["rx"]).cuda())
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - g["out"]).max() < 2e-6
+    assert np.abs(q.cpu().numpy() - g["q"]).max() < 3e-5
+    assert rel(loss, g["loss"]) < 1e-5 and rel(ve, g["var_est"]) < 1e-5
+    assert rel(gW, g["gW"]) < 1e-4 and rel(gh, g["gh"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", DP_CASES)
+def test_trajectory_vs_reference_golden(name):
+    g = load(name)
+    M = g["W0"].shape[-1]
+    eq = make_eq(g, M)
+    lr = float(g["lr"])
+    for s in range(g["rx"].shape[0]):
+        rx = T(g["rx"][s]).cuda()
+        # teacher-forced gradient check at the golden trajectory's taps, then the real step
+        q, out, loss, ve = eq.train_step(rx, lr, lr)
+        torch.cuda.synchronize()
+        assert np.abs(out.cpu().numpy() - g["out"][s]).max() < 5e-6, s
+        assert np.abs(q.cpu().numpy() - g["q"][s]).max() < 5e-5, s
+        assert rel(loss, g["loss"][s]) < 1e-4 and rel(ve, g["var_est"][s]) < 1e-4, s
+        assert rel(eq.gW, g["gW"][s]) < 2e-4 and rel(eq.gh, g["gh"][s]) < 2e-4, s
+        assert rel(eq.W, g["W"][s]) < 1e-4 and rel(eq.h, g["h"][s]) < 1e-4, s
+    assert eq.step_count() == g["rx"].shape[0]
+
+
+@pytest.mark.parametrize("mod,M,B,nu", [("64-QAM", 25, 3000, 0.0270955), ("16-QAM", 13, 1537, 0.0), ("64-QAM", 5, 777, 0.05),
+                                        ("4-QAM", 31, 2048, 0.0), ("64-QAM", 25, 40000, 0.0)])
+def test_multi_tile_against_closed_form(mod, M, B, nu):
+    """Sizes that span several tiles/CTAs; float64 closed form is the yardstick, and the fp32 torch
+    oracle's own error against it is printed beside ours."""
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", mod, "cpu", nu, 2, M, 20)
+    gen = torch.Generator().manual_seed(B + M)
+    sym = torch.tensor(amps, dtype=torch.float32)[torch.multinomial(torch.tensor(P), 4 * B, True, generator=gen)].reshape(2, 2, B)
+    rx = torch.zeros(2, 2, 2 * B)
+    rx[:, :, ::2] = sym
+    rx[:, :, 1::2] = 0.5 * (sym + torch.roll(sym, -1, -1))
+    c, s = np.cos(0.3), np.sin(0.3)
+    rx = torch.stack((c * rx[0] + s * rx[1], -s * rx[0] + c * rx[1])) + 0.05 * torch.randn(2, 2, 2 * B, generator=gen)
+    rx = rx.contiguous()
+    W0 = O.dirac_taps(M) + 0.03 * torch.randn(2, 4, M, generator=gen)
+    h0 = h_est.detach() + 0.03 * torch.randn(2, 2, 2, M, generator=gen)
+    Pt = torch.tensor(P, dtype=torch.float32)
+    from vae_equalizer_b200.dp import DPEqualizer
+    eq = DPEqualizer(M, 2, amp, Pt, var, nu_sc, W0=W0, h0=h0)
+    q, out, loss, ve, gW, gh = eq.forward_backward(rx.cuda())
+    torch.cuda.synchronize()
+    cf = CF.dp_step_closed_form(rx.numpy(), W0.numpy(), h0.numpy(), amp.numpy(), Pt.numpy(), var.numpy(), nu_sc)
+    assert np.abs(out.cpu().numpy() - cf["out"]).max() < 5e-6
+    assert np.abs(q.cpu().numpy() - cf["q"]).max() < 5e-5
+    assert rel(loss, cf["loss"]) < 1e-5 and rel(ve, cf["var_est"]) < 1e-5
+    e_gW, e_gh = rel(gW, cf["gW"]), rel(gh, cf["gh"])
+    print(f"{mod} M={M} B={B}: gW rel err {e_gW:.2e}, gh rel err {e_gh:.2e}")
+    assert e_gW < 1e-4 and e_gh < 1e-4
+    # decisions: argmax q must agree with the oracle wherever the top-2 gap is not a rounding tie
+    qo, outo = O.equalizer_forward(rx, W0, amp, var, nu_sc, 2)
+    n = amp.numel()
+    qg = q.cpu()
+    for rows in (slice(0, n), slice(n, 2 * n)):
+        dg, do = qg[:, rows].argmax(1), qo[:, rows].argmax(1)
+        top2 = torch.topk(qo[:, rows], 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+        assert bool((dg == do)[clear].all())
+
+
+def test_frame_api_matches_stepwise():
+    g = load("dp_step_64qam_M25_B100")
+    M, B = 25, 100
+    gen = torch.Generator().manual_seed(5)
+    frame = torch.cat([T(g["rx"][s]) for s in range(3)], dim=-1).contiguous()        # (2,2,600): 3 minibatches
+    lr = float(g["lr"])
+    eq = make_eq(g, M)
+    out_train = torch.zeros(2, 16, 300, device="cuda")
+    out_const = torch.zeros(2, 2, 300, device="cuda")
+    loss_s, var_s = eq.train_frame(frame.cuda(), B, B, 3, lr, lr, out_train, out_const, 0, B, keep_lo_in_dst=True)
+    torch.cuda.synchronize()
+    for s in range(3):
+        assert np.abs(out_const[:, :, s * B:(s + 1) * B].cpu().numpy() - g["out"][s]).max() < 5e-6
+        assert np.abs(out_train[:, :, s * B:(s + 1) * B].cpu().numpy() - g["q"][s]).max() < 5e-5
+        assert rel(loss_s[s], g["loss"][s]) < 1e-4 and rel(var_s[:, s], g["var_est"][s]) < 1e-4
+    assert rel(eq.W, g["W"][2]) < 1e-4 and rel(eq.h, g["h"][2]) < 1e-4
+    # VAE-flex style: window 100, stride 50, keep the centre 50 columns of every window
+    eq2 = make_eq(g, M)
+    ot = torch.zeros(2, 16, 250, device="cuda")
+    oc = torch.zeros(2, 2, 250, device="cuda")
+    eq2.train_frame(frame.cuda(), B, 50, 5, lr, lr, ot, oc, 25, 50)
+    tr = O.DPTrainer(M, 2, lr, W0=T(g["W0"]), h0=T(g["h0"]))
+    amp, var, P = T(g["amp"]), T(g["var"]), T(g["P"])
+    for m in range(5):
+        qo, oo, *_ = tr.step(frame[:, :, m * 100:m * 100 + 200], amp, var, float(g["nu_sc"]), P)
+        assert np.abs(oc[:, :, m * 50:m * 50 + 50].cpu().numpy() - oo[:, :, 25:75].numpy()).max() < 1e-4, m
+        assert np.abs(ot[:, :, m * 50:m * 50 + 50].cpu().numpy() - qo[:, :, 25:75].numpy()).max() < 2e-3, m
+    assert rel(eq2.W, tr.W.detach()) < 2e-4 and rel(eq2.h, tr.h.detach()) < 2e-4
+
+
+def test_bad_arguments_raise():
+    from vae_equalizer_b200 import VaeqError
+    from vae_equalizer_b200.dp import DPEqualizer
+    g = load("dp_step_16qam_M9_B64")
+    with pytest.raises(VaeqError):
+        DPEqualizer(8, 2, g["amp"], g["P"], g["var"], 0.0).forward(torch.zeros(2, 2, 128, device="cuda"))   # even M
+    with pytest.raises(VaeqError):
+        DPEqualizer(9, 2, g["amp"], g["P"], g["var"], 0.0).forward(torch.zeros(2, 2, 128))                  # CPU tensor
+    with pytest.raises(VaeqError):
+        DPEqualizer(9, 2, g["amp"], g["P"], g["var"], 0.0).forward(torch.zeros(2, 2, 12, device="cuda"))    # B <= Mh

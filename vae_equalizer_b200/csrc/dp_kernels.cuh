@@ -1,0 +1,50 @@
+// Kernel parameter block and workspace constants of the DP VAE step.
+#pragma once
+#include "common.cuh"
+
+namespace vaeq {
+
+constexpr int DP_NT = 256;        // threads per CTA
+constexpr int DP_TILE = 512;      // owned symbols per tile (generic kernels)
+constexpr int DP_GRID_CAP = 1184; // upper bound of any persistent grid (8 CTAs x 148 SMs)
+
+// float offsets inside the `scal` scratch block
+constexpr int DP_C_OFF = 0;       // C_chi                     (2)
+constexpr int DP_KAPPA_OFF = 2;   // (L-Mh)/C_chi              (2)
+constexpr int DP_LOSS_OFF = 4;    // loss                      (1)
+constexpr int DP_VAREST_OFF = 5;  // C/(L-Mh)                  (2)
+constexpr int DP_S_OFF = 8;       // S_nu(j)                   (2*M)
+
+constexpr int DP_MODE_FWD = 0, DP_MODE_FWDBWD = 1, DP_MODE_TRAIN = 2;
+
+struct DpK {
+    const float *rx;
+    int64_t ld_rx;
+    int B, L, M, mh, H;           // H = ceil(mh/2): halo in symbols of the channel convolution
+    const float *amp, *P, *var;
+    float nu_sc;
+    float *W, *h, *adam;
+    float *q;
+    int64_t ld_q;
+    float *out;
+    int64_t ld_out;
+    float *qk;
+    int64_t ld_qk;
+    float *outk;
+    int64_t ld_outk;
+    int keep_lo, keep_n;
+    int64_t keep_base;            // destination column of symbol keep_lo
+    double *part_fwd;             // [grid][8]: C0, C1, entropy, sum Var pol0, sum Var pol1
+    float *edge_vs;               // [2][2*mh]: Var_I+Var_Q of the first mh and last mh symbols
+    float *scal;
+    float4 *ebuf4;                // [L]: residual D - rx per sample (chi0 re, chi0 im, chi1 re, chi1 im)
+    float4 *m1buf4;               // [B]: E_q[x] per symbol (p0 I, p0 Q, p1 I, p1 Q)
+    float *gpart;                 // [grid][16*M]
+    float *gfinal;                // [16*M]: gW then gh
+    float *loss_out, *var_est_out;
+    int64_t var_est_stride;
+    float *gW_out, *gh_out;
+    int T, ntiles;
+};
+
+}  // namespace vaeq

@@ -1,0 +1,639 @@
+// DP VAE-LE / VAE-flex training step for B200 (sm_100a): generic-M reference kernels.
+//
+// One step = 4 launches on the caller's stream, all persistent over tiles of T symbols:
+//   k_dp_fwd   rx -> FIR -> soft demapper -> q, out (HBM), posterior moments -> estimated-channel
+//              convolution D -> residual e = D - rx (HBM scratch) -> per-CTA partial sums of C, entropy
+//   k_dp_fin   partials -> C, loss, var_est, kappa = (L-Mh)/C, S_nu(j)           (1 CTA)
+//   k_dp_bwd   e, moments, q, out, rx -> dL/dE_q -> softmin backward -> dL/dout -> per-CTA partial
+//              tap gradients (dW: correlation with rx, dh: correlation of e with E_q)
+//   k_dp_adam  deterministic reduction of the partial gradients (+ the E-term of dh) and Adam on
+//              both parameter groups                                              (1 CTA)
+// Reference: twoXtwoFIR.forward sf:500-527, loss_function_shaping sf:92-137, loss.backward() and
+// optimizer.step() at func_VAELE_DP_MQAM_shaping.py:60-66 (sf = optical_DP_channel/shared_funcs.py).
+// The closed form implemented here is restated (float64) in oracle/closed_form.py.
+#include "dp_math.cuh"
+#include "dp_kernels.cuh"
+
+namespace vaeq {
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
+    extern __shared__ __align__(16) float smem[];
+    const int M = p.M, mh = p.mh, H = p.H, T = p.T, TE = T + 2 * H, XN = 2 * TE + 2 * mh;
+    const int tid = threadIdx.x;
+    DemapConst *cst = reinterpret_cast<DemapConst *>(smem);
+    float4 *m1s = reinterpret_cast<float4 *>(cst + 1);  // E_q[x] per symbol of tile+halo
+    float *red = reinterpret_cast<float *>(m1s + TE);   // 5*32 floats
+    float *xs = red + 5 * 32;                           // 4 rows x XN samples (zero padded)
+    float *Ws = xs + 4 * XN;                            // (2,4,M)
+    float *hs = Ws + 8 * M;                             // (2,2,2,M)
+
+    for (int i = tid; i < 8 * M; i += DP_NT) {
+        Ws[i] = p.W[i];
+        hs[i] = p.h[i];
+    }
+    load_demap_const(cst, p.amp, p.P, p.var, p.nu_sc, NL);
+    __syncthreads();
+    const DemapConst &c = *cst;
+
+    float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
+
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int t0 = tile * T;
+        const int tn = min(T, p.B - t0);
+        const int sb = 2 * (t0 - H) - mh;               // first sample held in xs
+        for (int j = tid; j < 4 * XN; j += DP_NT) {
+            int r = j / XN, jj = j - r * XN, s = sb + jj;
+            xs[r * XN + jj] = (s >= 0 && s < p.L) ? p.rx[(int64_t)r * p.ld_rx + s] : 0.f;
+        }
+        __syncthreads();
+
+        // ---- FIR + demapper for the tile and its halo of H symbols each side -------------------
+        for (int i = tid; i < tn + 2 * H; i += DP_NT) {
+            const int u = t0 - H + i;
+            float4 mom = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u >= 0 && u < p.B) {
+                float y[4] = {0.f, 0.f, 0.f, 0.f};      // (p0 I, p0 Q, p1 I, p1 Q)
+                const float *x0 = xs + 2 * i;
+                for (int k = 0; k < M; ++k) {
+                    float xI0 = x0[k], xQ0 = x0[XN + k], xI1 = x0[2 * XN + k], xQ1 = x0[3 * XN + k];
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        float wr0 = Ws[(o * 4 + 0) * M + k], wr1 = Ws[(o * 4 + 1) * M + k];
+                        float wi0 = Ws[(o * 4 + 2) * M + k], wi1 = Ws[(o * 4 + 3) * M + k];
+                        y[2 * o] += wr0 * xI0 + wr1 * xI1 - wi0 * xQ0 - wi1 * xQ1;       // sf:505,509
+                        y[2 * o + 1] += wr0 * xQ0 + wr1 * xQ1 + wi0 * xI0 + wi1 * xI1;   // sf:507,509
+                    }
+                }
+                const bool owned = (i >= H) && (i < H + tn);
+                const bool ent_on = owned && (u >= mh) && (u < p.B - mh);                // sf:132 [mh:-mh] in symbols
+                const bool keep = owned && p.qk != nullptr && (u >= p.keep_lo) && (u < p.keep_lo + p.keep_n);
+                float m1v[4];
+                float vloc[2] = {0.f, 0.f};
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    float q[NL], m1, m2;
+                    demap_component<NL>(y[cc], c.var[cc >> 1], c, q, m1, m2);
+                    m1v[cc] = m1;
+                    if (owned) {
+                        float *qrow = p.q + (int64_t)(cc * NL) * p.ld_q + u;
+#pragma unroll
+                        for (int l = 0; l < NL; ++l) qrow[(int64_t)l * p.ld_q] = q[l];
+                        p.out[(int64_t)cc * p.ld_out + u] = y[cc];
+                        if (keep) {
+                            const int64_t col = p.keep_base + (u - p.keep_lo);
+                            float *krow = p.qk + (int64_t)(cc * NL) * p.ld_qk + col;
+#pragma unroll
+                            for (int l = 0; l < NL; ++l) krow[(int64_t)l * p.ld_qk] = q[l];
+                            p.outk[(int64_t)cc * p.ld_outk + col] = y[cc];
+                        }
+                        if (ent_on) accEnt += entropy_component<NL>(q, c);
+                    }
+                    vloc[cc >> 1] += m2 - m1 * m1;                                       // sf:113
+                }
+                mom = make_float4(m1v[0], m1v[1], m1v[2], m1v[3]);
+                if (owned) {
+                    accV[0] += vloc[0];
+                    accV[1] += vloc[1];
+                    if (u < mh || u >= p.B - mh) {       // S_nu(j) needs the first/last mh symbols individually
+                        const int slot = (u < mh) ? u : mh + (u - (p.B - mh));
+                        p.edge_vs[slot] = vloc[0];
+                        p.edge_vs[2 * mh + slot] = vloc[1];
+                    }
+                    p.m1buf4[u] = mom;
+                }
+            }
+            m1s[i] = mom;
+        }
+        __syncthreads();
+
+        // ---- estimated-channel convolution and residual for the owned samples (sf:123-134) -----
+        for (int i = tid; i < tn; i += DP_NT) {
+            const int u = t0 + i;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                const int s = 2 * u + ph;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s >= mh && s < p.L - mh) {                      // "valid" region, in samples
+                    float d0r = 0.f, d0i = 0.f, d1r = 0.f, d1i = 0.f;
+                    const int j0 = (s + mh) & 1;
+                    for (int j = j0; j < M; j += 2) {
+                        const int v = (2 * (i + H) + ph + mh - j) >> 1;     // local symbol index of E_q[n-j]
+                        const float4 m = m1s[v];
+                        // hs[chi][nu][c][j]
+                        float h00r = hs[(0 * 4 + 0) * M + j], h00i = hs[(0 * 4 + 1) * M + j];
+                        float h01r = hs[(0 * 4 + 2) * M + j], h01i = hs[(0 * 4 + 3) * M + j];
+                        float h10r = hs[(1 * 4 + 0) * M + j], h10i = hs[(1 * 4 + 1) * M + j];
+                        float h11r = hs[(1 * 4 + 2) * M + j], h11i = hs[(1 * 4 + 3) * M + j];
+                        d0r += h00r * m.x - h00i * m.y + h01r * m.z - h01i * m.w;     // sf:124-125
+                        d0i += h00i * m.x + h00r * m.y + h01i * m.z + h01r * m.w;     // sf:126-127
+                        d1r += h10r * m.x - h10i * m.y + h11r * m.z - h11i * m.w;
+                        d1i += h10i * m.x + h10r * m.y + h11i * m.z + h11r * m.w;
+                    }
+                    const float *xr = xs + 2 * (i + H) + ph + mh;   // rx sample s in the tile buffer
+                    e.x = d0r - xr[0];
+                    e.y = d0i - xr[XN];
+                    e.z = d1r - xr[2 * XN];
+                    e.w = d1i - xr[3 * XN];
+                    accC[0] += e.x * e.x + e.y * e.y;
+                    accC[1] += e.z * e.z + e.w * e.w;
+                }
+                p.ebuf4[2 * (int64_t)u + ph] = e;
+            }
+        }
+        __syncthreads();
+    }
+
+    float v[5] = {accC[0], accC[1], accEnt, accV[0], accV[1]};
+    block_sum<5>(v, red);
+    if (tid == 0) {
+        double *dst = p.part_fwd + (int64_t)blockIdx.x * 8;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) dst[i] = (double)v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize forward: C, loss, var_est, kappa, S_nu(j)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_dp_fin(DpK p, int nparts) {
+    __shared__ double tot[5];
+    __shared__ float Ssh[2 * VAEQ_MAX_TAPS];
+    const int tid = threadIdx.x, M = p.M, mh = p.mh, Mh = 2 * p.mh;
+    if (tid < 5) {
+        double a = 0.0;
+        for (int b = 0; b < nparts; ++b) a += p.part_fwd[(int64_t)b * 8 + tid];
+        tot[tid] = a;
+    }
+    __syncthreads();
+    // S_nu(j) = sum of (Var_I+Var_Q)[nu] over source symbols u with Mh <= 2u+j < L      (sf:128)
+    for (int idx = tid; idx < 2 * M; idx += blockDim.x) {
+        const int nu = idx / M, j = idx - nu * M;
+        double s = tot[3 + nu];
+        const int u_lo = (Mh - j + 1) >> 1;                 // first included symbol
+        const int u_hi = (p.L - 1 - j) >> 1;                // last included symbol
+        for (int u = 0; u < u_lo && u < mh; ++u) s -= (double)p.edge_vs[nu * 2 * mh + u];
+        for (int u = u_hi + 1; u < p.B; ++u) s -= (double)p.edge_vs[nu * 2 * mh + mh + (u - (p.B - mh))];
+        Ssh[idx] = (float)s;
+        p.scal[DP_S_OFF + idx] = (float)s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double width = (double)(p.L - Mh);
+        double loss = -tot[2];
+        for (int chi = 0; chi < 2; ++chi) {
+            double E = 0.0;
+            for (int nu = 0; nu < 2; ++nu)
+                for (int j = 0; j < M; ++j) {
+                    float hr = p.h[((chi * 2 + nu) * 2 + 0) * M + j], hi = p.h[((chi * 2 + nu) * 2 + 1) * M + j];
+                    E += (double)(hr * hr + hi * hi) * (double)Ssh[nu * M + j];             // sf:129
+                }
+            const double C = tot[chi] + E;                                                  // sf:133-134
+            loss += width * log(C);                                                         // sf:136
+            p.scal[DP_C_OFF + chi] = (float)C;
+            p.scal[DP_KAPPA_OFF + chi] = (float)(width / C);
+            const float ve = (float)(C / width);                                            // sf:137
+            p.scal[DP_VAREST_OFF + chi] = ve;
+            if (p.var_est_out) p.var_est_out[(int64_t)chi * p.var_est_stride] = ve;
+        }
+        p.scal[DP_LOSS_OFF] = (float)loss;
+        if (p.loss_out) *p.loss_out = (float)loss;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
+    extern __shared__ __align__(16) float smem[];
+    const int M = p.M, mh = p.mh, Mh = 2 * p.mh, H = p.H, T = p.T, TE = T + 2 * H, XN = 2 * TE + 2 * mh;
+    const int tid = threadIdx.x;
+    DemapConst *cst = reinterpret_cast<DemapConst *>(smem);
+    float4 *es = reinterpret_cast<float4 *>(cst + 1);   // 2*TE: gD per sample of tile+halo
+    float4 *m1s = es + 2 * TE;                          // TE
+    float4 *gys = m1s + TE;                             // T: dL/dout per owned symbol
+    float *xs = reinterpret_cast<float *>(gys + T);     // 4 rows x XN samples
+    float *hs = xs + 4 * XN;                            // (2,2,2,M)
+    float *PSg = hs + 8 * M;                            // (2, M+1) prefix sums of sum_chi kappa_chi |h|^2
+
+    for (int i = tid; i < 8 * M; i += DP_NT) hs[i] = p.h[i];
+    load_demap_const(cst, p.amp, p.P, p.var, p.nu_sc, NL);
+    const float kap0 = p.scal[DP_KAPPA_OFF], kap1 = p.scal[DP_KAPPA_OFF + 1];
+    __syncthreads();
+    if (tid < 2) {
+        const int nu = tid;
+        float a = 0.f;
+        PSg[nu * (M + 1)] = 0.f;
+        for (int j = 0; j < M; ++j) {
+            float h0r = hs[((0 * 2 + nu) * 2 + 0) * M + j], h0i = hs[((0 * 2 + nu) * 2 + 1) * M + j];
+            float h1r = hs[((1 * 2 + nu) * 2 + 0) * M + j], h1i = hs[((1 * 2 + nu) * 2 + 1) * M + j];
+            a += kap0 * (h0r * h0r + h0i * h0i) + kap1 * (h1r * h1r + h1i * h1i);
+            PSg[nu * (M + 1) + j + 1] = a;
+        }
+    }
+    __syncthreads();
+    const DemapConst &c = *cst;
+
+    // each thread owns up to two complex tap-gradient outputs: idx < 4M -> dh(chi,nu,j), else dW(o,in,k)
+    float accR[2] = {0.f, 0.f}, accI[2] = {0.f, 0.f};
+
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int t0 = tile * T;
+        const int tn = min(T, p.B - t0);
+        const int sb = 2 * (t0 - H) - mh;
+        for (int j = tid; j < 4 * XN; j += DP_NT) {
+            int r = j / XN, jj = j - r * XN, s = sb + jj;
+            xs[r * XN + jj] = (s >= 0 && s < p.L) ? p.rx[(int64_t)r * p.ld_rx + s] : 0.f;
+        }
+        for (int i = tid; i < 2 * TE; i += DP_NT) {          // gD = 2 kappa_chi (D - r), zero outside the valid region
+            const int64_t sidx = 2 * (int64_t)(t0 - H) + i;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sidx >= 0 && sidx < p.L) e = p.ebuf4[sidx];
+            e.x *= 2.f * kap0; e.y *= 2.f * kap0; e.z *= 2.f * kap1; e.w *= 2.f * kap1;
+            es[i] = e;
+        }
+        for (int i = tid; i < TE; i += DP_NT) {
+            const int u = t0 - H + i;
+            m1s[i] = (u >= 0 && u < p.B) ? p.m1buf4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        for (int i = tid; i < tn; i += DP_NT) {
+            const int u = t0 + i;
+            // dL/dE_q(u) = sum_chi sum_j conj(h[chi][nu][j]) gD_chi(2u - mh + j)
+            float g0r = 0.f, g0i = 0.f, g1r = 0.f, g1i = 0.f;
+            const int sl = 2 * (i + H) - mh;
+            for (int j = 0; j < M; ++j) {
+                const float4 e = es[sl + j];
+                float h00r = hs[(0 * 4 + 0) * M + j], h00i = hs[(0 * 4 + 1) * M + j];
+                float h01r = hs[(0 * 4 + 2) * M + j], h01i = hs[(0 * 4 + 3) * M + j];
+                float h10r = hs[(1 * 4 + 0) * M + j], h10i = hs[(1 * 4 + 1) * M + j];
+                float h11r = hs[(1 * 4 + 2) * M + j], h11i = hs[(1 * 4 + 3) * M + j];
+                g0r += h00r * e.x + h00i * e.y + h10r * e.z + h10i * e.w;
+                g0i += h00r * e.y - h00i * e.x + h10r * e.w - h10i * e.z;
+                g1r += h01r * e.x + h01i * e.y + h11r * e.z + h11i * e.w;
+                g1i += h01r * e.y - h01i * e.x + h11r * e.w - h11i * e.z;
+            }
+            // dL/dVar_nu(u) = sum_chi kappa_chi sum_{j: Mh <= 2u+j < L} |h|^2
+            const int jlo = max(0, Mh - 2 * u), jhi = min(M, p.L - 2 * u);
+            const float gV0 = PSg[jhi] - PSg[jlo];
+            const float gV1 = PSg[(M + 1) + jhi] - PSg[(M + 1) + jlo];
+            const float4 mom = m1s[i + H];
+            const float m1v[4] = {mom.x, mom.y, mom.z, mom.w};
+            const float gE[4] = {g0r, g0i, g1r, g1i};
+            const bool ent_on = (u >= mh) && (u < p.B - mh);
+            float gy[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float q[NL];
+                const float *qrow = p.q + (int64_t)(cc * NL) * p.ld_q + u;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) q[l] = qrow[(int64_t)l * p.ld_q];
+                const float y = p.out[(int64_t)cc * p.ld_out + u];
+                const float gV = (cc >> 1) ? gV1 : gV0;
+                const float g1 = gE[cc] - 2.f * m1v[cc] * gV;
+                gy[cc] = demap_backward<NL>(y, c.var[cc >> 1], c, q, g1, gV, ent_on);
+            }
+            gys[i] = make_float4(gy[0], gy[1], gy[2], gy[3]);
+        }
+        __syncthreads();
+
+        // ---- tap gradients: one complex output per thread slot, summed over the owned samples ----
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+            const int idx = tid + slot * DP_NT;
+            if (idx < 4 * M) {                               // dh[chi][nu][:, j]
+                const int j = idx % M, cn = idx / M, chi = cn >> 1, nu = cn & 1;
+                float ar = 0.f, ai = 0.f;
+                const int par = (mh + j) & 1;
+                for (int sl = 2 * H + par; sl < 2 * H + 2 * tn; sl += 2) {
+                    const float4 e = es[sl];
+                    const float4 m = m1s[(sl + mh - j) >> 1];
+                    const float gr = chi ? e.z : e.x, gi = chi ? e.w : e.y;
+                    const float er = nu ? m.z : m.x, ei = nu ? m.w : m.y;
+                    ar += gr * er + gi * ei;
+                    ai += gi * er - gr * ei;
+                }
+                accR[slot] += ar;
+                accI[slot] += ai;
+            } else if (idx < 8 * M) {                        // dW[o][in | 2+in][k]
+                const int id2 = idx - 4 * M;
+                const int k = id2 % M, oi = id2 / M, o = oi >> 1, in = oi & 1;
+                float ar = 0.f, ai = 0.f;
+                const float *xI = xs + (2 * in) * XN + 2 * H + k, *xQ = xs + (2 * in + 1) * XN + 2 * H + k;
+                for (int i = 0; i < tn; ++i) {
+                    const float4 g = gys[i];
+                    const float gI = o ? g.z : g.x, gQ = o ? g.w : g.y;
+                    const float a = xI[2 * i], b = xQ[2 * i];
+                    ar += gI * a + gQ * b;
+                    ai += gQ * a - gI * b;
+                }
+                accR[slot] += ar;
+                accI[slot] += ai;
+            }
+        }
+        __syncthreads();
+    }
+
+    float *gp = p.gpart + (int64_t)blockIdx.x * 16 * M;     // layout: gW (2,4,M) then gh (2,2,2,M)
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+        const int idx = tid + slot * DP_NT;
+        if (idx < 4 * M) {
+            const int j = idx % M, cn = idx / M;
+            gp[8 * M + (cn * 2 + 0) * M + j] = accR[slot];
+            gp[8 * M + (cn * 2 + 1) * M + j] = accI[slot];
+        } else if (idx < 8 * M) {
+            const int id2 = idx - 4 * M;
+            const int k = id2 % M, oi = id2 / M, o = oi >> 1, in = oi & 1;
+            gp[(o * 4 + in) * M + k] = accR[slot];
+            gp[(o * 4 + 2 + in) * M + k] = accI[slot];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient reduction + Adam (torch.optim.Adam single-tensor semantics, see oracle/closed_form.py)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_apply(float *param, float g, float *m, float *v, float *vmax, int i, float lr,
+                                           bool amsgrad, int step) {
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);                        // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * b2 + (1.f - b2) * g * g;                      // exp_avg_sq.mul_(beta2).addcmul_(g,g,1-beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const double bc1 = 1.0 - pow(0.9, (double)step);
+    const double bc2 = 1.0 - pow(0.999, (double)step);
+    const float step_size = (float)(-(double)lr / bc1);
+    const float bc2s = (float)sqrt(bc2);
+    float vv = vi;
+    if (amsgrad) {
+        vv = fmaxf(vmax[i], vi);
+        vmax[i] = vv;
+    }
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), bc2s), eps);
+    param[i] = __fadd_rn(param[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+}
+
+__global__ void k_dp_adam(DpK p, int nparts, int do_update, float lr_w, float lr_h, int amsgrad) {
+    const int M = p.M, n = 16 * M;
+    __shared__ int step_sh;
+    int *step_ptr = p.adam ? reinterpret_cast<int *>(p.adam + 48 * M) : nullptr;
+    if (threadIdx.x == 0 && do_update) {
+        step_sh = *step_ptr + 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = 0.0;
+        for (int b = 0; b < nparts; ++b) a += (double)p.gpart[(int64_t)b * n + i];
+        if (i >= 8 * M) {                                   // E-term of dh: 2 kappa_chi h S_nu(j)
+            const int r = i - 8 * M, j = r % M, cn = r / (2 * M), chi = cn >> 1, nu = cn & 1;
+            a += 2.0 * (double)p.scal[DP_KAPPA_OFF + chi] * (double)p.h[r] * (double)p.scal[DP_S_OFF + nu * M + j];
+        }
+        const float g = (float)a;
+        p.gfinal[i] = g;
+        if (i < 8 * M) {
+            if (p.gW_out) p.gW_out[i] = g;
+        } else {
+            if (p.gh_out) p.gh_out[i - 8 * M] = g;
+        }
+        if (do_update) {
+            if (i < 8 * M)
+                adam_apply(p.W, g, p.adam, p.adam + 8 * M, p.adam + 16 * M, i, lr_w, amsgrad != 0, step_sh);
+            else
+                adam_apply(p.h, g, p.adam + 24 * M, p.adam + 32 * M, p.adam + 40 * M, i - 8 * M, lr_h, amsgrad != 0, step_sh);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && do_update) *step_ptr = step_sh;
+}
+
+__global__ void k_adam_generic(float *param, const float *grad, float *state, int n, float lr, int amsgrad,
+                               int *step_count, int bump) {
+    __shared__ int step_sh;
+    if (threadIdx.x == 0) step_sh = *step_count + (bump ? 1 : 0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        adam_apply(param, grad[i], state, state + n, state + 2 * n, i, lr, amsgrad != 0, step_sh);
+    __syncthreads();
+    if (threadIdx.x == 0 && bump) *step_count = step_sh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// soft demapper alone (soft_dec, sf:529-542)
+// ---------------------------------------------------------------------------------------------
+template <int NL>
+__global__ void k_soft_dec(const float *out, int64_t ld_out, const float *var, const float *amp, float nu_sc, int N,
+                           float *q, int64_t ld_q) {
+    __shared__ DemapConst cst;
+    load_demap_const(&cst, amp, nullptr, var, nu_sc, NL);
+    __syncthreads();
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < N; u += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float qv[NL], m1, m2;
+            demap_component<NL>(out[(int64_t)cc * ld_out + u], cst.var[cc >> 1], cst, qv, m1, m2);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) q[(int64_t)(cc * NL + l) * ld_q + u] = qv[l];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static size_t dp_fwd_smem(int M, int T, int H, int mh) {
+    const int TE = T + 2 * H, XN = 2 * TE + 2 * mh;
+    size_t f = sizeof(DemapConst) / 4 + 4 * TE + 5 * 32 + 4 * XN + 16 * M;
+    return f * sizeof(float);
+}
+static size_t dp_bwd_smem(int M, int T, int H, int mh) {
+    const int TE = T + 2 * H, XN = 2 * TE + 2 * mh;
+    size_t f = sizeof(DemapConst) / 4 + 8 * TE + 4 * TE + 4 * T + 4 * XN + 8 * M + 2 * (M + 1);
+    return f * sizeof(float);
+}
+
+struct DpWsLayout {
+    size_t part_fwd, edge_vs, scal, ebuf, m1buf, gpart, gfinal, total;
+};
+static DpWsLayout dp_ws_layout(int B, int M) {
+    DpWsLayout w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    w.part_fwd = take((size_t)DP_GRID_CAP * 8 * sizeof(double));
+    w.edge_vs = take((size_t)4 * (VAEQ_MAX_TAPS / 2 + 1) * sizeof(float));
+    w.scal = take((size_t)(DP_S_OFF + 2 * VAEQ_MAX_TAPS) * sizeof(float));
+    w.ebuf = take((size_t)B * 8 * sizeof(float));
+    w.m1buf = take((size_t)B * 4 * sizeof(float));
+    w.gpart = take((size_t)DP_GRID_CAP * 16 * M * sizeof(float));
+    w.gfinal = take((size_t)16 * M * sizeof(float));
+    w.total = off;
+    return w;
+}
+
+static int dp_validate(const vaeq_dp_desc *d, bool need_grads, bool need_adam) {
+    VAEQ_CHECK_ARG(d != nullptr, "desc is NULL");
+    VAEQ_CHECK_ARG(d->sps == 2, "sps=%d: only sps=2 is implemented (every reference driver uses 2)", d->sps);
+    VAEQ_CHECK_ARG(d->M >= 1 && d->M <= VAEQ_MAX_TAPS && (d->M & 1), "M_est=%d must be odd and <= %d", d->M, VAEQ_MAX_TAPS);
+    VAEQ_CHECK_ARG(d->n_lev == 2 || d->n_lev == 4 || d->n_lev == 8, "n_lev=%d must be 2, 4 or 8", d->n_lev);
+    VAEQ_CHECK_ARG(d->B > 2 * (d->M / 2), "batch_len=%d must exceed M_est-1=%d (the loss's valid region is empty)", d->B, 2 * (d->M / 2));
+    VAEQ_CHECK_ARG(d->rx && d->amp && d->P && d->var && d->W && d->h && d->q && d->out, "NULL tensor pointer");
+    VAEQ_CHECK_ARG(d->ld_rx >= (int64_t)d->B * d->sps && d->ld_q >= d->B && d->ld_out >= d->B, "row stride smaller than the row");
+    VAEQ_CHECK_ARG(!need_grads || need_adam || (d->gW && d->gh), "gW/gh must be given");
+    VAEQ_CHECK_ARG(!need_adam || d->adam, "adam state is NULL");
+    VAEQ_CHECK_ARG(d->workspace != nullptr, "workspace is NULL");
+    if (d->workspace_bytes < vaeq_dp_workspace_bytes(d->B, d->M, d->n_lev)) {
+        set_error("workspace too small: %zu < %zu", d->workspace_bytes, vaeq_dp_workspace_bytes(d->B, d->M, d->n_lev));
+        return VAEQ_EWORKSPACE;
+    }
+    if (d->q_keep) VAEQ_CHECK_ARG(d->out_keep && d->keep_n >= 0 && d->keep_lo >= 0, "bad keep window");
+    return VAEQ_OK;
+}
+
+static DpK dp_make_params(const vaeq_dp_desc *d) {
+    DpK p;
+    memset(&p, 0, sizeof(p));
+    const DpWsLayout w = dp_ws_layout(d->B, d->M);
+    char *ws = static_cast<char *>(d->workspace);
+    p.rx = d->rx; p.ld_rx = d->ld_rx;
+    p.B = d->B; p.L = d->B * d->sps; p.M = d->M; p.mh = d->M / 2; p.H = (p.mh + 1) / 2;
+    p.W = d->W; p.h = d->h; p.amp = d->amp; p.P = d->P; p.var = d->var; p.nu_sc = d->nu_sc;
+    p.q = d->q; p.ld_q = d->ld_q; p.out = d->out; p.ld_out = d->ld_out;
+    p.qk = d->q_keep; p.ld_qk = d->ld_q_keep; p.outk = d->out_keep; p.ld_outk = d->ld_out_keep;
+    p.keep_lo = d->keep_lo; p.keep_n = d->keep_n; p.keep_base = 0;
+    p.part_fwd = reinterpret_cast<double *>(ws + w.part_fwd);
+    p.edge_vs = reinterpret_cast<float *>(ws + w.edge_vs);
+    p.scal = reinterpret_cast<float *>(ws + w.scal);
+    p.ebuf4 = reinterpret_cast<float4 *>(ws + w.ebuf);
+    p.m1buf4 = reinterpret_cast<float4 *>(ws + w.m1buf);
+    p.gpart = reinterpret_cast<float *>(ws + w.gpart);
+    p.gfinal = reinterpret_cast<float *>(ws + w.gfinal);
+    p.adam = d->adam;
+    p.loss_out = d->loss; p.var_est_out = d->var_est; p.var_est_stride = 1;
+    p.gW_out = d->gW; p.gh_out = d->gh;
+    p.T = DP_TILE;
+    p.ntiles = (d->B + p.T - 1) / p.T;
+    return p;
+}
+
+template <int NL>
+static int dp_run(const DpK &p, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
+    static int grid_fwd[VAEQ_MAX_TAPS + 1] = {0}, grid_bwd[VAEQ_MAX_TAPS + 1] = {0};   // cached per M_est
+    static size_t set_f = 0, set_b = 0;
+    const size_t sm_f = dp_fwd_smem(p.M, p.T, p.H, p.mh), sm_b = dp_bwd_smem(p.M, p.T, p.H, p.mh);
+    if (sm_f > set_f) {
+        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_fwd<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f));
+        set_f = sm_f;
+    }
+    if (sm_b > set_b) {
+        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_bwd<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+        set_b = sm_b;
+    }
+    if (!grid_fwd[p.M]) {
+        int per = 0;
+        VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_dp_fwd<NL>, DP_NT, sm_f));
+        grid_fwd[p.M] = max(1, per) * sm_count();
+        VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_dp_bwd<NL>, DP_NT, sm_b));
+        grid_bwd[p.M] = max(1, per) * sm_count();
+    }
+    const int gf = min(min(grid_fwd[p.M], DP_GRID_CAP), p.ntiles), gb = min(min(grid_bwd[p.M], DP_GRID_CAP), p.ntiles);
+    k_dp_fwd<NL><<<gf, DP_NT, sm_f, st>>>(p);
+    VAEQ_LAUNCH_CHECK("k_dp_fwd");
+    k_dp_fin<<<1, 64, 0, st>>>(p, gf);
+    VAEQ_LAUNCH_CHECK("k_dp_fin");
+    if (mode == DP_MODE_FWD) return VAEQ_OK;
+    k_dp_bwd<NL><<<gb, DP_NT, sm_b, st>>>(p);
+    VAEQ_LAUNCH_CHECK("k_dp_bwd");
+    k_dp_adam<<<1, 512, 0, st>>>(p, gb, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
+    VAEQ_LAUNCH_CHECK("k_dp_adam");
+    return VAEQ_OK;
+}
+
+static int dp_dispatch(const DpK &p, int n_lev, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
+    switch (n_lev) {
+        case 2: return dp_run<2>(p, mode, lr_w, lr_h, amsgrad, st);
+        case 4: return dp_run<4>(p, mode, lr_w, lr_h, amsgrad, st);
+        default: return dp_run<8>(p, mode, lr_w, lr_h, amsgrad, st);
+    }
+}
+
+}  // namespace vaeq
+
+using namespace vaeq;
+
+extern "C" size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev) {
+    (void)n_lev;
+    if (B <= 0 || M <= 0) return 0;
+    return dp_ws_layout(B, M).total;
+}
+
+extern "C" size_t vaeq_adam_state_floats(int32_t M) { return (size_t)48 * M + 4; }
+
+extern "C" int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream) {
+    int rc = dp_validate(d, false, false);
+    if (rc) return rc;
+    return dp_dispatch(dp_make_params(d), d->n_lev, DP_MODE_FWD, 0.f, 0.f, 0, (cudaStream_t)stream);
+}
+
+extern "C" int vaeq_dp_forward_backward(const vaeq_dp_desc *d, void *stream) {
+    int rc = dp_validate(d, true, false);
+    if (rc) return rc;
+    return dp_dispatch(dp_make_params(d), d->n_lev, DP_MODE_FWDBWD, 0.f, 0.f, 0, (cudaStream_t)stream);
+}
+
+extern "C" int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stream) {
+    int rc = dp_validate(d, true, true);
+    if (rc) return rc;
+    return dp_dispatch(dp_make_params(d), d->n_lev, DP_MODE_TRAIN, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
+                                   float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream) {
+    int rc = dp_validate(d, true, true);
+    if (rc) return rc;
+    VAEQ_CHECK_ARG(n_steps >= 0 && stride_sym > 0, "bad n_steps/stride");
+    VAEQ_CHECK_ARG(d->ld_rx >= ((int64_t)(n_steps - 1) * stride_sym + d->B) * d->sps, "frame shorter than the last window");
+    DpK base = dp_make_params(d);
+    for (int m = 0; m < n_steps; ++m) {
+        DpK p = base;
+        p.rx = d->rx + (int64_t)m * stride_sym * d->sps;
+        p.keep_base = (int64_t)m * stride_sym + (keep_lo_in_dst ? d->keep_lo : 0);
+        p.loss_out = loss_steps ? loss_steps + m : nullptr;
+        p.var_est_out = var_est_steps ? var_est_steps + m : nullptr;
+        p.var_est_stride = n_steps;
+        rc = dp_dispatch(p, d->n_lev, DP_MODE_TRAIN, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return VAEQ_OK;
+}
+
+extern "C" int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,
+                                int32_t *step_count, int32_t bump_step, void *stream) {
+    VAEQ_CHECK_ARG(param && grad && state && step_count && n > 0, "bad adam arguments");
+    k_adam_generic<<<1, 256, 0, (cudaStream_t)stream>>>(param, grad, state, n, lr, amsgrad, step_count, bump_step);
+    VAEQ_LAUNCH_CHECK("k_adam_generic");
+    return VAEQ_OK;
+}
+
+extern "C" int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var, const float *amp, float nu_sc,
+                             int32_t n_lev, int32_t N, float *q, int64_t ld_q, void *stream) {
+    VAEQ_CHECK_ARG(out && var && amp && q && N > 0, "bad soft_dec arguments");
+    VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
+    const int nt = 256, grid = min((N + nt - 1) / nt, sm_count() * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_lev == 2) k_soft_dec<2><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+    else if (n_lev == 4) k_soft_dec<4><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+    else k_soft_dec<8><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+    VAEQ_LAUNCH_CHECK("k_soft_dec");
+    return VAEQ_OK;
+}

@@ -1,0 +1,151 @@
+"""Host-side owner of one DP VAE-LE / VAE-flex run: taps, channel estimate, Adam state, scratch.
+
+Mirrors what func_VAELE_DP_MQAM_shaping.processing builds at lines 21-36 of the reference
+(net = twoXtwoFIR, optimizer = Adam(net.parameters()) + add_param_group(h_est)) and steps it with
+the fused CUDA path (vaeq_dp_* in include/vaeq.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_F32 = torch.float32
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.VaeqError(f"{name} must be a CUDA tensor: vae_equalizer_b200 has no CPU path")
+    if t.dtype != _F32:
+        raise _lib.VaeqError(f"{name} must be float32, got {t.dtype}")
+
+
+class DPEqualizer:
+    """Trainable state of one run + the fused step.
+
+    W (2,4,M): twoXtwoFIR.conv_w.weight, Dirac-initialised (sf:494-495);
+    h (2,2,2,M): h_est, Dirac-initialised (sf:583-585).
+    """
+
+    def __init__(self, M_est: int, sps: int, amp_levels, P, var, nu_sc: float, device="cuda", W0=None, h0=None,
+                 amsgrad=False):
+        self.lib = _lib.load()
+        self.M, self.sps, self.nu_sc = int(M_est), int(sps), float(nu_sc)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.VaeqError("DPEqualizer needs a CUDA device: there is no CPU path")
+        self.device = dev
+        self.amp = torch.as_tensor(amp_levels, dtype=_F32).to(dev).contiguous()
+        self.P = torch.as_tensor(P, dtype=_F32).to(dev).contiguous()
+        self.var = torch.as_tensor(var, dtype=_F32).to(dev).contiguous()
+        self.n_lev = int(self.amp.numel())
+        M = self.M
+        if W0 is None:
+            W0 = torch.zeros(2, 4, M, dtype=_F32)
+            W0[0, 0, M // 2] = 1.0
+            W0[1, 1, M // 2] = 1.0
+        if h0 is None:
+            h0 = torch.zeros(2, 2, 2, M, dtype=_F32)
+            h0[0, 0, 0, M // 2] = 1.0
+            h0[1, 1, 0, M // 2] = 1.0
+        self.W = torch.as_tensor(W0, dtype=_F32).detach().clone().to(dev).contiguous()
+        self.h = torch.as_tensor(h0, dtype=_F32).detach().clone().to(dev).contiguous()
+        self.adam = torch.zeros(int(self.lib.vaeq_adam_state_floats(M)), dtype=_F32, device=dev)
+        self.flags = 1 if amsgrad else 0
+        self.gW = torch.zeros(2, 4, M, dtype=_F32, device=dev)
+        self.gh = torch.zeros(2, 2, 2, M, dtype=_F32, device=dev)
+        self.loss = torch.zeros(1, dtype=_F32, device=dev)
+        self.var_est = torch.zeros(2, dtype=_F32, device=dev)
+        self._ws = None
+        self._ws_B = -1
+
+    # -- scratch ---------------------------------------------------------------------------------
+    def _workspace(self, B: int):
+        if self._ws is None or self._ws_B < B:
+            nbytes = int(self.lib.vaeq_dp_workspace_bytes(B, self.M, self.n_lev))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_B = B
+        return self._ws
+
+    def step_count(self) -> int:
+        return int(self.adam[48 * self.M:48 * self.M + 1].view(torch.int32).item())
+
+    def _desc(self, rx, q, out, B, ld_rx=None, q_keep=None, out_keep=None, keep_lo=0, keep_n=0):
+        _require_cuda(rx, "rx")
+        ws = self._workspace(B)
+        d = _lib.DpDesc()
+        d.B, d.sps, d.M, d.n_lev = B, self.sps, self.M, self.n_lev
+        d.nu_sc, d.flags = self.nu_sc, self.flags
+        d.rx, d.ld_rx = rx.data_ptr(), int(rx.stride(1) if ld_rx is None else ld_rx)
+        d.amp, d.P, d.var = self.amp.data_ptr(), self.P.data_ptr(), self.var.data_ptr()
+        d.W, d.h, d.adam = self.W.data_ptr(), self.h.data_ptr(), self.adam.data_ptr()
+        d.q, d.ld_q = q.data_ptr(), int(q.stride(1))
+        d.out, d.ld_out = out.data_ptr(), int(out.stride(1))
+        if q_keep is not None:
+            d.q_keep, d.ld_q_keep = q_keep.data_ptr(), int(q_keep.stride(1))
+            d.out_keep, d.ld_out_keep = out_keep.data_ptr(), int(out_keep.stride(1))
+            d.keep_lo, d.keep_n = int(keep_lo), int(keep_n)
+        d.loss, d.var_est = self.loss.data_ptr(), self.var_est.data_ptr()
+        d.gW, d.gh = self.gW.data_ptr(), self.gh.data_ptr()
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        return d
+
+    def _check_rx(self, rx):
+        if rx.dim() != 3 or rx.shape[0] != 2 or rx.shape[1] != 2 or rx.stride(2) != 1 or rx.stride(0) != 2 * rx.stride(1):
+            raise _lib.VaeqError(f"rx must be (2,2,L) with unit time stride, got {tuple(rx.shape)} strides {rx.stride()}")
+        return rx.shape[2] // self.sps
+
+    def _alloc_out(self, B):
+        q = torch.empty(2, 2 * self.n_lev, B, dtype=_F32, device=self.device)
+        out = torch.empty(2, 2, B, dtype=_F32, device=self.device)
+        return q, out
+
+    # -- the three entry points --------------------------------------------------------------------
+    def forward(self, rx, q=None, out=None):
+        """net(minibatch) + loss_function_shaping without gradients -> (q, out, loss(1), var_est(2))."""
+        B = self._check_rx(rx)
+        if q is None:
+            q, out = self._alloc_out(B)
+        d = self._desc(rx, q, out, B)
+        _lib.check(self.lib.vaeq_dp_forward(C.byref(d), _lib.current_stream()), "vaeq_dp_forward")
+        return q, out, self.loss, self.var_est
+
+    def forward_backward(self, rx, q=None, out=None):
+        """As forward, plus gW (2,4,M) and gh (2,2,2,M); parameters untouched."""
+        B = self._check_rx(rx)
+        if q is None:
+            q, out = self._alloc_out(B)
+        d = self._desc(rx, q, out, B)
+        _lib.check(self.lib.vaeq_dp_forward_backward(C.byref(d), _lib.current_stream()), "vaeq_dp_forward_backward")
+        return q, out, self.loss, self.var_est, self.gW, self.gh
+
+    def train_step(self, rx, lr_w, lr_h=None, q=None, out=None):
+        """One optimizer step (VAELE_DP:59-66).  lr_h defaults to lr_w."""
+        B = self._check_rx(rx)
+        if q is None:
+            q, out = self._alloc_out(B)
+        d = self._desc(rx, q, out, B)
+        lr_h = lr_w if lr_h is None else lr_h
+        _lib.check(self.lib.vaeq_dp_train_step(C.byref(d), float(lr_w), float(lr_h), _lib.current_stream()),
+                   "vaeq_dp_train_step")
+        return q, out, self.loss, self.var_est
+
+    def train_frame(self, rx_frame, batch_len, stride_sym, n_steps, lr_w, lr_h, out_train, out_const, keep_lo, keep_n,
+                    keep_lo_in_dst=False):
+        """All minibatches of one frame (VAELE_DP:57-66 / VAEflex_DP:59-70).
+
+        Returns (loss_steps (n_steps,), var_est_steps (2,n_steps)) device tensors."""
+        self._check_rx(rx_frame)
+        B = int(batch_len)
+        if not hasattr(self, "_q_scratch") or self._q_scratch.shape[-1] != B:
+            self._q_scratch, self._out_scratch = self._alloc_out(B)
+        d = self._desc(rx_frame, self._q_scratch, self._out_scratch, B, ld_rx=rx_frame.stride(1), q_keep=out_train,
+                       out_keep=out_const, keep_lo=keep_lo, keep_n=keep_n)
+        loss_steps = torch.empty(n_steps, dtype=_F32, device=self.device)
+        var_steps = torch.empty(2, n_steps, dtype=_F32, device=self.device)
+        _lib.check(self.lib.vaeq_dp_train_frame(C.byref(d), int(n_steps), int(stride_sym), 1 if keep_lo_in_dst else 0,
+                                                float(lr_w), float(lr_h), loss_steps.data_ptr(), var_steps.data_ptr(),
+                                                _lib.current_stream()), "vaeq_dp_train_frame")
+        return loss_steps, var_steps
