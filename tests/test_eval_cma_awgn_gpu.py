@@ -1,0 +1,189 @@
+"""GPU parity (through the C ABI / the shared_funcs mirror) of the evaluation kernels, the CMA family,
+CPE and the AWGN variant against the golden vectors generated from the reference and the CPU oracle.
+Integer work (decisions, error counts, shifts) must be bit-exact; floats within the stated tolerances."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vaeq_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+T = torch.from_numpy
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("name", ["eval_64qam_N2000", "eval_16qam_N1500_swap"])
+def test_eval_against_reference_golden(name):
+    import vae_equalizer_b200.shared_funcs as sfun
+    g = load(name)
+    amp, var, nu_sc = T(g["amp"]).cuda(), T(g["var"]).cuda(), float(g["nu_sc"])
+    q = sfun.soft_dec(T(g["out"]).cuda(), var, amp, nu_sc)
+    assert np.abs(q.cpu().numpy() - g["q"]).max() < 2e-5
+    tx = T(g["tx"]).cuda()
+    s, r = sfun.find_shift(T(g["q"]).cuda(), tx, 21, amp, 2)
+    assert s.dtype == torch.int16 and s.tolist() == g["shift_q"].tolist() and r == int(g["r_q"])
+    s, r, corr = sfun.find_shift_symb_full(T(g["out"]).cuda(), tx, 21, return_corr=True)
+    assert s.tolist() == g["shift_c"].tolist() and r == int(g["r_c"])
+    _, _, corr_o = O.find_shift_symb_full(T(g["out"]), T(g["tx"]), 21, return_corr=True)
+    assert rel(corr, corr_o) < 1e-5
+    # SER from posteriors: counts bit-exact against the oracle, SER equal to the reference's float
+    ser, counts = sfun.SER_IQflip(T(g["q_cut"]).cuda(), T(g["tx_cut_q"]).cuda(), return_counts=True)
+    counts_o, N = O.ser_iqflip_counts(T(g["q_cut"]), T(g["tx_cut_q"]))
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), counts_o.numpy())
+    assert np.array_equal(ser.cpu().numpy(), g["ser_q"])
+    # SER from the constellation: in-place rescale reproduced, counts bit-exact
+    rx = T(g["o_cut_in"].copy()).cuda()
+    ser, counts = sfun.SER_constell_shaping(rx, T(g["tx_cut_c"]).cuda(), amp, nu_sc, var, return_counts=True)
+    counts_o, N = O.ser_constell_counts(T(g["o_cut_in"].copy()), T(g["tx_cut_c"]), T(g["amp"]), nu_sc, T(g["var"]))
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), counts_o.numpy())
+    assert np.array_equal(ser.cpu().numpy(), g["ser_c"])
+    assert np.abs(rx.cpu().numpy() - g["o_cut_scaled"]).max() < 1e-6
+    # strided views (what the drivers pass): same answer as the contiguous call
+    big = torch.zeros(2, 16 if name.startswith("eval_64") else 8, g["q_cut"].shape[-1] + 30, device="cuda")
+    big[:, :, 7:7 + g["q_cut"].shape[-1]] = T(g["q_cut"]).cuda()
+    ser2 = sfun.SER_IQflip(big[:, :, 7:7 + g["q_cut"].shape[-1]], T(g["tx_cut_q"]).cuda())
+    assert np.array_equal(ser2.cpu().numpy(), g["ser_q"])
+    # GMI extension against its CPU definition
+    gmi = sfun.GMI(T(g["q_cut"]).cuda(), T(g["tx_cut_q"]).cuda(), g["P"])
+    gmi_o = O.gmi_from_posteriors(T(g["q_cut"]), T(g["tx_cut_q"]), T(g["P"]))
+    assert np.abs(gmi.cpu().numpy() - gmi_o.numpy()).max() < 1e-4
+
+
+def test_ser_large_random_counts_bit_exact():
+    import vae_equalizer_b200.shared_funcs as sfun
+    gen = torch.Generator().manual_seed(3)
+    N, n = 300001, 8
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, 25, 16)
+    idx = torch.randint(0, n, (2, 2, N), generator=gen)
+    tx = amp[idx].to(torch.float16)
+    out = (amp[idx] + 0.05 * torch.randn(2, 2, N, generator=gen)) * 1.1
+    q = O.soft_demap(out, var, amp, nu_sc)
+    _, c = sfun.SER_IQflip(q.cuda(), tx.cuda(), return_counts=True)
+    co, _ = O.ser_iqflip_counts(q, tx)
+    assert np.array_equal(c.cpu().numpy().astype(np.int64), co.numpy())
+    rx = out.clone().cuda()
+    _, c = sfun.SER_constell_shaping(rx, tx.cuda(), amp.cuda(), nu_sc, var.cuda(), return_counts=True)
+    co, _ = O.ser_constell_counts(out.clone(), tx, amp, nu_sc, var)
+    # the global rescale factor is a float reduction; a symbol within 1 ulp of a threshold may flip
+    assert np.abs(c.cpu().numpy().astype(np.int64) - co.numpy()).max() <= 2
+
+
+@pytest.mark.parametrize("name", ["cma_16qam_M25_N600", "cma_4qam_M7_N300"])
+def test_cma_family_against_reference_golden(name):
+    import vae_equalizer_b200.shared_funcs as sfun
+    g = load(name)
+    rx = T(g["rx"]).cuda()
+    bl, st = int(g["batchlen"]), int(g["symb_step"])
+    runs = {
+        "cma": lambda h: sfun.CMA(rx, 1, h, float(g["lr"]), 2, True),
+        "batch": lambda h: sfun.CMAbatch(rx, 1, h, float(g["lr_batch"]), bl, 2, True),
+        "flex": lambda h: sfun.CMAflex(rx, 1, h, float(g["lr_flex"]), bl, st, 2, True),
+        "eval": lambda h: sfun.CMA(rx, 1, h, float(g["lr"]), 2, False),
+    }
+    for tag, fn in runs.items():
+        h = T(g["h0"].copy()).cuda()
+        out, h_new, e = fn(h)
+        assert h_new is h
+        assert np.abs(out.cpu().numpy() - g[tag + "_out"]).max() < 5e-5, tag
+        assert np.abs(e.cpu().numpy() - g[tag + "_e"]).max() < 1e-4, tag
+        assert rel(h_new, g[tag + "_h"]) < 1e-4, tag
+    y = sfun.CPE(T(g["cpe_in"]).cuda())
+    assert np.abs(y.cpu().numpy() - g["cpe_out"]).max() < 5e-5
+
+
+def test_cpe_unwrap_against_reference_golden():
+    import vae_equalizer_b200.shared_funcs as sfun
+    g = load("cpe_N3000")
+    y = sfun.CPE(T(g["y"]).cuda())
+    assert np.abs(y.cpu().numpy() - g["out"]).max() < 5e-5
+
+
+@pytest.mark.parametrize("name", ["awgn_16qam_M25_B350", "awgn_64qam_M9_B200"])
+def test_awgn_trajectory_against_reference_golden(name):
+    from vae_equalizer_b200.awgn import AWGNEqualizer
+    from vae_equalizer_b200.processing import awgn_ser_q
+    g = load(name)
+    M = g["W0"].shape[-1]
+    eq = AWGNEqualizer(M, 2, g["amp"], g["P"], float(g["amp_mean"]), float(g["var"]), W0=T(g["W0"]), h0=T(g["h0"]))
+    lr = float(g["lr"])
+    for s in range(g["rx"].shape[0]):
+        rx = T(g["rx"][s]).cuda()
+        q, out, loss, gW, gh = eq.forward_backward(rx)
+        assert np.abs(out.cpu().numpy() - g["out"][s]).max() < 5e-6, s
+        assert np.abs(q.cpu().numpy() - g["q"][s]).max() < 5e-5, s
+        assert rel(loss, g["loss"][s]) < 1e-4, s
+        assert rel(gW, g["gW"][s]) < 2e-4 and rel(gh, g["gh"][s]) < 2e-4, s
+        eq.train_step(rx, lr, lr)
+        assert rel(eq.W, g["W"][s]) < 1e-4 and rel(eq.h, g["h"][s]) < 1e-4, s
+    ser, counts = awgn_ser_q(T(g["q"][-1]).cuda()[:, 11:-11].contiguous(), T(g["tx_last"]).cuda()[:, 11:-11].contiguous())
+    assert abs(float(ser) - float(g["ser_last"])) < 1e-7
+
+
+def test_operator_level_autograd_matches_oracle():
+    """The reference's call sequence: net(x) -> loss_function_shaping -> backward -> torch Adam."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    g = load("dp_step_16qam_M9_B64")
+    M = 9
+    dev = "cuda"
+    amp, var, P, nu_sc = T(g["amp"]).to(dev), T(g["var"]).to(dev), T(g["P"]).to(dev), float(g["nu_sc"])
+    net = sfun.twoXtwoFIR(M, 2).to(dev)
+    with torch.no_grad():
+        net.conv_w.weight.copy_(T(g["W0"]))
+    h_est = T(g["h0"]).to(dev).requires_grad_(True)
+    opt = torch.optim.Adam(net.parameters(), lr=float(g["lr"]))
+    opt.add_param_group({"params": h_est})
+    for s in range(g["rx"].shape[0]):
+        x = T(g["rx"][s]).to(dev)
+        opt.zero_grad()
+        q, out = net(x, amp, var, nu_sc)
+        loss, ve = sfun.loss_function_shaping(q.squeeze(), x.squeeze(), h_est, amp, P)
+        loss.backward()
+        assert rel(net.conv_w.weight.grad, g["gW"][s]) < 2e-4 and rel(h_est.grad, g["gh"][s]) < 2e-4
+        opt.step()
+        assert rel(loss, g["loss"][s]) < 1e-4 and rel(ve, g["var_est"][s]) < 1e-4
+        assert rel(net.conv_w.weight, g["W"][s]) < 1e-4 and rel(h_est, g["h"][s]) < 1e-4
+
+
+def test_dropin_processing_runs_and_converges():
+    """func_VAELE_DP_MQAM_shaping.processing with the Eval_run_DP defaults (shortened): the SER must fall the
+    way SURVEY.md §8c reports for the reference (converged SER of a few 1e-2 at SNR 23 dB)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "vae_equalizer_b200", "dropin"))
+    import func_VAELE_DP_MQAM_shaping as process
+    rng = np.random.default_rng(7)
+    phiIQ = np.array([0.0314, 0.0314], dtype=np.complex64)
+    SER, Var_est, var = process.processing("64-QAM", 2, 23, 0, 25, 0.0, np.pi / 10, 2.5e-3, 100, 10000, 24, 10, "h0", 90e9,
+                                           -26e-24, 0.1e-12 * np.sqrt(1000), phiIQ, 170, rng=rng, verbose=False)
+    SER = SER.cpu().numpy()
+    assert SER.shape == (4, 24) and Var_est.shape == (2, 24)
+    assert SER[:, 0].min() > 0.5                      # untrained
+    assert SER[:, -4:].max() < 0.08                   # converged
+    assert np.isfinite(Var_est.cpu().numpy()).all()
+
+
+def test_dropin_cma_variants_run():
+    from vae_equalizer_b200 import processing as pr
+    rng = np.random.default_rng(9)
+    phiIQ = np.array([0.0314, 0.0314], dtype=np.complex64)
+    for fn, lr in ((pr.processing_cma_dp, 1e-3), (pr.processing_cmabatch_dp, 1e-5), (pr.processing_cmaflex_dp, 1e-6)):
+        SER, Var_est, var = fn("16-QAM", 2, 23, 0, 25, 0.0, np.pi / 10, lr, 100, 3000, 3, 10, "h0", 90e9, -26e-24,
+                               0.1e-12 * np.sqrt(1000), phiIQ, 170, rng=rng, verbose=False)
+        assert SER.shape == (4, 3) and torch.isfinite(SER).all()
+
+
+def test_dropin_awgn_runs():
+    from vae_equalizer_b200 import processing as pr
+    SER = pr.processing_vaele_awgn("16-QAM", 2, 20, 0, 25, 5e-3, 350, 5000, 1200, 40, 10, "h1", rng=np.random.default_rng(1), verbose=False)
+    assert SER.shape == (4,) and torch.isfinite(SER).all() and float(SER[-1]) < float(SER[0]) + 1e-6

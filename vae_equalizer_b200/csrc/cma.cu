@@ -1,0 +1,377 @@
+// CMA / CMAbatch / CMAflex baselines and Viterbi-Viterbi CPE for B200.
+// Reference: optical_DP_channel/shared_funcs.py  CMA :341-379, CMAbatch :381-434, CMAflex :436-488, CPE :140-186.
+//
+// Data flow per run:  k_cma_power (mean power incl. the zero pads, sf:349-350) -> k_cma_scale (y = Rx / power)
+//   -> k_cma_sample  : one WARP per run, lanes own taps, per-symbol recurrence (inherently sequential, sf:355-378)
+//   or k_cma_block   : one CTA per run; taps are constant between two updates, so the symbols of a segment are
+//                      equalized in parallel and the update  h += 2 lr sum_k e_k * inc_k  (sf:424-433, :478-487) is
+//                      a correlation of g_k = e_k * out_k with the input window -- the dW contraction of the VAE step.
+// Index quirk reproduced: the reference writes symbol ks to out[k], e[k], buf[k] with k = (mh + ks*sps)//sps - mh
+// (sf:357), which is NEGATIVE for the first symbols and wraps to the end of the arrays (torch indexing).
+#include <algorithm>
+#include "common.cuh"
+
+namespace vaeq {
+
+constexpr int CMA_NT = 256;
+
+struct CmaRun {
+    const float *Rx;   // (2,2,N) of this run
+    float *y;          // scaled copy (2,2,N)
+    float *h;          // (2,2,2,M)
+    float *out;        // (2,2,Nsym)
+    float *e;          // (Nsym,2)
+};
+
+__device__ __forceinline__ CmaRun cma_run_ptrs(const float *Rx, float *ys, float *h, float *out, float *e, int run, int N,
+                                               int M, int Nsym) {
+    CmaRun r;
+    r.Rx = Rx + (int64_t)run * 4 * N;
+    r.y = ys + (int64_t)run * 4 * N;
+    r.h = h + (int64_t)run * 8 * M;
+    r.out = out + (int64_t)run * 4 * Nsym;
+    r.e = e + (int64_t)run * 2 * Nsym;
+    return r;
+}
+
+// mean(y_I^2 + y_Q^2) over both pols and the PADDED length N + 2*mh  (sf:350): one CTA per run
+__global__ void __launch_bounds__(CMA_NT) k_cma_power(const float *Rx, int N, int mh, float *pw) {
+    __shared__ double red[32];
+    const float *x = Rx + (int64_t)blockIdx.x * 4 * N;
+    double acc[1] = {0.0};
+    for (int i = threadIdx.x; i < 2 * N; i += CMA_NT) {
+        const int p = i / N, s = i - p * N;
+        const float a = x[(int64_t)(2 * p) * N + s], b = x[(int64_t)(2 * p + 1) * N + s];
+        acc[0] += (double)__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    }
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) pw[blockIdx.x] = (float)(acc[0] / (2.0 * (double)(N + 2 * mh)));
+}
+
+__global__ void k_cma_scale(const float *Rx, int N, const float *pw, float *ys, int n_runs) {
+    const int64_t total = (int64_t)n_runs * 4 * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        ys[i] = __fdiv_rn(Rx[i], pw[i / (4 * (int64_t)N)]);                       // y /= mean power (sf:350)
+}
+
+__device__ __forceinline__ int cma_out_index(int ks, int sps, int mh, int Nsym) {
+    const int k = (mh + ks * sps) / sps - mh;                                    // sf:357
+    return k;                                                                    // may be negative
+}
+
+// ---------------------------------------------------------------------------------------------
+// CMA: per-symbol update.  One warp per run; lane l owns taps k = l and k = l + 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, float *h, float *out, float *e, int N, int M,
+                                                   int sps, float R, float lr, int train) {
+    const int lane = threadIdx.x, mh = M / 2, Nsym = N / sps;
+    const CmaRun r = cma_run_ptrs(Rx, ys, h, out, e, blockIdx.x, N, M, Nsym);
+    float hr[2][2][2], hi[2][2][2];                                              // [tap slot][o][i]
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int k = lane + 32 * sl;
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                hr[sl][o][i] = k < M ? r.h[((o * 2 + i) * 2 + 0) * M + k] : 0.f;
+                hi[sl][o][i] = k < M ? r.h[((o * 2 + i) * 2 + 1) * M + k] : 0.f;
+            }
+    }
+    const float lr2 = 2.f * lr;
+    const int nsym_loop = (N + sps - 1) / sps;
+    for (int ks = 0; ks < nsym_loop; ++ks) {
+        float yI[2][2], yQ[2][2];                                               // [slot][in pol]
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const int k = lane + 32 * sl, s = ks * sps - mh + k;
+            const bool ok = (k < M) && (s >= 0) && (s < N);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                yI[sl][i] = ok ? r.y[(int64_t)(2 * i) * N + s] : 0.f;
+                yQ[sl][i] = ok ? r.y[(int64_t)(2 * i + 1) * N + s] : 0.f;
+            }
+        }
+        float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int o = 0; o < 2; ++o)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {                                    // sf:360-364
+                    oI[o] += yI[sl][i] * hr[sl][o][i] - yQ[sl][i] * hi[sl][o][i];
+                    oQ[o] += yI[sl][i] * hi[sl][o][i] + yQ[sl][i] * hr[sl][o][i];
+                }
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            oI[o] = warp_sum(oI[o]);
+            oQ[o] = warp_sum(oQ[o]);
+        }
+        float err[2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) err[o] = R - oI[o] * oI[o] - oQ[o] * oQ[o];  // sf:366-367
+        int k = cma_out_index(ks, sps, mh, Nsym);
+        if (k < 0) k += Nsym;
+        if (lane == 0 && k >= 0 && k < Nsym) {
+            r.out[0 * Nsym + k] = oI[0];
+            r.out[1 * Nsym + k] = oQ[0];
+            r.out[2 * Nsym + k] = oI[1];
+            r.out[3 * Nsym + k] = oQ[1];
+            r.e[2 * k + 0] = err[0];
+            r.e[2 * k + 1] = err[1];
+        }
+        if (train) {
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                    const float f = lr2 * err[o];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {                                // sf:370-378
+                        hr[sl][o][i] += f * (oI[o] * yI[sl][i] + oQ[o] * yQ[sl][i]);
+                        hi[sl][o][i] += f * (oQ[o] * yI[sl][i] - oI[o] * yQ[sl][i]);
+                    }
+                }
+        }
+    }
+    if (train) {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const int k = lane + 32 * sl;
+            if (k < M) {
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        r.h[((o * 2 + i) * 2 + 0) * M + k] = hr[sl][o][i];
+                        r.h[((o * 2 + i) * 2 + 1) * M + k] = hi[sl][o][i];
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CMAbatch / CMAflex: one CTA per run, segment-parallel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys, float *h, float *out, float *e, int N, int M,
+                                                      int sps, float R, float lr, int train, int mode, int batchlen,
+                                                      int symb_step) {
+    extern __shared__ float hs[];                                                // (2,2,2,M) taps of this run
+    const int tid = threadIdx.x, mh = M / 2, Nsym = N / sps;
+    const CmaRun r = cma_run_ptrs(Rx, ys, h, out, e, blockIdx.x, N, M, Nsym);
+    for (int i = tid; i < 8 * M; i += CMA_NT) hs[i] = r.h[i];
+    __syncthreads();
+    const int nsym_loop = (N + sps - 1) / sps;
+    const int k_first = cma_out_index(0, sps, mh, Nsym), k_last = cma_out_index(nsym_loop - 1, sps, mh, Nsym);
+    const int off = -k_first;                                                    // ks = k + off
+    const float lr2 = 2.f * lr;
+    int k_cur = k_first;
+    while (k_cur <= k_last) {
+        // next firing symbol index >= max(k_cur, 1)
+        int k_fire;
+        if (!train) {
+            k_fire = k_last + 1;
+        } else if (mode == VAEQ_CMA_BATCH) {                                     // k % batchlen == 0 and k != 0  (sf:424)
+            const int lo = max(k_cur, 1);
+            k_fire = ((lo + batchlen - 1) / batchlen) * batchlen;
+        } else {                                                                 // k % symb_step == 0 and k >= batchlen (sf:478)
+            const int lo = max(k_cur, batchlen);
+            k_fire = ((lo + symb_step - 1) / symb_step) * symb_step;
+        }
+        const int k_end = min(k_fire, k_last);                                   // inclusive
+        // ---- equalize symbols k_cur..k_end with the current taps ------------------------------
+        for (int k = k_cur + tid; k <= k_end; k += CMA_NT) {
+            const int ks = k + off;
+            float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
+            for (int m = 0; m < M; ++m) {
+                const int s = ks * sps - mh + m;
+                if (s < 0 || s >= N) continue;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float a = r.y[(int64_t)(2 * i) * N + s], b = r.y[(int64_t)(2 * i + 1) * N + s];
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        const float wr = hs[((o * 2 + i) * 2 + 0) * M + m], wi = hs[((o * 2 + i) * 2 + 1) * M + m];
+                        oI[o] += a * wr - b * wi;
+                        oQ[o] += a * wi + b * wr;
+                    }
+                }
+            }
+            const int kk = k < 0 ? k + Nsym : k;
+            if (kk >= 0 && kk < Nsym) {
+                r.out[0 * Nsym + kk] = oI[0];
+                r.out[1 * Nsym + kk] = oQ[0];
+                r.out[2 * Nsym + kk] = oI[1];
+                r.out[3 * Nsym + kk] = oQ[1];
+                r.e[2 * kk + 0] = R - oI[0] * oI[0] - oQ[0] * oQ[0];
+                r.e[2 * kk + 1] = R - oI[1] * oI[1] - oQ[1] * oQ[1];
+            }
+        }
+        __syncthreads();
+        // ---- tap update from the window [k_fire - batchlen, k_fire) ------------------------------
+        if (train && k_fire <= k_last) {
+            for (int idx = tid; idx < 8 * M; idx += CMA_NT) {
+                const int m = idx % M, oic = idx / M, c = oic & 1, oi = oic >> 1, i = oi & 1, o = oi >> 1;
+                float acc = 0.f;
+                for (int kap = k_fire - batchlen; kap < k_fire; ++kap) {
+                    const int ks = kap + off, s = ks * sps - mh + m;
+                    if (kap < 0 || s < 0 || s >= N) continue;                    // kap < 0 would read torch.empty garbage in the reference
+                    const float a = r.y[(int64_t)(2 * i) * N + s], b = r.y[(int64_t)(2 * i + 1) * N + s];
+                    const float vI = r.out[(2 * o) * Nsym + kap], vQ = r.out[(2 * o + 1) * Nsym + kap];
+                    const float inc = c ? (vQ * a - vI * b) : (vI * a + vQ * b);     // sf:414-422
+                    acc += r.e[2 * kap + o] * inc;
+                }
+                hs[idx] += lr2 * acc;                                            // sf:425-433
+            }
+            __syncthreads();
+        }
+        k_cur = k_end + 1;
+    }
+    if (train)
+        for (int i = tid; i < 8 * M; i += CMA_NT) r.h[i] = hs[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// CPE (sf:140-186)
+// ---------------------------------------------------------------------------------------------
+constexpr int CPE_MA = 501;
+
+__global__ void k_cpe_pow4(const float *y, int N, float *p4) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(t / N), s = (int)(t - (int64_t)p * N);
+        const float a = y[(int64_t)(2 * p) * N + s], b = y[(int64_t)(2 * p + 1) * N + s];
+        const float a2 = a * a, b2 = b * b;
+        p4[(int64_t)(2 * p) * N + s] = __fadd_rn(__fsub_rn(__fmul_rn(a2, a2), __fmul_rn(__fmul_rn(6.f, a2), b2)), __fmul_rn(b2, b2));   // sf:152
+        p4[(int64_t)(2 * p + 1) * N + s] = __fmul_rn(4.f, __fsub_rn(__fmul_rn(__fmul_rn(a2, a), b), __fmul_rn(__fmul_rn(a, b2), b)));     // sf:153
+    }
+}
+
+// phi[p][n] = atan2(ma_im, -ma_re)/4 with a zero-padded 501-tap moving average (sf:158-163)
+__global__ void k_cpe_phase(const float *p4, int N, float *phi) {
+    const float w = (float)(1.0 / CPE_MA);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(t / N), n = (int)(t - (int64_t)p * N);
+        const float *re = p4 + (int64_t)(2 * p) * N, *im = p4 + (int64_t)(2 * p + 1) * N;
+        float sr = 0.f, si = 0.f;
+        const int lo = max(0, n - CPE_MA / 2), hi = min(N - 1, n + CPE_MA / 2);
+        for (int m = lo; m <= hi; ++m) {
+            sr = fmaf(re[m], w, sr);
+            si = fmaf(im[m], w, si);
+        }
+        phi[(int64_t)p * N + n] = atan2f(si, -sr) * 0.25f;
+    }
+}
+
+// one CTA per pol: running counts of +/- jumps of the WRAPPED phase (sf:164-169), then derotation (sf:182-185)
+__global__ void __launch_bounds__(1024) k_cpe_unwrap_rotate(const float *y, const float *phi, int N, float *out) {
+    __shared__ int wsum[2][32];
+    __shared__ int carry[2];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float *ph = phi + (int64_t)p * N;
+    const float pi = 3.14159274101257324f, pi2 = pi * 0.5f, pi4 = pi * 0.25f;
+    if (tid < 2) carry[tid] = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += 1024) {
+        const int n = base + tid;
+        // flag at n: jump between n-1 and n  (phi[i+1:] is shifted when diff[i] crosses +-pi/4)
+        int fp = 0, fn = 0;
+        if (n < N && n >= 1) {
+            const float d = __fsub_rn(ph[n], ph[n - 1]);
+            fp = d > pi4;
+            fn = d < -pi4;
+        }
+        int sp = fp, sn = fn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, sp, o), b = __shfl_up_sync(0xffffffffu, sn, o);
+            if (lane >= o) {
+                sp += a;
+                sn += b;
+            }
+        }
+        if (lane == 31) {
+            wsum[0][wid] = sp;
+            wsum[1][wid] = sn;
+        }
+        __syncthreads();
+        int bp = carry[0], bn = carry[1];
+        for (int w = 0; w < wid; ++w) {
+            bp += wsum[0][w];
+            bn += wsum[1][w];
+        }
+        const int np = bp + sp, nn = bn + sn;                                    // inclusive counts up to n
+        if (n < N) {
+            float x = ph[n];
+            for (int i = 0; i < np; ++i) x = __fsub_rn(x, pi2);                  // same rounding sequence as the loops at sf:166-169
+            for (int i = 0; i < nn; ++i) x = __fadd_rn(x, pi2);
+            const float c = cosf(x), s = sinf(x);
+            const float a = y[(int64_t)(2 * p) * N + n], b = y[(int64_t)(2 * p + 1) * N + n];
+            out[(int64_t)(2 * p) * N + n] = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s));
+            out[(int64_t)(2 * p + 1) * N + n] = __fadd_rn(__fmul_rn(b, c), __fmul_rn(a, s));
+        }
+        __syncthreads();
+        if (tid == 1023) {
+            carry[0] = np;
+            carry[1] = nn;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace vaeq
+
+using namespace vaeq;
+
+extern "C" size_t vaeq_cma_scratch_bytes(int32_t N, int32_t M, int32_t n_runs) {
+    (void)M;
+    if (N <= 0 || n_runs <= 0) return 0;
+    return align_up((size_t)n_runs * 4 * N * sizeof(float), 256) + align_up((size_t)n_runs * sizeof(float), 256);
+}
+
+extern "C" int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float *h, int32_t M, float lr, int32_t batchlen,
+                        int32_t symb_step, int32_t sps, int32_t train, float *out, float *e, int32_t n_runs, void *scratch,
+                        void *stream) {
+    VAEQ_CHECK_ARG(Rx && h && out && e && scratch && N > 0 && n_runs > 0, "bad cma arguments");
+    VAEQ_CHECK_ARG(mode >= VAEQ_CMA_SAMPLE && mode <= VAEQ_CMA_FLEX, "bad cma mode %d", mode);
+    VAEQ_CHECK_ARG(M >= 1 && M <= VAEQ_MAX_TAPS && (M & 1), "M=%d must be odd and <= %d", M, VAEQ_MAX_TAPS);
+    VAEQ_CHECK_ARG(sps >= 1 && N % sps == 0, "N=%d must be a multiple of sps=%d", N, sps);
+    VAEQ_CHECK_ARG(mode == VAEQ_CMA_SAMPLE || batchlen > 0, "batchlen must be positive");
+    VAEQ_CHECK_ARG(mode != VAEQ_CMA_FLEX || symb_step > 0, "symb_step must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *ys = static_cast<float *>(scratch);
+    float *pw = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n_runs * 4 * N * sizeof(float), 256));
+    k_cma_power<<<n_runs, CMA_NT, 0, st>>>(Rx, N, M / 2, pw);
+    VAEQ_LAUNCH_CHECK("k_cma_power");
+    const int64_t total = (int64_t)n_runs * 4 * N;
+    k_cma_scale<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8), 256, 0, st>>>(Rx, N, pw, ys, n_runs);
+    VAEQ_LAUNCH_CHECK("k_cma_scale");
+    if (mode == VAEQ_CMA_SAMPLE) {
+        k_cma_sample<<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
+        VAEQ_LAUNCH_CHECK("k_cma_sample");
+    } else {
+        k_cma_block<<<n_runs, CMA_NT, 8 * M * sizeof(float), st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step);
+        VAEQ_LAUNCH_CHECK("k_cma_block");
+    }
+    return VAEQ_OK;
+}
+
+extern "C" size_t vaeq_cpe_scratch_bytes(int32_t N) {
+    if (N <= 0) return 0;
+    return align_up((size_t)4 * N * sizeof(float), 256) + align_up((size_t)2 * N * sizeof(float), 256);
+}
+
+extern "C" int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream) {
+    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1, "bad cpe arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *p4 = static_cast<float *>(scratch);
+    float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)4 * N * sizeof(float), 256));
+    const int grid = (int)std::min<int64_t>((2 * (int64_t)N + 255) / 256, (int64_t)sm_count() * 16);
+    k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, p4);
+    VAEQ_LAUNCH_CHECK("k_cpe_pow4");
+    k_cpe_phase<<<grid, 256, 0, st>>>(p4, N, phi);
+    VAEQ_LAUNCH_CHECK("k_cpe_phase");
+    k_cpe_unwrap_rotate<<<2, 1024, 0, st>>>(y, phi, N, y_corr);
+    VAEQ_LAUNCH_CHECK("k_cpe_unwrap_rotate");
+    return VAEQ_OK;
+}

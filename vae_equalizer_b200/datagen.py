@@ -1,0 +1,100 @@
+"""Synthetic dual-polarisation test signal (host side): PCS symbols -> RRC pulse -> channel IR ->
+residual CD / PMD / polarisation rotation / IQ phase -> AWGN.  Counterpart of the reference's
+generate_data_shaping / simulate_channel / simulate_dispersion / rrcfir
+(optical_DP_channel/shared_funcs.py:27-90).  The reference draws from unseeded numpy generators, so
+parity here is statistical; pass `rng` for reproducible runs.  `generate_data_gpu` is the device
+generator used by the benchmark (same statistics, torch.fft on the GPU)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+PULSE_SPAN, ROLLOFF = 8, 0.1          # sf:66-67
+
+
+def rrcfir(T, sps, beta):
+    t = np.arange(-T * sps / 2, T * sps / 2, 1 / sps, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        num = np.sin(np.pi * t * (1 - beta)) + 4 * beta * t * np.cos(np.pi * t * (1 + beta))
+        h = num / (np.pi * t * (1 - (4 * beta * t) ** 2))
+    h[np.abs(t) == 1 / 4 / beta] = beta / np.sqrt(2) * ((1 + 2 / np.pi) * np.sin(np.pi / 4 / beta) + (1 - 2 / np.pi) * np.cos(np.pi / 4 / beta))
+    h[t == 0] = 1 + beta * (4 / np.pi - 1)
+    return h / np.linalg.norm(h)
+
+
+def rcfir(T, sps, beta):
+    t = np.arange(-T * sps / 2, T * sps / 2, 1 / sps, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        h = np.sinc(t) * np.cos(np.pi * beta * t) / (1 - (2 * beta * t) ** 2)
+    h[np.abs(t) == 1 / 2 / beta] = np.pi / 4 * np.sinc(1 / (2 * beta))
+    return h / np.linalg.norm(h)
+
+
+def jones_response(n, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta):
+    """Per-bin 2x2 transfer matrix R^T diag(e_pmd, 1/e_pmd) R and the CD phase (sf:41-50)."""
+    f = np.fft.fftfreq(n, 1 / symb_rate / sps)
+    e_cd = np.exp(1j * 2 * (np.pi * f) ** 2 * tau_cd)
+    e_pmd = np.exp(1j * np.pi * tau_pmd * f)
+    c, s = np.cos(theta), np.sin(theta)
+    e0, e1 = np.exp(-1j * np.asarray(phiIQ))
+    R = ((c * e0, s * e0), (-s * e1, c * e1))
+    Rt = ((c * e0, -s * e0), (s * e1, c * e1))
+    d = (e_pmd, 1 / e_pmd)
+    H = [[sum(Rt[a][k] * d[k] * R[k][b] for k in range(2)) for b in range(2)] for a in range(2)]
+    return H, e_cd
+
+
+def simulate_dispersion(rx, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta):
+    X = np.fft.fft(rx, axis=1)
+    H, e_cd = jones_response(rx.shape[1], symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta)
+    Y = np.stack(((H[0][0] * X[0] + H[0][1] * X[1]) * e_cd, (H[1][0] * X[0] + H[1][1] * X[1]) * e_cd))
+    return np.complex64(np.fft.ifft(Y, axis=1))
+
+
+def simulate_channel(tx_up, h_pulse, h_channel):
+    return np.stack([np.convolve(np.convolve(row, h_pulse, mode="valid"), h_channel, mode="valid") for row in tx_up]).astype(np.complex64)
+
+
+def generate_data_shaping(N, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta, device, rng=None):
+    """rx (2,2,sps*N) f32, data (2,2,N) f16, sigma_n  -- same contract as the reference (sf:65-90)."""
+    rng = np.random.default_rng() if rng is None else rng
+    M = len(h_channel)
+    n_conv = N + M + 4 * PULSE_SPAN
+    data = rng.choice(amps, (pol * 2, n_conv), p=P)
+    tx_up = np.zeros((pol, sps * (n_conv - 1) + 1), dtype=np.complex64)
+    tx_up[:, ::sps] = data[0::pol, :] + 1j * data[1::pol, :]
+    sig = simulate_channel(tx_up, rrcfir(PULSE_SPAN, sps, ROLLOFF), h_channel)
+    sig = simulate_dispersion(sig, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta)
+    sigma_n = np.sqrt(np.mean(np.abs(sig) ** 2) * sps / 2 / 10 ** (SNR / 10))
+    sig = sig + sigma_n * (rng.standard_normal(sig.shape) + 1j * rng.standard_normal(sig.shape))
+    sig = sig[:, :sps * N]
+    rx = torch.from_numpy(np.stack((sig.real, sig.imag), axis=1).astype(np.float32)).to(device)
+    sl = slice(PULSE_SPAN + M - 1, N + PULSE_SPAN + M - 1)
+    tx = torch.from_numpy(np.stack((data[0::pol, sl], data[1::pol, sl]), axis=1)).to(device, torch.float16)
+    return rx.contiguous(), tx.contiguous(), sigma_n
+
+
+def generate_data_gpu(N, amps, SNR, P, sps, theta, device, seed, symb_rate=90e9, tau_cd=-26e-24,
+                      tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=(0.0314, 0.0314)):
+    """Device-side generator with the same signal model (channel 'h0'); statistics, not bits, match."""
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    n_conv = N + 1 + 4 * PULSE_SPAN
+    idx = torch.multinomial(torch.as_tensor(P, dtype=torch.float32, device=device), 4 * n_conv, True, generator=g).view(4, n_conv)
+    lev = torch.as_tensor(amps, dtype=torch.float32, device=device)[idx]
+    sym = torch.complex(lev[0::2], lev[1::2])
+    up = torch.zeros(2, sps * (n_conv - 1) + 1, dtype=torch.complex64, device=device)
+    up[:, ::sps] = sym
+    pulse = torch.as_tensor(rrcfir(PULSE_SPAN, sps, ROLLOFF), device=device).to(torch.complex64)
+    n_fft = up.shape[1] + pulse.numel() - 1
+    shaped = torch.fft.ifft(torch.fft.fft(up, n_fft) * torch.fft.fft(pulse, n_fft))[:, pulse.numel() - 1: up.shape[1]]
+    H, e_cd = jones_response(shaped.shape[1], symb_rate, sps, tau_cd, tau_pmd, np.asarray(phiIQ, dtype=np.complex64), theta)
+    Ht = [[torch.as_tensor(np.asarray(H[a][b] * e_cd), device=device).to(torch.complex64) for b in range(2)] for a in range(2)]
+    X = torch.fft.fft(shaped, dim=1)
+    sig = torch.fft.ifft(torch.stack((Ht[0][0] * X[0] + Ht[0][1] * X[1], Ht[1][0] * X[0] + Ht[1][1] * X[1])), dim=1)
+    sigma_n = torch.sqrt(torch.mean(sig.abs() ** 2) * sps / 2 / 10 ** (SNR / 10))
+    noise = torch.complex(torch.randn(sig.shape, device=device, generator=g), torch.randn(sig.shape, device=device, generator=g))
+    sig = (sig + sigma_n * noise)[:, :sps * N]
+    rx = torch.stack((sig.real, sig.imag), dim=1).to(torch.float32).contiguous()
+    sl = slice(PULSE_SPAN, N + PULSE_SPAN)
+    tx = torch.stack((lev[0::2][:, sl], lev[1::2][:, sl]), dim=1).to(torch.float16).contiguous()
+    return rx, tx, float(sigma_n)

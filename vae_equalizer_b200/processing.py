@@ -1,0 +1,252 @@
+"""The per-run `processing(...)` drivers of the reference, re-hosted on the CUDA path.
+
+Positional signatures, return values and the per-frame printed fields are the reference's
+(optical_DP_channel/func_VAELE_DP_MQAM_shaping.py:17-95, func_VAEflex_DP_MQAM_shaping.py:16-88,
+func_CMA*_DP_MQAM_shaping.py:16-56, AWGN_channel/func_VAELE_MQAM_shaping.py:235-324), so the unmodified
+Eval_run_*.py scripts run against them.  One whole frame of sequential minibatches is ONE C-ABI call
+(vaeq_dp_train_frame); the host syncs only where the reference does (.item() in the prints and the
+data-dependent slicing by the detected shift).  Extra keyword-only arguments (`rng`, `verbose`,
+`device`) are additions; the reference's generators are unseeded.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import shared_funcs as sfun
+from .awgn import AWGNEqualizer, generate_data
+from .constants import awgn_constants, upsampled_channel
+from .dp import DPEqualizer
+
+N_CUT = 10     # symbols cut per minibatch/frame edge (VAELE_DP:40, CMA_DP:26)
+
+
+def _cuda_device(device):
+    if device is None:
+        if not torch.cuda.is_available():
+            raise sfun._lib.VaeqError("no CUDA device: vae_equalizer_b200 has no CPU path")
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _align(t, shift_h, r):
+    """out.roll(r,0) then per-pol time roll by -shift (VAELE_DP:71-72)."""
+    t = t.roll(r, 0)
+    t[0], t[1] = t[0].roll(-shift_h[0], -1).clone(), t[1].roll(-shift_h[1], -1).clone()
+    return t
+
+
+def _print_frame(frame, loss, shift_h, r, snr_db, ser):
+    print(frame, '\t\ttraining: loss = ', loss, '\tshift_x = ', shift_h[0], '\tshift_y = ', shift_h[1], '\tr = ', r,
+          '\tSNR_est = ', snr_db)
+    print('\t\t\t\t\t\t\tSER_x = ', ser[0], '\tSER_y = ', ser[1], '\t(constell. with shaping)')
+    print('\t\t\t\t\t\t\tSER_x = ', ser[2], '\tSER_y = ', ser[3], '\t(soft demapper)')
+
+
+def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_frame_max, num_frames, flex_step,
+                        channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True):
+    """VAE-LE, non-overlapping minibatches (func_VAELE_DP_MQAM_shaping.py:17-95)."""
+    device = _cuda_device(device)
+    if verbose:
+        print("We are using the following device for learning:", device)
+    h_est, h_channel, P, amp_levels, amps, pol, nu_sc, var, pow_mean = sfun.init(channel, mod, device, nu, sps, M_est, SNR)
+    num_lev = amp_levels.shape[0]
+    eq = DPEqualizer(M_est, sps, amp_levels, P, var, nu_sc, device=device)
+    SER_valid = torch.empty(4, num_frames, device=device, dtype=torch.float32)
+    Var_est = torch.empty(pol, num_frames, device=device, dtype=torch.float32)
+    m_max = N_frame_max // batch_len
+    N_frame = m_max * batch_len
+    lr_w = lr_optim
+    for frame in range(num_frames):
+        if frame % N_lrhalf == 0 and frame != 0:
+            lr_w = lr_optim * 0.5                  # param_groups[0] only, not cumulative (VAELE_DP:45-46)
+        rx_tensor, data_tensor, _ = sfun.generate_data_shaping(N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd,
+                                                               tau_pmd, phiIQ, theta, device, rng=rng)
+        theta += theta_diff
+        out_train = torch.empty(pol, 2 * num_lev, N_frame, device=device, dtype=torch.float32)
+        out_const = torch.empty(pol, 2, N_frame, device=device, dtype=torch.float32)
+        loss_steps, var_est = eq.train_frame(rx_tensor, batch_len, batch_len, m_max, lr_w, lr_optim, out_train, out_const,
+                                             0, batch_len, keep_lo_in_dst=True)
+        SNR_est = pow_mean / torch.mean(var_est)
+        Var_est[:, frame] = torch.mean(var_est, dim=1)
+
+        shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
+        sh = [int(v) for v in shift.tolist()]
+        out_train = _align(out_train, sh, r)
+        keep = batch_len - sh[0] - N_CUT           # drop each minibatch's edge symbols (VAELE_DP:73-77)
+        q_cut = out_train.reshape(pol, 2 * num_lev, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2 * num_lev, -1)
+        d_cut = data_tensor.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
+        tail = 11 + max(abs(sh[0]), abs(sh[1]))
+        SER_valid[2:, frame] = sfun.SER_IQflip(q_cut[:, :, 11:-tail], d_cut[:, :, 11:-tail])
+
+        shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
+        sh = [int(v) for v in shift.tolist()]
+        out_const = _align(out_const, sh, r)
+        keep = batch_len - sh[0] - N_CUT
+        o_cut = out_const.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
+        d_cut = data_tensor.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
+        tail = 11 + max(abs(sh[0]), abs(sh[1]))
+        SER_valid[:2, frame] = sfun.SER_constell_shaping(o_cut[:, :, 11:-tail].detach().clone(), d_cut[:, :, 11:-tail],
+                                                         amp_levels, nu_sc, var)
+        if verbose:
+            _print_frame(frame, loss_steps[-1].item(), sh, r, (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
+    return SER_valid, Var_est, var
+
+
+def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
+                          channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True):
+    """VAE-flex, sliding window advanced by flex_step (func_VAEflex_DP_MQAM_shaping.py:16-88)."""
+    device = _cuda_device(device)
+    if verbose:
+        print("We are using the following device for learning:", device)
+    h_est, h_channel, P, amp_levels, amps, pol, nu_sc, var, pow_mean = sfun.init(channel, mod, device, nu, sps, M_est, SNR)
+    num_lev = amp_levels.shape[0]
+    eq = DPEqualizer(M_est, sps, amp_levels, P, var, nu_sc, device=device)
+    SER_valid = torch.empty(4, num_frames, device=device, dtype=torch.float32)
+    Var_est = torch.empty(pol, num_frames, device=device, dtype=torch.float32)
+    N_frame = (N_train_max // batch_len) * batch_len
+    m_max = (N_frame - batch_len) // flex_step * flex_step          # VAEflex_DP:39
+    n_steps = m_max // flex_step
+    keep_lo, keep_hi = (batch_len - flex_step) // 2, (batch_len + flex_step) // 2     # VAEflex_DP:64-65
+    lr_w = lr_optim
+    for frame in range(num_frames):
+        if frame % N_lrhalf == 0 and frame != 0:
+            lr_w = lr_optim * 0.5
+        rx_tensor, data_tensor, _ = sfun.generate_data_shaping(N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd,
+                                                               tau_pmd, phiIQ, theta, device, rng=rng)
+        data_tensor = data_tensor[:, :, batch_len // 2:m_max + batch_len // 2]                 # VAEflex_DP:51
+        theta += theta_diff
+        out_train = torch.empty(pol, 2 * num_lev, m_max, device=device, dtype=torch.float32)
+        out_const = torch.empty(pol, 2, m_max, device=device, dtype=torch.float32)
+        loss_steps, var_est = eq.train_frame(rx_tensor, batch_len, flex_step, n_steps, lr_w, lr_optim, out_train, out_const,
+                                             keep_lo, keep_hi - keep_lo, keep_lo_in_dst=False)
+        SNR_est = pow_mean / torch.mean(var_est)
+        Var_est[:, frame] = torch.mean(var_est, dim=1)
+
+        shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
+        sh = [int(v) for v in shift.tolist()]
+        out_train = _align(out_train, sh, r)
+        tail = 11 + max(abs(sh[0]), abs(sh[1]))
+        SER_valid[2:, frame] = sfun.SER_IQflip(out_train[:, :, 11:-tail], data_tensor[:, :, 11:-tail])
+        shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
+        sh = [int(v) for v in shift.tolist()]
+        out_const = _align(out_const, sh, r)
+        tail = 11 + max(abs(sh[0]), abs(sh[1]))
+        SER_valid[:2, frame] = sfun.SER_constell_shaping(out_const[:, :, 11:-tail].detach().clone(), data_tensor[:, :, 11:-tail],
+                                                         amp_levels, nu_sc, var)
+        if verbose:
+            _print_frame(frame, loss_steps[-1].item(), sh, r, (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
+    return SER_valid, Var_est, var
+
+
+def _processing_cma(kind, mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
+                    channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True):
+    """CMA / CMAbatch / CMAflex runs (func_CMA_DP_MQAM_shaping.py:16-56 and siblings)."""
+    device = _cuda_device(device)
+    if verbose:
+        print("We are using the following device for learning:", device)
+    h_est, h_channel, P, amp_levels, amps, pol, nu_sc, var, pow_mean = sfun.init(channel, mod, device, nu, sps, M_est, SNR)
+    h_est = h_est.detach()
+    SER_valid = torch.empty(4, num_frames, device=device, dtype=torch.float32)
+    Var_est = torch.zeros(pol, num_frames, device=device, dtype=torch.float32)
+    R = 1
+    for frame in range(num_frames):
+        if frame % N_lrhalf == 0 and frame != 0:
+            lr_optim *= 0.5                          # cumulative here, unlike the VAE drivers (CMA_DP:31-32)
+        rx_tensor, data_tensor, _ = sfun.generate_data_shaping(N_train_max, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd,
+                                                               tau_pmd, phiIQ, theta, device, rng=rng)
+        if kind == "CMA":
+            out_const, h_est, e = sfun.CMA(rx_tensor, R, h_est, lr_optim, sps, True)
+        elif kind == "CMAbatch":
+            out_const, h_est, e = sfun.CMAbatch(rx_tensor, R, h_est, lr_optim, batch_len, sps, True)
+        else:
+            out_const, h_est, e = sfun.CMAflex(rx_tensor, R, h_est, lr_optim, batch_len, flex_step, sps, True)
+        theta += theta_diff
+        out_const = sfun.CPE(out_const[:, :, N_CUT:-N_CUT])
+        data_tensor = data_tensor[:, :, N_CUT:-N_CUT]
+        shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
+        sh = [int(v) for v in shift.tolist()]
+        out_const = _align(out_const, sh, r)
+        tail = 11 + max(abs(sh[0]), abs(sh[1]))
+        # a VIEW is passed on purpose: the in-place rescale (sf:242) must be visible to soft_dec below (CMA_DP:44,48)
+        SER_valid[:2, frame] = sfun.SER_constell_shaping(out_const[:, :, 11:-tail], data_tensor[:, :, 11:-tail], amp_levels, nu_sc, var)
+        if verbose:
+            print(frame, '\t\ttraining: loss = ', torch.sum(e).item(), '\tshift_x = ', sh[0], '\tshift_y = ', sh[1], '\tr = ', r)
+            print('\t\t\t\t\t\t\tSER_x = ', SER_valid[0, frame].item(), '\tSER_y = ', SER_valid[1, frame].item(), '\t(constell. with shaping)')
+        out_train = sfun.soft_dec(out_const, var, amp_levels, nu_sc)
+        shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
+        sh = [int(v) for v in shift.tolist()]
+        out_train = _align(out_train, sh, r)
+        tail = 11 + max(abs(sh[0]), abs(sh[1]))
+        SER_valid[2:, frame] = sfun.SER_IQflip(out_train[:, :, 11:-tail], data_tensor[:, :, 11:-tail])
+        if verbose:
+            print('\t\t\t\t\t\t\tSER_x = ', SER_valid[2, frame].item(), '\tSER_y = ', SER_valid[3, frame].item(), '\t(soft demapper)')
+    return SER_valid, Var_est, var
+
+
+def processing_cma_dp(*a, **k):
+    return _processing_cma("CMA", *a, **k)
+
+
+def processing_cmabatch_dp(*a, **k):
+    return _processing_cma("CMAbatch", *a, **k)
+
+
+def processing_cmaflex_dp(*a, **k):
+    return _processing_cma("CMAflex", *a, **k)
+
+
+# -------------------------------------------------------------------------------------------------
+# AWGN single-polarisation VAE-LE (AWGN_channel/func_VAELE_MQAM_shaping.py:235-324)
+# -------------------------------------------------------------------------------------------------
+def awgn_find_shift(q, tx, N_shift, amp_levels):
+    """find_shift of the AWGN module (:188-204): first 1000 symbols, I first, Q as fallback."""
+    n = amp_levels.numel()
+    q2 = torch.stack((q[:, :1000], q[:, :1000])).contiguous()
+    tx2 = torch.stack((tx[:, :1000], tx[:, :1000])).contiguous()
+    _, _, corr = sfun.find_shift(q2, tx2, N_shift, amp_levels, 2, return_corr=True)
+    cI, cQ = corr[0, 0, 0].cpu(), corr[1, 0, 0].cpu()
+    half = N_shift // 2
+    if cI.max() >= 0.02 * q.shape[-1]:
+        return half - int(torch.argmax(cI))
+    if cQ.max() >= cI.max():
+        return half - int(torch.argmax(cQ))
+    return half - int(torch.argmax(cI))
+
+
+def awgn_ser_q(q, tx):
+    """SER_q (:97-124): min over 4 rotations, no IQ flip.  Returns (ser float32 0-dim tensor, counts (4,))."""
+    q2 = torch.stack((q, q)).contiguous()
+    tx2 = torch.stack((tx, tx)).contiguous()
+    _, counts = sfun.SER_IQflip(q2, tx2, return_counts=True)
+    c = counts[0, 0, :]
+    return (c.min().to(torch.float32) / q.shape[-1]), c
+
+
+def processing_vaele_awgn(mod, sps, SNR, nu, M_est, lr_optim, batch_len, N_valid, N_train, num_epochs, epe, channel, *,
+                          device=None, rng=None, verbose=True):
+    device = _cuda_device(device)
+    if verbose:
+        print("We are using the following device for learning:", device)
+    if channel not in ("h1", "h2"):
+        raise KeyError(f"AWGN driver knows channels h1/h2, got {channel!r}")       # :239-242
+    h_channel = upsampled_channel(channel, sps)
+    M = (len(h_channel) - 1) // sps + 1
+    amps, P, amp_mean, var = awgn_constants(mod, nu, SNR)
+    amp_levels = torch.tensor(amps, device=device, dtype=torch.float32)
+    eq = AWGNEqualizer(M_est, sps, amp_levels, P, amp_mean, var, device=device)
+    SER_valid = torch.empty(num_epochs // epe, device=device, dtype=torch.float32)
+    for epoch in range(num_epochs):
+        rx_tensor, _ = generate_data(N_train, M, amps, SNR, h_channel, sps, device, P, rng=rng)
+        for m in range(N_train // batch_len):
+            minibatch = rx_tensor[:, m * batch_len * sps:(m + 1) * batch_len * sps].contiguous()
+            _, _, loss = eq.train_step(minibatch, lr_optim, lr_optim)
+        if epoch % epe == 0:
+            rx_v, data_v = generate_data(N_valid, M, amps, SNR, h_channel, sps, device, P, rng=rng)
+            q_v, _, _ = eq.forward(rx_v)
+            shift = awgn_find_shift(q_v, data_v, 21, amp_levels)
+            ser, _ = awgn_ser_q(q_v[:, 11 + shift:-11], data_v[:, 11:-11 - shift])
+            SER_valid[epoch // epe] = ser
+            if verbose:
+                print(epoch, loss.item(), shift, '\t\t\t\t\t\tSER = ', SER_valid[epoch // epe].item())
+    return SER_valid
