@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- DP VAE-LE training throughput on B200 (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+A "step" is one full training step (butterfly FIR -> soft demapper -> ELBO -> backward -> Adam on both
+parameter groups) over one minibatch of B = 2^22 synthetic DP 64-QAM PCS symbols (BASELINE configs[1]:
+func_VAELE_DP, 2x2 butterfly, M_est = 25, sps = 2, SNR 23 dB, nu = 0.0270955).  With N > 1 every rank trains
+its own independent sweep point (different noise realisation / seed) -- the reference's sweep is embarrassingly
+parallel (Eval_run_DP.py:68-95) -- so scaling is weak and there is no data-path collective.
+
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DP VAE-LE train symbols/s"
+UNIT = "symbols/s"
+MOD, NU, SNR, M_EST, SPS, LR = "64-QAM", 0.0270955, 23, 25, 2, 2.5e-3
+N_LEV = 8
+ALG_BYTES_PER_SYMBOL = 4 * 2 * (2 * SPS + 2 * N_LEV + 2)        # read rx once, write q and out once = 176 B
+ALG_FLOP_PER_SYMBOL = 5 * 32 * M_EST + 1000                      # 5 tap contractions + point-wise work
+CPU_SAMPLE_LOG2 = 17
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_constants():
+    from vae_equalizer_b200.constants import init
+    h_est, h_channel, P, amp_levels, amps, pol, nu_sc, var, pow_mean = init("h0", MOD, "cpu", NU, SPS, M_EST, SNR)
+    return dict(P=P, amp=amp_levels, amps=amps, nu_sc=nu_sc, var=var)
+
+
+def cpu_step_rate(rx_cpu, cst, steps, warmup, max_seconds):
+    """The reference algorithm (oracle/vaeq_oracle.py: conv1d + softmin + per-tap gather loop + autograd + torch Adam)
+    on this box's host cores, on a bounded sample of the same workload."""
+    from oracle import vaeq_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr = O.DPTrainer(M_EST, SPS, LR)
+    Pt = torch.tensor(cst["P"], dtype=torch.float32)
+    B = rx_cpu.shape[-1] // SPS
+    for _ in range(warmup):
+        tr.step(rx_cpu, cst["amp"], cst["var"], cst["nu_sc"], Pt)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        tr.step(rx_cpu, cst["amp"], cst["var"], cst["nu_sc"], Pt)
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return B * done / dt, done, dt, torch.get_num_threads()
+
+
+def synth_cpu_sample(cst, log2_b, seed):
+    from vae_equalizer_b200.datagen import generate_data_shaping
+    from vae_equalizer_b200.constants import upsampled_channel
+    rng = np.random.default_rng(seed)
+    rx, _, _ = generate_data_shaping(1 << log2_b, cst["amps"], SNR, upsampled_channel("h0", SPS), cst["P"], 2, 90e9, SPS, -26e-24,
+                                     0.1e-12 * np.sqrt(1000), np.array([0.0314, 0.0314], dtype=np.complex64), np.pi / 10, "cpu", rng=rng)
+    return rx
+
+
+def workload_name(log2_b):
+    return (f"DP VAE-LE (func_VAELE_DP) train step, {MOD} PCS nu={NU}, 2x2 butterfly M_est={M_EST}, sps={SPS}, SNR {SNR} dB, "
+            f"batch_len=2^{log2_b} symbols/step, synthetic RRC+rotation+CD/PMD channel (BASELINE configs[1])")
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cst = run_constants()
+    rx = synth_cpu_sample(cst, CPU_SAMPLE_LOG2, 1234)
+    rate, done, dt, cores = cpu_step_rate(rx, cst, args.steps, max(1, min(args.warmup, 2)), max_seconds=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.batch_log2), "sample": f"each step = one full training step on 2^{CPU_SAMPLE_LOG2} symbols of the workload"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} steps x 2^{CPU_SAMPLE_LOG2} symbols, oracle/vaeq_oracle.py DPTrainer (torch CPU, autograd, torch Adam)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ours_arm(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.datagen import generate_data_gpu
+    from vae_equalizer_b200.dp import DPEqualizer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    cst = run_constants()
+    B = 1 << args.batch_log2
+    NB = args.buffers
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic inputs, resident in HBM before the timed region --------------------------------------------
+    theta = np.pi / 10 + 0.06 * np.pi * rank                     # each rank = another sweep point / realisation
+    rx_dev = [generate_data_gpu(B, cst["amps"], SNR, cst["P"], SPS, theta, dev, 1234 + 100 * rank + i)[0] for i in range(NB)]
+    eq = DPEqualizer(M_EST, SPS, cst["amp"], cst["P"], cst["var"], cst["nu_sc"], device=dev)
+    q = torch.empty(2, 2 * N_LEV, B, dtype=torch.float32, device=dev)
+    out = torch.empty(2, 2, B, dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        eq.train_step(rx_dev[i % NB], LR, LR, q=q, out=out)
+    barrier()
+
+    # ---- timed region: K steps, device timed, per-kernel events on the launching stream -------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = int(lib.vaeq_launch_count(-1))
+    _lib.check(lib.vaeq_kernel_timing(1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        eq.train_step(rx_dev[i % NB], LR, LR, q=q, out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    ms_sum = (C.c_float * 8)()
+    cnt = (C.c_int32 * 8)()
+    _lib.check(lib.vaeq_kernel_timing_read(ms_sum, cnt))
+    _lib.check(lib.vaeq_kernel_timing(0))
+    launches = int(lib.vaeq_launch_count(-1)) - launches0
+    clocks = sampler.finish()
+    loss_val = float(eq.loss.item())
+    if not np.isfinite(loss_val):
+        raise SystemExit(f"non-finite loss {loss_val} in the timed region")
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: H2D of each step's rx, D2H of loss/var_est ----------
+    rx_host = [r.cpu().pin_memory() for r in rx_dev[:2]]
+    stage = [torch.empty_like(rx_dev[0]) for _ in range(2)]
+    res_host = torch.empty(K + W, 3, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_steps(n, base):
+        for i in range(n):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[s])
+                stage[s].copy_(rx_host[(base + i) % 2], non_blocking=True)
+                ready[s].record(copy_stream)
+            main_stream.wait_event(ready[s])
+            eq.train_step(stage[s], LR, LR, q=q, out=out)
+            free[s].record(main_stream)
+            res_host[base + i, 0:1].copy_(eq.loss, non_blocking=True)
+            res_host[base + i, 1:3].copy_(eq.var_est, non_blocking=True)
+
+    for s in range(2):
+        free[s].record(main_stream)
+    e2e_steps(W, 0)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    e2e_steps(K, W)
+    f1.record()
+    barrier()
+    t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(t2.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    names = {0: "k_dp_fwd", 1: "k_dp_fin", 2: "k_dp_bwd", 3: "k_dp_adam"}
+    per_kernel = {names[k]: {"avg_ms": ms_sum[k] / cnt[k], "launches": int(cnt[k]), "share_of_step": ms_sum[k] / ms}
+                  for k in names if cnt[k] > 0}
+    dom = max((k for k in names if cnt[k] > 0), key=lambda k: ms_sum[k])
+    dom_ms = ms_sum[dom] / cnt[dom]
+    peak, peak_src = load_peaks()
+    achieved = B * ALG_BYTES_PER_SYMBOL / (dom_ms * 1e-3) / 1e9
+    step_gbs = B * ALG_BYTES_PER_SYMBOL * K / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "alg_bytes_per_symbol": ALG_BYTES_PER_SYMBOL,
+                "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
+                "fp32_issue": {"alg_flop_per_symbol": ALG_FLOP_PER_SYMBOL, "achieved_tflops": value / world * ALG_FLOP_PER_SYMBOL / 1e12,
+                               "peak_tflops": 72.0, "peak_source": "profiles/r01_ffma_issue_microbench.txt (FFMA reg,reg,reg on this pool)",
+                               "frac": value / world * ALG_FLOP_PER_SYMBOL / 72.0e12},
+                "kernels": per_kernel}
+
+    # ---- CPU baseline on a bounded sample (N=1 only) -----------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rx_cpu = rx_dev[0][:, :, :SPS << CPU_SAMPLE_LOG2].cpu().contiguous()
+        rate, done, dt, cores = cpu_step_rate(rx_cpu, cst, 4, 1, max_seconds=25.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{done} steps x 2^{CPU_SAMPLE_LOG2} symbols (first 2^{CPU_SAMPLE_LOG2} symbols of the workload), "
+                         f"oracle/vaeq_oracle.py DPTrainer on torch CPU, {dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch_log2), "batch_len": B, "M_est": M_EST, "n_lev": N_LEV,
+                   "l2": f"inputs larger than L2: {NB} rotating rx batches of {B * 16 >> 20} MiB, {B * 128 >> 20} MiB of q written per step (L2 = 126 MB)",
+                   "parallelism": "independent sweep points, one per GPU, no collective" if world > 1 else "1 GPU",
+                   "final_loss": loss_val},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": 12,
+                "note": "DPEqualizer.train_step on pinned host rx; H2D double-buffered on a copy stream, loss+var_est read back every step"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-log2", type=int, default=22)
+    ap.add_argument("--buffers", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    if args.gpus > 1 and "RANK" not in os.environ:          # launched bare: re-exec under torchrun (one rank per GPU)
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

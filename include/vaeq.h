@@ -47,6 +47,23 @@ const char *vaeq_last_error(void);
 /* number of SMs of the current device (persistent grids are sized from it) */
 int vaeq_sm_count(void);
 
+/* Measurement hooks (no reference counterpart): kernels are grouped into kinds; every launch is counted,
+ * and with timing enabled each launch is bracketed by a CUDA event pair on its own stream.
+ * vaeq_kernel_timing(1) resets and enables, (0) disables; vaeq_kernel_timing_read synchronises the recorded
+ * events and returns summed milliseconds and launch counts per kind (arrays of VAEQ_NKINDS). */
+#define VAEQ_K_DP_FWD 0
+#define VAEQ_K_DP_FIN 1
+#define VAEQ_K_DP_BWD 2
+#define VAEQ_K_DP_ADAM 3
+#define VAEQ_K_EVAL 4
+#define VAEQ_K_CMA 5
+#define VAEQ_K_AWGN 6
+#define VAEQ_K_OTHER 7
+#define VAEQ_NKINDS 8
+int vaeq_kernel_timing(int32_t enable);
+int vaeq_kernel_timing_read(float *ms_sum, int32_t *count);
+int64_t vaeq_launch_count(int32_t kind); /* kind < 0: all kinds */
+
 /* ------------------------------------------------------------------------------------------------
  * DP VAE-LE / VAE-flex training step
  *   replaces  twoXtwoFIR.forward (sf:500-527) + loss_function_shaping (sf:92-137) + loss.backward()

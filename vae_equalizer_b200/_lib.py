@@ -55,6 +55,9 @@ PROTOTYPES = {
     "vaeq_abi_version": (C.c_int, []),
     "vaeq_last_error": (C.c_char_p, []),
     "vaeq_sm_count": (C.c_int, []),
+    "vaeq_kernel_timing": (C.c_int, [_i32]),
+    "vaeq_kernel_timing_read": (C.c_int, [_vp, _vp]),
+    "vaeq_launch_count": (C.c_int64, [_i32]),
     "vaeq_dp_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_adam_state_floats": (_sz, [_i32]),
     "vaeq_dp_forward": (C.c_int, [C.POINTER(DpDesc), _vp]),

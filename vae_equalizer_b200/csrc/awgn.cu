@@ -277,6 +277,7 @@ static int awgn_launch(const vaeq_awgn_desc *d, int mode, float lr_w, float lr_h
         case 4: k_awgn_step<4><<<1, AW_NT, 0, st>>>(p); break;
         default: k_awgn_step<8><<<1, AW_NT, 0, st>>>(p); break;
     }
+    ktime_begin(VAEQ_K_AWGN, st); ktime_end(VAEQ_K_AWGN, st);
     VAEQ_LAUNCH_CHECK("k_awgn_step");
     return VAEQ_OK;
 }

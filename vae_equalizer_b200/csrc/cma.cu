@@ -342,15 +342,19 @@ extern "C" int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float
     float *ys = static_cast<float *>(scratch);
     float *pw = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n_runs * 4 * N * sizeof(float), 256));
     k_cma_power<<<n_runs, CMA_NT, 0, st>>>(Rx, N, M / 2, pw);
+    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cma_power");
     const int64_t total = (int64_t)n_runs * 4 * N;
     k_cma_scale<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8), 256, 0, st>>>(Rx, N, pw, ys, n_runs);
+    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cma_scale");
     if (mode == VAEQ_CMA_SAMPLE) {
         k_cma_sample<<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
+        ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_sample");
     } else {
         k_cma_block<<<n_runs, CMA_NT, 8 * M * sizeof(float), st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step);
+        ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_block");
     }
     return VAEQ_OK;
@@ -368,10 +372,13 @@ extern "C" int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch,
     float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)4 * N * sizeof(float), 256));
     const int grid = (int)std::min<int64_t>((2 * (int64_t)N + 255) / 256, (int64_t)sm_count() * 16);
     k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, p4);
+    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_pow4");
     k_cpe_phase<<<grid, 256, 0, st>>>(p4, N, phi);
+    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_phase");
     k_cpe_unwrap_rotate<<<2, 1024, 0, st>>>(y, phi, N, y_corr);
+    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_unwrap_rotate");
     return VAEQ_OK;
 }

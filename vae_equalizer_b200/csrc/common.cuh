@@ -11,6 +11,8 @@ namespace vaeq {
 
 void set_error(const char *fmt, ...);
 int sm_count();
+void ktime_begin(int kind, cudaStream_t st);   // counts the launch; records an event pair when timing is on
+void ktime_end(int kind, cudaStream_t st);
 
 #define VAEQ_CHECK_ARG(cond, ...)               \
     do {                                        \

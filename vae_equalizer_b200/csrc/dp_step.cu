@@ -546,14 +546,22 @@ static int dp_run(const DpK &p, int mode, float lr_w, float lr_h, int amsgrad, c
         grid_bwd[p.M] = max(1, per) * sm_count();
     }
     const int gf = min(min(grid_fwd[p.M], DP_GRID_CAP), p.ntiles), gb = min(min(grid_bwd[p.M], DP_GRID_CAP), p.ntiles);
+    ktime_begin(VAEQ_K_DP_FWD, st);
     k_dp_fwd<NL><<<gf, DP_NT, sm_f, st>>>(p);
+    ktime_end(VAEQ_K_DP_FWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_fwd");
+    ktime_begin(VAEQ_K_DP_FIN, st);
     k_dp_fin<<<1, 64, 0, st>>>(p, gf);
+    ktime_end(VAEQ_K_DP_FIN, st);
     VAEQ_LAUNCH_CHECK("k_dp_fin");
     if (mode == DP_MODE_FWD) return VAEQ_OK;
+    ktime_begin(VAEQ_K_DP_BWD, st);
     k_dp_bwd<NL><<<gb, DP_NT, sm_b, st>>>(p);
+    ktime_end(VAEQ_K_DP_BWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_bwd");
+    ktime_begin(VAEQ_K_DP_ADAM, st);
     k_dp_adam<<<1, 512, 0, st>>>(p, gb, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
+    ktime_end(VAEQ_K_DP_ADAM, st);
     VAEQ_LAUNCH_CHECK("k_dp_adam");
     return VAEQ_OK;
 }
@@ -620,7 +628,9 @@ extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32
 extern "C" int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,
                                 int32_t *step_count, int32_t bump_step, void *stream) {
     VAEQ_CHECK_ARG(param && grad && state && step_count && n > 0, "bad adam arguments");
+    ktime_begin(VAEQ_K_OTHER, (cudaStream_t)stream);
     k_adam_generic<<<1, 256, 0, (cudaStream_t)stream>>>(param, grad, state, n, lr, amsgrad, step_count, bump_step);
+    ktime_end(VAEQ_K_OTHER, (cudaStream_t)stream);
     VAEQ_LAUNCH_CHECK("k_adam_generic");
     return VAEQ_OK;
 }
@@ -631,9 +641,11 @@ extern "C" int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var,
     VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
     const int nt = 256, grid = min((N + nt - 1) / nt, sm_count() * 8);
     cudaStream_t st = (cudaStream_t)stream;
+    ktime_begin(VAEQ_K_EVAL, st);
     if (n_lev == 2) k_soft_dec<2><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
     else if (n_lev == 4) k_soft_dec<4><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
     else k_soft_dec<8><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_soft_dec");
     return VAEQ_OK;
 }

@@ -310,8 +310,10 @@ extern "C" int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, i
     double *part = static_cast<double *>(scratch);
     if (q) k_shift_corr<true><<<grid, EV_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, part);
     else k_shift_corr<false><<<grid, EV_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, part);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_shift_corr");
     k_shift_decide<<<1, 32, 0, st>>>(part, n_shift, chunks, corr_out, shift_out, r_out);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_shift_decide");
     return VAEQ_OK;
 }
@@ -326,8 +328,10 @@ extern "C" int vaeq_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx,
     if (n_lev == 2) k_ser_iqflip<2><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
     else if (n_lev == 4) k_ser_iqflip<4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
     else k_ser_iqflip<8><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_iqflip");
     k_ser_min<<<1, 32, 0, st>>>(counts_out, N, ser_out);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_min");
     return VAEQ_OK;
 }
@@ -343,12 +347,15 @@ extern "C" int vaeq_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, i
     VAEQ_CUDA(cudaMemsetAsync(counts_out, 0, 16 * sizeof(int), st));
     const int grid = ev_grid(N);
     k_constell_norms<<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, N, sums);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_constell_norms");
     if (n_lev == 2) k_ser_constell<2><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
     else if (n_lev == 4) k_ser_constell<4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
     else k_ser_constell<8><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_constell");
     k_ser_min<<<1, 32, 0, st>>>(counts_out, N, ser_out);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_min");
     return VAEQ_OK;
 }
@@ -364,8 +371,10 @@ extern "C" int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_
     if (n_lev == 2) k_gmi<2><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
     else if (n_lev == 4) k_gmi<4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
     else k_gmi<8><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_gmi");
     k_gmi_fin<<<1, 32, 0, st>>>(sums, P, n_lev, N, gmi_out);
+    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_gmi_fin");
     return VAEQ_OK;
 }
