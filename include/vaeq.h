@@ -59,7 +59,8 @@ int vaeq_sm_count(void);
 #define VAEQ_K_CMA 5
 #define VAEQ_K_AWGN 6
 #define VAEQ_K_OTHER 7
-#define VAEQ_NKINDS 8
+#define VAEQ_K_DP_BWD2 8
+#define VAEQ_NKINDS 9
 int vaeq_kernel_timing(int32_t enable);
 int vaeq_kernel_timing_read(float *ms_sum, int32_t *count);
 int64_t vaeq_launch_count(int32_t kind); /* kind < 0: all kinds */
@@ -111,6 +112,10 @@ typedef struct vaeq_dp_desc {
 size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev);
 /* floats of Adam state for one run: exp_avg, exp_avg_sq, max_exp_avg_sq for W and h, + step counter */
 size_t vaeq_adam_state_floats(int32_t M);
+
+/* Testing hook: != 0 routes every vaeq_dp_* call through the generic-M kernels (dp_step.cu) even when the
+ * register-blocked fast path (dp_fast.cu: B % 4 == 0, 16-byte aligned rows, M_est in {5,9,13,25}, B >= 2016) applies. */
+int vaeq_dp_force_generic(int32_t on);
 
 /* forward only: q, out, loss, var_est  (net(minibatch) + loss_function_shaping, no grad) */
 int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream);

@@ -66,7 +66,11 @@ def test_trajectory_vs_reference_golden(name):
 
 
 @pytest.mark.parametrize("mod,M,B,nu", [("64-QAM", 25, 3000, 0.0270955), ("16-QAM", 13, 1537, 0.0), ("64-QAM", 5, 777, 0.05),
-                                        ("4-QAM", 31, 2048, 0.0), ("64-QAM", 25, 40000, 0.0)])
+                                        ("4-QAM", 31, 2048, 0.0), ("64-QAM", 25, 40000, 0.0),
+                                        # register-blocked fast path (B % 4 == 0, B >= 2016, M in {5,9,13,25})
+                                        ("16-QAM", 25, 4096, 0.0), ("4-QAM", 25, 8192, 0.1), ("64-QAM", 13, 5000, 0.0270955),
+                                        ("64-QAM", 9, 6004, 0.0), ("64-QAM", 5, 4000, 0.05), ("64-QAM", 25, 2016, 0.0270955),
+                                        ("64-QAM", 25, 100800, 0.0270955)])
 def test_multi_tile_against_closed_form(mod, M, B, nu):
     """Sizes that span several tiles/CTAs; float64 closed form is the yardstick, and the fp32 torch
     oracle's own error against it is printed beside ours."""
@@ -144,3 +148,36 @@ def test_bad_arguments_raise():
         DPEqualizer(9, 2, g["amp"], g["P"], g["var"], 0.0).forward(torch.zeros(2, 2, 128))                  # CPU tensor
     with pytest.raises(VaeqError):
         DPEqualizer(9, 2, g["amp"], g["P"], g["var"], 0.0).forward(torch.zeros(2, 2, 12, device="cuda"))    # B <= Mh
+
+
+def test_fast_path_matches_generic_kernels_and_trains():
+    """Same inputs through the register-blocked kernels (dp_fast.cu) and the generic ones (dp_step.cu)."""
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    M, B = 25, 1 << 16
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rx, tx, _ = O.generate_data_shaping(B, amps, 23, h_ch, P, 2, 90e9, 2, -26e-24, 0.1e-12 * np.sqrt(1000),
+                                        np.array([0.0314, 0.0314], dtype=np.complex64), np.pi / 10, "cpu", rng=np.random.default_rng(2))
+    Pt = torch.tensor(P, dtype=torch.float32)
+    res = {}
+    for tag, force in (("fast", 0), ("generic", 1)):
+        lib.vaeq_dp_force_generic(force)
+        try:
+            eq = DPEqualizer(M, 2, amp, Pt, var, nu_sc)
+            n0 = lib.vaeq_launch_count(8)
+            losses = []
+            for _ in range(4):
+                q, out, loss, ve = eq.train_step(rx.cuda(), 2.5e-3, 2.5e-3)
+                losses.append(float(loss))
+            torch.cuda.synchronize()
+            res[tag] = (q.cpu(), out.cpu(), eq.gW.cpu(), eq.gh.cpu(), eq.W.cpu(), eq.h.cpu(), losses, lib.vaeq_launch_count(8) - n0)
+        finally:
+            lib.vaeq_dp_force_generic(0)
+    f, g = res["fast"], res["generic"]
+    assert f[7] == 4 and g[7] == 0                      # the fast path really ran (k_dp_bwd2_fast launches)
+    assert float((f[1] - g[1]).abs().max()) < 5e-6 and float((f[0] - g[0]).abs().max()) < 5e-5
+    assert rel(f[2], g[2]) < 2e-4 and rel(f[3], g[3]) < 2e-4
+    assert rel(f[4], g[4]) < 1e-4 and rel(f[5], g[5]) < 1e-4
+    assert max(abs(a - b) / abs(b) for a, b in zip(f[6], g[6])) < 1e-5
+    assert f[6][-1] < f[6][0]                           # and it trains

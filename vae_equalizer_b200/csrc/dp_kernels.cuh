@@ -39,6 +39,10 @@ struct DpK {
     float *scal;
     float4 *ebuf4;                // [L]: residual D - rx per sample (chi0 re, chi0 im, chi1 re, chi1 im)
     float4 *m1buf4;               // [B]: E_q[x] per symbol (p0 I, p0 Q, p1 I, p1 Q)
+    // fast path (dp_fast.cu) views of the same scratch as SoA rows of B floats
+    float *erows;                 // 8 rows: [phase][chi][re/im]
+    float *m1rows;                // 4 rows: (p0 I, p0 Q, p1 I, p1 Q)
+    float *gyrows;                // 4 rows: dL/dout
     float *gpart;                 // [grid][16*M]
     float *gfinal;                // [16*M]: gW then gh
     float *loss_out, *var_est_out;
@@ -46,5 +50,11 @@ struct DpK {
     float *gW_out, *gh_out;
     int T, ntiles;
 };
+
+// dp_step.cu
+int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st);
+// dp_fast.cu: returns 1 if the register-blocked path ran (then *rc is its status, *grid_bwd_out the number of
+// gradient partials), 0 if the problem does not qualify (alignment, M_est, size) and the generic kernels must run
+int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bwd_out, int *rc);
 
 }  // namespace vaeq

@@ -459,7 +459,7 @@ static size_t dp_bwd_smem(int M, int T, int H, int mh) {
 }
 
 struct DpWsLayout {
-    size_t part_fwd, edge_vs, scal, ebuf, m1buf, gpart, gfinal, total;
+    size_t part_fwd, edge_vs, scal, ebuf, m1buf, gybuf, gpart, gfinal, total;
 };
 static DpWsLayout dp_ws_layout(int B, int M) {
     DpWsLayout w;
@@ -474,6 +474,7 @@ static DpWsLayout dp_ws_layout(int B, int M) {
     w.scal = take((size_t)(DP_S_OFF + 2 * VAEQ_MAX_TAPS) * sizeof(float));
     w.ebuf = take((size_t)B * 8 * sizeof(float));
     w.m1buf = take((size_t)B * 4 * sizeof(float));
+    w.gybuf = take((size_t)B * 4 * sizeof(float));
     w.gpart = take((size_t)DP_GRID_CAP * 16 * M * sizeof(float));
     w.gfinal = take((size_t)16 * M * sizeof(float));
     w.total = off;
@@ -515,6 +516,9 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
     p.scal = reinterpret_cast<float *>(ws + w.scal);
     p.ebuf4 = reinterpret_cast<float4 *>(ws + w.ebuf);
     p.m1buf4 = reinterpret_cast<float4 *>(ws + w.m1buf);
+    p.erows = reinterpret_cast<float *>(ws + w.ebuf);
+    p.m1rows = reinterpret_cast<float *>(ws + w.m1buf);
+    p.gyrows = reinterpret_cast<float *>(ws + w.gybuf);
     p.gpart = reinterpret_cast<float *>(ws + w.gpart);
     p.gfinal = reinterpret_cast<float *>(ws + w.gfinal);
     p.adam = d->adam;
@@ -523,6 +527,22 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
     p.T = DP_TILE;
     p.ntiles = (d->B + p.T - 1) / p.T;
     return p;
+}
+
+int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st) {
+    ktime_begin(VAEQ_K_DP_FIN, st);
+    k_dp_fin<<<1, 64, 0, st>>>(p, nparts);
+    ktime_end(VAEQ_K_DP_FIN, st);
+    VAEQ_LAUNCH_CHECK("k_dp_fin");
+    return VAEQ_OK;
+}
+
+static int dp_launch_adam(const DpK &p, int nparts, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
+    ktime_begin(VAEQ_K_DP_ADAM, st);
+    k_dp_adam<<<1, 512, 0, st>>>(p, nparts, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
+    ktime_end(VAEQ_K_DP_ADAM, st);
+    VAEQ_LAUNCH_CHECK("k_dp_adam");
+    return VAEQ_OK;
 }
 
 template <int NL>
@@ -550,23 +570,28 @@ static int dp_run(const DpK &p, int mode, float lr_w, float lr_h, int amsgrad, c
     k_dp_fwd<NL><<<gf, DP_NT, sm_f, st>>>(p);
     ktime_end(VAEQ_K_DP_FWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_fwd");
-    ktime_begin(VAEQ_K_DP_FIN, st);
-    k_dp_fin<<<1, 64, 0, st>>>(p, gf);
-    ktime_end(VAEQ_K_DP_FIN, st);
-    VAEQ_LAUNCH_CHECK("k_dp_fin");
+    {
+        const int rc = dp_launch_fin(p, gf, st);
+        if (rc) return rc;
+    }
     if (mode == DP_MODE_FWD) return VAEQ_OK;
     ktime_begin(VAEQ_K_DP_BWD, st);
     k_dp_bwd<NL><<<gb, DP_NT, sm_b, st>>>(p);
     ktime_end(VAEQ_K_DP_BWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_bwd");
-    ktime_begin(VAEQ_K_DP_ADAM, st);
-    k_dp_adam<<<1, 512, 0, st>>>(p, gb, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
-    ktime_end(VAEQ_K_DP_ADAM, st);
-    VAEQ_LAUNCH_CHECK("k_dp_adam");
-    return VAEQ_OK;
+    return dp_launch_adam(p, gb, mode, lr_w, lr_h, amsgrad, st);
 }
 
+static bool g_force_generic = false;
+
 static int dp_dispatch(const DpK &p, int n_lev, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
+    if (!g_force_generic) {
+        int gb = 0, rc = VAEQ_OK;
+        if (dp_try_fast(p, n_lev, mode, st, &gb, &rc)) {
+            if (rc || mode == DP_MODE_FWD) return rc;
+            return dp_launch_adam(p, gb, mode, lr_w, lr_h, amsgrad, st);
+        }
+    }
     switch (n_lev) {
         case 2: return dp_run<2>(p, mode, lr_w, lr_h, amsgrad, st);
         case 4: return dp_run<4>(p, mode, lr_w, lr_h, amsgrad, st);
@@ -585,6 +610,11 @@ extern "C" size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev) {
 }
 
 extern "C" size_t vaeq_adam_state_floats(int32_t M) { return (size_t)48 * M + 4; }
+
+extern "C" int vaeq_dp_force_generic(int32_t on) {
+    g_force_generic = on != 0;
+    return VAEQ_OK;
+}
 
 extern "C" int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream) {
     int rc = dp_validate(d, false, false);
