@@ -49,44 +49,56 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~2 ms DURING the timed region."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.stop_flag, self.smax, self.err = index, [], set(), False, None, None
+        self.nv = self.h = None
+        try:                                 # NVML is initialised here, before the timed region
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:
+            self.err = repr(e)
 
     def run(self):
+        if self.nv is None:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
+            nv, h = self.nv, self.h
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as e:              # NVML unavailable: report that instead of inventing numbers
+            self.err = repr(e)
 
     def finish(self):
         self.stop_flag = True
+        self.join(timeout=2.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0, "error": self.err}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def _nvml_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
         try:
-            self.proc.terminate()
+            return int(vis.split(",")[local_rank])
         except Exception:
             pass
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+    return local_rank
 
 
 def run_constants():
@@ -185,21 +197,20 @@ def ours_arm(args, rank, local_rank, world):
     barrier()
 
     # ---- timed region: K steps, device timed, per-kernel events on the launching stream -------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
+    sampler = ClockSampler(_nvml_index(local_rank))
     launches0 = int(lib.vaeq_launch_count(-1))
     _lib.check(lib.vaeq_kernel_timing(1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.start()
     e0.record()
     for i in range(K):
         eq.train_step(rx_dev[i % NB], LR, LR, q=q, out=out)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    ms_sum = (C.c_float * 8)()
-    cnt = (C.c_int32 * 8)()
+    ms_sum = (C.c_float * 16)()
+    cnt = (C.c_int32 * 16)()
     _lib.check(lib.vaeq_kernel_timing_read(ms_sum, cnt))
     _lib.check(lib.vaeq_kernel_timing(0))
     launches = int(lib.vaeq_launch_count(-1)) - launches0
@@ -256,7 +267,7 @@ def ours_arm(args, rank, local_rank, world):
         return
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
-    names = {0: "k_dp_fwd", 1: "k_dp_fin", 2: "k_dp_bwd", 3: "k_dp_adam"}
+    names = {0: "k_dp_fwd", 1: "k_dp_fin", 2: "k_dp_bwd1 (dE_q + softmin backward)", 3: "k_dp_adam", 8: "k_dp_taps<W>", 9: "k_dp_taps<h>"}
     per_kernel = {names[k]: {"avg_ms": ms_sum[k] / cnt[k], "launches": int(cnt[k]), "share_of_step": ms_sum[k] / ms}
                   for k in names if cnt[k] > 0}
     dom = max((k for k in names if cnt[k] > 0), key=lambda k: ms_sum[k])
@@ -303,7 +314,7 @@ def ours_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-log2", type=int, default=22)

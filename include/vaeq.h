@@ -60,7 +60,8 @@ int vaeq_sm_count(void);
 #define VAEQ_K_AWGN 6
 #define VAEQ_K_OTHER 7
 #define VAEQ_K_DP_BWD2 8
-#define VAEQ_NKINDS 9
+#define VAEQ_K_DP_BWD3 9
+#define VAEQ_NKINDS 10
 int vaeq_kernel_timing(int32_t enable);
 int vaeq_kernel_timing_read(float *ms_sum, int32_t *count);
 int64_t vaeq_launch_count(int32_t kind); /* kind < 0: all kinds */

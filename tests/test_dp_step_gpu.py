@@ -175,7 +175,7 @@ def test_fast_path_matches_generic_kernels_and_trains():
         finally:
             lib.vaeq_dp_force_generic(0)
     f, g = res["fast"], res["generic"]
-    assert f[7] == 4 and g[7] == 0                      # the fast path really ran (k_dp_bwd2_fast launches)
+    assert f[7] == 4 and g[7] == 0                      # the fast path really ran (k_dp_taps_fast<W> launches)
     assert float((f[1] - g[1]).abs().max()) < 5e-6 and float((f[0] - g[0]).abs().max()) < 5e-5
     assert rel(f[2], g[2]) < 2e-4 and rel(f[3], g[3]) < 2e-4
     assert rel(f[4], g[4]) < 1e-4 and rel(f[5], g[5]) < 1e-4

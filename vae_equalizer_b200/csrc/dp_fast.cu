@@ -12,7 +12,11 @@
 //     is float4 per thread, 512 B per warp instruction;
 //   * point-wise math uses ex2/lg2/rcp approximations, a reciprocal multiply for 1/(2 var) and the analytic
 //     log q = (z_min - z_l) - log2 s for the entropy, ~100 instructions per component instead of ~450;
-//   * the backward pass is two kernels (dE_q + softmin backward + dh, then dW) so that 2-3 CTAs fit per SM.
+//   * the backward pass is three lean kernels (dE_q + softmin backward -> dL/dout rows; dW; dh) so that no tap
+//     accumulators live across the point-wise stage (no spills) and 2-3 CTAs fit per SM;
+//   * the sliding-window loops are runtime-parameterised with an unroll-by-4 body (the window rotates through 4
+//     register names) instead of being fully unrolled: ~25 KB of SASS per kernel instead of ~110 KB, which
+//     removed the instruction-cache stalls ncu showed for the fully unrolled version (profiles/r01_*).
 // Reference lines: twoXtwoFIR.forward sf:500-527, loss_function_shaping sf:92-137 (sf = optical_DP_channel/shared_funcs.py).
 #include "dp_math.cuh"
 #include "dp_kernels.cuh"
@@ -26,6 +30,9 @@ constexpr int FT_HP = 8;                   // halo per side in symbols (>= MH/2,
 constexpr int FT_T = FT_TE - 2 * FT_HP;    // owned symbols per tile (1008)
 constexpr int FT_XOFF = 8;                 // extra margin of the x phase arrays (FIR reaches MH/2 further)
 constexpr int FT_XN = FT_TE + 2 * FT_XOFF; // logical length of xe / xo
+#ifndef FT_MINB
+#define FT_MINB 2                          // min CTAs per SM the register allocator must allow (fwd / bwd1)
+#endif
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
 __host__ __device__ constexpr int fdiv4(int c) { return c >= 0 ? c / 4 : -((3 - c) / 4); }
@@ -129,39 +136,61 @@ __device__ __forceinline__ float demap_backward_fast(float y, float inv_var, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// FIR-like contraction: 4 consecutive outputs per thread, NLAG lags, 2x2 complex taps.
-//   acc[r][2o+c] += sum_i tap(o,i) * win[4l + r + a + C0]_i     (complex product, taps = {t00r,t00i,t01r,t01i | t10..t11})
-// win is a padded float4 array, pb = 5*l its base for this thread, taps: 2 float4 per lag (smem broadcast).
+// FIR-like contraction: 4 consecutive outputs per thread, nlag lags, 2x2 complex taps.
+//   acc[r][2o+c] += sum_a sum_i tap_a(o,i) * win[i0 + r + a]_i   (complex product; taps: 2 float4 per lag
+//   = {t00r,t00i,t01r,t01i},{t10r,t10i,t11r,t11i}, read as shared-memory broadcasts)
+// win is a padded float4 array (physical index j + j/4); i0 = logical index of (r = 0, a = 0).
 // ---------------------------------------------------------------------------------------------
-template <int NLAG, int C0>
-__device__ __forceinline__ void fir4(const float4 *__restrict__ win, int pb, const float4 *__restrict__ taps,
+__device__ __forceinline__ void fir_step(const float4 t0, const float4 t1, const float4 xa, const float4 xb, const float4 xc,
+                                         const float4 xd, float (&acc)[FT_R][4]) {
+    const float4 xs[4] = {xa, xb, xc, xd};
+#pragma unroll
+    for (int r = 0; r < FT_R; ++r) {
+        const float4 x = xs[r];
+        acc[r][0] = fmaf(t0.x, x.x, fmaf(-t0.y, x.y, fmaf(t0.z, x.z, fmaf(-t0.w, x.w, acc[r][0]))));
+        acc[r][1] = fmaf(t0.x, x.y, fmaf(t0.y, x.x, fmaf(t0.z, x.w, fmaf(t0.w, x.z, acc[r][1]))));
+        acc[r][2] = fmaf(t1.x, x.x, fmaf(-t1.y, x.y, fmaf(t1.z, x.z, fmaf(-t1.w, x.w, acc[r][2]))));
+        acc[r][3] = fmaf(t1.x, x.y, fmaf(t1.y, x.x, fmaf(t1.z, x.w, fmaf(t1.w, x.z, acc[r][3]))));
+    }
+}
+
+__device__ __forceinline__ void fir4(const float4 *__restrict__ win, int i0, const float4 *__restrict__ taps, int nlag,
                                      float (&acc)[FT_R][4]) {
-    float4 w[4];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) w[r] = win[pb + poff(C0 + r)];
-#pragma unroll
-    for (int a = 0; a < NLAG; ++a) {
-        w[(a + 3) & 3] = win[pb + poff(C0 + a + 3)];
-        const float4 t0 = taps[2 * a], t1 = taps[2 * a + 1];
-#pragma unroll
-        for (int r = 0; r < FT_R; ++r) {
-            const float4 x = w[(a + r) & 3];
-            acc[r][0] = fmaf(t0.x, x.x, fmaf(-t0.y, x.y, fmaf(t0.z, x.z, fmaf(-t0.w, x.w, acc[r][0]))));
-            acc[r][1] = fmaf(t0.x, x.y, fmaf(t0.y, x.x, fmaf(t0.z, x.w, fmaf(t0.w, x.z, acc[r][1]))));
-            acc[r][2] = fmaf(t1.x, x.x, fmaf(-t1.y, x.y, fmaf(t1.z, x.z, fmaf(-t1.w, x.w, acc[r][2]))));
-            acc[r][3] = fmaf(t1.x, x.y, fmaf(t1.y, x.x, fmaf(t1.z, x.w, fmaf(t1.w, x.z, acc[r][3]))));
-        }
+    auto LD = [win](int j) { return win[j + (j >> 2)]; };
+    float4 w0 = LD(i0), w1 = LD(i0 + 1), w2 = LD(i0 + 2), w3;
+    int a = 0;
+#pragma unroll 1
+    for (; a + 4 <= nlag; a += 4) {
+        w3 = LD(i0 + 3);
+        fir_step(taps[0], taps[1], w0, w1, w2, w3, acc);
+        w0 = LD(i0 + 4);
+        fir_step(taps[2], taps[3], w1, w2, w3, w0, acc);
+        w1 = LD(i0 + 5);
+        fir_step(taps[4], taps[5], w2, w3, w0, w1, acc);
+        w2 = LD(i0 + 6);
+        fir_step(taps[6], taps[7], w3, w0, w1, w2, acc);
+        i0 += 4;
+        taps += 8;
+    }
+#pragma unroll 1
+    for (; a < nlag; ++a) {                  // remainder (nlag % 4 lags): shift the window by register moves
+        w3 = LD(i0 + 3);
+        fir_step(taps[0], taps[1], w0, w1, w2, w3, acc);
+        w0 = w1; w1 = w2; w2 = w3;
+        i0 += 1;
+        taps += 2;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// tap-gradient correlation: acc[a][2(2o+i)+c] += sum_r g[r]_o * conj(win[4l + r + a + C0]_i)
+// tap-gradient correlation: acc[a][2(2o+i)+c] += sum_r g[r]_o * conj(win[i0 + r + a]_i),  a < A
 // ---------------------------------------------------------------------------------------------
-template <int A, int C0>
-__device__ __forceinline__ void corr4(const float4 *__restrict__ win, int pb, const float4 (&g)[FT_R], float (&acc)[A][8]) {
+template <int A>
+__device__ __forceinline__ void corr4(const float4 *__restrict__ win, int i0, const float4 (&g)[FT_R], float (&acc)[A][8]) {
 #pragma unroll
     for (int cpos = 0; cpos < A + FT_R - 1; ++cpos) {
-        const float4 x = win[pb + poff(C0 + cpos)];
+        const int j = i0 + cpos;
+        const float4 x = win[j + (j >> 2)];
 #pragma unroll
         for (int r = 0; r < FT_R; ++r) {
             const int a = cpos - r;
@@ -183,28 +212,29 @@ __device__ __forceinline__ void corr4(const float4 *__restrict__ win, int pb, co
 // load the even/odd phase arrays of rx for the tile starting at symbol t0 (logical position 0 <-> symbol t0-HP-XOFF)
 __device__ __forceinline__ void load_x_phases(const DpK &p, int t0, float4 *xe, float4 *xo) {
     const int sym0 = t0 - FT_HP - FT_XOFF;
+#pragma unroll 1
     for (int j = threadIdx.x; j < FT_XN / 2; j += FT_NT) {
         const int64_t s0 = 2 * (int64_t)sym0 + 4 * j;           // first of 4 consecutive samples
-        float v[4][4];
+        float4 v[4];
         if (s0 >= 0 && s0 + 3 < p.L) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(p.rx + (int64_t)r * p.ld_rx + s0));
-                v[r][0] = t.x; v[r][1] = t.y; v[r][2] = t.z; v[r][3] = t.w;
-            }
+            for (int r = 0; r < 4; ++r) v[r] = __ldg(reinterpret_cast<const float4 *>(p.rx + (int64_t)r * p.ld_rx + s0));
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r) {
+                float t[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int64_t s = s0 + k;
-                    v[r][k] = (s >= 0 && s < p.L) ? p.rx[(int64_t)r * p.ld_rx + s] : 0.f;
+                    t[k] = (s >= 0 && s < p.L) ? p.rx[(int64_t)r * p.ld_rx + s] : 0.f;
                 }
+                v[r] = make_float4(t[0], t[1], t[2], t[3]);
+            }
         }
-        xe[pidx(2 * j)] = make_float4(v[0][0], v[1][0], v[2][0], v[3][0]);
-        xo[pidx(2 * j)] = make_float4(v[0][1], v[1][1], v[2][1], v[3][1]);
-        xe[pidx(2 * j + 1)] = make_float4(v[0][2], v[1][2], v[2][2], v[3][2]);
-        xo[pidx(2 * j + 1)] = make_float4(v[0][3], v[1][3], v[2][3], v[3][3]);
+        xe[pidx(2 * j)] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+        xo[pidx(2 * j)] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+        xe[pidx(2 * j + 1)] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+        xo[pidx(2 * j + 1)] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
     }
 }
 
@@ -215,12 +245,13 @@ __device__ __forceinline__ float4 ld_row4(const float *base, int64_t ld, int row
 __device__ __forceinline__ void st_row4(float *base, int64_t ld, int row, int u, float4 v) {
     *reinterpret_cast<float4 *>(base + (int64_t)row * ld + u) = v;
 }
+__device__ __forceinline__ float f4c(const float4 &v, int r) { return r == 0 ? v.x : r == 1 ? v.y : r == 2 ? v.z : v.w; }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int NL, int MH>
-__global__ void __launch_bounds__(FT_NT, 2) k_dp_fwd_fast(DpK p) {
+__global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
     static_assert(MH % 2 == 0 && MH / 2 <= FT_HP - 2, "fast path needs M_est = 1 (mod 4) and M_est <= 25");
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
     extern __shared__ __align__(16) float4 smem4[];
@@ -231,7 +262,6 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_fwd_fast(DpK p) {
     float *red = reinterpret_cast<float *>(cst + 1);
     const int tid = threadIdx.x;
 
-    // tap tables (see file header of dp_step.cu for the W / h layouts)
     for (int idx = tid; idx < (NE + NO) * 8; idx += FT_NT) {
         const int e = idx & 7, la = idx >> 3;
         const int ph = la >= NE, a = ph ? la - NE : la;
@@ -244,23 +274,24 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_fwd_fast(DpK p) {
     load_fast_const(cst, p, NL);
     __syncthreads();
     const FastConst &c = *cst;
-    const float4 *tFe = tapF, *tFo = tapF + 2 * NE, *tDe = tapD, *tDo = tapD + 2 * NE;
 
     float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
-    const int pb = 5 * tid;
+    const int i0 = FT_R * tid;                               // local index of this thread's first symbol
 
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int t0 = tile * FT_T;
         load_x_phases(p, t0, xe, xo);
         __syncthreads();
 
-        const int i0 = FT_R * tid;                           // local symbol index of this thread's first symbol
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
-        float4 mom[FT_R];
+        float mom[FT_R][4];
 #pragma unroll
-        for (int r = 0; r < FT_R; ++r) mom[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < FT_R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mom[r][k] = 0.f;
         if (in_seq) {
             float y[FT_R][4];
 #pragma unroll
@@ -268,90 +299,99 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_fwd_fast(DpK p) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) y[r][k] = 0.f;
             // x[2u + k - MH]: even k = 2a -> xe[u + a - HF], odd k = 2a+1 -> xo[u + a - HF]
-            fir4<NE, FT_XOFF - HF>(xe, pb, tFe, y);
-            fir4<NO, FT_XOFF - HF>(xo, pb, tFo, y);
-            float vs[FT_R][2];
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph)
+                fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? 2 * NE : 0), ph ? NO : NE, y);
+            // point-wise stage, rolled over the polarisation (code size); y / mom rotate by two components per pass
+#pragma unroll 1
+            for (int pol = 0; pol < 2; ++pol) {
+                float vs[FT_R];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                float qv[FT_R][NL];
-                float m1v[FT_R];
+                for (int cq = 0; cq < 2; ++cq) {
+                    const int cc = 2 * pol + cq;
+                    float qv[FT_R][NL], m1v[FT_R];
 #pragma unroll
-                for (int r = 0; r < FT_R; ++r) {
-                    float m2, ent;
-                    demap_fast<NL>(y[r][cc], c.c2[cc >> 1], c, qv[r], m1v[r], m2, ent);
-                    const int u = u0 + r;
-                    if (owned && u >= MH && u < p.B - MH) accEnt += ent;                  // sf:132
-                    const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
-                    if (cc & 1) vs[r][cc >> 1] += v; else vs[r][cc >> 1] = v;
-                }
-                if (owned) {
+                    for (int r = 0; r < FT_R; ++r) {
+                        float m2, ent;
+                        demap_fast<NL>(y[r][cq], c.c2[pol], c, qv[r], m1v[r], m2, ent);
+                        const int u = u0 + r;
+                        if (owned && u >= MH && u < p.B - MH) accEnt += ent;                  // sf:132
+                        const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
+                        vs[r] = cq ? vs[r] + v : v;
+                        mom[r][cq] = m1v[r];
+                    }
+                    if (owned) {
 #pragma unroll
-                    for (int l = 0; l < NL; ++l)
-                        st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
-                    st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cc], y[1][cc], y[2][cc], y[3][cc]));
-                    st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
-                    if (p.qk != nullptr) {
-#pragma unroll
-                        for (int r = 0; r < FT_R; ++r) {
-                            const int u = u0 + r;
-                            if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
-                                const int64_t col = p.keep_base + (u - p.keep_lo);
-#pragma unroll
-                                for (int l = 0; l < NL; ++l) p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = qv[r][l];
-                                p.outk[(int64_t)cc * p.ld_outk + col] = y[r][cc];
+                        for (int l = 0; l < NL; ++l)
+                            st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
+                        st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
+                        st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
+                        if (p.qk != nullptr) {
+#pragma unroll 1
+                            for (int r = 0; r < FT_R; ++r) {
+                                const int u = u0 + r;
+                                if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
+                                    const int64_t col = p.keep_base + (u - p.keep_lo);
+                                    for (int l = 0; l < NL; ++l)
+                                        p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
+                                    p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
+                                }
                             }
                         }
                     }
                 }
+                if (owned) {
 #pragma unroll
-                for (int r = 0; r < FT_R; ++r) reinterpret_cast<float *>(&mom[r])[cc] = m1v[r];
-            }
-            if (owned) {
-#pragma unroll
-                for (int r = 0; r < FT_R; ++r) {
-                    const int u = u0 + r;
-                    accV[0] += vs[r][0];
-                    accV[1] += vs[r][1];
-                    if (u < MH || u >= p.B - MH) {
-                        const int slot = (u < MH) ? u : MH + (u - (p.B - MH));
-                        p.edge_vs[slot] = vs[r][0];
-                        p.edge_vs[2 * MH + slot] = vs[r][1];
+                    for (int r = 0; r < FT_R; ++r) {
+                        const int u = u0 + r;
+                        accV[pol] += vs[r];
+                        if (u < MH || u >= p.B - MH) {
+                            const int slot = (u < MH) ? u : MH + (u - (p.B - MH));
+                            p.edge_vs[2 * MH * pol + slot] = vs[r];
+                        }
                     }
+                }
+#pragma unroll
+                for (int r = 0; r < FT_R; ++r) {             // rotate: the next pass finds its components in slots 0,1
+                    float t;
+                    t = y[r][0]; y[r][0] = y[r][2]; y[r][2] = t;
+                    t = y[r][1]; y[r][1] = y[r][3]; y[r][3] = t;
+                    t = mom[r][0]; mom[r][0] = mom[r][2]; mom[r][2] = t;
+                    t = mom[r][1]; mom[r][1] = mom[r][3]; mom[r][3] = t;
                 }
             }
         }
 #pragma unroll
-        for (int r = 0; r < FT_R; ++r) m1s[pb + r] = mom[r];
+        for (int r = 0; r < FT_R; ++r) m1s[5 * tid + r] = make_float4(mom[r][0], mom[r][1], mom[r][2], mom[r][3]);
         __syncthreads();
 
         // ---- D = h * E_q for the owned samples, residual e = D - rx ------------------------------------
         if (owned) {
-            float de[FT_R][4], dod[FT_R][4];
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph) {
+                float d[FT_R][4];
 #pragma unroll
-            for (int r = 0; r < FT_R; ++r)
+                for (int r = 0; r < FT_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) de[r][k] = dod[r][k] = 0.f;
-            fir4<NE, -HF>(m1s, pb, tDe, de);                 // even samples: sum_a h[2MH-2a] E_q[u + a - HF]
-            fir4<NO, -HF + 1>(m1s, pb, tDo, dod);            // odd samples:  sum_b h[2MH-1-2b] E_q[u + b - HF + 1]
-            float ee[4][FT_R], eo[4][FT_R];
+                    for (int k = 0; k < 4; ++k) d[r][k] = 0.f;
+                // even samples: sum_a h[2MH-2a] E_q[u + a - HF];  odd: sum_b h[2MH-1-2b] E_q[u + b - HF + 1]
+                fir4(m1s, i0 - HF + ph, tapD + (ph ? 2 * NE : 0), ph ? NO : NE, d);
+                const float4 *xr = ph ? xo : xe;
+                float ev[4][FT_R];
 #pragma unroll
-            for (int r = 0; r < FT_R; ++r) {
-                const int u = u0 + r;
-                const float4 xr0 = xe[pb + poff(FT_XOFF + r)], xr1 = xo[pb + poff(FT_XOFF + r)];
-                const bool v0 = (2 * u >= MH) && (2 * u < p.L - MH), v1 = (2 * u + 1 >= MH) && (2 * u + 1 < p.L - MH);
-                const float e0[4] = {de[r][0] - xr0.x, de[r][1] - xr0.y, de[r][2] - xr0.z, de[r][3] - xr0.w};
-                const float e1[4] = {dod[r][0] - xr1.x, dod[r][1] - xr1.y, dod[r][2] - xr1.z, dod[r][3] - xr1.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    ee[k][r] = v0 ? e0[k] : 0.f;
-                    eo[k][r] = v1 ? e1[k] : 0.f;
-                    accC[k >> 1] += ee[k][r] * ee[k][r] + eo[k][r] * eo[k][r];
+                for (int r = 0; r < FT_R; ++r) {
+                    const int u = u0 + r, s = 2 * u + ph, j = i0 + FT_XOFF + r;
+                    const float4 x = xr[j + (j >> 2)];
+                    const bool valid = (s >= MH) && (s < p.L - MH);                         // sf:120 "valid" region
+                    ev[0][r] = valid ? d[r][0] - x.x : 0.f;
+                    ev[1][r] = valid ? d[r][1] - x.y : 0.f;
+                    ev[2][r] = valid ? d[r][2] - x.z : 0.f;
+                    ev[3][r] = valid ? d[r][3] - x.w : 0.f;
+                    accC[0] += ev[0][r] * ev[0][r] + ev[1][r] * ev[1][r];
+                    accC[1] += ev[2][r] * ev[2][r] + ev[3][r] * ev[3][r];
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                st_row4(p.erows, p.B, k, u0, make_float4(ee[k][0], ee[k][1], ee[k][2], ee[k][3]));
-                st_row4(p.erows, p.B, 4 + k, u0, make_float4(eo[k][0], eo[k][1], eo[k][2], eo[k][3]));
+                for (int k = 0; k < 4; ++k) st_row4(p.erows, p.B, 4 * ph + k, u0, make_float4(ev[k][0], ev[k][1], ev[k][2], ev[k][3]));
             }
         }
         __syncthreads();
@@ -366,58 +406,18 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_fwd_fast(DpK p) {
     }
 }
 
-// reduce the per-thread tap-gradient accumulators of one role over the CTA and add them to gpart
-template <int A>
-__device__ __forceinline__ void reduce_role(float (&acc)[A][8], float *red /* 8 warps x A*8 */, int role, int n_real,
-                                            float *dst_base, int M, int fam_is_h, int ph, int a0, int MH) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int a = 0; a < A; ++a)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float s = warp_sum(acc[a][k]);
-            if (lane == 0) red[wid * (A * 8) + a * 8 + k] = s;
-        }
-    __syncthreads();
-    // warps w and w+4 share a role
-    if (wid < 4 && wid == role) {
-        for (int idx = lane; idx < n_real * 8; idx += 32) {
-            const int a = idx >> 3, k = idx & 7, oi = k >> 1, c = k & 1, o = oi >> 1, i = oi & 1;
-            const float s = red[wid * (A * 8) + idx] + red[(wid + 4) * (A * 8) + idx];
-            const int lag = a0 + a;
-            if (fam_is_h) {                                   // dh[chi=o][nu=i][c][j], lags mirrored like the D taps
-                const int j = ph ? (2 * MH - 1 - 2 * lag) : (2 * MH - 2 * lag);
-                dst_base[8 * M + ((o * 2 + i) * 2 + c) * M + j] = s;
-            } else {                                          // dW[o][i | 2+i][k]
-                const int kk = 2 * lag + ph;
-                dst_base[(o * 4 + 2 * c + i) * M + kk] = s;
-            }
-        }
-    }
-}
-
-// roles: 0 = even phase lags [0, A0e), 1 = even [A0e, NE), 2 = odd [0, A0o), 3 = odd [A0o, NO)
-template <int MH>
-struct Roles {
-    static constexpr int NE = MH + 1, NO = MH;
-    static constexpr int A0e = (NE + 1) / 2, A1e = NE - A0e, A0o = (NO + 1) / 2, A1o = NO - A0o;
-    static constexpr int AMAX = A0e;
-};
-
 // ---------------------------------------------------------------------------------------------
-// backward 1: dL/dE_q (FIR-like over gD), softmin backward -> dL/dout rows, dh partials
+// backward 1: dL/dE_q (FIR-like over gD = 2 kappa e), softmin backward -> dL/dout rows
 // ---------------------------------------------------------------------------------------------
 template <int NL, int MH>
-__global__ void __launch_bounds__(FT_NT, 2) k_dp_bwd1_fast(DpK p) {
+__global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_bwd1_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
-    using RL = Roles<MH>;
     extern __shared__ __align__(16) float4 smem4[];
-    float4 *ge = smem4, *go = ge + FT_ES, *m1s = go + FT_ES;
-    float4 *tapG = m1s + FT_ES;                              // conj(h) taps for dE_q: [phase][lag][2]
+    float4 *ge = smem4, *go = ge + FT_ES;
+    float4 *tapG = go + FT_ES;                               // conj(h) taps for dE_q: [phase][lag][2]
     FastConst *cst = reinterpret_cast<FastConst *>(tapG + 2 * (NE + NO));
     float *PSg = reinterpret_cast<float *>(cst + 1);         // (2, M+1)
-    float *red = PSg + 2 * (M + 1) + 2;                      // 8 * AMAX * 8
-    const int tid = threadIdx.x, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const float kap0 = p.scal[DP_KAPPA_OFF], kap1 = p.scal[DP_KAPPA_OFF + 1];
 
     for (int idx = tid; idx < (NE + NO) * 8; idx += FT_NT) {
@@ -442,126 +442,108 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_bwd1_fast(DpK p) {
     }
     __syncthreads();
     const FastConst &c = *cst;
-    const float4 *tGe = tapG, *tGo = tapG + 2 * NE;
-    const int pb = 5 * tid;
-    const int role = wid & 3;
+    const int i0 = FT_R * tid;
 
-    float acc[RL::AMAX][8];
-#pragma unroll
-    for (int a = 0; a < RL::AMAX; ++a)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
-
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int t0 = tile * FT_T;
-        const int i0 = FT_R * tid, u0 = t0 - FT_HP + i0;
+        const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
-        // ---- stage gD = 2 kappa e (tile + halo) and E_q (tile + halo) -----------------------------------
-        {
-            float4 er[8], mr[4];
-            if (in_seq) {
+        {   // stage gD = 2 kappa e for the tile and its halo
+            float4 er[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) er[k] = ld_row4(p.erows, p.B, k, u0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mr[k] = ld_row4(p.m1rows, p.B, k, u0);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) er[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int k = 0; k < 8; ++k) er[k] = in_seq ? ld_row4(p.erows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float s0 = 2.f * kap0, s1 = 2.f * kap1;
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) {
-                auto comp = [r](const float4 &v) { return reinterpret_cast<const float *>(&v)[r]; };
-                ge[pb + r] = make_float4(s0 * comp(er[0]), s0 * comp(er[1]), s1 * comp(er[2]), s1 * comp(er[3]));
-                go[pb + r] = make_float4(s0 * comp(er[4]), s0 * comp(er[5]), s1 * comp(er[6]), s1 * comp(er[7]));
-                m1s[pb + r] = make_float4(comp(mr[0]), comp(mr[1]), comp(mr[2]), comp(mr[3]));
+                ge[5 * tid + r] = make_float4(s0 * f4c(er[0], r), s0 * f4c(er[1], r), s1 * f4c(er[2], r), s1 * f4c(er[3], r));
+                go[5 * tid + r] = make_float4(s0 * f4c(er[4], r), s0 * f4c(er[5], r), s1 * f4c(er[6], r), s1 * f4c(er[7], r));
             }
         }
         __syncthreads();
-
         if (owned) {
             float gE[FT_R][4];
 #pragma unroll
             for (int r = 0; r < FT_R; ++r)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) gE[r][k] = 0.f;
-            // dL/dE_q(u) = sum_chi sum_j conj(h[chi][nu][j]) gD_chi(2u - MH + j): even j -> ge[u+a-HF], odd -> go[u+a-HF]
-            fir4<NE, -HF>(ge, pb, tGe, gE);
-            fir4<NO, -HF>(go, pb, tGo, gE);
-            float gy[4][FT_R];
-            float gV[2][FT_R], entw[FT_R];
+            // dL/dE_q(u) = sum_chi sum_j conj(h[chi][nu][j]) gD_chi(2u - MH + j): even j -> ge[u+a-HF], odd j -> go[u+a-HF]
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph) fir4(ph ? go : ge, i0 - HF, tapG + (ph ? 2 * NE : 0), ph ? NO : NE, gE);
+            float entw[FT_R];
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) {
                 const int u = u0 + r;
-                const int jlo = max(0, 2 * MH - 2 * u), jhi = min(M, p.L - 2 * u);
-                gV[0][r] = PSg[jhi] - PSg[jlo];
-                gV[1][r] = PSg[(M + 1) + jhi] - PSg[(M + 1) + jlo];
                 entw[r] = (u >= MH && u < p.B - MH) ? LN2 : 0.f;
             }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                float4 q4[NL];
-#pragma unroll
-                for (int l = 0; l < NL; ++l) q4[l] = ld_row4(p.q, p.ld_q, cc * NL + l, u0);
-                const float4 y4 = ld_row4(p.out, p.ld_out, cc, u0);
+#pragma unroll 1
+            for (int pol = 0; pol < 2; ++pol) {
+                float gV[FT_R];
 #pragma unroll
                 for (int r = 0; r < FT_R; ++r) {
-                    float q[NL];
-#pragma unroll
-                    for (int l = 0; l < NL; ++l) q[l] = reinterpret_cast<const float *>(&q4[l])[r];
-                    const float y = reinterpret_cast<const float *>(&y4)[r];
-                    const float m1 = reinterpret_cast<const float *>(&m1s[pb + r])[cc];
-                    const float g2 = gV[cc >> 1][r];
-                    const float g1 = gE[r][cc] - 2.f * m1 * g2;
-                    gy[cc][r] = demap_backward_fast<NL>(y, c.inv_var[cc >> 1], c, q, g1, g2, entw[r]);
+                    const int u = u0 + r;
+                    const int jlo = max(0, 2 * MH - 2 * u), jhi = min(M, p.L - 2 * u);
+                    gV[r] = PSg[pol * (M + 1) + jhi] - PSg[pol * (M + 1) + jlo];
                 }
-            }
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) st_row4(p.gyrows, p.B, cc, u0, make_float4(gy[cc][0], gy[cc][1], gy[cc][2], gy[cc][3]));
-        }
-
-        // ---- dh partials: roles (phase, lag half); warp w handles symbol groups of parity w>>2 ----------
-        {
-            // this thread's 4 symbols are handled for ALL roles by the 8 warps in turn: loop over the 8 groups of 128 symbols
-            for (int g = (wid >> 2); g < FT_NT / 32; g += 2) {
-                const int l = g * 32 + (tid & 31);           // thread-slot whose 4 symbols we process
-                const int li0 = FT_R * l, uu0 = t0 - FT_HP + li0;
-                const bool own = (uu0 >= 0) && (uu0 < p.B) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T);
-                if (!own) continue;                          // halo slots carry no owned samples (and their windows leave the tile)
-                const int pbl = 5 * l;
-                float4 gd[FT_R];
-                const float4 *src = (role < 2) ? ge : go;
+                for (int cq = 0; cq < 2; ++cq) {
+                    const int cc = 2 * pol + cq;
+                    float4 q4[NL];
 #pragma unroll
-                for (int r = 0; r < FT_R; ++r) gd[r] = src[pbl + r];
-                // window over E_q[v + a' - HF] (even phase) or E_q[v + a'' - HF + 1] (odd phase)
-                if (role == 0) corr4<RL::AMAX, -HF>(m1s, pbl, gd, acc);
-                else if (role == 1) corr4<RL::AMAX, -HF + RL::A0e>(m1s, pbl, gd, acc);
-                else if (role == 2) corr4<RL::AMAX, -HF + 1>(m1s, pbl, gd, acc);
-                else corr4<RL::AMAX, -HF + 1 + RL::A0o>(m1s, pbl, gd, acc);
+                    for (int l = 0; l < NL; ++l) q4[l] = ld_row4(p.q, p.ld_q, cc * NL + l, u0);
+                    const float4 y4 = ld_row4(p.out, p.ld_out, cc, u0), m4 = ld_row4(p.m1rows, p.B, cc, u0);
+                    float gy[FT_R];
+#pragma unroll
+                    for (int r = 0; r < FT_R; ++r) {
+                        float q[NL];
+#pragma unroll
+                        for (int l = 0; l < NL; ++l) q[l] = f4c(q4[l], r);
+                        const float g1 = gE[r][cq] - 2.f * f4c(m4, r) * gV[r];
+                        gy[r] = demap_backward_fast<NL>(f4c(y4, r), c.inv_var[pol], c, q, g1, gV[r], entw[r]);
+                    }
+                    st_row4(p.gyrows, p.B, cc, u0, make_float4(gy[0], gy[1], gy[2], gy[3]));
+                }
+#pragma unroll
+                for (int r = 0; r < FT_R; ++r) {
+                    gE[r][0] = gE[r][2];
+                    gE[r][1] = gE[r][3];
+                }
             }
         }
         __syncthreads();
     }
-    const int n_real = role == 0 ? RL::A0e : role == 1 ? RL::A1e : role == 2 ? RL::A0o : RL::A1o;
-    const int a0 = role == 0 ? 0 : role == 1 ? RL::A0e : role == 2 ? 0 : RL::A0o;
-    reduce_role<RL::AMAX>(acc, red, role, n_real, p.gpart + (int64_t)blockIdx.x * 16 * M, M, 1, role >> 1, a0, MH);
 }
 
-// ---------------------------------------------------------------------------------------------
-// backward 2: dW partials = correlation of dL/dout with the rx phases
-// ---------------------------------------------------------------------------------------------
+// roles: 0 = even phase lags [0, A0e), 1 = even [A0e, NE), 2 = odd [0, A0o), 3 = odd [A0o, NO)
 template <int MH>
-__global__ void __launch_bounds__(FT_NT, 2) k_dp_bwd2_fast(DpK p) {
+struct Roles {
+    static constexpr int NE = MH + 1, NO = MH;
+    static constexpr int A0e = (NE + 1) / 2, A1e = NE - A0e, A0o = (NO + 1) / 2, A1o = NO - A0o;
+    static constexpr int AMAX = A0e;
+};
+
+// ---------------------------------------------------------------------------------------------
+// backward 2 (FAM = 0): dW[o][i][2a+ph]   = sum_u gy_o(u)      conj(x_ph,i[u + a - HF])
+// backward 3 (FAM = 1): dh[chi][nu][j(a)] = sum_v gD_ph,chi(v) conj(E_q,nu[v + a - HF + ph]),  j = 2MH - ph - 2a
+// Each warp owns one role = (phase, lag half) for the whole kernel (warps w and w+4 share a role and split the
+// symbol groups); its AMAX x 8 accumulators live in registers across all tiles of the persistent CTA.
+// ---------------------------------------------------------------------------------------------
+template <int MH, int FAM>
+__global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2;
     using RL = Roles<MH>;
     extern __shared__ __align__(16) float4 smem4[];
-    float4 *xe = smem4, *xo = xe + FT_XS, *gys = xo + FT_XS;
-    float *red = reinterpret_cast<float *>(gys + FT_ES);
-    const int tid = threadIdx.x, wid = tid >> 5, role = wid & 3;
-    const int pb = 5 * tid;
+    // FAM 0: s0 = xe, s1 = xo (windows), g0 = g1 = gy.   FAM 1: s0 = s1 = E_q (window), g0 = gD even, g1 = gD odd
+    float4 *s0 = smem4, *s1 = FAM == 0 ? s0 + FT_XS : s0;
+    float4 *g0 = FAM == 0 ? s1 + FT_XS : s0 + FT_ES, *g1 = FAM == 0 ? g0 : g0 + FT_ES;
+    float *red = reinterpret_cast<float *>((FAM == 0 ? g0 : g1) + FT_ES);
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, role = wid & 3, ph = role >> 1;
+    const int a0 = (role & 1) ? (ph ? RL::A0o : RL::A0e) : 0;
+    const int n_real = role == 0 ? RL::A0e : role == 1 ? RL::A1e : role == 2 ? RL::A0o : RL::A1o;
+    const float4 *win = ph ? s1 : s0, *gsrc = ph ? g1 : g0;
+    const int c0 = (FAM == 0 ? FT_XOFF - HF : -HF + ph) + a0;
+    const float kap0 = FAM ? p.scal[DP_KAPPA_OFF] : 0.f, kap1 = FAM ? p.scal[DP_KAPPA_OFF + 1] : 0.f;
 
     float acc[RL::AMAX][8];
 #pragma unroll
@@ -569,41 +551,68 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_bwd2_fast(DpK p) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
 
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int t0 = tile * FT_T;
-        load_x_phases(p, t0, xe, xo);
         {
             const int i0 = FT_R * tid, u0 = t0 - FT_HP + i0;
-            const bool owned = (u0 >= 0) && (u0 < p.B) && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
-            float4 gr[4];
+            const bool in_seq = (u0 >= 0) && (u0 < p.B);
+            const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
+            if (FAM == 0) {
+                load_x_phases(p, t0, s0, s1);
+                float4 gr[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gr[k] = owned ? ld_row4(p.gyrows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 4; ++k) gr[k] = owned ? ld_row4(p.gyrows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int r = 0; r < FT_R; ++r) {
-                auto comp = [r](const float4 &v) { return reinterpret_cast<const float *>(&v)[r]; };
-                gys[pb + r] = make_float4(comp(gr[0]), comp(gr[1]), comp(gr[2]), comp(gr[3]));
+                for (int r = 0; r < FT_R; ++r) g0[5 * tid + r] = make_float4(f4c(gr[0], r), f4c(gr[1], r), f4c(gr[2], r), f4c(gr[3], r));
+            } else {
+                float4 er[8], mr[4];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) er[k] = owned ? ld_row4(p.erows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mr[k] = in_seq ? ld_row4(p.m1rows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f0 = 2.f * kap0, f1 = 2.f * kap1;
+#pragma unroll
+                for (int r = 0; r < FT_R; ++r) {
+                    g0[5 * tid + r] = make_float4(f0 * f4c(er[0], r), f0 * f4c(er[1], r), f1 * f4c(er[2], r), f1 * f4c(er[3], r));
+                    g1[5 * tid + r] = make_float4(f0 * f4c(er[4], r), f0 * f4c(er[5], r), f1 * f4c(er[6], r), f1 * f4c(er[7], r));
+                    s0[5 * tid + r] = make_float4(f4c(mr[0], r), f4c(mr[1], r), f4c(mr[2], r), f4c(mr[3], r));
+                }
             }
         }
         __syncthreads();
+#pragma unroll 1
         for (int g = (wid >> 2); g < FT_NT / 32; g += 2) {
-            const int l = g * 32 + (tid & 31);
+            const int l = g * 32 + lane;                     // thread-slot whose 4 symbols this lane processes
             const int li0 = FT_R * l, uu0 = t0 - FT_HP + li0;
-            if (!((uu0 >= 0) && (uu0 < p.B) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T))) continue;
-            const int pbl = 5 * l;
+            if (!((uu0 >= 0) && (uu0 < p.B) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T))) continue;   // halo slots own nothing
             float4 gd[FT_R];
 #pragma unroll
-            for (int r = 0; r < FT_R; ++r) gd[r] = gys[pbl + r];
-            // dW[o][i][k = 2a + ph] = sum_u gy_o(u) conj(x_ph,i[u + a - HF])
-            if (role == 0) corr4<RL::AMAX, FT_XOFF - HF>(xe, pbl, gd, acc);
-            else if (role == 1) corr4<RL::AMAX, FT_XOFF - HF + RL::A0e>(xe, pbl, gd, acc);
-            else if (role == 2) corr4<RL::AMAX, FT_XOFF - HF>(xo, pbl, gd, acc);
-            else corr4<RL::AMAX, FT_XOFF - HF + RL::A0o>(xo, pbl, gd, acc);
+            for (int r = 0; r < FT_R; ++r) gd[r] = gsrc[5 * l + r];
+            corr4<RL::AMAX>(win, li0 + c0, gd, acc);
         }
         __syncthreads();
     }
-    const int n_real = role == 0 ? RL::A0e : role == 1 ? RL::A1e : role == 2 ? RL::A0o : RL::A1o;
-    const int a0 = role == 0 ? 0 : role == 1 ? RL::A0e : role == 2 ? 0 : RL::A0o;
-    reduce_role<RL::AMAX>(acc, red, role, n_real, p.gpart + (int64_t)blockIdx.x * 16 * M, M, 0, role >> 1, a0, MH);
+
+    // reduce over lanes, then over the two warps of a role, and publish this CTA's partial
+#pragma unroll
+    for (int a = 0; a < RL::AMAX; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float s = warp_sum(acc[a][k]);
+            if (lane == 0) red[wid * (RL::AMAX * 8) + a * 8 + k] = s;
+        }
+    __syncthreads();
+    if (wid < 4) {
+        float *dst = p.gpart + (int64_t)blockIdx.x * 16 * M;
+        for (int idx = lane; idx < n_real * 8; idx += 32) {
+            const int a = idx >> 3, k = idx & 7, oi = k >> 1, cidx = k & 1, o = oi >> 1, i = oi & 1;
+            const float s = red[wid * (RL::AMAX * 8) + idx] + red[(wid + 4) * (RL::AMAX * 8) + idx];
+            const int lag = a0 + a;
+            if (FAM == 1) dst[8 * M + ((o * 2 + i) * 2 + cidx) * M + (2 * MH - ph - 2 * lag)] = s;
+            else dst[(o * 4 + 2 * cidx + i) * M + (2 * lag + ph)] = s;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -615,47 +624,59 @@ static size_t fast_smem_fwd() {
 }
 template <int MH>
 static size_t fast_smem_bwd1() {
-    return (size_t)(3 * FT_ES + 2 * (2 * MH + 1)) * sizeof(float4) + sizeof(FastConst) +
-           (2 * (2 * MH + 2) + 2 + 8 * Roles<MH>::AMAX * 8) * sizeof(float) + 64;
+    return (size_t)(2 * FT_ES + 2 * (2 * MH + 1)) * sizeof(float4) + sizeof(FastConst) + (2 * (2 * MH + 2) + 2) * sizeof(float) + 64;
 }
-template <int MH>
-static size_t fast_smem_bwd2() {
-    return (size_t)(2 * FT_XS + FT_ES) * sizeof(float4) + 8 * Roles<MH>::AMAX * 8 * sizeof(float) + 64;
+template <int MH, int FAM>
+static size_t fast_smem_taps() {
+    return (size_t)(FAM == 0 ? 2 * FT_XS + FT_ES : 3 * FT_ES) * sizeof(float4) + 8 * Roles<MH>::AMAX * 8 * sizeof(float) + 64;
+}
+
+template <typename K>
+static int fast_prepare(K kern, size_t smem, int *grid) {
+    VAEQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per = 0;
+    VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, FT_NT, smem));
+    *grid = max(1, per) * sm_count();
+    return VAEQ_OK;
 }
 
 template <int NL, int MH>
 static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
-    static int gridF = 0, gridB = 0;
-    const size_t sf = fast_smem_fwd<MH>(), s1 = fast_smem_bwd1<MH>(), s2 = fast_smem_bwd2<MH>();
-    if (!gridF) {
-        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_fwd_fast<NL, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
-        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_bwd1_fast<NL, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_bwd2_fast<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-        int a = 0, b = 0, c = 0;
-        VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dp_fwd_fast<NL, MH>, FT_NT, sf));
-        VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_dp_bwd1_fast<NL, MH>, FT_NT, s1));
-        VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_dp_bwd2_fast<MH>, FT_NT, s2));
-        gridF = max(1, a) * sm_count();
-        gridB = max(1, min(b, c)) * sm_count();
+    static int gF = 0, g1 = 0, g2 = 0, g3 = 0;
+    const size_t sf = fast_smem_fwd<MH>(), s1 = fast_smem_bwd1<MH>(), s2 = fast_smem_taps<MH, 0>(), s3 = fast_smem_taps<MH, 1>();
+    if (!gF) {
+        int rc;
+        if ((rc = fast_prepare(k_dp_fwd_fast<NL, MH>, sf, &gF))) return rc;
+        if ((rc = fast_prepare(k_dp_bwd1_fast<NL, MH>, s1, &g1))) return rc;
+        if ((rc = fast_prepare(k_dp_taps_fast<MH, 0>, s2, &g2))) return rc;
+        if ((rc = fast_prepare(k_dp_taps_fast<MH, 1>, s3, &g3))) return rc;
+        g2 = g3 = min(g2, g3);                               // both write the same per-CTA partial slots
     }
     p.T = FT_T;
     p.ntiles = (p.B + FT_T - 1) / FT_T;
-    const int gf = min(min(gridF, DP_GRID_CAP), p.ntiles), gb = min(min(gridB, DP_GRID_CAP), p.ntiles);
+    const int gf = min(min(gF, DP_GRID_CAP), p.ntiles), gb1 = min(min(g1, DP_GRID_CAP), p.ntiles), gt = min(min(g2, DP_GRID_CAP), p.ntiles);
     ktime_begin(VAEQ_K_DP_FWD, st);
     k_dp_fwd_fast<NL, MH><<<gf, FT_NT, sf, st>>>(p);
     ktime_end(VAEQ_K_DP_FWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_fwd_fast");
-    dp_launch_fin(p, gf, st);
+    {
+        const int rc = dp_launch_fin(p, gf, st);
+        if (rc) return rc;
+    }
     if (mode == DP_MODE_FWD) return VAEQ_OK;
     ktime_begin(VAEQ_K_DP_BWD, st);
-    k_dp_bwd1_fast<NL, MH><<<gb, FT_NT, s1, st>>>(p);
+    k_dp_bwd1_fast<NL, MH><<<gb1, FT_NT, s1, st>>>(p);
     ktime_end(VAEQ_K_DP_BWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_bwd1_fast");
     ktime_begin(VAEQ_K_DP_BWD2, st);
-    k_dp_bwd2_fast<MH><<<gb, FT_NT, s2, st>>>(p);
+    k_dp_taps_fast<MH, 0><<<gt, FT_NT, s2, st>>>(p);
     ktime_end(VAEQ_K_DP_BWD2, st);
-    VAEQ_LAUNCH_CHECK("k_dp_bwd2_fast");
-    *grid_bwd_out = gb;
+    VAEQ_LAUNCH_CHECK("k_dp_taps_fast<W>");
+    ktime_begin(VAEQ_K_DP_BWD3, st);
+    k_dp_taps_fast<MH, 1><<<gt, FT_NT, s3, st>>>(p);
+    ktime_end(VAEQ_K_DP_BWD3, st);
+    VAEQ_LAUNCH_CHECK("k_dp_taps_fast<h>");
+    *grid_bwd_out = gt;
     return VAEQ_OK;
 }
 
