@@ -159,15 +159,18 @@ __global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
 // ---------------------------------------------------------------------------------------------
 // finalize forward: C, loss, var_est, kappa, S_nu(j)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_dp_fin(DpK p, int nparts) {
+__global__ void __launch_bounds__(256) k_dp_fin(DpK p, int nparts) {
     __shared__ double tot[5];
+    __shared__ double Esh[2];
     __shared__ float Ssh[2 * VAEQ_MAX_TAPS];
-    const int tid = threadIdx.x, M = p.M, mh = p.mh, Mh = 2 * p.mh;
-    if (tid < 5) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, M = p.M, mh = p.mh, Mh = 2 * p.mh;
+    if (wid < 5) {                                          // warp w reduces quantity w over the CTA partials
         double a = 0.0;
-        for (int b = 0; b < nparts; ++b) a += p.part_fwd[(int64_t)b * 8 + tid];
-        tot[tid] = a;
+        for (int b = lane; b < nparts; b += 32) a += p.part_fwd[(int64_t)b * 8 + wid];
+        a = warp_sum(a);
+        if (lane == 0) tot[wid] = a;
     }
+    if (tid < 2) Esh[tid] = 0.0;
     __syncthreads();
     // S_nu(j) = sum of (Var_I+Var_Q)[nu] over source symbols u with Mh <= 2u+j < L      (sf:128)
     for (int idx = tid; idx < 2 * M; idx += blockDim.x) {
@@ -181,17 +184,23 @@ __global__ void k_dp_fin(DpK p, int nparts) {
         p.scal[DP_S_OFF + idx] = (float)s;
     }
     __syncthreads();
+    if (wid < 2) {                                          // warp chi: E_chi = sum_{nu,j} |h|^2 S_nu(j)   (sf:129)
+        const int chi = wid;
+        double E = 0.0;
+        for (int idx = lane; idx < 2 * M; idx += 32) {
+            const int nu = idx / M, j = idx - nu * M;
+            const float hr = p.h[((chi * 2 + nu) * 2 + 0) * M + j], hi = p.h[((chi * 2 + nu) * 2 + 1) * M + j];
+            E += (double)(hr * hr + hi * hi) * (double)Ssh[idx];
+        }
+        E = warp_sum(E);
+        if (lane == 0) Esh[chi] = E;
+    }
+    __syncthreads();
     if (tid == 0) {
         const double width = (double)(p.L - Mh);
         double loss = -tot[2];
         for (int chi = 0; chi < 2; ++chi) {
-            double E = 0.0;
-            for (int nu = 0; nu < 2; ++nu)
-                for (int j = 0; j < M; ++j) {
-                    float hr = p.h[((chi * 2 + nu) * 2 + 0) * M + j], hi = p.h[((chi * 2 + nu) * 2 + 1) * M + j];
-                    E += (double)(hr * hr + hi * hi) * (double)Ssh[nu * M + j];             // sf:129
-                }
-            const double C = tot[chi] + E;                                                  // sf:133-134
+            const double C = tot[chi] + Esh[chi];                                           // sf:133-134
             loss += width * log(C);                                                         // sf:136
             p.scal[DP_C_OFF + chi] = (float)C;
             p.scal[DP_KAPPA_OFF + chi] = (float)(width / C);
@@ -380,37 +389,49 @@ __device__ __forceinline__ void adam_apply(float *param, float g, float *m, floa
     param[i] = __fadd_rn(param[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
 }
 
-__global__ void k_dp_adam(DpK p, int nparts, int do_update, float lr_w, float lr_h, int amsgrad) {
-    const int M = p.M, n = 16 * M;
-    __shared__ int step_sh;
+// one WARP per tap-gradient entry: lanes stride over the per-CTA partials (fixed order -> deterministic), then lane 0
+// adds the E-term of dh, exports the gradient and applies Adam.  The step counter is bumped by the last CTA to finish.
+constexpr int ADAM_WARPS = 8;
+__global__ void __launch_bounds__(ADAM_WARPS * 32) k_dp_adam(DpK p, int nparts, int do_update, float lr_w, float lr_h, int amsgrad) {
+    const int M = p.M, n = 16 * M, lane = threadIdx.x & 31;
     int *step_ptr = p.adam ? reinterpret_cast<int *>(p.adam + 48 * M) : nullptr;
-    if (threadIdx.x == 0 && do_update) {
-        step_sh = *step_ptr + 1;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int step = do_update ? *step_ptr + 1 : 0;         // every CTA reads the old value before taking its ticket
+    const int i = blockIdx.x * ADAM_WARPS + (threadIdx.x >> 5);
+    if (i < n) {
         double a = 0.0;
-        for (int b = 0; b < nparts; ++b) a += (double)p.gpart[(int64_t)b * n + i];
-        if (i >= 8 * M) {                                   // E-term of dh: 2 kappa_chi h S_nu(j)
-            const int r = i - 8 * M, j = r % M, cn = r / (2 * M), chi = cn >> 1, nu = cn & 1;
-            a += 2.0 * (double)p.scal[DP_KAPPA_OFF + chi] * (double)p.h[r] * (double)p.scal[DP_S_OFF + nu * M + j];
-        }
-        const float g = (float)a;
-        p.gfinal[i] = g;
-        if (i < 8 * M) {
-            if (p.gW_out) p.gW_out[i] = g;
-        } else {
-            if (p.gh_out) p.gh_out[i - 8 * M] = g;
-        }
-        if (do_update) {
-            if (i < 8 * M)
-                adam_apply(p.W, g, p.adam, p.adam + 8 * M, p.adam + 16 * M, i, lr_w, amsgrad != 0, step_sh);
-            else
-                adam_apply(p.h, g, p.adam + 24 * M, p.adam + 32 * M, p.adam + 40 * M, i - 8 * M, lr_h, amsgrad != 0, step_sh);
+        for (int b = lane; b < nparts; b += 32) a += (double)p.gpart[(int64_t)b * n + i];
+        a = warp_sum(a);
+        if (lane == 0) {
+            if (i >= 8 * M) {                               // E-term of dh: 2 kappa_chi h S_nu(j)
+                const int r = i - 8 * M, j = r % M, cn = r / (2 * M), chi = cn >> 1, nu = cn & 1;
+                a += 2.0 * (double)p.scal[DP_KAPPA_OFF + chi] * (double)p.h[r] * (double)p.scal[DP_S_OFF + nu * M + j];
+            }
+            const float g = (float)a;
+            p.gfinal[i] = g;
+            if (i < 8 * M) {
+                if (p.gW_out) p.gW_out[i] = g;
+            } else {
+                if (p.gh_out) p.gh_out[i - 8 * M] = g;
+            }
+            if (do_update) {
+                if (i < 8 * M)
+                    adam_apply(p.W, g, p.adam, p.adam + 8 * M, p.adam + 16 * M, i, lr_w, amsgrad != 0, step);
+                else
+                    adam_apply(p.h, g, p.adam + 24 * M, p.adam + 32 * M, p.adam + 40 * M, i - 8 * M, lr_h, amsgrad != 0, step);
+            }
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && do_update) *step_ptr = step_sh;
+    if (do_update) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int *ticket = step_ptr + 1;
+            __threadfence();
+            if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+                *step_ptr = step;
+                *ticket = 0;
+            }
+        }
+    }
 }
 
 __global__ void k_adam_generic(float *param, const float *grad, float *state, int n, float lr, int amsgrad,
@@ -531,7 +552,7 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
 
 int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st) {
     ktime_begin(VAEQ_K_DP_FIN, st);
-    k_dp_fin<<<1, 64, 0, st>>>(p, nparts);
+    k_dp_fin<<<1, 256, 0, st>>>(p, nparts);
     ktime_end(VAEQ_K_DP_FIN, st);
     VAEQ_LAUNCH_CHECK("k_dp_fin");
     return VAEQ_OK;
@@ -539,7 +560,7 @@ int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st) {
 
 static int dp_launch_adam(const DpK &p, int nparts, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
     ktime_begin(VAEQ_K_DP_ADAM, st);
-    k_dp_adam<<<1, 512, 0, st>>>(p, nparts, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
+    k_dp_adam<<<(16 * p.M + ADAM_WARPS - 1) / ADAM_WARPS, ADAM_WARPS * 32, 0, st>>>(p, nparts, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
     ktime_end(VAEQ_K_DP_ADAM, st);
     VAEQ_LAUNCH_CHECK("k_dp_adam");
     return VAEQ_OK;
