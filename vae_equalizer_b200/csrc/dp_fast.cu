@@ -238,6 +238,18 @@ __device__ __forceinline__ void load_x_phases(const DpK &p, int t0, float4 *xe, 
     }
 }
 
+// L2 prefetch of `nrows` rows x [first, first+count) floats (128-byte lines), spread over the CTA: issued right after a
+// tile is staged so that the NEXT tile of this persistent CTA is L2-resident when its loads are issued.
+__device__ __forceinline__ void prefetch_rows(const float *base, int64_t ld, int nrows, int64_t first, int count, int64_t limit) {
+    const int lines = (count + 31) / 32;
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < nrows * lines; idx += FT_NT) {
+        const int r = idx / lines, ln = idx - r * lines;
+        const int64_t off = first + 32 * (int64_t)ln;
+        if (off >= 0 && off < limit) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)r * ld + off));
+    }
+}
+
 // SoA row helpers: 4 consecutive symbols of one row as a float4
 __device__ __forceinline__ float4 ld_row4(const float *base, int64_t ld, int row, int u) {
     return __ldg(reinterpret_cast<const float4 *>(base + (int64_t)row * ld + u));
@@ -283,6 +295,8 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
         const int t0 = tile * FT_T;
         load_x_phases(p, t0, xe, xo);
         __syncthreads();
+        if (tile + (int)gridDim.x < p.ntiles)
+            prefetch_rows(p.rx, p.ld_rx, 4, 2 * (int64_t)(t0 + (int64_t)gridDim.x * FT_T - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
 
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
@@ -462,6 +476,13 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_bwd1_fast(DpK p) {
             }
         }
         __syncthreads();
+        if (tile + (int)gridDim.x < p.ntiles) {
+            const int64_t nu0 = t0 + (int64_t)gridDim.x * FT_T;
+            prefetch_rows(p.erows, p.B, 8, nu0 - FT_HP, FT_TE, p.B);
+            prefetch_rows(p.q, p.ld_q, 4 * NL, nu0, FT_T, p.B);
+            prefetch_rows(p.out, p.ld_out, 4, nu0, FT_T, p.B);
+            prefetch_rows(p.m1rows, p.B, 4, nu0, FT_T, p.B);
+        }
         if (owned) {
             float gE[FT_R][4];
 #pragma unroll
@@ -581,6 +602,16 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
             }
         }
         __syncthreads();
+        if (tile + (int)gridDim.x < p.ntiles) {
+            const int64_t nu0 = t0 + (int64_t)gridDim.x * FT_T;
+            if (FAM == 0) {
+                prefetch_rows(p.rx, p.ld_rx, 4, 2 * (nu0 - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
+                prefetch_rows(p.gyrows, p.B, 4, nu0, FT_T, p.B);
+            } else {
+                prefetch_rows(p.erows, p.B, 8, nu0, FT_T, p.B);
+                prefetch_rows(p.m1rows, p.B, 4, nu0 - FT_HP, FT_TE, p.B);
+            }
+        }
 #pragma unroll 1
         for (int g = (wid >> 2); g < FT_NT / 32; g += 2) {
             const int l = g * 32 + lane;                     // thread-slot whose 4 symbols this lane processes
