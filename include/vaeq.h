@@ -136,6 +136,22 @@ int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stre
 int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
                         float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream);
 
+/* Batch-split of ONE long minibatch across GPUs (the reference has no counterpart, it is what replaces
+ * "one process, one device" for func_VAEflex_DP_MQAM_shaping.py at large batch_len).  Every rank holds the whole rx
+ * window and the same W/h/Adam state and owns the symbols [sym_lo, sym_hi) (multiples of 4).  Per step:
+ *   1. vaeq_dp_split_forward   -> stats_out (vaeq_dp_split_stats_doubles(M) doubles): partial C, entropy, Var sums
+ *      host: all-reduce(SUM) stats over the ranks
+ *   2. vaeq_dp_split_backward  (stats_in = reduced stats) -> loss, var_est (identical on every rank) and
+ *      grads_out (16*M floats: gW then gh, this rank's share, without the rank-independent E-term of gh)
+ *      host: all-reduce(SUM) grads
+ *   3. vaeq_dp_split_update    (grads_in = reduced grads) -> adds the E-term, Adam on both groups (replicated).
+ * q / out are written for the owned symbols (plus a 16-symbol margin each side). */
+size_t vaeq_dp_split_stats_doubles(int32_t M);
+int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, double *stats_out, void *stream);
+int vaeq_dp_split_backward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, const double *stats_in, float *grads_out,
+                           void *stream);
+int vaeq_dp_split_update(const vaeq_dp_desc *d, const float *grads_in, float lr_w, float lr_h, void *stream);
+
 /* generic Adam update on n floats (torch.optim.Adam single-tensor semantics); state = [m|v|vmax] (3n floats),
  * step_count is a device int32 incremented by the call when bump_step != 0 */
 int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,

@@ -181,3 +181,42 @@ def test_fast_path_matches_generic_kernels_and_trains():
     assert rel(f[4], g[4]) < 1e-4 and rel(f[5], g[5]) < 1e-4
     assert max(abs(a - b) / abs(b) for a, b in zip(f[6], g[6])) < 1e-5
     assert f[6][-1] < f[6][0]                           # and it trains
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_batch_split_emulated_ranks_match_single_gpu(world):
+    """The batch-split protocol (vaeq_dp_split_*) with `world` ranks emulated one after the other on one GPU:
+    per-rank symbol ranges, host-side sums standing in for the two all-reduces.  Must match the single-call step."""
+    from vae_equalizer_b200.dp import DPEqualizer
+    from vae_equalizer_b200.parallel import split_ranges
+    M, B = 25, 1008 * 10 + 400
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rx, tx, _ = O.generate_data_shaping(B, amps, 23, h_ch, P, 2, 90e9, 2, -26e-24, 0.1e-12 * np.sqrt(1000),
+                                        np.array([0.0314, 0.0314], dtype=np.complex64), np.pi / 10, "cpu", rng=np.random.default_rng(4))
+    Pt = torch.tensor(P, dtype=torch.float32)
+    gen = torch.Generator().manual_seed(1)
+    W0 = O.dirac_taps(M) + 0.02 * torch.randn(2, 4, M, generator=gen)
+    h0 = h_est.detach() + 0.02 * torch.randn(2, 2, 2, M, generator=gen)
+    rxd = rx.cuda()
+    ref = DPEqualizer(M, 2, amp, Pt, var, nu_sc, W0=W0, h0=h0)
+    q_ref, out_ref, loss_ref, ve_ref = ref.train_step(rxd, 2.5e-3, 2.5e-3)
+    ranks = [DPEqualizer(M, 2, amp, Pt, var, nu_sc, W0=W0, h0=h0) for _ in range(world)]
+    bufs = [(torch.zeros_like(q_ref), torch.zeros_like(out_ref)) for _ in range(world)]
+    ranges = split_ranges(B, world)
+    stats = [eq.split_forward(rxd, lo, hi, *b).clone() for eq, (lo, hi), b in zip(ranks, ranges, bufs)]
+    total = torch.stack(stats).sum(0)                                  # all-reduce #1
+    grads = []
+    for eq, (lo, hi), b in zip(ranks, ranges, bufs):
+        eq._stats.copy_(total)
+        grads.append(eq.split_backward(rxd, lo, hi, *b).clone())
+    gsum = torch.stack(grads).sum(0)                                   # all-reduce #2
+    for eq, b in zip(ranks, bufs):
+        eq._grads.copy_(gsum)
+        eq.split_update(rxd, *b, 2.5e-3, 2.5e-3)
+    torch.cuda.synchronize()
+    for eq, (lo, hi), (q, out) in zip(ranks, ranges, bufs):
+        assert rel(eq.loss, loss_ref) < 1e-6 and rel(eq.var_est, ve_ref) < 1e-6
+        assert rel(eq.W, ref.W) < 1e-5 and rel(eq.h, ref.h) < 1e-5
+        assert torch.equal(q[:, :, lo:hi], q_ref[:, :, lo:hi]) and torch.equal(out[:, :, lo:hi], out_ref[:, :, lo:hi])
+        assert eq.step_count() == 1
+    assert rel(gsum[:8 * M] , ref.gW.flatten()) < 1e-5

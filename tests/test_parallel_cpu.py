@@ -1,0 +1,70 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo processes exercise the sweep sharder, the result gather and the
+all-reduce plumbing of vae_equalizer_b200.parallel; the symbol-range partition is checked directly."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vae_equalizer_b200 import parallel as par
+
+
+def test_split_ranges_cover_and_align():
+    for B, world in ((1 << 22, 8), (1 << 22, 4), (4032, 2), (100800, 3), (1 << 20, 1)):
+        r = par.split_ranges(B, world)
+        assert r[0][0] == 0 and r[-1][1] == B and len(r) == world
+        for (a, b), (c, d) in zip(r, r[1:]):
+            assert b == c
+        assert all(lo % 4 == 0 and hi % 4 == 0 and hi > lo for lo, hi in r)
+        sizes = [hi - lo for lo, hi in r]
+        assert max(sizes) - min(sizes) <= 2 * par.TILE
+    with pytest.raises(ValueError):
+        par.split_ranges(1002, 2)
+    with pytest.raises(ValueError):
+        par.split_ranges(2016, 8)
+
+
+def test_sweep_cells_order_matches_reference_loops():
+    cells = par.sweep_cells(nu=[0, 0.027], lr=[2.5e-3, 2e-3, 3e-3], SNR=[20, 23], it=list(range(5)))
+    assert len(cells) == 60 and cells[0] == dict(nu=0, lr=2.5e-3, SNR=20, it=0) and cells[1]["it"] == 1 and cells[5]["SNR"] == 23
+    mine = [par.shard_cells(cells, r, 8) for r in range(8)]
+    assert sorted(i for m in mine for i, _ in m) == list(range(60))
+    assert max(len(m) for m in mine) - min(len(m) for m in mine) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cells = par.sweep_cells(SNR=[15, 17, 19], it=[0, 1, 2])
+        mine = par.shard_cells(cells, rank, world)
+        local = {i: torch.full((4, 3), float(100 * c["SNR"] + c["it"])) for i, c in mine}      # stands for SER_valid of a run
+        full = par.gather_cell_results(local, len(cells), (4, 3), rank, world)
+        stats = torch.tensor([1.0 + rank, 10.0 * (rank + 1)], dtype=torch.float64)
+        par.allreduce_sum_(stats)
+        ranges = par.split_ranges(8064, world)
+        q.put((rank, None if full is None else full[:, 0, 0].tolist(), stats.tolist(), ranges[rank]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_shard_gather_allreduce():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, full0, st0, rg0), (r1, full1, st1, rg1) = res
+    assert full1 is None and full0 == [1500.0, 1501.0, 1502.0, 1700.0, 1701.0, 1702.0, 1900.0, 1901.0, 1902.0]
+    assert st0 == st1 == [3.0, 30.0]
+    assert rg0 == (0, 4032) and rg1 == (4032, 8064)

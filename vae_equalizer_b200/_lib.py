@@ -65,6 +65,10 @@ PROTOTYPES = {
     "vaeq_dp_forward_backward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_train_step": (C.c_int, [C.POINTER(DpDesc), _f, _f, _vp]),
     "vaeq_dp_train_frame": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
+    "vaeq_dp_split_stats_doubles": (_sz, [_i32]),
+    "vaeq_dp_split_forward": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _vp, _vp]),
+    "vaeq_dp_split_backward": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _vp, _vp, _vp]),
+    "vaeq_dp_split_update": (C.c_int, [C.POINTER(DpDesc), _vp, _f, _f, _vp]),
     "vaeq_adam_update": (C.c_int, [_vp, _vp, _vp, _i32, _f, _i32, _vp, _i32, _vp]),
     "vaeq_soft_dec": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i32, _i32, _vp, _i64, _vp]),
     "vaeq_find_shift": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

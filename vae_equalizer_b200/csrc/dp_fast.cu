@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int t0 = tile * FT_T;
+        const int t0 = p.clo + tile * FT_T;
         load_x_phases(p, t0, xe, xo);
         __syncthreads();
         if (tile + (int)gridDim.x < p.ntiles)
@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
 
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
-        const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
+        const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.chi);
+        const bool counted = owned && (u0 >= p.sym_lo) && (u0 < p.sym_hi);   // sums only over this rank's symbols
         float mom[FT_R][4];
 #pragma unroll
         for (int r = 0; r < FT_R; ++r)
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
                         float m2, ent;
                         demap_fast<NL>(y[r][cq], c.c2[pol], c, qv[r], m1v[r], m2, ent);
                         const int u = u0 + r;
-                        if (owned && u >= MH && u < p.B - MH) accEnt += ent;                  // sf:132
+                        if (counted && u >= MH && u < p.B - MH) accEnt += ent;                // sf:132
                         const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
                         vs[r] = cq ? vs[r] + v : v;
                         mom[r][cq] = m1v[r];
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
                         }
                     }
                 }
-                if (owned) {
+                if (counted) {
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r) {
                         const int u = u0 + r;
@@ -401,8 +402,10 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
                     ev[1][r] = valid ? d[r][1] - x.y : 0.f;
                     ev[2][r] = valid ? d[r][2] - x.z : 0.f;
                     ev[3][r] = valid ? d[r][3] - x.w : 0.f;
-                    accC[0] += ev[0][r] * ev[0][r] + ev[1][r] * ev[1][r];
-                    accC[1] += ev[2][r] * ev[2][r] + ev[3][r] * ev[3][r];
+                    if (counted) {
+                        accC[0] += ev[0][r] * ev[0][r] + ev[1][r] * ev[1][r];
+                        accC[1] += ev[2][r] * ev[2][r] + ev[3][r] * ev[3][r];
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) st_row4(p.erows, p.B, 4 * ph + k, u0, make_float4(ev[k][0], ev[k][1], ev[k][2], ev[k][3]));
@@ -460,10 +463,10 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_bwd1_fast(DpK p) {
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int t0 = tile * FT_T;
+        const int t0 = p.sym_lo + tile * FT_T;
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);
-        const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
+        const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
         {   // stage gD = 2 kappa e for the tile and its halo
             float4 er[8];
 #pragma unroll
@@ -476,13 +479,6 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_bwd1_fast(DpK p) {
             }
         }
         __syncthreads();
-        if (tile + (int)gridDim.x < p.ntiles) {
-            const int64_t nu0 = t0 + (int64_t)gridDim.x * FT_T;
-            prefetch_rows(p.erows, p.B, 8, nu0 - FT_HP, FT_TE, p.B);
-            prefetch_rows(p.q, p.ld_q, 4 * NL, nu0, FT_T, p.B);
-            prefetch_rows(p.out, p.ld_out, 4, nu0, FT_T, p.B);
-            prefetch_rows(p.m1rows, p.B, 4, nu0, FT_T, p.B);
-        }
         if (owned) {
             float gE[FT_R][4];
 #pragma unroll
@@ -574,11 +570,11 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int t0 = tile * FT_T;
+        const int t0 = p.sym_lo + tile * FT_T;
         {
             const int i0 = FT_R * tid, u0 = t0 - FT_HP + i0;
             const bool in_seq = (u0 >= 0) && (u0 < p.B);
-            const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T);
+            const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
             if (FAM == 0) {
                 load_x_phases(p, t0, s0, s1);
                 float4 gr[4];
@@ -616,7 +612,7 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
         for (int g = (wid >> 2); g < FT_NT / 32; g += 2) {
             const int l = g * 32 + lane;                     // thread-slot whose 4 symbols this lane processes
             const int li0 = FT_R * l, uu0 = t0 - FT_HP + li0;
-            if (!((uu0 >= 0) && (uu0 < p.B) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T))) continue;   // halo slots own nothing
+            if (!((uu0 >= 0) && (uu0 < p.sym_hi) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T))) continue;   // halo slots own nothing
             float4 gd[FT_R];
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) gd[r] = gsrc[5 * l + r];
@@ -684,17 +680,21 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
         g2 = g3 = min(g2, g3);                               // both write the same per-CTA partial slots
     }
     p.T = FT_T;
-    p.ntiles = (p.B + FT_T - 1) / FT_T;
-    const int gf = min(min(gF, DP_GRID_CAP), p.ntiles), gb1 = min(min(g1, DP_GRID_CAP), p.ntiles), gt = min(min(g2, DP_GRID_CAP), p.ntiles);
-    ktime_begin(VAEQ_K_DP_FWD, st);
-    k_dp_fwd_fast<NL, MH><<<gf, FT_NT, sf, st>>>(p);
-    ktime_end(VAEQ_K_DP_FWD, st);
-    VAEQ_LAUNCH_CHECK("k_dp_fwd_fast");
-    {
+    const int nt_f = (p.chi - p.clo + FT_T - 1) / FT_T, nt_b = (p.sym_hi - p.sym_lo + FT_T - 1) / FT_T;
+    const int gf = min(min(gF, DP_GRID_CAP), nt_f), gb1 = min(min(g1, DP_GRID_CAP), nt_b), gt = min(min(g2, DP_GRID_CAP), nt_b);
+    if (mode != DP_MODE_SPLIT_BWD) {
+        p.ntiles = nt_f;
+        ktime_begin(VAEQ_K_DP_FWD, st);
+        k_dp_fwd_fast<NL, MH><<<gf, FT_NT, sf, st>>>(p);
+        ktime_end(VAEQ_K_DP_FWD, st);
+        VAEQ_LAUNCH_CHECK("k_dp_fwd_fast");
+        *grid_bwd_out = gf;                                  // split forward: number of forward partials
+        if (mode == DP_MODE_SPLIT_FWD) return VAEQ_OK;
         const int rc = dp_launch_fin(p, gf, st);
         if (rc) return rc;
     }
     if (mode == DP_MODE_FWD) return VAEQ_OK;
+    p.ntiles = nt_b;
     ktime_begin(VAEQ_K_DP_BWD, st);
     k_dp_bwd1_fast<NL, MH><<<gb1, FT_NT, s1, st>>>(p);
     ktime_end(VAEQ_K_DP_BWD, st);
@@ -716,6 +716,7 @@ int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bw
     const bool aligned = (p.B % 4 == 0) && (p.ld_rx % 4 == 0) && (p.ld_q % 4 == 0) && (p.ld_out % 4 == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.rx) | reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.out)) % 16 == 0);
     if (!aligned || p.B < 2 * FT_T) return 0;                // small batches: the generic kernels (one tile) are as good
+    if ((p.sym_lo | p.sym_hi | p.clo | p.chi) % 4 != 0) return 0;
     *rc = VAEQ_OK;
 #define FAST_CASE(NL_, MH_)                                             \
     if (n_lev == NL_ && p.mh == MH_) {                                  \

@@ -49,12 +49,18 @@ struct DpK {
     int64_t var_est_stride;
     float *gW_out, *gh_out;
     int T, ntiles;
+    // batch-split across GPUs: this rank accumulates sums / gradients over symbols [sym_lo, sym_hi)
+    // only, and its forward pass also produces the scratch rows for [clo, chi) = that range widened by DP_SPLIT_EXT
+    // symbols, so that the backward halo needs no exchange.  Single GPU: 0, B, 0, B.
+    int sym_lo, sym_hi, clo, chi;
 };
+constexpr int DP_SPLIT_EXT = 16;
 
 // dp_step.cu
 int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st);
 // dp_fast.cu: returns 1 if the register-blocked path ran (then *rc is its status, *grid_bwd_out the number of
 // gradient partials), 0 if the problem does not qualify (alignment, M_est, size) and the generic kernels must run
 int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bwd_out, int *rc);
+constexpr int DP_MODE_SPLIT_FWD = 3, DP_MODE_SPLIT_BWD = 4;   // forward kernel only / backward kernels only (no fin, no adam)
 
 }  // namespace vaeq

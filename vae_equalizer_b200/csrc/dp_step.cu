@@ -547,6 +547,7 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
     p.gW_out = d->gW; p.gh_out = d->gh;
     p.T = DP_TILE;
     p.ntiles = (d->B + p.T - 1) / p.T;
+    p.sym_lo = 0; p.sym_hi = d->B; p.clo = 0; p.chi = d->B;
     return p;
 }
 
@@ -674,6 +675,97 @@ extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32
         if (rc) return rc;
     }
     return VAEQ_OK;
+}
+
+// ---- batch-split phases: the host all-reduces `stats` and `grads` between them ----------------
+namespace vaeq {
+__global__ void k_dp_pack_stats(DpK p, int nparts, double *stats) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid < 5) {
+        double a = 0.0;
+        for (int b = lane; b < nparts; b += 32) a += p.part_fwd[(int64_t)b * 8 + wid];
+        a = warp_sum(a);
+        if (lane == 0) stats[wid] = a;
+    }
+    if (threadIdx.x >= 5 && threadIdx.x < 8) stats[threadIdx.x] = 0.0;
+    for (int i = threadIdx.x; i < 4 * p.mh; i += blockDim.x) stats[8 + i] = (double)p.edge_vs[i];
+}
+__global__ void k_dp_unpack_stats(DpK p, const double *stats) {
+    if (threadIdx.x < 8) p.part_fwd[threadIdx.x] = stats[threadIdx.x];
+    for (int i = threadIdx.x; i < 4 * p.mh; i += blockDim.x) p.edge_vs[i] = (float)stats[8 + i];
+}
+__global__ void k_dp_reduce_gpart(DpK p, int nparts, float *grads) {
+    const int n = 16 * p.M, lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    double a = 0.0;
+    for (int b = lane; b < nparts; b += 32) a += (double)p.gpart[(int64_t)b * n + i];
+    a = warp_sum(a);
+    if (lane == 0) grads[i] = (float)a;
+}
+static int split_check(const vaeq_dp_desc *d, int32_t lo, int32_t hi) {
+    VAEQ_CHECK_ARG(lo >= 0 && hi <= d->B && lo < hi && lo % 4 == 0 && hi % 4 == 0, "bad symbol range [%d,%d) (multiples of 4 inside [0,B))", lo, hi);
+    return VAEQ_OK;
+}
+}  // namespace vaeq
+
+extern "C" size_t vaeq_dp_split_stats_doubles(int32_t M) { return (size_t)8 + 4 * (M / 2); }
+
+extern "C" int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, double *stats_out, void *stream) {
+    int rc = dp_validate(d, false, false);
+    if (rc) return rc;
+    if ((rc = split_check(d, sym_lo, sym_hi))) return rc;
+    VAEQ_CHECK_ARG(stats_out != nullptr, "stats_out is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    DpK p = dp_make_params(d);
+    p.sym_lo = sym_lo; p.sym_hi = sym_hi;
+    p.clo = max(0, sym_lo - DP_SPLIT_EXT); p.chi = min(d->B, sym_hi + DP_SPLIT_EXT);
+    VAEQ_CUDA(cudaMemsetAsync(p.edge_vs, 0, 4 * (VAEQ_MAX_TAPS / 2 + 1) * sizeof(float), st));
+    int nparts = 0, rc2 = VAEQ_OK;
+    if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_FWD, st, &nparts, &rc2)) {
+        set_error("batch-split needs the fast path: M_est in {5,9,13,25}, 16-byte aligned rows, B %% 4 == 0, B >= 2016");
+        return VAEQ_EINVAL;
+    }
+    if (rc2) return rc2;
+    ktime_begin(VAEQ_K_DP_FIN, st);
+    k_dp_pack_stats<<<1, 256, 0, st>>>(p, nparts, stats_out);
+    ktime_end(VAEQ_K_DP_FIN, st);
+    VAEQ_LAUNCH_CHECK("k_dp_pack_stats");
+    return VAEQ_OK;
+}
+
+extern "C" int vaeq_dp_split_backward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, const double *stats_in,
+                                      float *grads_out, void *stream) {
+    int rc = dp_validate(d, false, false);
+    if (rc) return rc;
+    if ((rc = split_check(d, sym_lo, sym_hi))) return rc;
+    VAEQ_CHECK_ARG(stats_in && grads_out, "stats_in / grads_out is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    DpK p = dp_make_params(d);
+    p.sym_lo = sym_lo; p.sym_hi = sym_hi;
+    p.clo = max(0, sym_lo - DP_SPLIT_EXT); p.chi = min(d->B, sym_hi + DP_SPLIT_EXT);
+    k_dp_unpack_stats<<<1, 128, 0, st>>>(p, stats_in);
+    VAEQ_LAUNCH_CHECK("k_dp_unpack_stats");
+    if ((rc = dp_launch_fin(p, 1, st))) return rc;
+    int nparts = 0, rc2 = VAEQ_OK;
+    if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_BWD, st, &nparts, &rc2)) {
+        set_error("batch-split needs the fast path");
+        return VAEQ_EINVAL;
+    }
+    if (rc2) return rc2;
+    ktime_begin(VAEQ_K_DP_ADAM, st);
+    k_dp_reduce_gpart<<<(16 * p.M + 7) / 8, 256, 0, st>>>(p, nparts, grads_out);
+    ktime_end(VAEQ_K_DP_ADAM, st);
+    VAEQ_LAUNCH_CHECK("k_dp_reduce_gpart");
+    return VAEQ_OK;
+}
+
+extern "C" int vaeq_dp_split_update(const vaeq_dp_desc *d, const float *grads_in, float lr_w, float lr_h, void *stream) {
+    int rc = dp_validate(d, true, true);
+    if (rc) return rc;
+    VAEQ_CHECK_ARG(grads_in != nullptr, "grads_in is NULL");
+    DpK p = dp_make_params(d);
+    p.gpart = const_cast<float *>(grads_in);
+    return dp_launch_adam(p, 1, DP_MODE_TRAIN, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0, (cudaStream_t)stream);
 }
 
 extern "C" int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,

@@ -149,3 +149,27 @@ class DPEqualizer:
                                                 float(lr_w), float(lr_h), loss_steps.data_ptr(), var_steps.data_ptr(),
                                                 _lib.current_stream()), "vaeq_dp_train_frame")
         return loss_steps, var_steps
+
+    # -- batch-split phases (vaeq_dp_split_*; the caller all-reduces `stats` and `grads` between them) ---------------
+    def split_forward(self, rx, sym_lo, sym_hi, q, out):
+        B = self._check_rx(rx)
+        d = self._desc(rx, q, out, B)
+        if not hasattr(self, "_stats"):
+            self._stats = torch.zeros(int(self.lib.vaeq_dp_split_stats_doubles(self.M)), dtype=torch.float64, device=self.device)
+            self._grads = torch.zeros(16 * self.M, dtype=_F32, device=self.device)
+        _lib.check(self.lib.vaeq_dp_split_forward(C.byref(d), int(sym_lo), int(sym_hi), self._stats.data_ptr(),
+                                                  _lib.current_stream()), "vaeq_dp_split_forward")
+        return self._stats
+
+    def split_backward(self, rx, sym_lo, sym_hi, q, out):
+        B = self._check_rx(rx)
+        d = self._desc(rx, q, out, B)
+        _lib.check(self.lib.vaeq_dp_split_backward(C.byref(d), int(sym_lo), int(sym_hi), self._stats.data_ptr(),
+                                                   self._grads.data_ptr(), _lib.current_stream()), "vaeq_dp_split_backward")
+        return self._grads
+
+    def split_update(self, rx, q, out, lr_w, lr_h):
+        B = self._check_rx(rx)
+        d = self._desc(rx, q, out, B)
+        _lib.check(self.lib.vaeq_dp_split_update(C.byref(d), self._grads.data_ptr(), float(lr_w), float(lr_h),
+                                                 _lib.current_stream()), "vaeq_dp_split_update")
