@@ -261,6 +261,34 @@ def ours_arm(args, rank, local_rank, world):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (float(t2.item()) * 1e-3)
 
+    # ---- config 3: ONE long minibatch (world x 2^batch_log2 symbols) batch-split over the ranks, two tiny NCCL all-reduces/step
+    split = None
+    if world > 1 and not args.no_split:
+        from vae_equalizer_b200.parallel import BatchSplitDP
+        del rx_host, stage
+        Bt = B * world
+        rx_big = generate_data_gpu(Bt, cst["amps"], SNR, cst["P"], SPS, np.pi / 10, dev, 4321)[0]     # same seed: replicated window
+        eq2 = DPEqualizer(M_EST, SPS, cst["amp"], cst["P"], cst["var"], cst["nu_sc"], device=dev)
+        bs = BatchSplitDP(eq2)
+        del q, out
+        qb = torch.empty(2, 2 * N_LEV, Bt, dtype=torch.float32, device=dev)
+        ob = torch.empty(2, 2, Bt, dtype=torch.float32, device=dev)
+        for _ in range(W):
+            bs.train_step(rx_big, LR, LR, qb, ob)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(K):
+            bs.train_step(rx_big, LR, LR, qb, ob)
+        g1.record()
+        barrier()
+        t3 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        split = {"value": Bt * K / (float(t3.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t3.item()) / K, "batch_len": Bt,
+                 "scaling": "weak (batch_len grows with N)", "allreduce_bytes_per_step": 8 * (8 + 2 * (M_EST - 1)) + 4 * 16 * M_EST,
+                 "note": "BASELINE configs[2]: one minibatch split in contiguous symbol ranges, NCCL all-reduce of the ELBO partial sums and of the 400 tap-gradient floats, replicated Adam",
+                 "final_loss": float(eq2.loss.item())}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,6 +334,8 @@ def ours_arm(args, rank, local_rank, world):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if split is not None:
+        line["batch_split"] = split
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -320,6 +350,7 @@ def main():
     ap.add_argument("--batch-log2", type=int, default=22)
     ap.add_argument("--buffers", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="skip the batch-split (configs[2]) leg at N > 1")
     args = ap.parse_args()
 
     if args.gpus > 1 and "RANK" not in os.environ:          # launched bare: re-exec under torchrun (one rank per GPU)
