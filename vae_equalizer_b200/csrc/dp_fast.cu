@@ -23,16 +23,25 @@
 
 namespace vaeq {
 
-constexpr int FT_NT = 256;                 // threads per CTA
+#ifndef FT_NT_DEF
+#define FT_NT_DEF 256
+#endif
+constexpr int FT_NT = FT_NT_DEF;           // threads per CTA.  Two co-resident 256-thread CTAs are served unevenly by the warp
+                                           // scheduler (187 vs 270 us for identical work, profiles/r01_cta_imbalance.txt); one
+                                           // 512-thread CTA per SM (-DFT_NT_DEF=512) removes that tail but loses as much at its
+                                           // per-tile barriers (0.782 vs 0.744 ms per step), so 256 stays the default.
+constexpr int FT_NW = FT_NT / 32;          // warps per CTA
+constexpr int FT_CTAS_PER_SM = 512 / FT_NT;   // 128 registers per thread either way
 constexpr int FT_R = 4;                    // consecutive symbols per thread
 constexpr int FT_TE = FT_NT * FT_R;        // symbols per tile incl. halo (1024)
 constexpr int FT_HP = 8;                   // halo per side in symbols (>= MH/2, multiple of 4)
 constexpr int FT_T = FT_TE - 2 * FT_HP;    // owned symbols per tile (1008)
 constexpr int FT_XOFF = 8;                 // extra margin of the x phase arrays (FIR reaches MH/2 further)
 constexpr int FT_XN = FT_TE + 2 * FT_XOFF; // logical length of xe / xo
-#ifndef FT_MINB
-#define FT_MINB 2                          // min CTAs per SM the register allocator must allow (fwd / bwd1)
+#ifndef FT_MINB_PW
+#define FT_MINB_PW FT_CTAS_PER_SM           // min CTAs per SM for the point-wise heavy kernels (fwd, bwd1)
 #endif
+#define FT_MINB FT_CTAS_PER_SM              // ... and for the tap-gradient kernels (56 live accumulators)
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
 __host__ __device__ constexpr int fdiv4(int c) { return c >= 0 ? c / 4 : -((3 - c) / 4); }
@@ -57,6 +66,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+#ifdef VAEQ_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_phase_wall[4];
+__device__ unsigned long long g_cta_t0[2048], g_cta_t1[2048];
+__device__ unsigned int g_cta_sm[2048];
+#define PT_DECL long long _pt = clock64(); const long long _c0 = _pt; const unsigned long long _g0 = gtime_ns(); unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PT(i) { long long _n = clock64(); _acc[i] += (unsigned long long)(_n - _pt); _pt = _n; }
+#define PT_FLUSH if (threadIdx.x == 64) { g_cta_t0[blockIdx.x] = _g0; g_cta_t1[blockIdx.x] = gtime_ns(); unsigned int _sm; asm("mov.u32 %0, %%smid;" : "=r"(_sm)); g_cta_sm[blockIdx.x] = _sm; } if (threadIdx.x == 64 && blockIdx.x == 3) { for (int i = 0; i < 8; ++i) g_phase_cycles[i] = _acc[i]; g_phase_wall[0] = (unsigned long long)(clock64() - _c0); g_phase_wall[1] = gtime_ns() - _g0; }
+#else
+#define PT_DECL
+#define PT(i)
+#define PT_FLUSH
+#endif
 
 struct FastConst {
     float amp[VAEQ_MAX_LEVELS], a2[VAEQ_MAX_LEVELS];
@@ -141,21 +165,48 @@ __device__ __forceinline__ float demap_backward_fast(float y, float inv_var, con
 //   = {t00r,t00i,t01r,t01i},{t10r,t10i,t11r,t11i}, read as shared-memory broadcasts)
 // win is a padded float4 array (physical index j + j/4); i0 = logical index of (r = 0, a = 0).
 // ---------------------------------------------------------------------------------------------
+// Packed form: for every (symbol r, output o) two float2 accumulators A = sum t_re * (x_re, x_im) and
+// Bq = sum t_im * (x_re, x_im); the complex result is (A.x - Bq.y, A.y + Bq.x).  One FFMA2 (fma.rn.f32x2) replaces two
+// FFMA, the tap is a scalar-broadcast operand and (x_re, x_im) is a natural register pair of the LDS.128 window.
+struct FirAcc {
+    float2 A[FT_R][2], Bq[FT_R][2];
+};
+__device__ __forceinline__ void fir_acc_zero(FirAcc &a) {
+#pragma unroll
+    for (int r = 0; r < FT_R; ++r)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) a.A[r][o] = a.Bq[r][o] = make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ void fir_acc_finish(const FirAcc &a, float (&acc)[FT_R][4]) {
+#pragma unroll
+    for (int r = 0; r < FT_R; ++r)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            acc[r][2 * o] += a.A[r][o].x - a.Bq[r][o].y;
+            acc[r][2 * o + 1] += a.A[r][o].y + a.Bq[r][o].x;
+        }
+}
 __device__ __forceinline__ void fir_step(const float4 t0, const float4 t1, const float4 xa, const float4 xb, const float4 xc,
-                                         const float4 xd, float (&acc)[FT_R][4]) {
+                                         const float4 xd, FirAcc &a) {
     const float4 xs[4] = {xa, xb, xc, xd};
 #pragma unroll
     for (int r = 0; r < FT_R; ++r) {
-        const float4 x = xs[r];
-        acc[r][0] = fmaf(t0.x, x.x, fmaf(-t0.y, x.y, fmaf(t0.z, x.z, fmaf(-t0.w, x.w, acc[r][0]))));
-        acc[r][1] = fmaf(t0.x, x.y, fmaf(t0.y, x.x, fmaf(t0.z, x.w, fmaf(t0.w, x.z, acc[r][1]))));
-        acc[r][2] = fmaf(t1.x, x.x, fmaf(-t1.y, x.y, fmaf(t1.z, x.z, fmaf(-t1.w, x.w, acc[r][2]))));
-        acc[r][3] = fmaf(t1.x, x.y, fmaf(t1.y, x.x, fmaf(t1.z, x.w, fmaf(t1.w, x.z, acc[r][3]))));
+        const float2 x0 = make_float2(xs[r].x, xs[r].y), x1 = make_float2(xs[r].z, xs[r].w);
+        a.A[r][0] = __ffma2_rn(make_float2(t0.x, t0.x), x0, a.A[r][0]);
+        a.Bq[r][0] = __ffma2_rn(make_float2(t0.y, t0.y), x0, a.Bq[r][0]);
+        a.A[r][0] = __ffma2_rn(make_float2(t0.z, t0.z), x1, a.A[r][0]);
+        a.Bq[r][0] = __ffma2_rn(make_float2(t0.w, t0.w), x1, a.Bq[r][0]);
+        a.A[r][1] = __ffma2_rn(make_float2(t1.x, t1.x), x0, a.A[r][1]);
+        a.Bq[r][1] = __ffma2_rn(make_float2(t1.y, t1.y), x0, a.Bq[r][1]);
+        a.A[r][1] = __ffma2_rn(make_float2(t1.z, t1.z), x1, a.A[r][1]);
+        a.Bq[r][1] = __ffma2_rn(make_float2(t1.w, t1.w), x1, a.Bq[r][1]);
     }
 }
 
 __device__ __forceinline__ void fir4(const float4 *__restrict__ win, int i0, const float4 *__restrict__ taps, int nlag,
-                                     float (&acc)[FT_R][4]) {
+                                     float (&out)[FT_R][4]) {
+    FirAcc acc;
+    fir_acc_zero(acc);
     auto LD = [win](int j) { return win[j + (j >> 2)]; };
     float4 w0 = LD(i0), w1 = LD(i0 + 1), w2 = LD(i0 + 2), w3;
     int a = 0;
@@ -180,6 +231,7 @@ __device__ __forceinline__ void fir4(const float4 *__restrict__ win, int i0, con
         i0 += 1;
         taps += 2;
     }
+    fir_acc_finish(acc, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -263,7 +315,7 @@ __device__ __forceinline__ float f4c(const float4 &v, int r) { return r == 0 ? v
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int NL, int MH>
-__global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
+__global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
     static_assert(MH % 2 == 0 && MH / 2 <= FT_HP - 2, "fast path needs M_est = 1 (mod 4) and M_est <= 25");
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
     extern __shared__ __align__(16) float4 smem4[];
@@ -289,12 +341,16 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
 
     float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
     const int i0 = FT_R * tid;                               // local index of this thread's first symbol
+    PT_DECL
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int t0 = p.clo + tile * FT_T;
+        PT(7)
         load_x_phases(p, t0, xe, xo);
+        PT(0)
         __syncthreads();
+        PT(1)
         if (tile + (int)gridDim.x < p.ntiles)
             prefetch_rows(p.rx, p.ld_rx, 4, 2 * (int64_t)(t0 + (int64_t)gridDim.x * FT_T - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
 
@@ -317,6 +373,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
 #pragma unroll 1
             for (int ph = 0; ph < 2; ++ph)
                 fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? 2 * NE : 0), ph ? NO : NE, y);
+            PT(2)
             // point-wise stage, rolled over the polarisation (code size); y / mom rotate by two components per pass
 #pragma unroll 1
             for (int pol = 0; pol < 2; ++pol) {
@@ -376,9 +433,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
                 }
             }
         }
+        PT(3)
 #pragma unroll
         for (int r = 0; r < FT_R; ++r) m1s[5 * tid + r] = make_float4(mom[r][0], mom[r][1], mom[r][2], mom[r][3]);
         __syncthreads();
+        PT(4)
 
         // ---- D = h * E_q for the owned samples, residual e = D - rx ------------------------------------
         if (owned) {
@@ -411,8 +470,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
                 for (int k = 0; k < 4; ++k) st_row4(p.erows, p.B, 4 * ph + k, u0, make_float4(ev[k][0], ev[k][1], ev[k][2], ev[k][3]));
             }
         }
+        PT(5)
         __syncthreads();
+        PT(6)
     }
+    PT_FLUSH
 
     float v[5] = {accC[0], accC[1], accEnt, accV[0], accV[1]};
     block_sum<5>(v, red);
@@ -427,7 +489,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_fwd_fast(DpK p) {
 // backward 1: dL/dE_q (FIR-like over gD = 2 kappa e), softmin backward -> dL/dout rows
 // ---------------------------------------------------------------------------------------------
 template <int NL, int MH>
-__global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_bwd1_fast(DpK p) {
+__global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
     extern __shared__ __align__(16) float4 smem4[];
     float4 *ge = smem4, *go = ge + FT_ES;
@@ -547,7 +609,7 @@ struct Roles {
 // symbol groups); its AMAX x 8 accumulators live in registers across all tiles of the persistent CTA.
 // ---------------------------------------------------------------------------------------------
 template <int MH, int FAM>
-__global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
+__global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2;
     using RL = Roles<MH>;
     extern __shared__ __align__(16) float4 smem4[];
@@ -609,7 +671,7 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
             }
         }
 #pragma unroll 1
-        for (int g = (wid >> 2); g < FT_NT / 32; g += 2) {
+        for (int g = (wid >> 2); g < FT_NW; g += FT_NW / 4) {
             const int l = g * 32 + lane;                     // thread-slot whose 4 symbols this lane processes
             const int li0 = FT_R * l, uu0 = t0 - FT_HP + li0;
             if (!((uu0 >= 0) && (uu0 < p.sym_hi) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T))) continue;   // halo slots own nothing
@@ -630,11 +692,13 @@ __global__ void __launch_bounds__(FT_NT, 2) k_dp_taps_fast(DpK p) {
             if (lane == 0) red[wid * (RL::AMAX * 8) + a * 8 + k] = s;
         }
     __syncthreads();
-    if (wid < 4) {
+    if (wid < 4) {                                           // warps wid, wid+4, wid+8, ... share this role
         float *dst = p.gpart + (int64_t)blockIdx.x * 16 * M;
         for (int idx = lane; idx < n_real * 8; idx += 32) {
             const int a = idx >> 3, k = idx & 7, oi = k >> 1, cidx = k & 1, o = oi >> 1, i = oi & 1;
-            const float s = red[wid * (RL::AMAX * 8) + idx] + red[(wid + 4) * (RL::AMAX * 8) + idx];
+            float s = 0.f;
+#pragma unroll
+            for (int w = wid; w < FT_NW; w += 4) s += red[w * (RL::AMAX * 8) + idx];
             const int lag = a0 + a;
             if (FAM == 1) dst[8 * M + ((o * 2 + i) * 2 + cidx) * M + (2 * MH - ph - 2 * lag)] = s;
             else dst[(o * 4 + 2 * cidx + i) * M + (2 * lag + ph)] = s;
@@ -655,7 +719,7 @@ static size_t fast_smem_bwd1() {
 }
 template <int MH, int FAM>
 static size_t fast_smem_taps() {
-    return (size_t)(FAM == 0 ? 2 * FT_XS + FT_ES : 3 * FT_ES) * sizeof(float4) + 8 * Roles<MH>::AMAX * 8 * sizeof(float) + 64;
+    return (size_t)(FAM == 0 ? 2 * FT_XS + FT_ES : 3 * FT_ES) * sizeof(float4) + FT_NW * Roles<MH>::AMAX * 8 * sizeof(float) + 64;
 }
 
 template <typename K>
@@ -734,3 +798,13 @@ int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bw
 }
 
 }  // namespace vaeq
+
+#ifdef VAEQ_PHASE_TIMING
+extern "C" int vaeq_debug_phase_cycles(unsigned long long *out8) {
+    cudaMemcpyFromSymbol(out8 + 8, vaeq::g_phase_wall, 4 * sizeof(unsigned long long));
+    cudaMemcpyFromSymbol(out8 + 12, vaeq::g_cta_t0, 296 * sizeof(unsigned long long));
+    cudaMemcpyFromSymbol(out8 + 12 + 296, vaeq::g_cta_t1, 296 * sizeof(unsigned long long));
+    { unsigned int sm[296]; cudaMemcpyFromSymbol(sm, vaeq::g_cta_sm, 296 * sizeof(unsigned int)); for (int i = 0; i < 296; ++i) out8[12 + 592 + i] = sm[i]; }
+    return (int)cudaMemcpyFromSymbol(out8, vaeq::g_phase_cycles, 8 * sizeof(unsigned long long));
+}
+#endif
