@@ -118,6 +118,11 @@ size_t vaeq_adam_state_floats(int32_t M);
  * register-blocked fast path (dp_fast.cu: B % 4 == 0, 16-byte aligned rows, M_est in {5,9,13,25}, B >= 2016) applies. */
 int vaeq_dp_force_generic(int32_t on);
 
+/* Tile scheduling of the fast path: != 0 (default) lets every persistent CTA pull its next tile from an atomic counter
+ * (no SM idles while its slower CTA finishes; ~10 % faster), at the price of run-to-run differences in the LAST BITS of
+ * loss / gradients (summation order of the per-CTA partials); 0 = static striding, bitwise reproducible. */
+int vaeq_dp_dynamic_tiles(int32_t on);
+
 /* forward only: q, out, loss, var_est  (net(minibatch) + loss_function_shaping, no grad) */
 int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream);
 /* forward + backward: additionally gW, gh (must be non-NULL); parameters are NOT updated */

@@ -220,3 +220,30 @@ def test_batch_split_emulated_ranks_match_single_gpu(world):
         assert torch.equal(q[:, :, lo:hi], q_ref[:, :, lo:hi]) and torch.equal(out[:, :, lo:hi], out_ref[:, :, lo:hi])
         assert eq.step_count() == 1
     assert rel(gsum[:8 * M] , ref.gW.flatten()) < 1e-5
+
+
+def test_static_tiles_are_bitwise_reproducible_and_dynamic_agrees():
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    M, B = 25, 1 << 18
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rx, tx, _ = O.generate_data_shaping(B, amps, 23, h_ch, P, 2, 90e9, 2, -26e-24, 0.1e-12 * np.sqrt(1000),
+                                        np.array([0.0314, 0.0314], dtype=np.complex64), np.pi / 10, "cpu", rng=np.random.default_rng(8))
+    Pt = torch.tensor(P, dtype=torch.float32)
+    rxd = rx.cuda()
+
+    def run(dynamic):
+        lib.vaeq_dp_dynamic_tiles(dynamic)
+        try:
+            eq = DPEqualizer(M, 2, amp, Pt, var, nu_sc)
+            for _ in range(3):
+                eq.train_step(rxd, 2.5e-3, 2.5e-3)
+            torch.cuda.synchronize()
+            return eq.W.cpu().clone(), eq.h.cpu().clone(), float(eq.loss)
+        finally:
+            lib.vaeq_dp_dynamic_tiles(1)
+
+    a, b, d = run(0), run(0), run(1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2]
+    assert rel(d[0], a[0]) < 1e-5 and rel(d[1], a[1]) < 1e-5 and abs(d[2] - a[2]) / abs(a[2]) < 1e-6

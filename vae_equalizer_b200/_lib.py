@@ -61,6 +61,7 @@ PROTOTYPES = {
     "vaeq_dp_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_adam_state_floats": (_sz, [_i32]),
     "vaeq_dp_force_generic": (C.c_int, [_i32]),
+    "vaeq_dp_dynamic_tiles": (C.c_int, [_i32]),
     "vaeq_dp_forward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_forward_backward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_train_step": (C.c_int, [C.POINTER(DpDesc), _f, _f, _vp]),

@@ -302,6 +302,17 @@ __device__ __forceinline__ void prefetch_rows(const float *base, int64_t ld, int
     }
 }
 
+// Tile iteration of a persistent CTA.  Static: tile += gridDim.x (bitwise reproducible partial sums).  Dynamic: the
+// next tile index comes from an atomic counter, fetched ONE TILE AHEAD by thread 0 and published through shared memory
+// at the barrier that follows the staging of the current tile, so faster CTAs take more tiles and no SM idles at the end
+// (profiles/r01_cta_imbalance.txt); the summation order of the per-CTA partials then varies from run to run.
+struct TileIter {
+    int cur, next;
+};
+__device__ __forceinline__ void tile_fetch_next(const DpK &p, int k, int cur, int *s_next) {
+    if (threadIdx.x == 0) *s_next = p.dyn ? atomicAdd(p.tile_ctr + k, 1) + (int)gridDim.x : cur + (int)gridDim.x;
+}
+
 // SoA row helpers: 4 consecutive symbols of one row as a float4
 __device__ __forceinline__ float4 ld_row4(const float *base, int64_t ld, int row, int u) {
     return __ldg(reinterpret_cast<const float4 *>(base + (int64_t)row * ld + u));
@@ -342,17 +353,20 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
     float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
     const int i0 = FT_R * tid;                               // local index of this thread's first symbol
     PT_DECL
+    __shared__ int s_next;
 
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.ntiles;) {
         const int t0 = p.clo + tile * FT_T;
         PT(7)
+        tile_fetch_next(p, 0, tile, &s_next);
         load_x_phases(p, t0, xe, xo);
         PT(0)
         __syncthreads();
         PT(1)
-        if (tile + (int)gridDim.x < p.ntiles)
-            prefetch_rows(p.rx, p.ld_rx, 4, 2 * (int64_t)(t0 + (int64_t)gridDim.x * FT_T - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
+        const int tile_next = s_next;
+        if (tile_next < p.ntiles)
+            prefetch_rows(p.rx, p.ld_rx, 4, 2 * (int64_t)(p.clo + (int64_t)tile_next * FT_T - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
 
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
@@ -473,6 +487,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
         PT(5)
         __syncthreads();
         PT(6)
+        tile = tile_next;
     }
     PT_FLUSH
 
@@ -522,10 +537,12 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
     __syncthreads();
     const FastConst &c = *cst;
     const int i0 = FT_R * tid;
+    __shared__ int s_next;
 
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.ntiles;) {
         const int t0 = p.sym_lo + tile * FT_T;
+        tile_fetch_next(p, 1, tile, &s_next);
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
@@ -590,7 +607,9 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
                 }
             }
         }
+        const int tile_next = s_next;                        // written before the staging barrier of this iteration
         __syncthreads();
+        tile = tile_next;
     }
 }
 
@@ -630,9 +649,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
 
+    __shared__ int s_next;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.ntiles;) {
         const int t0 = p.sym_lo + tile * FT_T;
+        tile_fetch_next(p, 2 + FAM, tile, &s_next);
         {
             const int i0 = FT_R * tid, u0 = t0 - FT_HP + i0;
             const bool in_seq = (u0 >= 0) && (u0 < p.B);
@@ -660,8 +681,9 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
             }
         }
         __syncthreads();
-        if (tile + (int)gridDim.x < p.ntiles) {
-            const int64_t nu0 = t0 + (int64_t)gridDim.x * FT_T;
+        const int tile_next = s_next;
+        if (tile_next < p.ntiles) {
+            const int64_t nu0 = p.sym_lo + (int64_t)tile_next * FT_T;
             if (FAM == 0) {
                 prefetch_rows(p.rx, p.ld_rx, 4, 2 * (nu0 - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
                 prefetch_rows(p.gyrows, p.B, 4, nu0, FT_T, p.B);
@@ -681,6 +703,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
             corr4<RL::AMAX>(win, li0 + c0, gd, acc);
         }
         __syncthreads();
+        tile = tile_next;
     }
 
     // reduce over lanes, then over the two warps of a role, and publish this CTA's partial

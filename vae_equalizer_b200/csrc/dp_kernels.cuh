@@ -53,6 +53,9 @@ struct DpK {
     // only, and its forward pass also produces the scratch rows for [clo, chi) = that range widened by DP_SPLIT_EXT
     // symbols, so that the backward halo needs no exchange.  Single GPU: 0, B, 0, B.
     int sym_lo, sym_hi, clo, chi;
+    // dynamic tile scheduling of the fast kernels: tile_ctr[k] is the atomic tile counter of kernel k (zeroed per step)
+    int *tile_ctr;
+    int dyn;
 };
 constexpr int DP_SPLIT_EXT = 16;
 

@@ -480,7 +480,7 @@ static size_t dp_bwd_smem(int M, int T, int H, int mh) {
 }
 
 struct DpWsLayout {
-    size_t part_fwd, edge_vs, scal, ebuf, m1buf, gybuf, gpart, gfinal, total;
+    size_t part_fwd, edge_vs, scal, tile_ctr, ebuf, m1buf, gybuf, gpart, gfinal, total;
 };
 static DpWsLayout dp_ws_layout(int B, int M) {
     DpWsLayout w;
@@ -493,6 +493,7 @@ static DpWsLayout dp_ws_layout(int B, int M) {
     w.part_fwd = take((size_t)DP_GRID_CAP * 8 * sizeof(double));
     w.edge_vs = take((size_t)4 * (VAEQ_MAX_TAPS / 2 + 1) * sizeof(float));
     w.scal = take((size_t)(DP_S_OFF + 2 * VAEQ_MAX_TAPS) * sizeof(float));
+    w.tile_ctr = take(4 * sizeof(int));
     w.ebuf = take((size_t)B * 8 * sizeof(float));
     w.m1buf = take((size_t)B * 4 * sizeof(float));
     w.gybuf = take((size_t)B * 4 * sizeof(float));
@@ -501,6 +502,8 @@ static DpWsLayout dp_ws_layout(int B, int M) {
     w.total = off;
     return w;
 }
+
+static bool g_dynamic_tiles = true;
 
 static int dp_validate(const vaeq_dp_desc *d, bool need_grads, bool need_adam) {
     VAEQ_CHECK_ARG(d != nullptr, "desc is NULL");
@@ -548,6 +551,8 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
     p.T = DP_TILE;
     p.ntiles = (d->B + p.T - 1) / p.T;
     p.sym_lo = 0; p.sym_hi = d->B; p.clo = 0; p.chi = d->B;
+    p.tile_ctr = reinterpret_cast<int *>(ws + w.tile_ctr);
+    p.dyn = g_dynamic_tiles ? 1 : 0;
     return p;
 }
 
@@ -609,6 +614,7 @@ static bool g_force_generic = false;
 static int dp_dispatch(const DpK &p, int n_lev, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
     if (!g_force_generic) {
         int gb = 0, rc = VAEQ_OK;
+        if (p.dyn) VAEQ_CUDA(cudaMemsetAsync(p.tile_ctr, 0, 4 * sizeof(int), st));
         if (dp_try_fast(p, n_lev, mode, st, &gb, &rc)) {
             if (rc || mode == DP_MODE_FWD) return rc;
             return dp_launch_adam(p, gb, mode, lr_w, lr_h, amsgrad, st);
@@ -632,6 +638,11 @@ extern "C" size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev) {
 }
 
 extern "C" size_t vaeq_adam_state_floats(int32_t M) { return (size_t)48 * M + 4; }
+
+extern "C" int vaeq_dp_dynamic_tiles(int32_t on) {
+    g_dynamic_tiles = on != 0;
+    return VAEQ_OK;
+}
 
 extern "C" int vaeq_dp_force_generic(int32_t on) {
     g_force_generic = on != 0;
@@ -720,6 +731,7 @@ extern "C" int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int3
     p.sym_lo = sym_lo; p.sym_hi = sym_hi;
     p.clo = max(0, sym_lo - DP_SPLIT_EXT); p.chi = min(d->B, sym_hi + DP_SPLIT_EXT);
     VAEQ_CUDA(cudaMemsetAsync(p.edge_vs, 0, 4 * (VAEQ_MAX_TAPS / 2 + 1) * sizeof(float), st));
+    if (p.dyn) VAEQ_CUDA(cudaMemsetAsync(p.tile_ctr, 0, 4 * sizeof(int), st));
     int nparts = 0, rc2 = VAEQ_OK;
     if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_FWD, st, &nparts, &rc2)) {
         set_error("batch-split needs the fast path: M_est in {5,9,13,25}, 16-byte aligned rows, B %% 4 == 0, B >= 2016");
