@@ -83,7 +83,7 @@ __device__ unsigned int g_cta_sm[2048];
 #endif
 
 struct FastConst {
-    float amp[VAEQ_MAX_LEVELS], a2[VAEQ_MAX_LEVELS];
+    float amp[VAEQ_MAX_LEVELS], a2[VAEQ_MAX_LEVELS], a3[VAEQ_MAX_LEVELS];
     float nua2l[VAEQ_MAX_LEVELS];          // nu_sc a^2 log2(e)
     float lgP[VAEQ_MAX_LEVELS];            // log2 P_l
     float c2[2];                           // log2(e) / (2 var_p)
@@ -96,6 +96,7 @@ __device__ __forceinline__ void load_fast_const(FastConst *c, const DpK &p, int 
         const float a = t < n_lev ? p.amp[t] : 0.f;
         c->amp[t] = a;
         c->a2[t] = a * a;
+        c->a3[t] = a * a * a;
         c->nua2l[t] = p.nu_sc * (a * a) * LOG2E;
         c->lgP[t] = t < n_lev ? log2f(p.P[t]) : 0.f;
     }
@@ -105,10 +106,16 @@ __device__ __forceinline__ void load_fast_const(FastConst *c, const DpK &p, int 
     }
 }
 
-// soft demapper for one component: q, first two moments and the entropy term  sum_l -q_l ln(q_l / P_l)
-template <int NL>
-__device__ __forceinline__ void demap_fast(float y, float c2, const FastConst &c, float (&q)[NL], float &m1, float &m2,
-                                           float &ent) {
+// soft demapper for one component: q, first two moments and the entropy term  sum_l -q_l ln(q_l / P_l).
+// With BWD it also returns the three coefficients of the (linear) backward map of this component,
+//     dL/dy = g1 * S1 + g2 * S2 + w * S3,   g1 = dL/dE_q[x], g2 = dL/dE_q[x^2], w = ln2 * [symbol inside the entropy window]
+//     S1 = (m2 - m1^2)/var,  S2 = (m3 - m1 m2)/var,  S3 = (dotE (y - m1) - sum_l q_l ge_l (y - a_l))/var,
+//     ge_l = log2(q_l / P_l), dotE = sum_l q_l ge_l
+// (softmin + moments + entropy backward, closed form in oracle/closed_form.py, regrouped by input; S1 is d m1/dy).
+// The backward kernel then needs neither q nor any transcendental.
+template <int NL, bool BWD>
+__device__ __forceinline__ void demap_fast(float y, float c2, float inv_var, const FastConst &c, float (&q)[NL], float &m1,
+                                           float &m2, float &ent, float &S1, float &S2, float &S3) {
     float z[NL];
     float zmin = 3.0e38f;
 #pragma unroll
@@ -127,44 +134,30 @@ __device__ __forceinline__ void demap_fast(float y, float c2, const FastConst &c
     const float r = rcp_approx(s), lgs = lg2_approx(s);
     m1 = 0.f;
     m2 = 0.f;
-    float e = 0.f;
+    float e = 0.f, m3 = 0.f, ea = 0.f;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         q[l] *= r;
-        m1 = fmaf(c.amp[l], q[l], m1);
-        m2 = fmaf(c.a2[l], q[l], m2);
-        e = fmaf(q[l], (z[l] - lgs) - c.lgP[l], e);          // q log2(q/P); the 1e-12 of sf:132 only matters where q/P < 1e-9
+        const float qa = q[l] * c.amp[l];
+        m1 += qa;
+        m2 = fmaf(qa, c.amp[l], m2);
+        const float ge = z[l] - c.lgP[l];                   // log2(q_l / P_l) + lgs; the 1e-12 of sf:132 only matters where q/P < 1e-9
+        e = fmaf(q[l], ge, e);
+        if (BWD) {
+            m3 = fmaf(qa, c.a2[l], m3);
+            ea = fmaf(qa, ge, ea);
+        }
     }
-    ent = -LN2 * e;
+    ent = -LN2 * (e - lgs);                                 // sum_l q_l = 1
+    if (BWD) {
+        // S3 var = dotE (y - m1) - sum_l q_l ge'_l (y - a_l) with ge' = ge - lgs: the y and lgs terms cancel, leaving
+        //        = sum_l q_l ge_l a_l - m1 sum_l q_l ge_l
+        S1 = (m2 - m1 * m1) * inv_var;
+        S2 = (m3 - m1 * m2) * inv_var;
+        S3 = fmaf(-e, m1, ea) * inv_var;
+    }
 }
 
-// softmin + moments + entropy backward for one component (closed form in oracle/closed_form.py)
-template <int NL>
-__device__ __forceinline__ float demap_backward_fast(float y, float inv_var, const FastConst &c, const float (&q)[NL],
-                                                     float g1, float g2, float ent_w) {
-    float gq[NL];
-    float dot = 0.f;
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        float g = fmaf(c.amp[l], g1, c.a2[l] * g2);
-        // d/dq [ q ln(q/P + eps) ] = ln(q/P + eps) + (q/P)/(q/P + eps); the second term is a constant 1 wherever
-        // q matters and a per-symbol constant cancels in (gq - dot) because sum_l q_l = 1
-        g = fmaf(ent_w, lg2_approx(fmaxf(q[l], 1e-37f)) - c.lgP[l], g);
-        gq[l] = g;
-        dot = fmaf(q[l], g, dot);
-    }
-    float gy = 0.f;
-#pragma unroll
-    for (int l = 0; l < NL; ++l) gy = fmaf(q[l] * (dot - gq[l]), y - c.amp[l], gy);
-    return gy * inv_var;
-}
-
-// ---------------------------------------------------------------------------------------------
-// FIR-like contraction: 4 consecutive outputs per thread, nlag lags, 2x2 complex taps.
-//   acc[r][2o+c] += sum_a sum_i tap_a(o,i) * win[i0 + r + a]_i   (complex product; taps: 2 float4 per lag
-//   = {t00r,t00i,t01r,t01i},{t10r,t10i,t11r,t11i}, read as shared-memory broadcasts)
-// win is a padded float4 array (physical index j + j/4); i0 = logical index of (r = 0, a = 0).
-// ---------------------------------------------------------------------------------------------
 // Packed form: for every (symbol r, output o) two float2 accumulators A = sum t_re * (x_re, x_im) and
 // Bq = sum t_im * (x_re, x_im); the complex result is (A.x - Bq.y, A.y + Bq.x).  One FFMA2 (fma.rn.f32x2) replaces two
 // FFMA, the tap is a scalar-broadcast operand and (x_re, x_im) is a natural register pair of the LDS.128 window.
@@ -395,11 +388,12 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
 #pragma unroll
                 for (int cq = 0; cq < 2; ++cq) {
                     const int cc = 2 * pol + cq;
-                    float qv[FT_R][NL], m1v[FT_R];
+                    float qv[FT_R][NL], m1v[FT_R], s1v[FT_R], t2v[FT_R], s3v[FT_R];
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r) {
-                        float m2, ent;
-                        demap_fast<NL>(y[r][cq], c.c2[pol], c, qv[r], m1v[r], m2, ent);
+                        float m2, ent, S2;
+                        demap_fast<NL, true>(y[r][cq], c.c2[pol], c.inv_var[pol], c, qv[r], m1v[r], m2, ent, s1v[r], S2, s3v[r]);
+                        t2v[r] = fmaf(-2.f * m1v[r], s1v[r], S2);
                         const int u = u0 + r;
                         if (counted && u >= MH && u < p.B - MH) accEnt += ent;                // sf:132
                         const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
@@ -412,6 +406,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                             st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
                         st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
                         st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
+                        if (p.need_bwd) {
+                            st_row4(p.srows, p.B, cc, u0, make_float4(s1v[0], s1v[1], s1v[2], s1v[3]));
+                            st_row4(p.srows, p.B, 4 + cc, u0, make_float4(t2v[0], t2v[1], t2v[2], t2v[3]));
+                            st_row4(p.srows, p.B, 8 + cc, u0, make_float4(s3v[0], s3v[1], s3v[2], s3v[3]));
+                        }
                         if (p.qk != nullptr) {
 #pragma unroll 1
                             for (int r = 0; r < FT_R; ++r) {
@@ -501,7 +500,8 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward 1: dL/dE_q (FIR-like over gD = 2 kappa e), softmin backward -> dL/dout rows
+// backward 1: dL/dE_q (FIR-like over gD = 2 kappa e), then dL/dout = dL/dE_q*S1 + dL/dVar*T2 + w*S3 (coefficients from
+// the forward pass) -> dL/dout rows.  No q, no transcendental: 400 FFMA + ~30 other instructions per symbol.
 // ---------------------------------------------------------------------------------------------
 template <int NL, int MH>
 __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
@@ -509,8 +509,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
     extern __shared__ __align__(16) float4 smem4[];
     float4 *ge = smem4, *go = ge + FT_ES;
     float4 *tapG = go + FT_ES;                               // conj(h) taps for dE_q: [phase][lag][2]
-    FastConst *cst = reinterpret_cast<FastConst *>(tapG + 2 * (NE + NO));
-    float *PSg = reinterpret_cast<float *>(cst + 1);         // (2, M+1)
+    float *PSg = reinterpret_cast<float *>(tapG + 2 * (NE + NO));   // (2, M+1)
     const int tid = threadIdx.x;
     const float kap0 = p.scal[DP_KAPPA_OFF], kap1 = p.scal[DP_KAPPA_OFF + 1];
 
@@ -522,7 +521,6 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
         const float hv = p.h[((chi * 2 + nu) * 2 + c) * M + j];
         reinterpret_cast<float *>(tapG)[idx] = c ? -hv : hv;       // conj(h)
     }
-    load_fast_const(cst, p, NL);
     if (tid < 2) {
         const int nu = tid;
         float a = 0.f;
@@ -535,7 +533,6 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
         }
     }
     __syncthreads();
-    const FastConst &c = *cst;
     const int i0 = FT_R * tid;
     __shared__ int s_next;
 
@@ -585,19 +582,12 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
 #pragma unroll
                 for (int cq = 0; cq < 2; ++cq) {
                     const int cc = 2 * pol + cq;
-                    float4 q4[NL];
-#pragma unroll
-                    for (int l = 0; l < NL; ++l) q4[l] = ld_row4(p.q, p.ld_q, cc * NL + l, u0);
-                    const float4 y4 = ld_row4(p.out, p.ld_out, cc, u0), m4 = ld_row4(p.m1rows, p.B, cc, u0);
+                    // dL/dout = dL/dE_q * S1 + dL/dVar * T2 + w * S3 with the coefficients the forward pass left in srows
+                    const float4 s1 = ld_row4(p.srows, p.B, cc, u0), t2 = ld_row4(p.srows, p.B, 4 + cc, u0), s3 = ld_row4(p.srows, p.B, 8 + cc, u0);
                     float gy[FT_R];
 #pragma unroll
-                    for (int r = 0; r < FT_R; ++r) {
-                        float q[NL];
-#pragma unroll
-                        for (int l = 0; l < NL; ++l) q[l] = f4c(q4[l], r);
-                        const float g1 = gE[r][cq] - 2.f * f4c(m4, r) * gV[r];
-                        gy[r] = demap_backward_fast<NL>(f4c(y4, r), c.inv_var[pol], c, q, g1, gV[r], entw[r]);
-                    }
+                    for (int r = 0; r < FT_R; ++r)
+                        gy[r] = fmaf(gE[r][cq], f4c(s1, r), fmaf(gV[r], f4c(t2, r), entw[r] * f4c(s3, r)));
                     st_row4(p.gyrows, p.B, cc, u0, make_float4(gy[0], gy[1], gy[2], gy[3]));
                 }
 #pragma unroll

@@ -43,6 +43,8 @@ struct DpK {
     float *erows;                 // 8 rows: [phase][chi][re/im]
     float *m1rows;                // 4 rows: (p0 I, p0 Q, p1 I, p1 Q)
     float *gyrows;                // 4 rows: dL/dout
+    float *srows;                 // 12 rows: [S1 | T2 | S3][component]: dL/dout = gE*S1 + gV*T2 + w*S3 (see dp_fast.cu)
+    int need_bwd;                 // forward kernel also emits srows (skipped in forward-only mode)
     float *gpart;                 // [grid][16*M]
     float *gfinal;                // [16*M]: gW then gh
     float *loss_out, *var_est_out;

@@ -480,7 +480,7 @@ static size_t dp_bwd_smem(int M, int T, int H, int mh) {
 }
 
 struct DpWsLayout {
-    size_t part_fwd, edge_vs, scal, tile_ctr, ebuf, m1buf, gybuf, gpart, gfinal, total;
+    size_t part_fwd, edge_vs, scal, tile_ctr, ebuf, m1buf, gybuf, sbuf, gpart, gfinal, total;
 };
 static DpWsLayout dp_ws_layout(int B, int M) {
     DpWsLayout w;
@@ -497,6 +497,7 @@ static DpWsLayout dp_ws_layout(int B, int M) {
     w.ebuf = take((size_t)B * 8 * sizeof(float));
     w.m1buf = take((size_t)B * 4 * sizeof(float));
     w.gybuf = take((size_t)B * 4 * sizeof(float));
+    w.sbuf = take((size_t)B * 12 * sizeof(float));
     w.gpart = take((size_t)DP_GRID_CAP * 16 * M * sizeof(float));
     w.gfinal = take((size_t)16 * M * sizeof(float));
     w.total = off;
@@ -543,6 +544,8 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
     p.erows = reinterpret_cast<float *>(ws + w.ebuf);
     p.m1rows = reinterpret_cast<float *>(ws + w.m1buf);
     p.gyrows = reinterpret_cast<float *>(ws + w.gybuf);
+    p.srows = reinterpret_cast<float *>(ws + w.sbuf);
+    p.need_bwd = 1;
     p.gpart = reinterpret_cast<float *>(ws + w.gpart);
     p.gfinal = reinterpret_cast<float *>(ws + w.gfinal);
     p.adam = d->adam;
