@@ -21,6 +21,18 @@ from .dp import DPEqualizer
 N_CUT = 10     # symbols cut per minibatch/frame edge (VAELE_DP:40, CMA_DP:26)
 
 
+def _make_frame(datagen, N, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta, device, rng, frame_seed):
+    """One frame of test signal.  datagen="numpy": the reference's host-side generator restated (sf:65-90);
+    datagen="gpu": the same signal model generated on the device (statistical, not bitwise, parity; channel 'h0' only)."""
+    if datagen == "gpu":
+        if len(h_channel) != 1:
+            raise sfun._lib.VaeqError("datagen='gpu' implements the optical channel 'h0' only")
+        from .datagen import generate_data_gpu
+        return generate_data_gpu(N, amps, SNR, P, sps, theta, device, frame_seed, symb_rate=symb_rate, tau_cd=tau_cd,
+                                 tau_pmd=tau_pmd, phiIQ=phiIQ)
+    return sfun.generate_data_shaping(N, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta, device, rng=rng)
+
+
 def _cuda_device(device):
     if device is None:
         if not torch.cuda.is_available():
@@ -44,7 +56,7 @@ def _print_frame(frame, loss, shift_h, r, snr_db, ser):
 
 
 def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_frame_max, num_frames, flex_step,
-                        channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True):
+                        channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0):
     """VAE-LE, non-overlapping minibatches (func_VAELE_DP_MQAM_shaping.py:17-95)."""
     device = _cuda_device(device)
     if verbose:
@@ -60,8 +72,8 @@ def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, b
     for frame in range(num_frames):
         if frame % N_lrhalf == 0 and frame != 0:
             lr_w = lr_optim * 0.5                  # param_groups[0] only, not cumulative (VAELE_DP:45-46)
-        rx_tensor, data_tensor, _ = sfun.generate_data_shaping(N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd,
-                                                               tau_pmd, phiIQ, theta, device, rng=rng)
+        rx_tensor, data_tensor, _ = _make_frame(datagen, N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd,
+                                                phiIQ, theta, device, rng, seed * 100003 + frame)
         theta += theta_diff
         out_train = torch.empty(pol, 2 * num_lev, N_frame, device=device, dtype=torch.float32)
         out_const = torch.empty(pol, 2, N_frame, device=device, dtype=torch.float32)
@@ -94,7 +106,7 @@ def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, b
 
 
 def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
-                          channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True):
+                          channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0):
     """VAE-flex, sliding window advanced by flex_step (func_VAEflex_DP_MQAM_shaping.py:16-88)."""
     device = _cuda_device(device)
     if verbose:
@@ -112,8 +124,8 @@ def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
     for frame in range(num_frames):
         if frame % N_lrhalf == 0 and frame != 0:
             lr_w = lr_optim * 0.5
-        rx_tensor, data_tensor, _ = sfun.generate_data_shaping(N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd,
-                                                               tau_pmd, phiIQ, theta, device, rng=rng)
+        rx_tensor, data_tensor, _ = _make_frame(datagen, N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd,
+                                                phiIQ, theta, device, rng, seed * 100003 + frame)
         data_tensor = data_tensor[:, :, batch_len // 2:m_max + batch_len // 2]                 # VAEflex_DP:51
         theta += theta_diff
         out_train = torch.empty(pol, 2 * num_lev, m_max, device=device, dtype=torch.float32)
@@ -140,7 +152,7 @@ def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
 
 
 def _processing_cma(kind, mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
-                    channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True):
+                    channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0):
     """CMA / CMAbatch / CMAflex runs (func_CMA_DP_MQAM_shaping.py:16-56 and siblings)."""
     device = _cuda_device(device)
     if verbose:
@@ -153,8 +165,8 @@ def _processing_cma(kind, mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
     for frame in range(num_frames):
         if frame % N_lrhalf == 0 and frame != 0:
             lr_optim *= 0.5                          # cumulative here, unlike the VAE drivers (CMA_DP:31-32)
-        rx_tensor, data_tensor, _ = sfun.generate_data_shaping(N_train_max, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd,
-                                                               tau_pmd, phiIQ, theta, device, rng=rng)
+        rx_tensor, data_tensor, _ = _make_frame(datagen, N_train_max, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd,
+                                                phiIQ, theta, device, rng, seed * 100003 + frame)
         if kind == "CMA":
             out_const, h_est, e = sfun.CMA(rx_tensor, R, h_est, lr_optim, sps, True)
         elif kind == "CMAbatch":
