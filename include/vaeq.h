@@ -61,7 +61,8 @@ int vaeq_sm_count(void);
 #define VAEQ_K_OTHER 7
 #define VAEQ_K_DP_BWD2 8
 #define VAEQ_K_DP_BWD3 9
-#define VAEQ_NKINDS 10
+#define VAEQ_K_DP_FRAME 10 /* persistent frame kernel: all steps of a frame (and all batched runs) in one launch */
+#define VAEQ_NKINDS 11
 int vaeq_kernel_timing(int32_t enable);
 int vaeq_kernel_timing_read(float *ms_sum, int32_t *count);
 int64_t vaeq_launch_count(int32_t kind); /* kind < 0: all kinds */
@@ -140,6 +141,27 @@ int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stre
  * values (var_est[:,m] at func_VAELE_DP_MQAM_shaping.py:64). */
 int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
                         float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream);
+
+/* Reference-size minibatches (batch_len <= 512, Eval_run_DP.py:38 uses 100): vaeq_dp_train_frame runs the whole frame in
+ * ONE persistent launch: one CTA walks the sequential steps with taps, Adam state and all intermediates in shared memory
+ * (dp_small.cu).  Testing hook vaeq_dp_persistent_frames(mode): 1 = that kernel (default); 0 = one set of launches per
+ * step; 2 = the per-step kernels' own bodies inside one launch (bitwise identical to mode 0). */
+int vaeq_dp_persistent_frames(int32_t mode);
+
+/* The same frame for n_runs INDEPENDENT runs in one launch, one CTA per run -- the sweep cells of Eval_run_DP.py:68-95
+ * (SNR x realisation x lr ...) that share batch_len, M_est and n_lev.  Every tensor of the desc addresses run 0; run r
+ * is found rs_* ELEMENTS further (0 = shared by all runs).  d->loss (n_runs), d->var_est (n_runs,2), d->gW (n_runs,2,4,M),
+ * d->gh (n_runs,2,2,2,M) get a leading run dimension; d->workspace holds n_runs x vaeq_dp_workspace_bytes(B,M,n_lev);
+ * loss_steps (n_runs,n_steps), var_est_steps (n_runs,2,n_steps).  nu_sc / lr_w / lr_h: optional per-run device arrays. */
+typedef struct vaeq_dp_runs {
+    int32_t n_runs;
+    int64_t rs_rx, rs_amp, rs_P, rs_var, rs_W, rs_h, rs_adam, rs_q, rs_out, rs_q_keep, rs_out_keep;
+    const float *nu_sc;
+    const float *lr_w, *lr_h;
+} vaeq_dp_runs;
+int vaeq_dp_train_frame_runs(const vaeq_dp_desc *d, const vaeq_dp_runs *runs, int32_t n_steps, int32_t stride_sym,
+                             int32_t keep_lo_in_dst, float lr_w, float lr_h, float *loss_steps, float *var_est_steps,
+                             void *stream);
 
 /* Batch-split of ONE long minibatch across GPUs (the reference has no counterpart, it is what replaces
  * "one process, one device" for func_VAEflex_DP_MQAM_shaping.py at large batch_len).  Every rank holds the whole rx

@@ -1,0 +1,143 @@
+"""Persistent frame kernels (reference-size minibatches) and batched independent runs, through the C ABI.
+
+vaeq_dp_persistent_frames(mode): 0 = one set of launches per step (the path pinned to the reference's golden vectors in
+test_dp_step_gpu.py), 1 = dp_small.cu (default: state and intermediates in shared memory, fast point-wise math),
+2 = the per-step kernels' bodies inside one launch.  Mode 2 must be BITWISE identical to mode 0; mode 1 must agree with
+mode 0 within the step tolerances, and its first steps are also compared with the CPU oracle directly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vaeq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def synth_frame(mod, M, N, nu, seed, snr=20):
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", mod, "cpu", nu, 2, M, snr)
+    rx, tx, _ = O.generate_data_shaping(N, amps, snr, h_ch, P, 2, 90e9, 2, -26e-24, 0.1e-12 * np.sqrt(1000),
+                                        np.array([0.0314, 0.0314], dtype=np.complex64), np.pi / 10, "cpu", rng=np.random.default_rng(seed))
+    return dict(P=P, amp=amp, nu_sc=nu_sc, var=var), rx, tx
+
+
+def run_frame(c, rx, M, B, stride, n_steps, keep_lo, keep_n, keep_lo_in_dst, lr_w, lr_h, persistent):
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    n = c["amp"].numel()
+    eq = DPEqualizer(M, 2, c["amp"], c["P"], c["var"], c["nu_sc"])
+    N_keep = (n_steps - 1) * stride + keep_n + keep_lo
+    ot = torch.zeros(2, 2 * n, N_keep, device="cuda")
+    oc = torch.zeros(2, 2, N_keep, device="cuda")
+    _lib.check(lib.vaeq_dp_persistent_frames(int(persistent)))
+    try:
+        n0 = int(lib.vaeq_launch_count(-1))
+        loss, ve = eq.train_frame(rx.cuda(), B, stride, n_steps, lr_w, lr_h, ot, oc, keep_lo, keep_n, keep_lo_in_dst=keep_lo_in_dst)
+        torch.cuda.synchronize()
+        launches = int(lib.vaeq_launch_count(-1)) - n0
+    finally:
+        _lib.check(lib.vaeq_dp_persistent_frames(1))
+    return dict(loss=loss.cpu(), ve=ve.cpu(), ot=ot.cpu(), oc=oc.cpu(), W=eq.W.cpu(), h=eq.h.cpu(), gW=eq.gW.cpu(), gh=eq.gh.cpu(),
+                last_loss=eq.loss.cpu(), last_ve=eq.var_est.cpu(), steps=eq.step_count(), launches=launches)
+
+
+FRAME_CASES = [  # mod, M, B, stride, n_steps, keep_lo, keep_n, keep_lo_in_dst, nu
+    ("64-QAM", 25, 100, 100, 12, 0, 100, True, 0.0270955),      # VAE-LE at the reference's own batch_len (RUN_DP:38)
+    ("64-QAM", 25, 100, 10, 30, 45, 10, False, 0.0),            # VAE-flex: window 100, flex_step 10 (RUN_DP:39)
+    ("16-QAM", 9, 64, 64, 7, 0, 64, True, 0.0),
+    ("4-QAM", 5, 48, 16, 9, 16, 16, False, 0.05),
+    ("64-QAM", 13, 500, 500, 3, 0, 500, True, 0.0270955),
+]
+
+
+@pytest.mark.parametrize("mod,M,B,stride,n_steps,keep_lo,keep_n,kd,nu", FRAME_CASES)
+def test_persistent_frame_is_bitwise_the_stepped_frame(mod, M, B, stride, n_steps, keep_lo, keep_n, kd, nu):
+    c, rx, _ = synth_frame(mod, M, (n_steps - 1) * stride + B, nu, seed=B + M)
+    a = run_frame(c, rx, M, B, stride, n_steps, keep_lo, keep_n, kd, 2.5e-3, 1.5e-3, persistent=2)
+    b = run_frame(c, rx, M, B, stride, n_steps, keep_lo, keep_n, kd, 2.5e-3, 1.5e-3, persistent=0)
+    assert a["launches"] == 1 and b["launches"] == 4 * n_steps
+    assert a["steps"] == n_steps == b["steps"]
+    for k in ("loss", "ve", "ot", "oc", "W", "h", "gW", "gh"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.isfinite(a["loss"]).all()
+    # the desc's own loss / var_est outputs hold the frame's last step
+    assert torch.equal(a["last_loss"].reshape(()), a["loss"][-1]) and torch.equal(a["last_ve"], a["ve"][:, -1])
+
+
+def rel(x, y):
+    return float((x.double() - y.double()).abs().max() / y.double().abs().max())
+
+
+@pytest.mark.parametrize("mod,M,B,stride,n_steps,keep_lo,keep_n,kd,nu", FRAME_CASES + [("64-QAM", 63, 256, 256, 4, 0, 256, True, 0.0),
+                                                                                 ("16-QAM", 3, 40, 8, 11, 16, 8, False, 0.0),
+                                                                                 ("64-QAM", 7, 130, 130, 5, 0, 130, True, 0.02)])
+def test_fast_persistent_frame_matches_stepped_frame(mod, M, B, stride, n_steps, keep_lo, keep_n, kd, nu):
+    """dp_small.cu against the launch-by-launch path on the same frame: every step's loss / var_est, the kept q / out
+    columns and the taps after the last step."""
+    c, rx, _ = synth_frame(mod, M, (n_steps - 1) * stride + B, nu, seed=B + M)
+    a = run_frame(c, rx, M, B, stride, n_steps, keep_lo, keep_n, kd, 2.5e-3, 1.5e-3, persistent=1)
+    b = run_frame(c, rx, M, B, stride, n_steps, keep_lo, keep_n, kd, 2.5e-3, 1.5e-3, persistent=0)
+    assert a["launches"] == 1 and a["steps"] == n_steps
+    # first step: same taps on both sides -> the single-step tolerances
+    n0 = keep_n + (keep_lo if kd else 0)
+    assert float((a["oc"][:, :, :n0] - b["oc"][:, :, :n0]).abs().max()) < 5e-6
+    assert float((a["ot"][:, :, :n0] - b["ot"][:, :, :n0]).abs().max()) < 5e-5
+    assert rel(a["loss"][:1], b["loss"][:1]) < 1e-5 and rel(a["ve"][:, :1], b["ve"][:, :1]) < 1e-5
+    # whole frame: the two trajectories drift apart by the taps' 1e-4 (q amplifies out by ~1/(2 var) in the logits)
+    assert float((a["oc"] - b["oc"]).abs().max()) < 1e-4
+    assert float((a["ot"] - b["ot"]).abs().max()) < 3e-3
+    assert rel(a["loss"], b["loss"]) < 1e-4 and rel(a["ve"], b["ve"]) < 1e-4
+    assert rel(a["W"], b["W"]) < 1e-4 and rel(a["h"], b["h"]) < 1e-4
+    assert rel(a["gW"], b["gW"]) < 2e-4 and rel(a["gh"], b["gh"]) < 2e-4
+    assert torch.equal(a["last_loss"].reshape(()), a["loss"][-1]) and torch.equal(a["last_ve"], a["ve"][:, -1])
+
+
+def test_persistent_frame_against_cpu_oracle():
+    """The first steps of a VAE-LE frame at batch_len = 100 against the torch CPU port (autograd + torch Adam)."""
+    M, B, n_steps, lr = 25, 100, 6, 2.5e-3
+    c, rx, _ = synth_frame("64-QAM", M, n_steps * B, 0.0270955, seed=5)
+    a = run_frame(c, rx, M, B, B, n_steps, 0, B, True, lr, lr, persistent=1)
+    tr = O.DPTrainer(M, 2, lr)
+    Pt = torch.tensor(c["P"], dtype=torch.float32)
+    for m in range(n_steps):
+        qo, oo, lo, vo, gWo, gho = tr.step(rx[:, :, 2 * m * B:2 * (m + 1) * B].contiguous(), c["amp"], c["var"], c["nu_sc"], Pt)
+        assert float((a["oc"][:, :, m * B:(m + 1) * B] - oo).abs().max()) < 5e-6, m
+        assert float((a["ot"][:, :, m * B:(m + 1) * B] - qo).abs().max()) < 5e-5, m
+        assert rel(a["loss"][m], lo.reshape(())) < 1e-4 and rel(a["ve"][:, m], vo) < 1e-4, m
+    assert rel(a["W"], tr.W.detach()) < 1e-4 and rel(a["h"], tr.h.detach()) < 1e-4
+    assert rel(a["gW"], gWo) < 2e-4 and rel(a["gh"], gho) < 2e-4
+
+
+def test_batched_runs_equal_single_runs():
+    """R runs with different SNR (var), PCS (P, nu_sc), learning rates and data in ONE launch == each run on its own."""
+    from vae_equalizer_b200.dp import DPEqualizerRuns
+    M, B, n_steps, R = 25, 100, 8, 5
+    cs, rxs = [], []
+    for r in range(R):
+        c, rx, _ = synth_frame("64-QAM", M, n_steps * B, [0.0, 0.0270955, 0.05, 0.0270955, 0.01][r], seed=100 + r, snr=[17, 20, 23, 26, 29][r])
+        cs.append(c)
+        rxs.append(rx)
+    lr_w = torch.tensor([2.5e-3, 1e-3, 2.5e-3, 5e-3, 2e-3])
+    lr_h = torch.tensor([2.5e-3, 2.5e-3, 1e-3, 5e-3, 3e-3])
+    eqr = DPEqualizerRuns(R, M, 2, cs[0]["amp"], torch.stack([torch.as_tensor(c["P"], dtype=torch.float32) for c in cs]),
+                          torch.stack([torch.as_tensor(c["var"], dtype=torch.float32) for c in cs]),
+                          torch.tensor([c["nu_sc"] for c in cs], dtype=torch.float32))
+    rx_all = torch.stack(rxs).cuda()
+    ot = torch.zeros(R, 2, 16, n_steps * B, device="cuda")
+    oc = torch.zeros(R, 2, 2, n_steps * B, device="cuda")
+    from vae_equalizer_b200 import _lib
+    lib = _lib.load()
+    n0 = int(lib.vaeq_launch_count(-1))
+    loss, ve = eqr.train_frame(rx_all, B, B, n_steps, lr_w, lr_h, ot, oc, 0, B, keep_lo_in_dst=True)
+    torch.cuda.synchronize()
+    assert int(lib.vaeq_launch_count(-1)) - n0 == 1
+    for r in range(R):
+        a = run_frame(cs[r], rxs[r], M, B, B, n_steps, 0, B, True, float(lr_w[r]), float(lr_h[r]), persistent=1)
+        assert torch.equal(a["loss"], loss[r].cpu()) and torch.equal(a["ve"], ve[r].cpu()), r
+        assert torch.equal(a["ot"], ot[r].cpu()) and torch.equal(a["oc"], oc[r].cpu()), r
+        assert torch.equal(a["W"], eqr.W[r].cpu()) and torch.equal(a["h"], eqr.h[r].cpu()), r
+        assert torch.equal(a["gW"], eqr.gW[r].cpu()) and torch.equal(a["last_loss"].reshape(()), eqr.loss[r].cpu()), r
+    # a second frame continues from the state (Adam moments, step counter) of the first
+    loss2, _ = eqr.train_frame(rx_all, B, B, n_steps, lr_w, lr_h, ot, oc, 0, B, keep_lo_in_dst=True)
+    torch.cuda.synchronize()
+    assert (loss2[:, -1] < loss[:, 0]).all()

@@ -36,6 +36,17 @@ class DpDesc(C.Structure):
     ]
 
 
+class DpRuns(C.Structure):
+    """Mirror of `struct vaeq_dp_runs`: run strides (elements) of the batched-runs frame call."""
+    _fields_ = [
+        ("n_runs", C.c_int32),
+        ("rs_rx", C.c_int64), ("rs_amp", C.c_int64), ("rs_P", C.c_int64), ("rs_var", C.c_int64),
+        ("rs_W", C.c_int64), ("rs_h", C.c_int64), ("rs_adam", C.c_int64), ("rs_q", C.c_int64), ("rs_out", C.c_int64),
+        ("rs_q_keep", C.c_int64), ("rs_out_keep", C.c_int64),
+        ("nu_sc", C.c_void_p), ("lr_w", C.c_void_p), ("lr_h", C.c_void_p),
+    ]
+
+
 class AwgnDesc(C.Structure):
     """Mirror of `struct vaeq_awgn_desc`."""
     _fields_ = [
@@ -66,6 +77,8 @@ PROTOTYPES = {
     "vaeq_dp_forward_backward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_train_step": (C.c_int, [C.POINTER(DpDesc), _f, _f, _vp]),
     "vaeq_dp_train_frame": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
+    "vaeq_dp_persistent_frames": (C.c_int, [_i32]),
+    "vaeq_dp_train_frame_runs": (C.c_int, [C.POINTER(DpDesc), C.POINTER(DpRuns), _i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
     "vaeq_dp_split_stats_doubles": (_sz, [_i32]),
     "vaeq_dp_split_forward": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _vp, _vp]),
     "vaeq_dp_split_backward": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _vp, _vp, _vp]),

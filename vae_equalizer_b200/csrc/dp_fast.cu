@@ -42,7 +42,6 @@ constexpr int FT_XN = FT_TE + 2 * FT_XOFF; // logical length of xe / xo
 #define FT_MINB_PW FT_CTAS_PER_SM           // min CTAs per SM for the point-wise heavy kernels (fwd, bwd1)
 #endif
 #define FT_MINB FT_CTAS_PER_SM              // ... and for the tap-gradient kernels (56 live accumulators)
-constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
 __host__ __device__ constexpr int fdiv4(int c) { return c >= 0 ? c / 4 : -((3 - c) / 4); }
 // padded float4 index of logical position 4*l + c (c compile-time, may be negative)
@@ -50,22 +49,6 @@ __host__ __device__ constexpr int poff(int c) { return c + fdiv4(c); }
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 2); }
 constexpr int FT_XS = FT_XN + FT_XN / 4 + 4;   // padded lengths (float4)
 constexpr int FT_ES = FT_TE + FT_TE / 4 + 4;
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 #ifdef VAEQ_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[8];
@@ -81,82 +64,6 @@ __device__ unsigned int g_cta_sm[2048];
 #define PT(i)
 #define PT_FLUSH
 #endif
-
-struct FastConst {
-    float amp[VAEQ_MAX_LEVELS], a2[VAEQ_MAX_LEVELS], a3[VAEQ_MAX_LEVELS];
-    float nua2l[VAEQ_MAX_LEVELS];          // nu_sc a^2 log2(e)
-    float lgP[VAEQ_MAX_LEVELS];            // log2 P_l
-    float c2[2];                           // log2(e) / (2 var_p)
-    float inv_var[2];
-};
-
-__device__ __forceinline__ void load_fast_const(FastConst *c, const DpK &p, int n_lev) {
-    const int t = threadIdx.x;
-    if (t < VAEQ_MAX_LEVELS) {
-        const float a = t < n_lev ? p.amp[t] : 0.f;
-        c->amp[t] = a;
-        c->a2[t] = a * a;
-        c->a3[t] = a * a * a;
-        c->nua2l[t] = p.nu_sc * (a * a) * LOG2E;
-        c->lgP[t] = t < n_lev ? log2f(p.P[t]) : 0.f;
-    }
-    if (t < 2) {
-        c->c2[t] = LOG2E / (2.f * p.var[t]);
-        c->inv_var[t] = 1.f / p.var[t];
-    }
-}
-
-// soft demapper for one component: q, first two moments and the entropy term  sum_l -q_l ln(q_l / P_l).
-// With BWD it also returns the three coefficients of the (linear) backward map of this component,
-//     dL/dy = g1 * S1 + g2 * S2 + w * S3,   g1 = dL/dE_q[x], g2 = dL/dE_q[x^2], w = ln2 * [symbol inside the entropy window]
-//     S1 = (m2 - m1^2)/var,  S2 = (m3 - m1 m2)/var,  S3 = (dotE (y - m1) - sum_l q_l ge_l (y - a_l))/var,
-//     ge_l = log2(q_l / P_l), dotE = sum_l q_l ge_l
-// (softmin + moments + entropy backward, closed form in oracle/closed_form.py, regrouped by input; S1 is d m1/dy).
-// The backward kernel then needs neither q nor any transcendental.
-template <int NL, bool BWD>
-__device__ __forceinline__ void demap_fast(float y, float c2, float inv_var, const FastConst &c, float (&q)[NL], float &m1,
-                                           float &m2, float &ent, float &S1, float &S2, float &S3) {
-    float z[NL];
-    float zmin = 3.0e38f;
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        const float d = y - c.amp[l];
-        z[l] = fmaf(d * c2, d, c.nua2l[l]);                 // ((y-a)^2/(2 var) + nu_sc a^2) * log2 e   (sf:521)
-        zmin = fminf(zmin, z[l]);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        z[l] = zmin - z[l];                                 // log2 of the unnormalised posterior
-        q[l] = ex2_approx(z[l]);
-        s += q[l];
-    }
-    const float r = rcp_approx(s), lgs = lg2_approx(s);
-    m1 = 0.f;
-    m2 = 0.f;
-    float e = 0.f, m3 = 0.f, ea = 0.f;
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        q[l] *= r;
-        const float qa = q[l] * c.amp[l];
-        m1 += qa;
-        m2 = fmaf(qa, c.amp[l], m2);
-        const float ge = z[l] - c.lgP[l];                   // log2(q_l / P_l) + lgs; the 1e-12 of sf:132 only matters where q/P < 1e-9
-        e = fmaf(q[l], ge, e);
-        if (BWD) {
-            m3 = fmaf(qa, c.a2[l], m3);
-            ea = fmaf(qa, ge, ea);
-        }
-    }
-    ent = -LN2 * (e - lgs);                                 // sum_l q_l = 1
-    if (BWD) {
-        // S3 var = dotE (y - m1) - sum_l q_l ge'_l (y - a_l) with ge' = ge - lgs: the y and lgs terms cancel, leaving
-        //        = sum_l q_l ge_l a_l - m1 sum_l q_l ge_l
-        S1 = (m2 - m1 * m1) * inv_var;
-        S2 = (m3 - m1 * m2) * inv_var;
-        S3 = fmaf(-e, m1, ea) * inv_var;
-    }
-}
 
 // Packed form: for every (symbol r, output o) two float2 accumulators A = sum t_re * (x_re, x_im) and
 // Bq = sum t_im * (x_re, x_im); the complex result is (A.x - Bq.y, A.y + Bq.x).  One FFMA2 (fma.rn.f32x2) replaces two
@@ -339,7 +246,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
         const int j = ph ? (2 * MH - 1 - 2 * a) : (2 * MH - 2 * a);
         reinterpret_cast<float *>(tapD)[idx] = p.h[((o * 2 + i) * 2 + c) * M + j];
     }
-    load_fast_const(cst, p, NL);
+    load_fast_const(cst, p.amp, p.P, p.var, p.nu_sc, NL);
     __syncthreads();
     const FastConst &c = *cst;
 

@@ -68,4 +68,20 @@ int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st);
 int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bwd_out, int *rc);
 constexpr int DP_MODE_SPLIT_FWD = 3, DP_MODE_SPLIT_BWD = 4;   // forward kernel only / backward kernels only (no fin, no adam)
 
+// batched independent runs of the frame kernels (vaeq_dp_train_frame_runs): blockIdx.x = run
+struct DpRunsK {
+    int64_t rs_rx, rs_amp, rs_P, rs_var, rs_W, rs_h, rs_adam, rs_q, rs_out, rs_qk, rs_outk;   // elements between runs
+    int64_t ws_stride;                      // bytes between the workspaces of consecutive runs
+    const float *nu_sc, *lr_w, *lr_h;       // optional per-run values (device), else the scalars
+    float *loss_steps, *var_steps;          // (n_runs, n_steps), (n_runs, 2, n_steps); may be NULL
+    float *loss_last, *var_last, *gW_last, *gh_last;   // (n_runs,1) (n_runs,2) (n_runs,8M) (n_runs,8M): the desc's loss/var_est/gW/gh
+};
+
+
+// dp_small.cu: persistent frame kernel for batch_len <= DP_SMALL_MAX_B (state and intermediates in shared memory)
+constexpr int DP_SMALL_MAX_B = 512;
+size_t dp_small_smem(int B, int M);
+int dp_small_launch(const DpK &p, const DpRunsK &rs, int n_lev, int n_runs, int n_steps, int stride_sym, int keep_lo_in_dst,
+                    float lr_w, float lr_h, int amsgrad, cudaStream_t st);
+
 }  // namespace vaeq

@@ -93,4 +93,129 @@ __device__ __forceinline__ float demap_backward(float y, float var, const DemapC
     return __fdiv_rn(gy, var);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast point-wise math of the register-blocked path (dp_fast.cu) and the persistent small-minibatch kernel (dp_small.cu):
+// ex2 / lg2 / rcp approximations, validated against the same tolerances as the precise functions above.
+// ---------------------------------------------------------------------------------------------
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct FastConst {
+    float amp[VAEQ_MAX_LEVELS], a2[VAEQ_MAX_LEVELS], a3[VAEQ_MAX_LEVELS];
+    float nua2l[VAEQ_MAX_LEVELS];          // nu_sc a^2 log2(e)
+    float lgP[VAEQ_MAX_LEVELS];            // log2 P_l
+    float c2[2];                           // log2(e) / (2 var_p)
+    float inv_var[2];
+};
+
+__device__ __forceinline__ void load_fast_const(FastConst *c, const float *amp, const float *P, const float *var, float nu_sc, int n_lev) {
+    const int t = threadIdx.x;
+    if (t < VAEQ_MAX_LEVELS) {
+        const float a = t < n_lev ? amp[t] : 0.f;
+        c->amp[t] = a;
+        c->a2[t] = a * a;
+        c->a3[t] = a * a * a;
+        c->nua2l[t] = nu_sc * (a * a) * LOG2E;
+        c->lgP[t] = t < n_lev ? log2f(P[t]) : 0.f;
+    }
+    if (t < 2) {
+        c->c2[t] = LOG2E / (2.f * var[t]);
+        c->inv_var[t] = 1.f / var[t];
+    }
+}
+
+// soft demapper for one component: q, first two moments and the entropy term  sum_l -q_l ln(q_l / P_l).
+// With BWD it also returns the three coefficients of the (linear) backward map of this component,
+//     dL/dy = g1 * S1 + g2 * S2 + w * S3,   g1 = dL/dE_q[x], g2 = dL/dE_q[x^2], w = ln2 * [symbol inside the entropy window]
+//     S1 = (m2 - m1^2)/var,  S2 = (m3 - m1 m2)/var,  S3 = (dotE (y - m1) - sum_l q_l ge_l (y - a_l))/var,
+//     ge_l = log2(q_l / P_l), dotE = sum_l q_l ge_l
+// (softmin + moments + entropy backward, closed form in oracle/closed_form.py, regrouped by input; S1 is d m1/dy).
+// The backward kernel then needs neither q nor any transcendental.
+template <int NL, bool BWD>
+__device__ __forceinline__ void demap_fast(float y, float c2, float inv_var, const FastConst &c, float (&q)[NL], float &m1,
+                                           float &m2, float &ent, float &S1, float &S2, float &S3) {
+    float z[NL];
+    float zmin = 3.0e38f;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const float d = y - c.amp[l];
+        z[l] = fmaf(d * c2, d, c.nua2l[l]);                 // ((y-a)^2/(2 var) + nu_sc a^2) * log2 e   (sf:521)
+        zmin = fminf(zmin, z[l]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        z[l] = zmin - z[l];                                 // log2 of the unnormalised posterior
+        q[l] = ex2_approx(z[l]);
+        s += q[l];
+    }
+    const float r = rcp_approx(s), lgs = lg2_approx(s);
+    m1 = 0.f;
+    m2 = 0.f;
+    float e = 0.f, m3 = 0.f, ea = 0.f;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        q[l] *= r;
+        const float qa = q[l] * c.amp[l];
+        m1 += qa;
+        m2 = fmaf(qa, c.amp[l], m2);
+        const float ge = z[l] - c.lgP[l];                   // log2(q_l / P_l) + lgs; the 1e-12 of sf:132 only matters where q/P < 1e-9
+        e = fmaf(q[l], ge, e);
+        if (BWD) {
+            m3 = fmaf(qa, c.a2[l], m3);
+            ea = fmaf(qa, ge, ea);
+        }
+    }
+    ent = -LN2 * (e - lgs);                                 // sum_l q_l = 1
+    if (BWD) {
+        // S3 var = dotE (y - m1) - sum_l q_l ge'_l (y - a_l) with ge' = ge - lgs: the y and lgs terms cancel, leaving
+        //        = sum_l q_l ge_l a_l - m1 sum_l q_l ge_l
+        S1 = (m2 - m1 * m1) * inv_var;
+        S2 = (m3 - m1 * m2) * inv_var;
+        S3 = fmaf(-e, m1, ea) * inv_var;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam single-tensor semantics, see oracle/closed_form.py)
+// ---------------------------------------------------------------------------------------------
+// Bias corrections of one Adam step (torch single-tensor path: step_size = -lr / (1 - beta1^t), denom uses sqrt(1 - beta2^t));
+// double-precision pow is slow and identical for every parameter, so ONE thread computes it per CTA.
+__device__ __forceinline__ void adam_bias(int step, double *bc1, float *bc2s) {
+    *bc1 = 1.0 - pow(0.9, (double)step);
+    *bc2s = (float)sqrt(1.0 - pow(0.999, (double)step));
+}
+__device__ __forceinline__ void adam_apply(float *param, float g, float *m, float *v, float *vmax, int i, float lr,
+                                           bool amsgrad, double bc1, float bc2s) {
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);                        // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * b2 + (1.f - b2) * g * g;                      // exp_avg_sq.mul_(beta2).addcmul_(g,g,1-beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float step_size = (float)(-(double)lr / bc1);
+    float vv = vi;
+    if (amsgrad) {
+        vv = fmaxf(vmax[i], vi);
+        vmax[i] = vv;
+    }
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), bc2s), eps);
+    param[i] = __fadd_rn(param[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+}
+
 }  // namespace vaeq

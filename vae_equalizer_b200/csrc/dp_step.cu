@@ -16,12 +16,21 @@
 
 namespace vaeq {
 
+#ifdef VAEQ_FRAME_TIMING
+__device__ unsigned long long g_ph[32];
+__device__ long long g_ph_last;
+#define PH(i) { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) { long long _n = clock64(); g_ph[i] += (unsigned long long)(_n - g_ph_last); g_ph_last = _n; } }
+#else
+#define PH(i)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// `cta` of `ncta` CTAs strides over the tiles and publishes partial sums in slot `cta`.  The kernels below pass
+// (blockIdx.x, gridDim.x); the persistent frame kernel k_dp_frame_small passes (0, 1): one CTA is the whole run.
 template <int NL>
-__global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
-    extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void dp_fwd_body(const DpK &p, float *smem, int cta, int ncta) {
     const int M = p.M, mh = p.mh, H = p.H, T = p.T, TE = T + 2 * H, XN = 2 * TE + 2 * mh;
     const int tid = threadIdx.x;
     DemapConst *cst = reinterpret_cast<DemapConst *>(smem);
@@ -40,8 +49,9 @@ __global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
     const DemapConst &c = *cst;
 
     float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
+    PH(0)
 
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = cta; tile < p.ntiles; tile += ncta) {
         const int t0 = tile * T;
         const int tn = min(T, p.B - t0);
         const int sb = 2 * (t0 - H) - mh;               // first sample held in xs
@@ -50,6 +60,7 @@ __global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
             xs[r * XN + jj] = (s >= 0 && s < p.L) ? p.rx[(int64_t)r * p.ld_rx + s] : 0.f;
         }
         __syncthreads();
+        PH(1)
 
         // ---- FIR + demapper for the tile and its halo of H symbols each side -------------------
         for (int i = tid; i < tn + 2 * H; i += DP_NT) {
@@ -109,6 +120,7 @@ __global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
             m1s[i] = mom;
         }
         __syncthreads();
+        PH(2)
 
         // ---- estimated-channel convolution and residual for the owned samples (sf:123-134) -----
         for (int i = tid; i < tn; i += DP_NT) {
@@ -145,32 +157,49 @@ __global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
             }
         }
         __syncthreads();
+        PH(3)
     }
 
     float v[5] = {accC[0], accC[1], accEnt, accV[0], accV[1]};
     block_sum<5>(v, red);
+    PH(4)
     if (tid == 0) {
-        double *dst = p.part_fwd + (int64_t)blockIdx.x * 8;
+        double *dst = p.part_fwd + (int64_t)cta * 8;
 #pragma unroll
         for (int i = 0; i < 5; ++i) dst[i] = (double)v[i];
     }
 }
 
+template <int NL>
+__global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
+    extern __shared__ __align__(16) float smem[];
+    dp_fwd_body<NL>(p, smem, blockIdx.x, gridDim.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // finalize forward: C, loss, var_est, kappa, S_nu(j)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_dp_fin(DpK p, int nparts) {
+__device__ __forceinline__ void dp_fin_body(const DpK &p, int nparts) {      // one CTA of 256 threads
     __shared__ double tot[5];
     __shared__ double Esh[2];
     __shared__ float Ssh[2 * VAEQ_MAX_TAPS];
+    __shared__ float edge_sh[4 * (VAEQ_MAX_TAPS / 2 + 1)];
+    __shared__ float hsq[4 * VAEQ_MAX_TAPS];                // |h[chi][nu][j]|^2
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, M = p.M, mh = p.mh, Mh = 2 * p.mh;
     if (wid < 5) {                                          // warp w reduces quantity w over the CTA partials
         double a = 0.0;
+#pragma unroll 4
         for (int b = lane; b < nparts; b += 32) a += p.part_fwd[(int64_t)b * 8 + wid];
         a = warp_sum(a);
         if (lane == 0) tot[wid] = a;
     }
-    if (tid < 2) Esh[tid] = 0.0;
+    // stage the edge variances and |h|^2 (one global round trip instead of a chain of dependent loads)
+    for (int i = tid; i < 4 * mh; i += blockDim.x) edge_sh[i] = p.edge_vs[i];
+    for (int i = tid; i < 4 * M; i += blockDim.x) {
+        const int cn = i / M, j = i - cn * M;
+        const float hr = p.h[(cn * 2 + 0) * M + j], hi = p.h[(cn * 2 + 1) * M + j];
+        hsq[i] = hr * hr + hi * hi;
+    }
     __syncthreads();
     // S_nu(j) = sum of (Var_I+Var_Q)[nu] over source symbols u with Mh <= 2u+j < L      (sf:128)
     for (int idx = tid; idx < 2 * M; idx += blockDim.x) {
@@ -178,8 +207,8 @@ __global__ void __launch_bounds__(256) k_dp_fin(DpK p, int nparts) {
         double s = tot[3 + nu];
         const int u_lo = (Mh - j + 1) >> 1;                 // first included symbol
         const int u_hi = (p.L - 1 - j) >> 1;                // last included symbol
-        for (int u = 0; u < u_lo && u < mh; ++u) s -= (double)p.edge_vs[nu * 2 * mh + u];
-        for (int u = u_hi + 1; u < p.B; ++u) s -= (double)p.edge_vs[nu * 2 * mh + mh + (u - (p.B - mh))];
+        for (int u = 0; u < u_lo && u < mh; ++u) s -= (double)edge_sh[nu * 2 * mh + u];
+        for (int u = u_hi + 1; u < p.B; ++u) s -= (double)edge_sh[nu * 2 * mh + mh + (u - (p.B - mh))];
         Ssh[idx] = (float)s;
         p.scal[DP_S_OFF + idx] = (float)s;
     }
@@ -187,38 +216,37 @@ __global__ void __launch_bounds__(256) k_dp_fin(DpK p, int nparts) {
     if (wid < 2) {                                          // warp chi: E_chi = sum_{nu,j} |h|^2 S_nu(j)   (sf:129)
         const int chi = wid;
         double E = 0.0;
-        for (int idx = lane; idx < 2 * M; idx += 32) {
-            const int nu = idx / M, j = idx - nu * M;
-            const float hr = p.h[((chi * 2 + nu) * 2 + 0) * M + j], hi = p.h[((chi * 2 + nu) * 2 + 1) * M + j];
-            E += (double)(hr * hr + hi * hi) * (double)Ssh[idx];
-        }
+        for (int idx = lane; idx < 2 * M; idx += 32) E += (double)hsq[chi * 2 * M + idx] * (double)Ssh[idx];
         E = warp_sum(E);
         if (lane == 0) Esh[chi] = E;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 2) {                                          // thread chi: C_chi, its log term; thread 0 assembles the loss
+        const int chi = tid;
         const double width = (double)(p.L - Mh);
-        double loss = -tot[2];
-        for (int chi = 0; chi < 2; ++chi) {
-            const double C = tot[chi] + Esh[chi];                                           // sf:133-134
-            loss += width * log(C);                                                         // sf:136
-            p.scal[DP_C_OFF + chi] = (float)C;
-            p.scal[DP_KAPPA_OFF + chi] = (float)(width / C);
-            const float ve = (float)(C / width);                                            // sf:137
-            p.scal[DP_VAREST_OFF + chi] = ve;
-            if (p.var_est_out) p.var_est_out[(int64_t)chi * p.var_est_stride] = ve;
+        const double C = tot[chi] + Esh[chi];                                               // sf:133-134
+        const double term = width * log(C);                                                 // sf:136
+        p.scal[DP_C_OFF + chi] = (float)C;
+        p.scal[DP_KAPPA_OFF + chi] = (float)(width / C);
+        const float ve = (float)(C / width);                                                // sf:137
+        p.scal[DP_VAREST_OFF + chi] = ve;
+        if (p.var_est_out) p.var_est_out[(int64_t)chi * p.var_est_stride] = ve;
+        const double term1 = __shfl_sync(0x3u, term, 1);
+        if (chi == 0) {
+            const double loss = (-tot[2] + term) + term1;
+            p.scal[DP_LOSS_OFF] = (float)loss;
+            if (p.loss_out) *p.loss_out = (float)loss;
         }
-        p.scal[DP_LOSS_OFF] = (float)loss;
-        if (p.loss_out) *p.loss_out = (float)loss;
     }
 }
+
+__global__ void __launch_bounds__(256) k_dp_fin(DpK p, int nparts) { dp_fin_body(p, nparts); }
 
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 template <int NL>
-__global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
-    extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void dp_bwd_body(const DpK &p, float *smem, int cta, int ncta) {
     const int M = p.M, mh = p.mh, Mh = 2 * p.mh, H = p.H, T = p.T, TE = T + 2 * H, XN = 2 * TE + 2 * mh;
     const int tid = threadIdx.x;
     DemapConst *cst = reinterpret_cast<DemapConst *>(smem);
@@ -249,8 +277,9 @@ __global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
 
     // each thread owns up to two complex tap-gradient outputs: idx < 4M -> dh(chi,nu,j), else dW(o,in,k)
     float accR[2] = {0.f, 0.f}, accI[2] = {0.f, 0.f};
+    PH(8)
 
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = cta; tile < p.ntiles; tile += ncta) {
         const int t0 = tile * T;
         const int tn = min(T, p.B - t0);
         const int sb = 2 * (t0 - H) - mh;
@@ -270,6 +299,7 @@ __global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
             m1s[i] = (u >= 0 && u < p.B) ? p.m1buf4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
+        PH(9)
 
         for (int i = tid; i < tn; i += DP_NT) {
             const int u = t0 + i;
@@ -310,6 +340,7 @@ __global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
             gys[i] = make_float4(gy[0], gy[1], gy[2], gy[3]);
         }
         __syncthreads();
+        PH(10)
 
         // ---- tap gradients: one complex output per thread slot, summed over the owned samples ----
 #pragma unroll
@@ -346,9 +377,10 @@ __global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
             }
         }
         __syncthreads();
+        PH(11)
     }
 
-    float *gp = p.gpart + (int64_t)blockIdx.x * 16 * M;     // layout: gW (2,4,M) then gh (2,2,2,M)
+    float *gp = p.gpart + (int64_t)cta * 16 * M;            // layout: gW (2,4,M) then gh (2,2,2,M)
 #pragma unroll
     for (int slot = 0; slot < 2; ++slot) {
         const int idx = tid + slot * DP_NT;
@@ -365,62 +397,60 @@ __global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
     }
 }
 
+template <int NL>
+__global__ void __launch_bounds__(DP_NT) k_dp_bwd(DpK p) {
+    extern __shared__ __align__(16) float smem[];
+    dp_bwd_body<NL>(p, smem, blockIdx.x, gridDim.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // gradient reduction + Adam (torch.optim.Adam single-tensor semantics, see oracle/closed_form.py)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void adam_apply(float *param, float g, float *m, float *v, float *vmax, int i, float lr,
-                                           bool amsgrad, int step) {
-    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-    float mi = m[i], vi = v[i];
-    mi = mi + (g - mi) * (1.f - b1);                        // exp_avg.lerp_(grad, 1-beta1)
-    vi = vi * b2 + (1.f - b2) * g * g;                      // exp_avg_sq.mul_(beta2).addcmul_(g,g,1-beta2)
-    m[i] = mi;
-    v[i] = vi;
-    const double bc1 = 1.0 - pow(0.9, (double)step);
-    const double bc2 = 1.0 - pow(0.999, (double)step);
-    const float step_size = (float)(-(double)lr / bc1);
-    const float bc2s = (float)sqrt(bc2);
-    float vv = vi;
-    if (amsgrad) {
-        vv = fmaxf(vmax[i], vi);
-        vmax[i] = vv;
+// gradient entry i given the sum `a` of its partials: add the E-term of dh, export, Adam
+__device__ __forceinline__ void dp_adam_finish(const DpK &p, int i, double a, int do_update, float lr_w, float lr_h, int amsgrad,
+                                               double bc1, float bc2s) {
+    const int M = p.M;
+    if (i >= 8 * M) {                                       // E-term of dh: 2 kappa_chi h S_nu(j)
+        const int r = i - 8 * M, j = r % M, cn = r / (2 * M), chi = cn >> 1, nu = cn & 1;
+        a += 2.0 * (double)p.scal[DP_KAPPA_OFF + chi] * (double)p.h[r] * (double)p.scal[DP_S_OFF + nu * M + j];
     }
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), bc2s), eps);
-    param[i] = __fadd_rn(param[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    const float g = (float)a;
+    p.gfinal[i] = g;
+    if (i < 8 * M) {
+        if (p.gW_out) p.gW_out[i] = g;
+    } else {
+        if (p.gh_out) p.gh_out[i - 8 * M] = g;
+    }
+    if (do_update) {
+        if (i < 8 * M)
+            adam_apply(p.W, g, p.adam, p.adam + 8 * M, p.adam + 16 * M, i, lr_w, amsgrad != 0, bc1, bc2s);
+        else
+            adam_apply(p.h, g, p.adam + 24 * M, p.adam + 32 * M, p.adam + 40 * M, i - 8 * M, lr_h, amsgrad != 0, bc1, bc2s);
+    }
 }
 
 // one WARP per tap-gradient entry: lanes stride over the per-CTA partials (fixed order -> deterministic), then lane 0
-// adds the E-term of dh, exports the gradient and applies Adam.  The step counter is bumped by the last CTA to finish.
+// finishes the entry.  The step counter is bumped by the last CTA to finish.
 constexpr int ADAM_WARPS = 8;
 __global__ void __launch_bounds__(ADAM_WARPS * 32) k_dp_adam(DpK p, int nparts, int do_update, float lr_w, float lr_h, int amsgrad) {
+    __shared__ double bc1_sh;
+    __shared__ float bc2s_sh;
     const int M = p.M, n = 16 * M, lane = threadIdx.x & 31;
     int *step_ptr = p.adam ? reinterpret_cast<int *>(p.adam + 48 * M) : nullptr;
     const int step = do_update ? *step_ptr + 1 : 0;         // every CTA reads the old value before taking its ticket
+    if (threadIdx.x == ADAM_WARPS * 32 - 1) {
+        if (do_update) adam_bias(step, &bc1_sh, &bc2s_sh);
+        else { bc1_sh = 1.0; bc2s_sh = 1.f; }
+    }
     const int i = blockIdx.x * ADAM_WARPS + (threadIdx.x >> 5);
+    double a = 0.0;
     if (i < n) {
-        double a = 0.0;
+#pragma unroll 4
         for (int b = lane; b < nparts; b += 32) a += (double)p.gpart[(int64_t)b * n + i];
         a = warp_sum(a);
-        if (lane == 0) {
-            if (i >= 8 * M) {                               // E-term of dh: 2 kappa_chi h S_nu(j)
-                const int r = i - 8 * M, j = r % M, cn = r / (2 * M), chi = cn >> 1, nu = cn & 1;
-                a += 2.0 * (double)p.scal[DP_KAPPA_OFF + chi] * (double)p.h[r] * (double)p.scal[DP_S_OFF + nu * M + j];
-            }
-            const float g = (float)a;
-            p.gfinal[i] = g;
-            if (i < 8 * M) {
-                if (p.gW_out) p.gW_out[i] = g;
-            } else {
-                if (p.gh_out) p.gh_out[i - 8 * M] = g;
-            }
-            if (do_update) {
-                if (i < 8 * M)
-                    adam_apply(p.W, g, p.adam, p.adam + 8 * M, p.adam + 16 * M, i, lr_w, amsgrad != 0, step);
-                else
-                    adam_apply(p.h, g, p.adam + 24 * M, p.adam + 32 * M, p.adam + 40 * M, i - 8 * M, lr_h, amsgrad != 0, step);
-            }
-        }
     }
+    __syncthreads();
+    if (i < n && lane == 0) dp_adam_finish(p, i, a, do_update, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
     if (do_update) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -434,13 +464,103 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32) k_dp_adam(DpK p, int nparts, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent frame kernel for reference-size minibatches (batch_len <= DP_TILE: the whole minibatch is ONE tile).
+// One CTA owns one run and walks its sequential minibatches (VAELE_DP:57-66 / VAEflex_DP:59-70) inside a single
+// launch: forward -> fin -> backward -> gradient reduction + Adam, separated by __syncthreads() instead of kernel
+// boundaries (at batch_len = 100 a frame is 100-990 steps; launched separately they are launch-latency bound).
+// blockIdx.x = run: independent runs (sweep cells: SNR x realisation x lr ..., Eval_run_DP.py:68-95) are batched in the
+// same launch, every per-run tensor addressed with a run stride.  The bodies are the generic kernels' own, so a frame
+// stepped here is bitwise identical to the same frame stepped launch by launch.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T *byte_off(T *ptr, int64_t bytes) {
+    return ptr ? reinterpret_cast<T *>(reinterpret_cast<char *>(ptr) + bytes) : nullptr;
+}
+
+#ifdef VAEQ_FRAME_TIMING
+__device__ unsigned long long g_frame_cycles[8];
+#define FT_T0 long long _ft = clock64(); unsigned long long _fa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define FT_P(i) { long long _n = clock64(); _fa[i] += (unsigned long long)(_n - _ft); _ft = _n; }
+#define FT_END if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 8; ++i) g_frame_cycles[i] = _fa[i];
+#else
+#define FT_T0
+#define FT_P(i)
+#define FT_END
+#endif
+
+template <int NL>
+__global__ void __launch_bounds__(DP_NT) k_dp_frame_small(DpK p, DpRunsK rs, int n_steps, int stride_sym, int keep_lo_in_dst,
+                                                          float lr_w, float lr_h, int amsgrad) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double bc1_sh;
+    __shared__ float bc2s_sh;
+    const int run = blockIdx.x, M = p.M, n = 16 * M;
+    // ---- this run's tensors ------------------------------------------------------------------
+    p.rx += run * rs.rs_rx; p.amp += run * rs.rs_amp; p.P += run * rs.rs_P; p.var += run * rs.rs_var;
+    p.W += run * rs.rs_W; p.h += run * rs.rs_h; p.adam += run * rs.rs_adam;
+    p.q += run * rs.rs_q; p.out += run * rs.rs_out;
+    if (p.qk) { p.qk += run * rs.rs_qk; p.outk += run * rs.rs_outk; }
+    {
+        const int64_t wo = run * rs.ws_stride;
+        p.part_fwd = byte_off(p.part_fwd, wo); p.edge_vs = byte_off(p.edge_vs, wo); p.scal = byte_off(p.scal, wo);
+        p.ebuf4 = byte_off(p.ebuf4, wo); p.m1buf4 = byte_off(p.m1buf4, wo); p.gpart = byte_off(p.gpart, wo);
+        p.gfinal = byte_off(p.gfinal, wo);
+    }
+    if (rs.nu_sc) p.nu_sc = rs.nu_sc[run];
+    if (rs.lr_w) lr_w = rs.lr_w[run];
+    if (rs.lr_h) lr_h = rs.lr_h[run];
+    p.gW_out = rs.gW_last ? rs.gW_last + (int64_t)run * 8 * M : nullptr;
+    p.gh_out = rs.gh_last ? rs.gh_last + (int64_t)run * 8 * M : nullptr;
+    const float *rx0 = p.rx;
+    int *step_ptr = reinterpret_cast<int *>(p.adam + 48 * M);
+
+    FT_T0
+    for (int m = 0; m < n_steps; ++m) {
+        p.rx = rx0 + (int64_t)m * stride_sym * 2;
+        p.keep_base = (int64_t)m * stride_sym + (keep_lo_in_dst ? p.keep_lo : 0);
+        const bool last = m == n_steps - 1;
+        p.loss_out = rs.loss_steps ? rs.loss_steps + (int64_t)run * n_steps + m : nullptr;
+        p.var_est_out = rs.var_steps ? rs.var_steps + (int64_t)run * 2 * n_steps + m : nullptr;
+        p.var_est_stride = n_steps;
+        FT_P(0)
+        dp_fwd_body<NL>(p, smem, 0, 1);
+        __syncthreads();
+        FT_P(1)
+        dp_fin_body(p, 1);
+        __syncthreads();
+        FT_P(2)
+        if (last && threadIdx.x < 3) {                       // the desc's loss / var_est keep the last step's values
+            if (threadIdx.x == 0 && rs.loss_last) rs.loss_last[run] = p.scal[DP_LOSS_OFF];
+            if (threadIdx.x > 0 && rs.var_last) rs.var_last[2 * run + threadIdx.x - 1] = p.scal[DP_VAREST_OFF + threadIdx.x - 1];
+        }
+        dp_bwd_body<NL>(p, smem, 0, 1);
+        __syncthreads();
+        FT_P(3)
+        // gradient "reduction" over the single partial + Adam: one THREAD per entry (same arithmetic as k_dp_adam's lane 0)
+        const int step = *step_ptr + 1;
+        if (threadIdx.x == 0) adam_bias(step, &bc1_sh, &bc2s_sh);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += DP_NT) dp_adam_finish(p, i, (double)p.gpart[i], 1, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
+        __syncthreads();
+        if (threadIdx.x == 0) *step_ptr = step;
+        FT_P(4)
+    }
+    FT_END
+}
+
 __global__ void k_adam_generic(float *param, const float *grad, float *state, int n, float lr, int amsgrad,
                                int *step_count, int bump) {
     __shared__ int step_sh;
-    if (threadIdx.x == 0) step_sh = *step_count + (bump ? 1 : 0);
+    __shared__ double bc1_sh;
+    __shared__ float bc2s_sh;
+    if (threadIdx.x == 0) {
+        step_sh = *step_count + (bump ? 1 : 0);
+        adam_bias(step_sh, &bc1_sh, &bc2s_sh);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
-        adam_apply(param, grad[i], state, state + n, state + 2 * n, i, lr, amsgrad != 0, step_sh);
+        adam_apply(param, grad[i], state, state + n, state + 2 * n, i, lr, amsgrad != 0, bc1_sh, bc2s_sh);
     __syncthreads();
     if (threadIdx.x == 0 && bump) *step_count = step_sh;
 }
@@ -671,12 +791,77 @@ extern "C" int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h,
                        (cudaStream_t)stream);
 }
 
+static int g_persistent_frames = 1;   // 0: per-step launches, 1: dp_small.cu (default), 2: generic bodies in one launch
+
+extern "C" int vaeq_dp_persistent_frames(int32_t mode) {
+    VAEQ_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    g_persistent_frames = mode;
+    return VAEQ_OK;
+}
+
+namespace vaeq {
+// one launch for the whole frame of every run (batch_len <= DP_TILE)
+static int dp_frame_persistent(const vaeq_dp_desc *d, const vaeq_dp_runs *runs, int n_steps, int stride_sym, int keep_lo_in_dst,
+                               float lr_w, float lr_h, float *loss_steps, float *var_est_steps, cudaStream_t st) {
+    DpK p = dp_make_params(d);
+    p.T = d->B;                                              // the minibatch is the tile: shared memory sized for it
+    p.ntiles = 1;
+    DpRunsK rs;
+    memset(&rs, 0, sizeof(rs));
+    const int n_runs = runs ? runs->n_runs : 1;
+    if (runs) {
+        rs.rs_rx = runs->rs_rx; rs.rs_amp = runs->rs_amp; rs.rs_P = runs->rs_P; rs.rs_var = runs->rs_var;
+        rs.rs_W = runs->rs_W; rs.rs_h = runs->rs_h; rs.rs_adam = runs->rs_adam; rs.rs_q = runs->rs_q; rs.rs_out = runs->rs_out;
+        rs.rs_qk = runs->rs_q_keep; rs.rs_outk = runs->rs_out_keep;
+        rs.nu_sc = runs->nu_sc; rs.lr_w = runs->lr_w; rs.lr_h = runs->lr_h;
+    }
+    rs.ws_stride = (int64_t)vaeq_dp_workspace_bytes(d->B, d->M, d->n_lev);
+    rs.loss_steps = loss_steps; rs.var_steps = var_est_steps;
+    rs.loss_last = d->loss; rs.var_last = d->var_est; rs.gW_last = d->gW; rs.gh_last = d->gh;
+    const size_t smem = max(dp_fwd_smem(p.M, p.T, p.H, p.mh), dp_bwd_smem(p.M, p.T, p.H, p.mh));
+    const int amsgrad = (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0;
+    if (g_persistent_frames != 2)
+        return dp_small_launch(p, rs, d->n_lev, n_runs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad, st);
+    static size_t set_smem[3] = {0, 0, 0};
+#define FRAME_CASE(NL_, IDX_)                                                                                             \
+    {                                                                                                                     \
+        if (smem > set_smem[IDX_]) {                                                                                      \
+            VAEQ_CUDA(cudaFuncSetAttribute(k_dp_frame_small<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            set_smem[IDX_] = smem;                                                                                        \
+        }                                                                                                                 \
+        ktime_begin(VAEQ_K_DP_FRAME, st);                                                                                 \
+        k_dp_frame_small<NL_><<<n_runs, DP_NT, smem, st>>>(p, rs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad); \
+        ktime_end(VAEQ_K_DP_FRAME, st);                                                                                   \
+    }
+    if (d->n_lev == 2) FRAME_CASE(2, 0)
+    else if (d->n_lev == 4) FRAME_CASE(4, 1)
+    else FRAME_CASE(8, 2)
+#undef FRAME_CASE
+    VAEQ_LAUNCH_CHECK("k_dp_frame_small");
+    return VAEQ_OK;
+}
+}  // namespace vaeq
+
+#ifdef VAEQ_FRAME_TIMING
+extern "C" int vaeq_debug_frame_cycles(unsigned long long *out8) {
+    return (int)cudaMemcpyFromSymbol(out8, vaeq::g_frame_cycles, 8 * sizeof(unsigned long long));
+}
+extern "C" int vaeq_debug_phase32(unsigned long long *out32, int reset) {
+    if (reset) { unsigned long long z[32] = {0}; return (int)cudaMemcpyToSymbol(vaeq::g_ph, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(out32, vaeq::g_ph, 32 * sizeof(unsigned long long));
+}
+#endif
+
 extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
                                    float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream) {
     int rc = dp_validate(d, true, true);
     if (rc) return rc;
     VAEQ_CHECK_ARG(n_steps >= 0 && stride_sym > 0, "bad n_steps/stride");
     VAEQ_CHECK_ARG(d->ld_rx >= ((int64_t)(n_steps - 1) * stride_sym + d->B) * d->sps, "frame shorter than the last window");
+    if (n_steps == 0) return VAEQ_OK;
+    if (g_persistent_frames && d->B <= DP_TILE)
+        return dp_frame_persistent(d, nullptr, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, loss_steps, var_est_steps,
+                                   (cudaStream_t)stream);
     DpK base = dp_make_params(d);
     for (int m = 0; m < n_steps; ++m) {
         DpK p = base;
@@ -689,6 +874,21 @@ extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32
         if (rc) return rc;
     }
     return VAEQ_OK;
+}
+
+extern "C" int vaeq_dp_train_frame_runs(const vaeq_dp_desc *d, const vaeq_dp_runs *runs, int32_t n_steps, int32_t stride_sym,
+                                        int32_t keep_lo_in_dst, float lr_w, float lr_h, float *loss_steps, float *var_est_steps,
+                                        void *stream) {
+    VAEQ_CHECK_ARG(d != nullptr && runs != nullptr && runs->n_runs >= 1, "desc / runs is NULL or n_runs < 1");
+    VAEQ_CHECK_ARG(d->B <= DP_TILE, "batched runs need batch_len <= %d (one CTA per run), got %d", DP_TILE, d->B);
+    vaeq_dp_desc one = *d;
+    one.workspace_bytes = d->workspace_bytes / (size_t)runs->n_runs;      // every run needs a full workspace
+    int rc = dp_validate(&one, true, true);
+    if (rc) return rc;
+    VAEQ_CHECK_ARG(n_steps >= 0 && stride_sym > 0, "bad n_steps/stride");
+    VAEQ_CHECK_ARG(d->ld_rx >= ((int64_t)(n_steps - 1) * stride_sym + d->B) * d->sps, "frame shorter than the last window");
+    if (n_steps == 0) return VAEQ_OK;
+    return dp_frame_persistent(d, runs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, loss_steps, var_est_steps, (cudaStream_t)stream);
 }
 
 // ---- batch-split phases: the host all-reduces `stats` and `grads` between them ----------------

@@ -173,3 +173,91 @@ class DPEqualizer:
         d = self._desc(rx, q, out, B)
         _lib.check(self.lib.vaeq_dp_split_update(C.byref(d), self._grads.data_ptr(), float(lr_w), float(lr_h),
                                                  _lib.current_stream()), "vaeq_dp_split_update")
+
+
+class DPEqualizerRuns:
+    """R independent DP VAE runs (sweep cells of Eval_run_DP.py:68-95 that share batch_len, M_est and the modulation
+    order) stepped together: one persistent launch per frame, one CTA per run (vaeq_dp_train_frame_runs).
+
+    Per-run state has a leading run dimension: W (R,2,4,M), h (R,2,2,2,M), var (R,2), P (R,n), nu_sc (R), lr_w / lr_h (R).
+    """
+
+    def __init__(self, n_runs, M_est, sps, amp_levels, P, var, nu_sc, device="cuda", amsgrad=False):
+        self.lib = _lib.load()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.VaeqError("DPEqualizerRuns needs a CUDA device: there is no CPU path")
+        self.device, self.R, self.M, self.sps = dev, int(n_runs), int(M_est), int(sps)
+        R, M = self.R, self.M
+        self.amp = torch.as_tensor(amp_levels, dtype=_F32).to(dev).contiguous()
+        self.n_lev = int(self.amp.numel())
+
+        def per_run(x, tail):
+            t = torch.as_tensor(x, dtype=_F32).to(dev)
+            return t.expand(R, *tail).contiguous() if t.dim() == len(tail) else t.reshape(R, *tail).contiguous()
+
+        self.P = per_run(P, (self.n_lev,))
+        self.var = per_run(var, (2,))
+        self.nu_sc = per_run(nu_sc, ())
+        self.W = torch.zeros(R, 2, 4, M, dtype=_F32, device=dev)
+        self.W[:, 0, 0, M // 2] = 1.0
+        self.W[:, 1, 1, M // 2] = 1.0
+        self.h = torch.zeros(R, 2, 2, 2, M, dtype=_F32, device=dev)
+        self.h[:, 0, 0, 0, M // 2] = 1.0
+        self.h[:, 1, 1, 0, M // 2] = 1.0
+        self.n_adam = int(self.lib.vaeq_adam_state_floats(M))
+        self.adam = torch.zeros(R, self.n_adam, dtype=_F32, device=dev)
+        self.flags = 1 if amsgrad else 0
+        self.gW = torch.zeros(R, 2, 4, M, dtype=_F32, device=dev)
+        self.gh = torch.zeros(R, 2, 2, 2, M, dtype=_F32, device=dev)
+        self.loss = torch.zeros(R, dtype=_F32, device=dev)
+        self.var_est = torch.zeros(R, 2, dtype=_F32, device=dev)
+        self._ws = None
+        self._B = -1
+
+    def train_frame(self, rx_frames, batch_len, stride_sym, n_steps, lr_w, lr_h, out_train, out_const, keep_lo, keep_n,
+                    keep_lo_in_dst=False):
+        """rx_frames (R,2,2,L_frame); out_train (R,2,2n,N_keep), out_const (R,2,2,N_keep); lr_w / lr_h: floats or (R,) tensors.
+        Returns (loss_steps (R,n_steps), var_est_steps (R,2,n_steps))."""
+        R, B, dev = self.R, int(batch_len), self.device
+        _require_cuda(rx_frames, "rx_frames")
+        if rx_frames.dim() != 4 or rx_frames.shape[:3] != (R, 2, 2) or not rx_frames.is_contiguous():
+            raise _lib.VaeqError(f"rx_frames must be contiguous (R,2,2,L), got {tuple(rx_frames.shape)}")
+        if not (out_train.is_contiguous() and out_const.is_contiguous()):
+            raise _lib.VaeqError("out_train / out_const must be contiguous")
+        if self._B != B:
+            self._ws_one = int(self.lib.vaeq_dp_workspace_bytes(B, self.M, self.n_lev))
+            self._ws = torch.empty(R * self._ws_one, dtype=torch.uint8, device=dev)
+            self._q = torch.empty(R, 2, 2 * self.n_lev, B, dtype=_F32, device=dev)
+            self._out = torch.empty(R, 2, 2, B, dtype=_F32, device=dev)
+            self._B = B
+        lrw = torch.as_tensor(lr_w, dtype=_F32).to(dev).expand(R).contiguous()
+        lrh = torch.as_tensor(lr_h, dtype=_F32).to(dev).expand(R).contiguous()
+        d = _lib.DpDesc()
+        d.B, d.sps, d.M, d.n_lev = B, self.sps, self.M, self.n_lev
+        d.nu_sc, d.flags = 0.0, self.flags
+        d.rx, d.ld_rx = rx_frames.data_ptr(), int(rx_frames.stride(2))
+        d.amp, d.P, d.var = self.amp.data_ptr(), self.P.data_ptr(), self.var.data_ptr()
+        d.W, d.h, d.adam = self.W.data_ptr(), self.h.data_ptr(), self.adam.data_ptr()
+        d.q, d.ld_q = self._q.data_ptr(), B
+        d.out, d.ld_out = self._out.data_ptr(), B
+        d.q_keep, d.ld_q_keep = out_train.data_ptr(), int(out_train.stride(2))
+        d.out_keep, d.ld_out_keep = out_const.data_ptr(), int(out_const.stride(2))
+        d.keep_lo, d.keep_n = int(keep_lo), int(keep_n)
+        d.loss, d.var_est = self.loss.data_ptr(), self.var_est.data_ptr()
+        d.gW, d.gh = self.gW.data_ptr(), self.gh.data_ptr()
+        d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        r = _lib.DpRuns()
+        r.n_runs = R
+        r.rs_rx, r.rs_amp, r.rs_P, r.rs_var = int(rx_frames.stride(0)), 0, self.n_lev, 2
+        r.rs_W, r.rs_h, r.rs_adam = 8 * self.M, 8 * self.M, self.n_adam
+        r.rs_q, r.rs_out = int(self._q.stride(0)), int(self._out.stride(0))
+        r.rs_q_keep, r.rs_out_keep = int(out_train.stride(0)), int(out_const.stride(0))
+        r.nu_sc, r.lr_w, r.lr_h = self.nu_sc.data_ptr(), lrw.data_ptr(), lrh.data_ptr()
+        loss_steps = torch.empty(R, n_steps, dtype=_F32, device=dev)
+        var_steps = torch.empty(R, 2, n_steps, dtype=_F32, device=dev)
+        _lib.check(self.lib.vaeq_dp_train_frame_runs(C.byref(d), C.byref(r), int(n_steps), int(stride_sym),
+                                                     1 if keep_lo_in_dst else 0, 0.0, 0.0, loss_steps.data_ptr(),
+                                                     var_steps.data_ptr(), _lib.current_stream()), "vaeq_dp_train_frame_runs")
+        self._keepalive = (lrw, lrh)
+        return loss_steps, var_steps
