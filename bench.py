@@ -261,6 +261,32 @@ def ours_arm(args, rank, local_rank, world):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (float(t2.item()) * 1e-3)
 
+    # ---- configs[1] at the reference's OWN batch_len = 100 (Eval_run_DP.py:38): one frame = 100 sequential steps in one
+    # persistent launch (dp_small.cu); many independent sweep cells batched per launch (configs[4]) --------------------------
+    small = None
+    if rank == 0 and not args.no_small:
+        from vae_equalizer_b200.dp import DPEqualizerRuns
+        Bs, ns = 100, 100
+        small = {"batch_len": Bs, "steps_per_frame": ns, "note": "VAE-LE frame of 10 000 symbols as 100 sequential minibatches of 100 "
+                 "(func_VAELE_DP_MQAM_shaping.py:57-66), one persistent launch per frame; R independent runs batched per launch"}
+        for R in (1, 592):
+            rxs = torch.stack([generate_data_gpu(Bs * ns, cst["amps"], SNR, cst["P"], SPS, np.pi / 10 + 0.01 * r, dev, 77 + r)[0] for r in range(R)])
+            eqr = DPEqualizerRuns(R, M_EST, SPS, cst["amp"], cst["P"], cst["var"], cst["nu_sc"], device=dev)
+            otr = torch.empty(R, 2, 2 * N_LEV, Bs * ns, device=dev)
+            ocr = torch.empty(R, 2, 2, Bs * ns, device=dev)
+            for _ in range(2):
+                eqr.train_frame(rxs, Bs, Bs, ns, LR, LR, otr, ocr, 0, Bs, keep_lo_in_dst=True)
+            torch.cuda.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(5):
+                eqr.train_frame(rxs, Bs, Bs, ns, LR, LR, otr, ocr, 0, Bs, keep_lo_in_dst=True)
+            h1.record()
+            torch.cuda.synchronize()
+            msf = h0.elapsed_time(h1) / 5
+            small[f"runs_{R}"] = {"ms_per_frame": msf, "us_per_step": msf * 1e3 / ns, "symbols_per_s": R * Bs * ns / (msf * 1e-3)}
+            del rxs, eqr, otr, ocr
+
     # ---- config 3: ONE long minibatch (world x 2^batch_log2 symbols) batch-split over the ranks, two tiny NCCL all-reduces/step
     split = None
     if world > 1 and not args.no_split:
@@ -329,13 +355,17 @@ def ours_arm(args, rank, local_rank, world):
                    "final_loss": loss_val},
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": 12,
-                "note": "DPEqualizer.train_step on pinned host rx; H2D double-buffered on a copy stream, loss+var_est read back every step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 4 * 2 * 2 * SPS, "d2h_bytes_per_step": 12,
+                "h2d_gbs": B * 4 * 2 * 2 * SPS * K / (float(t2.item()) * 1e-3) / 1e9,
+                "note": "DPEqualizer.train_step on pinned host rx (fp32, 32 B/symbol); H2D double-buffered on a copy stream, loss+var_est "
+                        "read back every step; bound by the PCIe Gen5 x16 link (tools/h2d_probe.py measures 55 GB/s on this pool)"},
         "gpu_launches": launches,
         "clocks": clocks,
     }
     if split is not None:
         line["batch_split"] = split
+    if small is not None:
+        line["reference_batch_len"] = small
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -350,6 +380,7 @@ def main():
     ap.add_argument("--batch-log2", type=int, default=22)
     ap.add_argument("--buffers", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the batch_len = 100 persistent-frame leg")
     ap.add_argument("--no-split", action="store_true", help="skip the batch-split (configs[2]) leg at N > 1")
     args = ap.parse_args()
 

@@ -141,3 +141,23 @@ def test_batched_runs_equal_single_runs():
     loss2, _ = eqr.train_frame(rx_all, B, B, n_steps, lr_w, lr_h, ot, oc, 0, B, keep_lo_in_dst=True)
     torch.cuda.synchronize()
     assert (loss2[:, -1] < loss[:, 0]).all()
+
+
+def test_sweep_engine_equals_single_run_drivers():
+    """sweep.sweep_vae_dp (all cells in one batched run set) returns, cell by cell, exactly what the single-run drivers
+    processing_vaele_dp / processing_vaeflex_dp return for the same cell and seed."""
+    from vae_equalizer_b200.processing import processing_vaele_dp, processing_vaeflex_dp
+    from vae_equalizer_b200.sweep import sweep_vae_dp
+    cells = [dict(SNR=20, nu=0.0270955, lr_optim=2.5e-3, theta=np.pi / 10, theta_diff=0.06 * np.pi, seed=3),
+             dict(SNR=24, nu=0.0, lr_optim=5e-3, theta=0.2, theta_diff=0.0, seed=4),
+             dict(SNR=17, nu=0.0270955, lr_optim=1e-3, theta=0.0, theta_diff=0.01, seed=5)]
+    common = dict(symb_rate=90e9, tau_cd=-26e-24, tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=np.array([0.0314, 0.0314], dtype=np.complex64))
+    for kind, fn, flex in (("VAE", processing_vaele_dp, 10), ("VAEflex", processing_vaeflex_dp, 20)):
+        ser, ve, var = sweep_vae_dp(cells, "64-QAM", 2, 25, 100, 2000, 3, flex_step=flex, channel="h0", N_lrhalf=2, kind=kind, **common)
+        torch.cuda.synchronize()
+        for r, c in enumerate(cells):
+            s1, v1, var1 = fn("64-QAM", 2, c["SNR"], c["nu"], 25, c["theta_diff"], c["theta"], c["lr_optim"], 100, 2000, 3, flex, "h0",
+                              common["symb_rate"], common["tau_cd"], common["tau_pmd"], common["phiIQ"], 2, verbose=False, datagen="gpu",
+                              seed=c["seed"])
+            assert torch.equal(s1, ser[r]) and torch.equal(v1, ve[r]) and torch.equal(var1, var[r]), (kind, r)
+        assert torch.isfinite(ser).all() and float(ser.max()) <= 1.0

@@ -175,7 +175,7 @@ def SER_constell_shaping(rx, tx, amp_levels, nu_sc, var, return_counts=False):
     return (ser, counts) if return_counts else ser
 
 
-def _find_shift(q, out, tx, N_shift, amp_levels, return_corr):
+def _find_shift(q, out, tx, N_shift, amp_levels, return_corr, sync=True):
     lib = _lib.load()
     ref = q if q is not None else out
     _require_cuda(ref, "q/rx")
@@ -193,6 +193,8 @@ def _find_shift(q, out, tx, N_shift, amp_levels, return_corr):
                                    None if q is None else amp_levels.contiguous().data_ptr(), n, N, int(N_shift),
                                    corr.data_ptr(), shift.data_ptr(), r.data_ptr(), scr.data_ptr(), _lib.current_stream()),
                "vaeq_find_shift")
+    if not sync:                                           # batched callers (sweep.py) read many results with one sync
+        return shift, r
     r_host = int(r.item())                                 # the reference returns a Python int here (sf:312,314)
     return (shift, r_host, corr) if return_corr else (shift, r_host)
 

@@ -1,0 +1,144 @@
+"""Sweep engine: many independent VAE-LE / VAE-flex runs of the reference's parameter sweep stepped TOGETHER on one GPU.
+
+The reference's Eval_run_DP.py (lines 68-95) walks a 10-deep nest of loops and calls `processing()` once per cell; cells
+are independent.  At the reference's batch_len = 100 one run cannot fill a B200 (one CTA's worth of work per step), so
+here all cells that share (mod, sps, M_est, batch_len, frame length, flex_step) become ONE batched run set: per frame a
+single persistent launch trains every cell's 100-990 sequential minibatches (vaeq_dp_train_frame_runs, one CTA per
+cell), then each cell is aligned and scored with the same evaluation kernels as the single-run drivers.  Across GPUs the
+cells are dealt round-robin (parallel.shard_cells), no data-path collective.
+
+`sweep_vae_dp` returns the same three result tensors as `processing()` with a leading cell dimension.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import shared_funcs as sfun
+from .dp import DPEqualizerRuns
+from .processing import N_CUT, _align, _cuda_device, _make_frame
+
+
+def _cell(c, key):
+    if key not in c:
+        raise KeyError(f"sweep cell {c} lacks {key!r}")
+    return c[key]
+
+
+def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, flex_step=None, channel="h0", symb_rate=90e9,
+                 tau_cd=-26e-24, tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=(0.0314, 0.0314), N_lrhalf=None, *, kind="VAE",
+                 device=None, datagen="gpu", eval_every=1, verbose=False):
+    """Train and score R = len(cells) independent runs in lockstep.
+
+    cells: list of dicts with per-cell values: SNR, nu, lr_optim, theta, theta_diff, and optionally seed.
+    kind: "VAE" (func_VAELE_DP_MQAM_shaping.py: non-overlapping minibatches) or "VAEflex" (func_VAEflex_DP_MQAM_shaping.py:
+    window batch_len advanced by flex_step).  eval_every: score every k-th frame (and the last); unscored frames hold NaN.
+    Returns (SER_valid (R,4,num_frames), Var_est (R,2,num_frames), var (R,2))."""
+    device = _cuda_device(device)
+    R = len(cells)
+    if R == 0:
+        raise ValueError("no cells")
+    if kind not in ("VAE", "VAEflex"):
+        raise KeyError(kind)
+    N_lrhalf = num_frames if N_lrhalf is None else N_lrhalf
+    phiIQ = np.asarray(phiIQ, dtype=np.complex64)
+    consts = [sfun.init(channel, mod, device, _cell(c, "nu"), sps, M_est, _cell(c, "SNR")) for c in cells]
+    h_channel, amp_levels, amps, pol = consts[0][1], consts[0][3], consts[0][4], consts[0][5]
+    num_lev = int(amp_levels.numel())
+    P_all = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in consts])
+    var_all = torch.stack([k[7].to(torch.float32).cpu() for k in consts])
+    nu_sc_all = torch.tensor([k[6] for k in consts], dtype=torch.float32)
+    pow_mean = [k[8] for k in consts]
+    lr0 = torch.tensor([float(_cell(c, "lr_optim")) for c in cells], dtype=torch.float32)
+    theta = [float(c.get("theta", 0.0)) for c in cells]
+    theta_diff = [float(c.get("theta_diff", 0.0)) for c in cells]
+    seeds = [int(c.get("seed", i)) for i, c in enumerate(cells)]
+    rngs = [np.random.default_rng(s) for s in seeds]
+    eqr = DPEqualizerRuns(R, M_est, sps, amp_levels, P_all, var_all, nu_sc_all, device=device)
+
+    if kind == "VAE":
+        m_max = N_frame_max // batch_len
+        N_frame = m_max * batch_len                                      # VAELE_DP:38-39
+        stride, n_steps, keep_lo, keep_n, N_keep, kd = batch_len, m_max, 0, batch_len, N_frame, True
+    else:
+        N_frame = (N_frame_max // batch_len) * batch_len
+        m_max = (N_frame - batch_len) // flex_step * flex_step           # VAEflex_DP:39
+        stride, n_steps = flex_step, m_max // flex_step
+        keep_lo, keep_hi = (batch_len - flex_step) // 2, (batch_len + flex_step) // 2
+        keep_n, N_keep, kd = keep_hi - keep_lo, m_max, False
+
+    SER_valid = torch.full((R, 4, num_frames), float("nan"), device=device, dtype=torch.float32)
+    Var_est = torch.empty(R, pol, num_frames, device=device, dtype=torch.float32)
+    rx_all = torch.empty(R, 2, 2, sps * N_frame, device=device, dtype=torch.float32)
+    out_train = torch.empty(R, pol, 2 * num_lev, N_keep, device=device, dtype=torch.float32)
+    out_const = torch.empty(R, pol, 2, N_keep, device=device, dtype=torch.float32)
+    lr_w = lr0
+    for frame in range(num_frames):
+        if frame % N_lrhalf == 0 and frame != 0:
+            lr_w = lr0 * 0.5                                             # group 0 only, not cumulative (VAELE_DP:45-46)
+        tx_all = []
+        for r in range(R):
+            rx, tx, _ = _make_frame(datagen, N_frame, amps, cells[r]["SNR"], h_channel, consts[r][2], pol, symb_rate, sps, tau_cd,
+                                    tau_pmd, phiIQ, theta[r], device, rngs[r], seeds[r] * 100003 + frame)
+            rx_all[r].copy_(rx)
+            tx_all.append(tx if kind == "VAE" else tx[:, :, batch_len // 2:m_max + batch_len // 2])     # VAEflex_DP:51
+            theta[r] += theta_diff[r]
+        loss_steps, var_steps = eqr.train_frame(rx_all, batch_len, stride, n_steps, lr_w, lr0, out_train, out_const, keep_lo, keep_n,
+                                                keep_lo_in_dst=kd)
+        Var_est[:, :, frame] = var_steps.mean(dim=2)
+        if frame % eval_every and frame != num_frames - 1:
+            continue
+        # pass 1: both shift searches of every cell, ONE host sync for all of them
+        found = [(sfun._find_shift(out_train[r], None, tx_all[r], 21, amp_levels, False, sync=False),
+                  sfun._find_shift(None, out_const[r], tx_all[r], 21, None, False, sync=False)) for r in range(R)]
+        shifts = torch.stack([torch.cat((a[0].to(torch.int32), a[1], b[0].to(torch.int32), b[1])) for a, b in found]).cpu().tolist()
+        # pass 2: align and score (no sync)
+        for r in range(R):
+            sq, rq, so, ro = shifts[r][0:2], shifts[r][2], shifts[r][3:5], shifts[r][5]
+            SER_valid[r, 2:, frame] = _score(kind, "q", _align(out_train[r].clone(), sq, rq), tx_all[r], sq, batch_len, m_max, pol,
+                                             num_lev, amp_levels, consts[r])
+            SER_valid[r, :2, frame] = _score(kind, "c", _align(out_const[r].clone(), so, ro), tx_all[r], so, batch_len, m_max, pol,
+                                             num_lev, amp_levels, consts[r])
+        if verbose:
+            snr_db = 10 * torch.log10(torch.tensor(pow_mean, device=device) / var_steps.mean(dim=(1, 2)))
+            print(frame, "loss", loss_steps[:, -1].tolist(), "SNR_est", snr_db.tolist(), "SER", SER_valid[:, :, frame].tolist())
+    return SER_valid, Var_est, var_all.to(device)
+
+
+def _score(kind, what, aligned, tx, sh, batch_len, m_max, pol, num_lev, amp_levels, const):
+    """Cut the edges like the single-run drivers (VAELE_DP:73-89 / VAEflex_DP:74-84) and run the SER estimator."""
+    tail = 11 + max(abs(sh[0]), abs(sh[1]))
+    if kind == "VAE":
+        keep = batch_len - sh[0] - N_CUT
+        rows = aligned.shape[1]
+        a = aligned.reshape(pol, rows, m_max, batch_len)[:, :, :, :keep].reshape(pol, rows, -1)
+        d = tx.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
+    else:
+        a, d = aligned, tx
+    a, d = a[:, :, 11:-tail], d[:, :, 11:-tail]
+    if what == "q":
+        return sfun.SER_IQflip(a, d)
+    return sfun.SER_constell_shaping(a.detach().clone(), d, amp_levels, const[6], const[7])
+
+
+def sweep_vae_dp_sharded(cells, *args, rank=0, world=1, group=None, **kw):
+    """Round-robin the cells over the ranks (one process per GPU), run each share as one batched run set, and reassemble
+    (SER_valid, Var_est, var) for ALL cells on rank 0 (None elsewhere).  No data-path collective."""
+    from .parallel import gather_cell_results, shard_cells
+    mine = shard_cells(cells, rank, world)
+    num_frames = args[5] if len(args) > 5 else kw["num_frames"]
+    dev = _cuda_device(kw.get("device"))
+    if mine:
+        ser, ve, var = sweep_vae_dp([c for _, c in mine], *args, **kw)
+    loc_ser = {i: ser[k] for k, (i, _) in enumerate(mine)} if mine else {}
+    loc_ve = {i: ve[k] for k, (i, _) in enumerate(mine)} if mine else {}
+    loc_var = {i: var[k] for k, (i, _) in enumerate(mine)} if mine else {}
+    n = len(cells)
+    # NaN marks unscored frames: carry it through the sum-based gather with a mask
+    ser_g = gather_cell_results({i: torch.nan_to_num(t, nan=-1.0) for i, t in loc_ser.items()}, n, (4, num_frames), rank, world, group, dev)
+    ve_g = gather_cell_results(loc_ve, n, (2, num_frames), rank, world, group, dev)
+    var_g = gather_cell_results(loc_var, n, (2,), rank, world, group, dev)
+    if rank != 0:
+        return None
+    ser_g = torch.where(ser_g < 0, torch.full_like(ser_g, float("nan")), ser_g)
+    return ser_g, ve_g, var_g
