@@ -116,7 +116,7 @@ size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev);
 size_t vaeq_adam_state_floats(int32_t M);
 
 /* Testing hook: != 0 routes every vaeq_dp_* call through the generic-M kernels (dp_step.cu) even when the
- * register-blocked fast path (dp_fast.cu: B % 4 == 0, 16-byte aligned rows, M_est in {5,9,13,25}, B >= 2016) applies. */
+ * register-blocked fast path (dp_fast.cu: B % 4 == 0, 16-byte aligned rows, M_est in {5,9,13,25}, B >= 992) applies. */
 int vaeq_dp_force_generic(int32_t on);
 
 /* Tile scheduling of the fast path: != 0 (default) lets every persistent CTA pull its next tile from an atomic counter

@@ -67,9 +67,9 @@ def test_trajectory_vs_reference_golden(name):
 
 @pytest.mark.parametrize("mod,M,B,nu", [("64-QAM", 25, 3000, 0.0270955), ("16-QAM", 13, 1537, 0.0), ("64-QAM", 5, 777, 0.05),
                                         ("4-QAM", 31, 2048, 0.0), ("64-QAM", 25, 40000, 0.0),
-                                        # register-blocked fast path (B % 4 == 0, B >= 2016, M in {5,9,13,25})
+                                        # register-blocked fast path (B % 4 == 0, B >= 992, M in {5,9,13,25})
                                         ("16-QAM", 25, 4096, 0.0), ("4-QAM", 25, 8192, 0.1), ("64-QAM", 13, 5000, 0.0270955),
-                                        ("64-QAM", 9, 6004, 0.0), ("64-QAM", 5, 4064, 0.05), ("64-QAM", 25, 2016, 0.0270955), ("64-QAM", 25, 4068, 0.0270955),
+                                        ("64-QAM", 9, 6004, 0.0), ("64-QAM", 5, 4064, 0.05), ("64-QAM", 25, 2016, 0.0270955), ("64-QAM", 25, 4068, 0.0270955), ("64-QAM", 25, 992, 0.0270955), ("16-QAM", 9, 1000, 0.0),
                                         ("64-QAM", 25, 100800, 0.0270955)])
 def test_multi_tile_against_closed_form(mod, M, B, nu):
     """Sizes that span several tiles/CTAs; float64 closed form is the yardstick, and the fp32 torch

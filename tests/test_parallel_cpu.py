@@ -23,7 +23,7 @@ def test_split_ranges_cover_and_align():
     with pytest.raises(ValueError):
         par.split_ranges(1002, 2)
     with pytest.raises(ValueError):
-        par.split_ranges(2016, 8)
+        par.split_ranges(992, 8)
 
 
 def test_sweep_cells_order_matches_reference_loops():
@@ -44,7 +44,7 @@ def _worker(rank, world, port, q):
         full = par.gather_cell_results(local, len(cells), (4, 3), rank, world)
         stats = torch.tensor([1.0 + rank, 10.0 * (rank + 1)], dtype=torch.float64)
         par.allreduce_sum_(stats)
-        ranges = par.split_ranges(8064, world)
+        ranges = par.split_ranges(16 * par.TILE, world)
         q.put((rank, None if full is None else full[:, 0, 0].tolist(), stats.tolist(), ranges[rank]))
     finally:
         dist.destroy_process_group()
@@ -67,4 +67,4 @@ def test_gloo_world2_shard_gather_allreduce():
     (r0, full0, st0, rg0), (r1, full1, st1, rg1) = res
     assert full1 is None and full0 == [1500.0, 1501.0, 1502.0, 1700.0, 1701.0, 1702.0, 1900.0, 1901.0, 1902.0]
     assert st0 == st1 == [3.0, 30.0]
-    assert rg0 == (0, 4032) and rg1 == (4032, 8064)
+    assert rg0 == (0, 8 * par.TILE) and rg1 == (8 * par.TILE, 16 * par.TILE)

@@ -16,7 +16,7 @@ for _ in range(3):
     eq.train_step(rx, 2.5e-3, 2.5e-3, q=q, out=out)
 torch.cuda.synchronize()
 raw = C.CDLL(_lib.LIB_PATH)
-NC = 148
+NC = 296
 buf = (C.c_ulonglong * (12 + 3 * NC))()
 raw.vaeq_debug_phase_cycles(buf)
 names = ["load_x", "sync1", "FIR", "pointwise+q stores", "m1s+sync2", "D+e stores", "sync3", "loop/prefetch"]

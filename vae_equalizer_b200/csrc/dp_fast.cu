@@ -24,12 +24,13 @@
 namespace vaeq {
 
 #ifndef FT_NT_DEF
-#define FT_NT_DEF 256
+#define FT_NT_DEF 128
 #endif
-constexpr int FT_NT = FT_NT_DEF;           // threads per CTA.  Two co-resident 256-thread CTAs are served unevenly by the warp
-                                           // scheduler (187 vs 270 us for identical work, profiles/r01_cta_imbalance.txt); one
-                                           // 512-thread CTA per SM (-DFT_NT_DEF=512) removes that tail but loses as much at its
-                                           // per-tile barriers (0.782 vs 0.744 ms per step), so 256 stays the default.
+constexpr int FT_NT = FT_NT_DEF;           // threads per CTA.  Every tile is load -> barrier -> FIR -> point-wise -> barrier -> ...,
+                                           // so what hides one CTA's load / barrier phases is the OTHER CTAs of the SM: four
+                                           // 128-thread CTAs per SM interleave better than two of 256 (0.664 -> 0.627 ms per step,
+                                           // profiles/r01b_*), one of 512 is worst (0.782 vs 0.744, profiles/r01_cta_imbalance.txt).
+                                           // The tap-gradient kernels need >= 4 warps (one per role), so 128 is the floor.
 constexpr int FT_NW = FT_NT / 32;          // warps per CTA
 constexpr int FT_CTAS_PER_SM = 512 / FT_NT;   // 128 registers per thread either way
 constexpr int FT_R = 4;                    // consecutive symbols per thread
@@ -65,41 +66,60 @@ __device__ unsigned int g_cta_sm[2048];
 #define PT_FLUSH
 #endif
 
-// Packed form: for every (symbol r, output o) two float2 accumulators A = sum t_re * (x_re, x_im) and
-// Bq = sum t_im * (x_re, x_im); the complex result is (A.x - Bq.y, A.y + Bq.x).  One FFMA2 (fma.rn.f32x2) replaces two
-// FFMA, the tap is a scalar-broadcast operand and (x_re, x_im) is a natural register pair of the LDS.128 window.
+// FIR-like contraction  y_o(u) = sum_lag sum_i t_{o,i,lag} * x_i(u + lag)  (complex 2x2, 4 consecutive symbols per thread)
+// with the 3-multiplication form of the complex product (Gauss):  for t = tr + j ti, x = xr + j xi
+//     P1 = sum tr (xr + xi),  P2 = sum xr (ti - tr),  P3 = sum xi (tr + ti)   =>   Re = P1 - P3,  Im = P1 + P2.
+// The three sums run over all lags and both inputs, so the tap-side terms (ti - tr, tr + ti) are tabulated once per kernel
+// and the data-side term (xr + xi) once per window element: 3 FMA per complex MAC instead of 4 (-22 % FP32 pipe time in
+// these loops incl. the two adds per window element).  Packed as fma.rn.f32x2:
+//     P23[r][o] += (xr_i, xi_i) * (td_{o,i}, ts_{o,i})      (window pair x tap pair, i = 0, 1)
+//     P1[r][o]  += (tr_{o,0}, tr_{o,1}) * (xs_0, xs_1)      (pair over the two inputs, halves summed at the end)
+// Tap table per lag: T0 = {tr00, tr01, tr10, tr11}, T1 = {td00, ts00, td01, ts01}, T2 = {td10, ts10, td11, ts11}  (index o,i).
+constexpr int FT_TAPV = 3;                 // float4 per lag in a tap table
 struct FirAcc {
-    float2 A[FT_R][2], Bq[FT_R][2];
+    float2 P1[FT_R][2], P23[FT_R][2];
+};
+struct WinEl {
+    float4 x;                              // {re_0, im_0, re_1, im_1}
+    float2 s;                              // {re_0 + im_0, re_1 + im_1}
 };
 __device__ __forceinline__ void fir_acc_zero(FirAcc &a) {
 #pragma unroll
     for (int r = 0; r < FT_R; ++r)
 #pragma unroll
-        for (int o = 0; o < 2; ++o) a.A[r][o] = a.Bq[r][o] = make_float2(0.f, 0.f);
+        for (int o = 0; o < 2; ++o) a.P1[r][o] = a.P23[r][o] = make_float2(0.f, 0.f);
 }
 __device__ __forceinline__ void fir_acc_finish(const FirAcc &a, float (&acc)[FT_R][4]) {
 #pragma unroll
     for (int r = 0; r < FT_R; ++r)
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-            acc[r][2 * o] += a.A[r][o].x - a.Bq[r][o].y;
-            acc[r][2 * o + 1] += a.A[r][o].y + a.Bq[r][o].x;
+            const float p1 = a.P1[r][o].x + a.P1[r][o].y;
+            acc[r][2 * o] += p1 - a.P23[r][o].y;
+            acc[r][2 * o + 1] += p1 + a.P23[r][o].x;
         }
 }
-__device__ __forceinline__ void fir_step(const float4 t0, const float4 t1, const float4 xa, const float4 xb, const float4 xc,
-                                         const float4 xd, FirAcc &a) {
-    const float4 xs[4] = {xa, xb, xc, xd};
+// fill one tap-table entry: e in [0,12) within the lag, (tr, ti) supplied by the caller for (o, i)
+__device__ __forceinline__ void tap_entry_oi(int e, int &o, int &i) {
+    if (e < 4) { o = e >> 1; i = e & 1; }
+    else { o = (e - 4) >> 2; i = ((e - 4) >> 1) & 1; }
+}
+__device__ __forceinline__ float tap_entry_val(int e, float tr, float ti) {
+    return e < 4 ? tr : (((e - 4) & 1) ? tr + ti : ti - tr);
+}
+__device__ __forceinline__ void fir_step(const float4 T0, const float4 T1, const float4 T2, const WinEl &xa, const WinEl &xb,
+                                         const WinEl &xc, const WinEl &xd, FirAcc &a) {
+    const WinEl *xs[4] = {&xa, &xb, &xc, &xd};
 #pragma unroll
     for (int r = 0; r < FT_R; ++r) {
-        const float2 x0 = make_float2(xs[r].x, xs[r].y), x1 = make_float2(xs[r].z, xs[r].w);
-        a.A[r][0] = __ffma2_rn(make_float2(t0.x, t0.x), x0, a.A[r][0]);
-        a.Bq[r][0] = __ffma2_rn(make_float2(t0.y, t0.y), x0, a.Bq[r][0]);
-        a.A[r][0] = __ffma2_rn(make_float2(t0.z, t0.z), x1, a.A[r][0]);
-        a.Bq[r][0] = __ffma2_rn(make_float2(t0.w, t0.w), x1, a.Bq[r][0]);
-        a.A[r][1] = __ffma2_rn(make_float2(t1.x, t1.x), x0, a.A[r][1]);
-        a.Bq[r][1] = __ffma2_rn(make_float2(t1.y, t1.y), x0, a.Bq[r][1]);
-        a.A[r][1] = __ffma2_rn(make_float2(t1.z, t1.z), x1, a.A[r][1]);
-        a.Bq[r][1] = __ffma2_rn(make_float2(t1.w, t1.w), x1, a.Bq[r][1]);
+        const float4 x = xs[r]->x;
+        const float2 s = xs[r]->s, x0 = make_float2(x.x, x.y), x1 = make_float2(x.z, x.w);
+        a.P1[r][0] = __ffma2_rn(make_float2(T0.x, T0.y), s, a.P1[r][0]);
+        a.P1[r][1] = __ffma2_rn(make_float2(T0.z, T0.w), s, a.P1[r][1]);
+        a.P23[r][0] = __ffma2_rn(x0, make_float2(T1.x, T1.y), a.P23[r][0]);
+        a.P23[r][0] = __ffma2_rn(x1, make_float2(T1.z, T1.w), a.P23[r][0]);
+        a.P23[r][1] = __ffma2_rn(x0, make_float2(T2.x, T2.y), a.P23[r][1]);
+        a.P23[r][1] = __ffma2_rn(x1, make_float2(T2.z, T2.w), a.P23[r][1]);
     }
 }
 
@@ -107,29 +127,34 @@ __device__ __forceinline__ void fir4(const float4 *__restrict__ win, int i0, con
                                      float (&out)[FT_R][4]) {
     FirAcc acc;
     fir_acc_zero(acc);
-    auto LD = [win](int j) { return win[j + (j >> 2)]; };
-    float4 w0 = LD(i0), w1 = LD(i0 + 1), w2 = LD(i0 + 2), w3;
+    auto LD = [win](int j) {
+        WinEl w;
+        w.x = win[j + (j >> 2)];
+        w.s = make_float2(w.x.x + w.x.y, w.x.z + w.x.w);
+        return w;
+    };
+    WinEl w0 = LD(i0), w1 = LD(i0 + 1), w2 = LD(i0 + 2), w3;
     int a = 0;
 #pragma unroll 1
     for (; a + 4 <= nlag; a += 4) {
         w3 = LD(i0 + 3);
-        fir_step(taps[0], taps[1], w0, w1, w2, w3, acc);
+        fir_step(taps[0], taps[1], taps[2], w0, w1, w2, w3, acc);
         w0 = LD(i0 + 4);
-        fir_step(taps[2], taps[3], w1, w2, w3, w0, acc);
+        fir_step(taps[3], taps[4], taps[5], w1, w2, w3, w0, acc);
         w1 = LD(i0 + 5);
-        fir_step(taps[4], taps[5], w2, w3, w0, w1, acc);
+        fir_step(taps[6], taps[7], taps[8], w2, w3, w0, w1, acc);
         w2 = LD(i0 + 6);
-        fir_step(taps[6], taps[7], w3, w0, w1, w2, acc);
+        fir_step(taps[9], taps[10], taps[11], w3, w0, w1, w2, acc);
         i0 += 4;
-        taps += 8;
+        taps += 4 * FT_TAPV;
     }
 #pragma unroll 1
     for (; a < nlag; ++a) {                  // remainder (nlag % 4 lags): shift the window by register moves
         w3 = LD(i0 + 3);
-        fir_step(taps[0], taps[1], w0, w1, w2, w3, acc);
+        fir_step(taps[0], taps[1], taps[2], w0, w1, w2, w3, acc);
         w0 = w1; w1 = w2; w2 = w3;
         i0 += 1;
-        taps += 2;
+        taps += FT_TAPV;
     }
     fir_acc_finish(acc, out);
 }
@@ -137,31 +162,45 @@ __device__ __forceinline__ void fir4(const float4 *__restrict__ win, int i0, con
 // ---------------------------------------------------------------------------------------------
 // tap-gradient correlation: acc[a][2(2o+i)+c] += sum_r g[r]_o * conj(win[i0 + r + a]_i),  a < A
 // ---------------------------------------------------------------------------------------------
+// The window is stored SWIZZLED for these kernels, {re_0, re_1, im_0, im_1} (both inputs' real parts, then both imaginary
+// parts), so that one packed fma.rn.f32x2 with a scalar-broadcast g operand updates the pair (i = 0, 1) of an output:
+//     RE[o] += g_o.re * (x_0.re, x_1.re) + g_o.im * (x_0.im, x_1.im)      IM[o] += g_o.im * (x.re pair) - g_o.re * (x.im pair)
+// 4 FFMA2 per (lag, symbol, o) instead of 8 FFMA: the tap-gradient kernels were issue-bound (66-73 % issue-active, 52-58 % FP32
+// pipe, profiles/r01_*), the packed form halves their FMA issue slots.  acc2[a] = {RE[o0], IM[o0], RE[o1], IM[o1]}.
 template <int A>
-__device__ __forceinline__ void corr4(const float4 *__restrict__ win, int i0, const float4 (&g)[FT_R], float (&acc)[A][8]) {
+__device__ __forceinline__ void corr4(const float4 *__restrict__ win, int i0, const float4 (&g)[FT_R], float2 (&acc2)[A][4]) {
+    float ng[FT_R][2];
+#pragma unroll
+    for (int r = 0; r < FT_R; ++r) {
+        ng[r][0] = -g[r].x;
+        ng[r][1] = -g[r].z;
+    }
 #pragma unroll
     for (int cpos = 0; cpos < A + FT_R - 1; ++cpos) {
         const int j = i0 + cpos;
         const float4 x = win[j + (j >> 2)];
+        const float2 xr = make_float2(x.x, x.y), xi = make_float2(x.z, x.w);
 #pragma unroll
         for (int r = 0; r < FT_R; ++r) {
             const int a = cpos - r;
             if (a >= 0 && a < A) {
                 const float4 gg = g[r];
-                acc[a][0] = fmaf(gg.x, x.x, fmaf(gg.y, x.y, acc[a][0]));      // (o0,i0) re
-                acc[a][1] = fmaf(gg.y, x.x, fmaf(-gg.x, x.y, acc[a][1]));     //         im
-                acc[a][2] = fmaf(gg.x, x.z, fmaf(gg.y, x.w, acc[a][2]));      // (o0,i1)
-                acc[a][3] = fmaf(gg.y, x.z, fmaf(-gg.x, x.w, acc[a][3]));
-                acc[a][4] = fmaf(gg.z, x.x, fmaf(gg.w, x.y, acc[a][4]));      // (o1,i0)
-                acc[a][5] = fmaf(gg.w, x.x, fmaf(-gg.z, x.y, acc[a][5]));
-                acc[a][6] = fmaf(gg.z, x.z, fmaf(gg.w, x.w, acc[a][6]));      // (o1,i1)
-                acc[a][7] = fmaf(gg.w, x.z, fmaf(-gg.z, x.w, acc[a][7]));
+                acc2[a][0] = __ffma2_rn(make_float2(gg.x, gg.x), xr, acc2[a][0]);
+                acc2[a][1] = __ffma2_rn(make_float2(gg.y, gg.y), xr, acc2[a][1]);
+                acc2[a][2] = __ffma2_rn(make_float2(gg.z, gg.z), xr, acc2[a][2]);
+                acc2[a][3] = __ffma2_rn(make_float2(gg.w, gg.w), xr, acc2[a][3]);
+                acc2[a][0] = __ffma2_rn(make_float2(gg.y, gg.y), xi, acc2[a][0]);
+                acc2[a][1] = __ffma2_rn(make_float2(ng[r][0], ng[r][0]), xi, acc2[a][1]);
+                acc2[a][2] = __ffma2_rn(make_float2(gg.w, gg.w), xi, acc2[a][2]);
+                acc2[a][3] = __ffma2_rn(make_float2(ng[r][1], ng[r][1]), xi, acc2[a][3]);
             }
         }
     }
 }
 
 // load the even/odd phase arrays of rx for the tile starting at symbol t0 (logical position 0 <-> symbol t0-HP-XOFF)
+// SWZ = false: {I0,Q0,I1,Q1} per position (FIR windows); SWZ = true: {I0,I1,Q0,Q1} (tap-gradient windows, see corr4)
+template <bool SWZ = false>
 __device__ __forceinline__ void load_x_phases(const DpK &p, int t0, float4 *xe, float4 *xo) {
     const int sym0 = t0 - FT_HP - FT_XOFF;
 #pragma unroll 1
@@ -183,13 +222,61 @@ __device__ __forceinline__ void load_x_phases(const DpK &p, int t0, float4 *xe, 
                 v[r] = make_float4(t[0], t[1], t[2], t[3]);
             }
         }
-        xe[pidx(2 * j)] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
-        xo[pidx(2 * j)] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-        xe[pidx(2 * j + 1)] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
-        xo[pidx(2 * j + 1)] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+        constexpr int r1 = SWZ ? 2 : 1, r2 = SWZ ? 1 : 2;
+        xe[pidx(2 * j)] = make_float4(v[0].x, v[r1].x, v[r2].x, v[3].x);
+        xo[pidx(2 * j)] = make_float4(v[0].y, v[r1].y, v[r2].y, v[3].y);
+        xe[pidx(2 * j + 1)] = make_float4(v[0].z, v[r1].z, v[r2].z, v[3].z);
+        xo[pidx(2 * j + 1)] = make_float4(v[0].w, v[r1].w, v[r2].w, v[3].w);
     }
 }
 
+// ---- asynchronous staging of the NEXT tile's rx (cp.async, 16 bytes, L1 bypass) ---------------------------------------------
+// The raw rows (4 rows x 2*FT_XN samples, as they lie in HBM) are copied into a staging buffer while the current tile is being
+// computed; at the top of the next iteration they are transposed smem -> smem into the even/odd phase arrays.  This takes
+// the HBM/L2 load latency (8.6 % of the forward kernel's stall samples sat on the first use of the tile loader's LDG,
+// profiles/r01b_*) off the critical path without holding the tile in registers.
+constexpr int FT_RAWROW = FT_XN / 2;                    // float4 per raw row
+constexpr int FT_RAW = 4 * FT_RAWROW;                   // float4 of the staging buffer
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void issue_x_raw(const DpK &p, int t0, float4 *raw) {
+    const int sym0 = t0 - FT_HP - FT_XOFF;
+#pragma unroll 1
+    for (int j = threadIdx.x; j < FT_RAWROW; j += FT_NT) {
+        const int64_t s0 = 2 * (int64_t)sym0 + 4 * j;           // chunks are entirely inside or outside [0, L): s0 and L are multiples of 4
+        if (s0 >= 0 && s0 + 3 < p.L) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) cp_async16(raw + r * FT_RAWROW + j, p.rx + (int64_t)r * p.ld_rx + s0);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) raw[r * FT_RAWROW + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    cp_async_commit();
+}
+template <bool SWZ = false>
+__device__ __forceinline__ void transpose_x_raw(const float4 *raw, float4 *xe, float4 *xo) {
+#pragma unroll 1
+    for (int j = threadIdx.x; j < FT_RAWROW; j += FT_NT) {
+        float4 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = raw[r * FT_RAWROW + j];
+        constexpr int r1 = SWZ ? 2 : 1, r2 = SWZ ? 1 : 2;
+        xe[pidx(2 * j)] = make_float4(v[0].x, v[r1].x, v[r2].x, v[3].x);
+        xo[pidx(2 * j)] = make_float4(v[0].y, v[r1].y, v[r2].y, v[3].y);
+        xe[pidx(2 * j + 1)] = make_float4(v[0].z, v[r1].z, v[r2].z, v[3].z);
+        xo[pidx(2 * j + 1)] = make_float4(v[0].w, v[r1].w, v[r2].w, v[3].w);
+    }
+}
+
+#ifndef VAEQ_PREFETCH_OP
+#define VAEQ_PREFETCH_OP "prefetch.global.L2"
+#endif
 // L2 prefetch of `nrows` rows x [first, first+count) floats (128-byte lines), spread over the CTA: issued right after a
 // tile is staged so that the NEXT tile of this persistent CTA is L2-resident when its loads are issued.
 __device__ __forceinline__ void prefetch_rows(const float *base, int64_t ld, int nrows, int64_t first, int count, int64_t limit) {
@@ -198,7 +285,7 @@ __device__ __forceinline__ void prefetch_rows(const float *base, int64_t ld, int
     for (int idx = threadIdx.x; idx < nrows * lines; idx += FT_NT) {
         const int r = idx / lines, ln = idx - r * lines;
         const int64_t off = first + 32 * (int64_t)ln;
-        if (off >= 0 && off < limit) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)r * ld + off));
+        if (off >= 0 && off < limit) asm volatile(VAEQ_PREFETCH_OP " [%0];" ::"l"(base + (int64_t)r * ld + off));
     }
 }
 
@@ -231,22 +318,26 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
     extern __shared__ __align__(16) float4 smem4[];
     float4 *xe = smem4, *xo = xe + FT_XS, *m1s = xo + FT_XS;
-    float4 *tapF = m1s + FT_ES;                              // FIR taps: [phase][lag][2]
-    float4 *tapD = tapF + 2 * (NE + NO);                     // channel taps, reversed per phase
-    FastConst *cst = reinterpret_cast<FastConst *>(tapD + 2 * (NE + NO));
+    float4 *tapF = m1s + FT_ES;                              // FIR taps: [phase][lag][FT_TAPV]
+    float4 *tapD = tapF + FT_TAPV * (NE + NO);               // channel taps, reversed per phase
+    float4 *raw = tapD + FT_TAPV * (NE + NO);                // staging of the next tile's raw rx rows (cp.async)
+    FastConst *cst = reinterpret_cast<FastConst *>(raw + FT_RAW);
     float *red = reinterpret_cast<float *>(cst + 1);
     const int tid = threadIdx.x;
 
-    for (int idx = tid; idx < (NE + NO) * 8; idx += FT_NT) {
-        const int e = idx & 7, la = idx >> 3;
+    if ((int)blockIdx.x < p.ntiles) issue_x_raw(p, p.clo + (int)blockIdx.x * FT_T, raw);     // first tile: in flight during the setup
+    for (int idx = tid; idx < (NE + NO) * 4 * FT_TAPV; idx += FT_NT) {
+        const int la = idx / (4 * FT_TAPV), e = idx - la * (4 * FT_TAPV);
         const int ph = la >= NE, a = ph ? la - NE : la;
-        const int o = e >> 2, i = (e >> 1) & 1, c = e & 1;
+        int o, i;
+        tap_entry_oi(e, o, i);
         const int k = 2 * a + ph;
-        reinterpret_cast<float *>(tapF)[idx] = p.W[(o * 4 + 2 * c + i) * M + k];
+        reinterpret_cast<float *>(tapF)[idx] = tap_entry_val(e, p.W[(o * 4 + i) * M + k], p.W[(o * 4 + 2 + i) * M + k]);
         const int j = ph ? (2 * MH - 1 - 2 * a) : (2 * MH - 2 * a);
-        reinterpret_cast<float *>(tapD)[idx] = p.h[((o * 2 + i) * 2 + c) * M + j];
+        reinterpret_cast<float *>(tapD)[idx] = tap_entry_val(e, p.h[((o * 2 + i) * 2 + 0) * M + j], p.h[((o * 2 + i) * 2 + 1) * M + j]);
     }
     load_fast_const(cst, p.amp, p.P, p.var, p.nu_sc, NL);
+    cp_async_wait_all();
     __syncthreads();
     const FastConst &c = *cst;
 
@@ -260,13 +351,12 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
         const int t0 = p.clo + tile * FT_T;
         PT(7)
         tile_fetch_next(p, 0, tile, &s_next);
-        load_x_phases(p, t0, xe, xo);
+        transpose_x_raw(raw, xe, xo);                        // this tile's rows were staged while the previous one was computed
         PT(0)
         __syncthreads();
         PT(1)
         const int tile_next = s_next;
-        if (tile_next < p.ntiles)
-            prefetch_rows(p.rx, p.ld_rx, 4, 2 * (int64_t)(p.clo + (int64_t)tile_next * FT_T - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
+        if (tile_next < p.ntiles) issue_x_raw(p, p.clo + tile_next * FT_T, raw);      // lands during this tile's compute
 
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
@@ -286,7 +376,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
             // x[2u + k - MH]: even k = 2a -> xe[u + a - HF], odd k = 2a+1 -> xo[u + a - HF]
 #pragma unroll 1
             for (int ph = 0; ph < 2; ++ph)
-                fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? 2 * NE : 0), ph ? NO : NE, y);
+#ifdef VAEQ_EXP_NOFIR
+                if (ph == 0) { const float4 xx = xe[pidx(i0 + FT_XOFF)]; for (int r = 0; r < FT_R; ++r) { y[r][0] = xx.x + r; y[r][1] = xx.y; y[r][2] = xx.z; y[r][3] = xx.w; } }
+#else
+                fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? FT_TAPV * NE : 0), ph ? NO : NE, y);
+#endif
             PT(2)
             // point-wise stage, rolled over the polarisation (code size); y / mom rotate by two components per pass
 #pragma unroll 1
@@ -308,9 +402,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                         mom[r][cq] = m1v[r];
                     }
                     if (owned) {
+#ifndef VAEQ_EXP_NOQ
 #pragma unroll
                         for (int l = 0; l < NL; ++l)
                             st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
+#endif
                         st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
                         st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
                         if (p.need_bwd) {
@@ -369,7 +465,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) d[r][k] = 0.f;
                 // even samples: sum_a h[2MH-2a] E_q[u + a - HF];  odd: sum_b h[2MH-1-2b] E_q[u + b - HF + 1]
-                fir4(m1s, i0 - HF + ph, tapD + (ph ? 2 * NE : 0), ph ? NO : NE, d);
+                fir4(m1s, i0 - HF + ph, tapD + (ph ? FT_TAPV * NE : 0), ph ? NO : NE, d);
                 const float4 *xr = ph ? xo : xe;
                 float ev[4][FT_R];
 #pragma unroll
@@ -391,6 +487,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
             }
         }
         PT(5)
+        cp_async_wait_all();
         __syncthreads();
         PT(6)
         tile = tile_next;
@@ -415,18 +512,19 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
     extern __shared__ __align__(16) float4 smem4[];
     float4 *ge = smem4, *go = ge + FT_ES;
-    float4 *tapG = go + FT_ES;                               // conj(h) taps for dE_q: [phase][lag][2]
-    float *PSg = reinterpret_cast<float *>(tapG + 2 * (NE + NO));   // (2, M+1)
+    float4 *tapG = go + FT_ES;                               // 2 kappa_chi conj(h) taps for dE_q: [phase][lag][FT_TAPV]
+    float *PSg = reinterpret_cast<float *>(tapG + FT_TAPV * (NE + NO));   // (2, M+1)
     const int tid = threadIdx.x;
     const float kap0 = p.scal[DP_KAPPA_OFF], kap1 = p.scal[DP_KAPPA_OFF + 1];
 
-    for (int idx = tid; idx < (NE + NO) * 8; idx += FT_NT) {
-        const int e = idx & 7, la = idx >> 3;
+    for (int idx = tid; idx < (NE + NO) * 4 * FT_TAPV; idx += FT_NT) {
+        const int la = idx / (4 * FT_TAPV), e = idx - la * (4 * FT_TAPV);
         const int ph = la >= NE, a = ph ? la - NE : la;
-        const int nu = e >> 2, chi = (e >> 1) & 1, c = e & 1;     // out index nu, in index chi
+        int nu, chi;                                              // out index nu, in index chi
+        tap_entry_oi(e, nu, chi);
         const int j = 2 * a + ph;
-        const float hv = p.h[((chi * 2 + nu) * 2 + c) * M + j];
-        reinterpret_cast<float *>(tapG)[idx] = c ? -hv : hv;       // conj(h)
+        const float sc = 2.f * (chi ? kap1 : kap0);               // gD = 2 kappa_chi e folded into the taps
+        reinterpret_cast<float *>(tapG)[idx] = tap_entry_val(e, sc * p.h[((chi * 2 + nu) * 2 + 0) * M + j], -sc * p.h[((chi * 2 + nu) * 2 + 1) * M + j]);
     }
     if (tid < 2) {
         const int nu = tid;
@@ -450,15 +548,14 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
-        {   // stage gD = 2 kappa e for the tile and its halo
+        {   // stage the residual e for the tile and its halo (gD = 2 kappa e: the factor sits in the taps)
             float4 er[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) er[k] = in_seq ? ld_row4(p.erows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float s0 = 2.f * kap0, s1 = 2.f * kap1;
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) {
-                ge[5 * tid + r] = make_float4(s0 * f4c(er[0], r), s0 * f4c(er[1], r), s1 * f4c(er[2], r), s1 * f4c(er[3], r));
-                go[5 * tid + r] = make_float4(s0 * f4c(er[4], r), s0 * f4c(er[5], r), s1 * f4c(er[6], r), s1 * f4c(er[7], r));
+                ge[5 * tid + r] = make_float4(f4c(er[0], r), f4c(er[1], r), f4c(er[2], r), f4c(er[3], r));
+                go[5 * tid + r] = make_float4(f4c(er[4], r), f4c(er[5], r), f4c(er[6], r), f4c(er[7], r));
             }
         }
         __syncthreads();
@@ -470,7 +567,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
                 for (int k = 0; k < 4; ++k) gE[r][k] = 0.f;
             // dL/dE_q(u) = sum_chi sum_j conj(h[chi][nu][j]) gD_chi(2u - MH + j): even j -> ge[u+a-HF], odd j -> go[u+a-HF]
 #pragma unroll 1
-            for (int ph = 0; ph < 2; ++ph) fir4(ph ? go : ge, i0 - HF, tapG + (ph ? 2 * NE : 0), ph ? NO : NE, gE);
+            for (int ph = 0; ph < 2; ++ph) fir4(ph ? go : ge, i0 - HF, tapG + (ph ? FT_TAPV * NE : 0), ph ? NO : NE, gE);
             float entw[FT_R];
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) {
@@ -540,11 +637,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
     const int c0 = (FAM == 0 ? FT_XOFF - HF : -HF + ph) + a0;
     const float kap0 = FAM ? p.scal[DP_KAPPA_OFF] : 0.f, kap1 = FAM ? p.scal[DP_KAPPA_OFF + 1] : 0.f;
 
-    float acc[RL::AMAX][8];
+    float2 acc2[RL::AMAX][4];
 #pragma unroll
     for (int a = 0; a < RL::AMAX; ++a)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+        for (int k = 0; k < 4; ++k) acc2[a][k] = make_float2(0.f, 0.f);
 
     __shared__ int s_next;
 #pragma unroll 1
@@ -556,7 +653,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
             const bool in_seq = (u0 >= 0) && (u0 < p.B);
             const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
             if (FAM == 0) {
-                load_x_phases(p, t0, s0, s1);
+                load_x_phases<true>(p, t0, s0, s1);
                 float4 gr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) gr[k] = owned ? ld_row4(p.gyrows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -573,7 +670,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
                 for (int r = 0; r < FT_R; ++r) {
                     g0[5 * tid + r] = make_float4(f0 * f4c(er[0], r), f0 * f4c(er[1], r), f1 * f4c(er[2], r), f1 * f4c(er[3], r));
                     g1[5 * tid + r] = make_float4(f0 * f4c(er[4], r), f0 * f4c(er[5], r), f1 * f4c(er[6], r), f1 * f4c(er[7], r));
-                    s0[5 * tid + r] = make_float4(f4c(mr[0], r), f4c(mr[1], r), f4c(mr[2], r), f4c(mr[3], r));
+                    s0[5 * tid + r] = make_float4(f4c(mr[0], r), f4c(mr[2], r), f4c(mr[1], r), f4c(mr[3], r));     // swizzled window
                 }
             }
         }
@@ -597,18 +694,20 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
             float4 gd[FT_R];
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) gd[r] = gsrc[5 * l + r];
-            corr4<RL::AMAX>(win, li0 + c0, gd, acc);
+            corr4<RL::AMAX>(win, li0 + c0, gd, acc2);
         }
         __syncthreads();
         tile = tile_next;
     }
 
     // reduce over lanes, then over the two warps of a role, and publish this CTA's partial
+    // acc[a][2(2o+i)+c]: c = 0 real, 1 imaginary part of output (o, i)
 #pragma unroll
     for (int a = 0; a < RL::AMAX; ++a)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float s = warp_sum(acc[a][k]);
+            const float2 v2 = acc2[a][2 * (k >> 2) + (k & 1)];
+            const float s = warp_sum(((k >> 1) & 1) ? v2.y : v2.x);
             if (lane == 0) red[wid * (RL::AMAX * 8) + a * 8 + k] = s;
         }
     __syncthreads();
@@ -631,11 +730,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
 // ---------------------------------------------------------------------------------------------
 template <int MH>
 static size_t fast_smem_fwd() {
-    return (size_t)(2 * FT_XS + FT_ES + 4 * (2 * MH + 1)) * sizeof(float4) + sizeof(FastConst) + 5 * 32 * sizeof(float) + 64;
+    return (size_t)(2 * FT_XS + FT_ES + 2 * FT_TAPV * (2 * MH + 1) + FT_RAW) * sizeof(float4) + sizeof(FastConst) + 5 * 32 * sizeof(float) + 64;
 }
 template <int MH>
 static size_t fast_smem_bwd1() {
-    return (size_t)(2 * FT_ES + 2 * (2 * MH + 1)) * sizeof(float4) + sizeof(FastConst) + (2 * (2 * MH + 2) + 2) * sizeof(float) + 64;
+    return (size_t)(2 * FT_ES + FT_TAPV * (2 * MH + 1)) * sizeof(float4) + sizeof(FastConst) + (2 * (2 * MH + 2) + 2) * sizeof(float) + 64;
 }
 template <int MH, int FAM>
 static size_t fast_smem_taps() {

@@ -937,7 +937,7 @@ extern "C" int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int3
     if (p.dyn) VAEQ_CUDA(cudaMemsetAsync(p.tile_ctr, 0, 4 * sizeof(int), st));
     int nparts = 0, rc2 = VAEQ_OK;
     if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_FWD, st, &nparts, &rc2)) {
-        set_error("batch-split needs the fast path: M_est in {5,9,13,25}, 16-byte aligned rows, B %% 4 == 0, B >= 2016");
+        set_error("batch-split needs the fast path: M_est in {5,9,13,25}, 16-byte aligned rows, B %% 4 == 0, B >= 992");
         return VAEQ_EINVAL;
     }
     if (rc2) return rc2;

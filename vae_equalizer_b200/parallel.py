@@ -17,7 +17,7 @@ import itertools
 import torch
 import torch.distributed as dist
 
-TILE = 1008                     # owned symbols per tile of the fast kernels (csrc/dp_fast.cu FT_T)
+TILE = 496                      # owned symbols per tile of the fast kernels (csrc/dp_fast.cu FT_T = 4 * 128 - 16)
 
 
 def split_ranges(B: int, world: int, align: int = TILE):
