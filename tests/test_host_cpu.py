@@ -103,3 +103,21 @@ def test_data_generator_matches_oracle_with_same_rng():
     assert torch.equal(tx1, tx2) and abs(s1 - s2) < 1e-9
     # signal power ~ 1/sps, noise level as requested
     assert abs(float((rx1 ** 2).sum(1).mean()) - 0.5 * (1 + 10 ** -1.8)) < 0.05
+
+
+def test_batched_frame_generator_matches_single_generator():
+    """datagen.generate_frames_gpu (all sweep cells in one batched call) against generate_data_gpu: R = 1 with the same seed draws
+    the same symbols and the same noise-free signal; per-run SNR and rotation are honoured."""
+    import numpy as np
+    import torch
+    from vae_equalizer_b200.constants import init
+    from vae_equalizer_b200.datagen import generate_data_gpu, generate_frames_gpu
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pm = init("h0", "64-QAM", "cpu", 0.0270955, 2, 25, 23)
+    a, ta, _ = generate_data_gpu(1500, amps, 200, P, 2, 0.3, "cpu", 7)
+    b, tb, _ = generate_frames_gpu(1500, amps, [200], P, 2, [0.3], "cpu", 7)
+    assert torch.equal(ta, tb[0]) and float((a - b[0]).abs().max()) < 5e-6
+    rx, tx, sig = generate_frames_gpu(3000, amps, [23, 13, 23], np.stack([P, P, P]), 2, [0.3, 0.3, 1.0], "cpu", 11)
+    assert rx.shape == (3, 2, 2, 6000) and tx.shape == (3, 2, 2, 3000) and tx.dtype == torch.float16
+    assert abs(float(sig[1] / sig[0]) - 10 ** 0.5) < 0.05 * 10 ** 0.5          # 10 dB lower SNR -> sqrt(10) more noise
+    p0, p2 = float((rx[0] ** 2).mean()), float((rx[2] ** 2).mean())
+    assert abs(p0 - p2) / p0 < 0.05                                            # a rotation keeps the power

@@ -98,3 +98,66 @@ def generate_data_gpu(N, amps, SNR, P, sps, theta, device, seed, symb_rate=90e9,
     sl = slice(PULSE_SPAN, N + PULSE_SPAN)
     tx = torch.stack((lev[0::2][:, sl], lev[1::2][:, sl]), dim=1).to(torch.float16).contiguous()
     return rx, tx, float(sigma_n)
+
+
+_GPU_CACHE: dict = {}
+
+
+def _cached_channel_terms(n_up, symb_rate, sps, tau_cd, tau_pmd, device):
+    """Per-bin CD phase and PMD term exp(j pi tau_pmd f) (sf:41-45) and the RRC pulse spectrum, cached per frame geometry."""
+    key = (n_up, float(symb_rate), sps, float(tau_cd), float(tau_pmd), str(device))
+    hit = _GPU_CACHE.get(key)
+    if hit is None:
+        n = n_up - len(rrcfir(PULSE_SPAN, sps, ROLLOFF)) + 1                         # length after the 'valid' pulse convolution
+        f = np.fft.fftfreq(n, 1 / symb_rate / sps)
+        e_cd = torch.as_tensor(np.exp(1j * 2 * (np.pi * f) ** 2 * tau_cd), device=device).to(torch.complex64)
+        e_pmd = torch.as_tensor(np.exp(1j * np.pi * tau_pmd * f), device=device).to(torch.complex64)
+        pulse = torch.as_tensor(rrcfir(PULSE_SPAN, sps, ROLLOFF), device=device).to(torch.complex64)
+        n_fft = n_up + pulse.numel() - 1
+        hit = (e_cd, e_pmd, 1 / e_pmd, torch.fft.fft(pulse, n_fft), n_fft, pulse.numel())
+        if len(_GPU_CACHE) > 16:
+            _GPU_CACHE.clear()
+        _GPU_CACHE[key] = hit
+    return hit
+
+
+def generate_frames_gpu(N, amps, SNR, P, sps, theta, device, seed, symb_rate=90e9, tau_cd=-26e-24,
+                        tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=(0.0314, 0.0314)):
+    """R frames at once (one batched launch sequence for all runs of a sweep): SNR (R,), P (R,n), theta (R,) per run, one
+    seed for the batch.  Same signal model as generate_data_gpu (channel 'h0'); returns rx (R,2,2,sps*N) f32,
+    tx (R,2,2,N) f16, sigma_n (R,)."""
+    dev = torch.device(device)
+    P = torch.as_tensor(np.asarray(P), dtype=torch.float32, device=dev)
+    if P.dim() == 1:
+        P = P[None]
+    R = P.shape[0]
+    snr = torch.as_tensor(np.broadcast_to(np.asarray(SNR, dtype=np.float64), (R,)).copy(), dtype=torch.float32, device=dev)
+    th = torch.as_tensor(np.broadcast_to(np.asarray(theta, dtype=np.float64), (R,)).copy(), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(int(seed))
+    n_conv = N + 1 + 4 * PULSE_SPAN
+    idx = torch.multinomial(P, 4 * n_conv, True, generator=g).view(R, 4, n_conv)
+    lev = torch.as_tensor(np.asarray(amps), dtype=torch.float32, device=dev)[idx]
+    sym = torch.complex(lev[:, 0::2], lev[:, 1::2])                                # (R, 2, n_conv)
+    n_up = sps * (n_conv - 1) + 1
+    up = torch.zeros(R, 2, n_up, dtype=torch.complex64, device=dev)
+    up[:, :, ::sps] = sym
+    e_cd, e_pmd, e_pmd_inv, pulse_f, n_fft, n_pulse = _cached_channel_terms(n_up, symb_rate, sps, tau_cd, tau_pmd, dev)
+    shaped = torch.fft.ifft(torch.fft.fft(up, n_fft) * pulse_f)[:, :, n_pulse - 1: n_up]
+    c, s = torch.cos(th)[:, None], torch.sin(th)[:, None]                            # (R,1)
+    e0, e1 = np.exp(-1j * np.asarray(phiIQ, dtype=np.complex64))
+    # H = R^T diag(e_pmd, 1/e_pmd) R with R = [[c e0, s e0], [-s e1, c e1]]  (sf:46-50), per run and per bin
+    R00, R01, R10, R11 = c * complex(e0), s * complex(e0), -s * complex(e1), c * complex(e1)
+    T00, T01, T10, T11 = c * complex(e0), -s * complex(e0), s * complex(e1), c * complex(e1)
+    H00 = T00 * e_pmd * R00 + T01 * e_pmd_inv * R10
+    H01 = T00 * e_pmd * R01 + T01 * e_pmd_inv * R11
+    H10 = T10 * e_pmd * R00 + T11 * e_pmd_inv * R10
+    H11 = T10 * e_pmd * R01 + T11 * e_pmd_inv * R11
+    X = torch.fft.fft(shaped, dim=-1)
+    sig = torch.fft.ifft(torch.stack(((H00 * X[:, 0] + H01 * X[:, 1]) * e_cd, (H10 * X[:, 0] + H11 * X[:, 1]) * e_cd), dim=1), dim=-1)
+    sigma_n = torch.sqrt(torch.mean(sig.abs() ** 2, dim=(1, 2)) * sps / 2 / 10 ** (snr / 10))
+    noise = torch.complex(torch.randn(sig.shape, device=dev, generator=g), torch.randn(sig.shape, device=dev, generator=g))
+    sig = (sig + sigma_n[:, None, None] * noise)[:, :, :sps * N]
+    rx = torch.stack((sig.real, sig.imag), dim=2).to(torch.float32).contiguous()
+    sl = slice(PULSE_SPAN, N + PULSE_SPAN)
+    tx = torch.stack((lev[:, 0::2][:, :, sl], lev[:, 1::2][:, :, sl]), dim=2).to(torch.float16).contiguous()
+    return rx, tx, sigma_n

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import shared_funcs as sfun
+from .datagen import generate_frames_gpu
 from .dp import DPEqualizerRuns
 from .processing import N_CUT, _align, _cuda_device, _make_frame
 
@@ -31,6 +32,9 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
     """Train and score R = len(cells) independent runs in lockstep.
 
     cells: list of dicts with per-cell values: SNR, nu, lr_optim, theta, theta_diff, and optionally seed.
+    datagen: "numpy" (the reference's host generator, per cell), "gpu" (device generator, per cell: a cell's data depends on
+    its own seed only, so a cell gives the same result alone or in any batch) or "gpu_batched" (one batched generation for all
+    cells per frame, seeded by the first cell's seed: fastest).
     kind: "VAE" (func_VAELE_DP_MQAM_shaping.py: non-overlapping minibatches) or "VAEflex" (func_VAEflex_DP_MQAM_shaping.py:
     window batch_len advanced by flex_step).  eval_every: score every k-th frame (and the last); unscored frames hold NaN.
     Returns (SER_valid (R,4,num_frames), Var_est (R,2,num_frames), var (R,2))."""
@@ -77,12 +81,21 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
         if frame % N_lrhalf == 0 and frame != 0:
             lr_w = lr0 * 0.5                                             # group 0 only, not cumulative (VAELE_DP:45-46)
         tx_all = []
-        for r in range(R):
-            rx, tx, _ = _make_frame(datagen, N_frame, amps, cells[r]["SNR"], h_channel, consts[r][2], pol, symb_rate, sps, tau_cd,
-                                    tau_pmd, phiIQ, theta[r], device, rngs[r], seeds[r] * 100003 + frame)
-            rx_all[r].copy_(rx)
-            tx_all.append(tx if kind == "VAE" else tx[:, :, batch_len // 2:m_max + batch_len // 2])     # VAEflex_DP:51
-            theta[r] += theta_diff[r]
+        if datagen == "gpu_batched":                                     # all cells' frames in one batched launch sequence
+            if len(h_channel) != 1:
+                raise sfun._lib.VaeqError("datagen='gpu_batched' implements the optical channel 'h0' only")
+            rx_b, tx_b, _ = generate_frames_gpu(N_frame, amps, [c["SNR"] for c in cells], P_all, sps, theta, device,
+                                                seeds[0] * 100003 + frame, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ)
+            rx_all.copy_(rx_b)
+            tx_all = [tx_b[r] if kind == "VAE" else tx_b[r][:, :, batch_len // 2:m_max + batch_len // 2] for r in range(R)]
+            theta = [t + d for t, d in zip(theta, theta_diff)]
+        else:
+            for r in range(R):
+                rx, tx, _ = _make_frame(datagen, N_frame, amps, cells[r]["SNR"], h_channel, consts[r][2], pol, symb_rate, sps, tau_cd,
+                                        tau_pmd, phiIQ, theta[r], device, rngs[r], seeds[r] * 100003 + frame)
+                rx_all[r].copy_(rx)
+                tx_all.append(tx if kind == "VAE" else tx[:, :, batch_len // 2:m_max + batch_len // 2])     # VAEflex_DP:51
+                theta[r] += theta_diff[r]
         loss_steps, var_steps = eqr.train_frame(rx_all, batch_len, stride, n_steps, lr_w, lr0, out_train, out_const, keep_lo, keep_n,
                                                 keep_lo_in_dst=kd)
         Var_est[:, :, frame] = var_steps.mean(dim=2)
