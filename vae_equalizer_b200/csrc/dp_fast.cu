@@ -507,8 +507,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
 // backward 1: dL/dE_q (FIR-like over gD = 2 kappa e), then dL/dout = dL/dE_q*S1 + dL/dVar*T2 + w*S3 (coefficients from
 // the forward pass) -> dL/dout rows.  No q, no transcendental: 400 FFMA + ~30 other instructions per symbol.
 // ---------------------------------------------------------------------------------------------
+#ifndef FT_MINB_BWD1
+#define FT_MINB_BWD1 FT_MINB_PW
+#endif
 template <int NL, int MH>
-__global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_bwd1_fast(DpK p) {
+__global__ void __launch_bounds__(FT_NT, FT_MINB_BWD1) k_dp_bwd1_fast(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH;
     extern __shared__ __align__(16) float4 smem4[];
     float4 *ge = smem4, *go = ge + FT_ES;

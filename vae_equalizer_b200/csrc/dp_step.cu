@@ -179,19 +179,32 @@ __global__ void __launch_bounds__(DP_NT) k_dp_fwd(DpK p) {
 // ---------------------------------------------------------------------------------------------
 // finalize forward: C, loss, var_est, kappa, S_nu(j)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dp_fin_body(const DpK &p, int nparts) {      // one CTA of 256 threads
+__device__ __forceinline__ void dp_fin_body(const DpK &p, int nparts) {      // one CTA of 256 ... 1024 threads
     __shared__ double tot[5];
     __shared__ double Esh[2];
     __shared__ float Ssh[2 * VAEQ_MAX_TAPS];
     __shared__ float edge_sh[4 * (VAEQ_MAX_TAPS / 2 + 1)];
     __shared__ float hsq[4 * VAEQ_MAX_TAPS];                // |h[chi][nu][j]|^2
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, M = p.M, mh = p.mh, Mh = 2 * p.mh;
-    if (wid < 5) {                                          // warp w reduces quantity w over the CTA partials
+    {   // quantity w = tid & 7 (5 used), slot = tid >> 3: every thread sums a strided share of the CTA partials (592 partials
+        // over the 128 slots of the 1024-thread fin CTA = 5 independent loads per thread instead of a chain of 19), then the
+        // shares are combined in fixed order (deterministic)
+        __shared__ double wq[32][8];
+        const int w = tid & 7, slot = tid >> 3, nslot = blockDim.x >> 3, nwarp = blockDim.x >> 5;
         double a = 0.0;
+        if (w < 5) {
 #pragma unroll 4
-        for (int b = lane; b < nparts; b += 32) a += p.part_fwd[(int64_t)b * 8 + wid];
-        a = warp_sum(a);
-        if (lane == 0) tot[wid] = a;
+            for (int b = slot; b < nparts; b += nslot) a += p.part_fwd[(int64_t)b * 8 + w];
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+        if (lane < 8) wq[wid][lane] = a;
+        __syncthreads();
+        if (tid < 5) {
+            double v = 0.0;
+            for (int k = 0; k < nwarp; ++k) v += wq[k][tid];
+            tot[tid] = v;
+        }
     }
     // stage the edge variances and |h|^2 (one global round trip instead of a chain of dependent loads)
     for (int i = tid; i < 4 * mh; i += blockDim.x) edge_sh[i] = p.edge_vs[i];
@@ -240,7 +253,7 @@ __device__ __forceinline__ void dp_fin_body(const DpK &p, int nparts) {      // 
     }
 }
 
-__global__ void __launch_bounds__(256) k_dp_fin(DpK p, int nparts) { dp_fin_body(p, nparts); }
+__global__ void __launch_bounds__(1024) k_dp_fin(DpK p, int nparts) { dp_fin_body(p, nparts); }
 
 // ---------------------------------------------------------------------------------------------
 // backward
@@ -429,28 +442,36 @@ __device__ __forceinline__ void dp_adam_finish(const DpK &p, int i, double a, in
     }
 }
 
-// one WARP per tap-gradient entry: lanes stride over the per-CTA partials (fixed order -> deterministic), then lane 0
-// finishes the entry.  The step counter is bumped by the last CTA to finish.
-constexpr int ADAM_WARPS = 8;
-__global__ void __launch_bounds__(ADAM_WARPS * 32) k_dp_adam(DpK p, int nparts, int do_update, float lr_w, float lr_h, int amsgrad) {
+// ADAM_TPE threads per tap-gradient entry stride over the per-CTA partials (fixed order -> deterministic; with 592 partials
+// each thread has <= 5 independent loads in flight instead of a chain of 19), warp + shared-memory reduction, then one
+// thread finishes the entry.  The step counter is bumped by the last CTA to finish.
+constexpr int ADAM_TPE = 128, ADAM_EPC = 2;                 // threads per entry, entries per CTA
+__global__ void __launch_bounds__(ADAM_TPE * ADAM_EPC) k_dp_adam(DpK p, int nparts, int do_update, float lr_w, float lr_h, int amsgrad) {
     __shared__ double bc1_sh;
     __shared__ float bc2s_sh;
-    const int M = p.M, n = 16 * M, lane = threadIdx.x & 31;
+    __shared__ double wsum[ADAM_EPC][ADAM_TPE / 32];
+    const int M = p.M, n = 16 * M, lane = threadIdx.x & 31, sub = threadIdx.x % ADAM_TPE, e = threadIdx.x / ADAM_TPE;
     int *step_ptr = p.adam ? reinterpret_cast<int *>(p.adam + 48 * M) : nullptr;
     const int step = do_update ? *step_ptr + 1 : 0;         // every CTA reads the old value before taking its ticket
-    if (threadIdx.x == ADAM_WARPS * 32 - 1) {
+    if (threadIdx.x == ADAM_TPE * ADAM_EPC - 1) {
         if (do_update) adam_bias(step, &bc1_sh, &bc2s_sh);
         else { bc1_sh = 1.0; bc2s_sh = 1.f; }
     }
-    const int i = blockIdx.x * ADAM_WARPS + (threadIdx.x >> 5);
+    const int i = blockIdx.x * ADAM_EPC + e;
     double a = 0.0;
     if (i < n) {
 #pragma unroll 4
-        for (int b = lane; b < nparts; b += 32) a += (double)p.gpart[(int64_t)b * n + i];
+        for (int b = sub; b < nparts; b += ADAM_TPE) a += (double)p.gpart[(int64_t)b * n + i];
         a = warp_sum(a);
+        if (lane == 0) wsum[e][sub >> 5] = a;
     }
     __syncthreads();
-    if (i < n && lane == 0) dp_adam_finish(p, i, a, do_update, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
+    if (i < n && sub == 0) {
+        a = 0.0;
+#pragma unroll
+        for (int w = 0; w < ADAM_TPE / 32; ++w) a += wsum[e][w];
+        dp_adam_finish(p, i, a, do_update, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
+    }
     if (do_update) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -681,7 +702,7 @@ static DpK dp_make_params(const vaeq_dp_desc *d) {
 
 int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st) {
     ktime_begin(VAEQ_K_DP_FIN, st);
-    k_dp_fin<<<1, 256, 0, st>>>(p, nparts);
+    k_dp_fin<<<1, nparts > 64 ? 1024 : 256, 0, st>>>(p, nparts);
     ktime_end(VAEQ_K_DP_FIN, st);
     VAEQ_LAUNCH_CHECK("k_dp_fin");
     return VAEQ_OK;
@@ -689,7 +710,7 @@ int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st) {
 
 static int dp_launch_adam(const DpK &p, int nparts, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
     ktime_begin(VAEQ_K_DP_ADAM, st);
-    k_dp_adam<<<(16 * p.M + ADAM_WARPS - 1) / ADAM_WARPS, ADAM_WARPS * 32, 0, st>>>(p, nparts, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
+    k_dp_adam<<<(16 * p.M + ADAM_EPC - 1) / ADAM_EPC, ADAM_TPE * ADAM_EPC, 0, st>>>(p, nparts, mode == DP_MODE_TRAIN ? 1 : 0, lr_w, lr_h, amsgrad);
     ktime_end(VAEQ_K_DP_ADAM, st);
     VAEQ_LAUNCH_CHECK("k_dp_adam");
     return VAEQ_OK;
