@@ -333,7 +333,7 @@ def ours_arm(args, rank, local_rank, world):
     achieved = B * ALG_BYTES_PER_SYMBOL / (dom_ms * 1e-3) / 1e9
     step_gbs = B * ALG_BYTES_PER_SYMBOL * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (FWD_DRAM_BYTES_PER_SYMBOL * B if names[dom] == "k_dp_fwd" else None),
+                "traffic": (FWD_DRAM_BYTES_PER_SYMBOL * B if names[dom] == "k_dp_fwd" and M_EST == 25 else None),
                 "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01b_ncu_full_summary.json, scaled to this batch_len)",
                 "peak_source": peak_src, "alg_bytes_per_symbol": ALG_BYTES_PER_SYMBOL,
                 "alg_bytes_per_launch": B * ALG_BYTES_PER_SYMBOL,
@@ -388,7 +388,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the batch_len = 100 persistent-frame leg")
     ap.add_argument("--no-split", action="store_true", help="skip the batch-split (configs[2]) leg at N > 1")
+    ap.add_argument("--m-est", type=int, default=M_EST, help="equalizer / channel-estimate taps (default 25 = the BASELINE config; "
+                    "5, 9, 13 show the HBM-bound regime, SURVEY.md §8d)")
     args = ap.parse_args()
+    if args.m_est != M_EST:
+        globals()["M_EST"] = args.m_est
+        globals()["ALG_FLOP_PER_SYMBOL"] = 5 * 32 * args.m_est + 1000
 
     if args.gpus > 1 and "RANK" not in os.environ:          # launched bare: re-exec under torchrun (one rank per GPU)
         import socket

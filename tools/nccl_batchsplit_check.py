@@ -16,7 +16,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-M, B = 25, 1008 * 64
+M, B = 25, 496 * 128
 h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
 rx, tx, _ = generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, dev, 77)          # same seed on every rank = replicated window
 eq = DPEqualizer(M, 2, amp, P, var, nu_sc, device=dev)
