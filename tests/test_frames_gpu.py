@@ -161,3 +161,20 @@ def test_sweep_engine_equals_single_run_drivers():
                               seed=c["seed"])
             assert torch.equal(s1, ser[r]) and torch.equal(v1, ve[r]) and torch.equal(var1, var[r]), (kind, r)
         assert torch.isfinite(ser).all() and float(ser.max()) <= 1.0
+
+
+def test_run_dp_sweep_end_to_end(tmp_path):
+    """Eval_run_DP.py's sweep through the batched engine (VAE, VAEflex) and cell by cell (CMAbatch): shapes, finite SERs, .mat file."""
+    from vae_equalizer_b200 import sweep
+    lists = dict(nu_vec=[0.0270955], symb_rate_vec=[90e9], theta_vec=[np.pi / 10], theta_diff_vec=[0.0], SNR_vec=[20, 26], M_vec=[25],
+                 batch_len_vec=[100], flex_step_vec=[20], lr_optim_vec=[2.5e-3, 2e-3])
+    for loss_type in ("VAE", "VAEflex", "CMAbatch"):
+        SER, Var_est, var_real = sweep.run_dp_sweep(loss_type=loss_type, iter=2, num_frames=2, N_frame_max=1500, N_lrhalf=170, **lists)
+        assert SER.shape == (4, 2, 1, 1, 1, 1, 2, 1, 1, 1, 2, 2)
+        assert torch.isfinite(SER).all() and float(SER.min()) >= 0.0 and float(SER.max()) <= 1.0
+        assert torch.isfinite(Var_est).all() and (var_real > 0).all()
+        if loss_type != "CMAbatch":
+            assert (Var_est > 0).all()
+    sweep.save_mat(str(tmp_path / "s.mat"), SER, Var_est, var_real, SNR_vec=lists["SNR_vec"], nu_vec=lists["nu_vec"],
+                   theta_diff_vec=lists["theta_diff_vec"], theta_vec=lists["theta_vec"], M_vec=lists["M_vec"], lr_optim_vec=lists["lr_optim_vec"],
+                   batch_len_vec=lists["batch_len_vec"], symb_rate_vec=lists["symb_rate_vec"], flex_step_vec=lists["flex_step_vec"])

@@ -121,3 +121,37 @@ def test_batched_frame_generator_matches_single_generator():
     assert abs(float(sig[1] / sig[0]) - 10 ** 0.5) < 0.05 * 10 ** 0.5          # 10 dB lower SNR -> sqrt(10) more noise
     p0, p2 = float((rx[0] ** 2).mean()), float((rx[2] ** 2).mean())
     assert abs(p0 - p2) / p0 < 0.05                                            # a rotation keeps the power
+
+
+def test_run_dp_sweep_layout_and_mat_schema(tmp_path):
+    """sweep.run_dp_sweep reproduces the index order of Eval_run_DP.py:52,86 and save_mat the .mat schema of :99-114 (stub runner:
+    no GPU); cells that share (M, batch_len, flex_step, symb_rate) arrive at the runner as ONE batched set."""
+    import numpy as np
+    import torch
+    from scipy import io
+    from vae_equalizer_b200 import sweep
+    calls = []
+
+    def runner(cells, mod, sps, M, batch_len, N_frame_max, num_frames, **kw):
+        calls.append((M, batch_len, len(cells)))
+        ser = torch.stack([torch.full((4, num_frames), 1000.0 * c["SNR"] + 10 * c["lr_optim"] * 1e3 + M + c["seed"] * 1e-3) for c in cells])
+        ve = torch.stack([torch.full((2, num_frames), float(c["nu"])) for c in cells])
+        var = torch.stack([torch.full((2,), float(c["theta"])) for c in cells])
+        return ser, ve, var
+
+    lists = dict(nu_vec=[0, 0.027], symb_rate_vec=[90e9], theta_vec=[0.3], theta_diff_vec=[0.0, 0.1], SNR_vec=[20, 23, 26], M_vec=[9, 25],
+                 batch_len_vec=[100], flex_step_vec=[10], lr_optim_vec=[2e-3, 3e-3])
+    SER, Var_est, var_real = sweep.run_dp_sweep(iter=2, num_frames=3, runner=runner, **lists)
+    assert SER.shape == (4, 3, 1, 2, 2, 2, 2, 1, 1, 1, 2, 3) and Var_est.shape == (2,) + SER.shape[1:] and var_real.shape == (2,) + SER.shape[1:-1] + (1,)
+    assert sorted(calls) == [(9, 100, 48), (25, 100, 48)]                         # two batched sets, 3*2*2*2*2 cells each
+    # SER[:, s, sr, n, t1, m, l, nt, ss, v, i, :]
+    v = float(SER[0, 2, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0])
+    assert abs(v - (1000.0 * 26 + 10 * 2.0 + 25)) < 1.0
+    assert float(Var_est[1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 2]) == np.float32(0.027) and float(var_real[0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]) == np.float32(0.3)
+    path = str(tmp_path / "sweep.mat")
+    sweep.save_mat(path, SER, Var_est, var_real, SNR_vec=lists["SNR_vec"], nu_vec=lists["nu_vec"], theta_diff_vec=lists["theta_diff_vec"],
+                   theta_vec=lists["theta_vec"], M_vec=lists["M_vec"], lr_optim_vec=lists["lr_optim_vec"], batch_len_vec=lists["batch_len_vec"],
+                   symb_rate_vec=lists["symb_rate_vec"], flex_step_vec=lists["flex_step_vec"])
+    d = io.loadmat(path)["dict"]
+    assert set(d.dtype.names) == {"SER", "Var_est", "var_real", "SNR", "nu", "theta_diff", "theta", "M", "lr", "batch_len", "symb_rate", "symb_step"}
+    assert d["SER"][0, 0].shape == SER.shape and list(d["SNR"][0, 0].ravel()) == [20, 23, 26]

@@ -155,3 +155,81 @@ def sweep_vae_dp_sharded(cells, *args, rank=0, world=1, group=None, **kw):
         return None
     ser_g = torch.where(ser_g < 0, torch.full_like(ser_g, float("nan")), ser_g)
     return ser_g, ve_g, var_g
+
+
+# -------------------------------------------------------------------------------------------------
+# The whole sweep of Eval_run_DP.py (lines 17-114): same parameter lists in, same result arrays and .mat schema out
+# -------------------------------------------------------------------------------------------------
+AXES = ("SNR", "symb_rate", "nu", "theta_diff", "M", "lr_optim", "batch_len", "flex_step", "theta")   # index order of SER[...] (RUN_DP:52,86)
+
+
+def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,), symb_rate_vec=(90e9,), theta_vec=(np.pi / 10,),
+                 theta_diff_vec=(0.06 * np.pi,), SNR_vec=(23,), M_vec=(25,), batch_len_vec=(100,), flex_step_vec=(10,),
+                 lr_optim_vec=(2.5e-3, 2e-3, 3e-3), iter=5, N_lrhalf=170, num_frames=170, N_frame_max=10000,
+                 tau_pmd=0.1e-12 * np.sqrt(1000), tau_cd=-26e-24, phiIQ=(0.0314, 0.0314), *, device=None, datagen="gpu_batched",
+                 eval_every=1, rank=0, world=1, group=None, runner=None, verbose=False):
+    """Eval_run_DP.py's ten nested loops (RUN_DP:68-95) as batched run sets.  Cells that share (M, batch_len, flex_step, symb_rate)
+    train in the same persistent launch; with world > 1 every rank takes a round-robin share of each set.  Returns the
+    reference's result arrays on rank 0 (None elsewhere):
+        SER (4, SNR, symb_rate, nu, theta_diff, M, lr, batch_len, flex_step, theta, iter, num_frames), Var_est (2, ...), var_real (2, ..., 1)
+    loss_type 'VAE' / 'VAEflex' use the batched engine; the CMA variants have a per-symbol tap recurrence and run cell by cell."""
+    vecs = dict(SNR=list(SNR_vec), symb_rate=list(symb_rate_vec), nu=list(nu_vec), theta_diff=list(theta_diff_vec), M=list(M_vec),
+                lr_optim=list(lr_optim_vec), batch_len=list(batch_len_vec), flex_step=list(flex_step_vec), theta=list(theta_vec))
+    shape = tuple(len(vecs[a]) for a in AXES) + (iter,)
+    dev = torch.device("cpu") if runner is not None and device is None else _cuda_device(device)
+    SER = torch.full((4,) + shape + (num_frames,), float("nan"), dtype=torch.float32, device=dev)
+    Var_est = torch.zeros((2,) + shape + (num_frames,), dtype=torch.float32, device=dev)
+    var_real = torch.zeros((2,) + shape + (1,), dtype=torch.float32, device=dev)
+    groups = {}
+    for idx in np.ndindex(*shape):
+        c = {a: vecs[a][i] for a, i in zip(AXES, idx[:-1])}
+        c["seed"] = int(np.ravel_multi_index(idx, shape))            # one realisation per (cell, iteration), reproducible
+        groups.setdefault((c["M"], c["batch_len"], c["flex_step"], c["symb_rate"]), []).append((idx, c))
+    for (M, batch_len, flex_step, symb_rate), members in groups.items():
+        cells = [c for _, c in members]
+        common = (mod, sps, M, batch_len, N_frame_max, num_frames)
+        kw = dict(flex_step=flex_step, channel=channel, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ, N_lrhalf=N_lrhalf)
+        if runner is not None:                                       # test hook: stands for sweep_vae_dp_sharded
+            res = runner(cells, *common, **kw)
+        elif loss_type in ("VAE", "VAEflex"):
+            res = sweep_vae_dp_sharded(cells, *common, kind=loss_type, device=dev, datagen=datagen, eval_every=eval_every,
+                                       verbose=verbose, rank=rank, world=world, group=group, **kw)
+        else:
+            res = _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames)
+        if res is None:
+            continue
+        ser, ve, var = res
+        for k, (idx, _) in enumerate(members):
+            SER[(slice(None),) + idx] = ser[k].to(dev)
+            Var_est[(slice(None),) + idx] = ve[k].to(dev)
+            var_real[(slice(None),) + idx + (0,)] = var[k].to(dev)
+    if rank != 0:
+        return None
+    return SER, Var_est, var_real
+
+
+def _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames):
+    from . import processing as proc
+    from .parallel import gather_cell_results, shard_cells
+    fn = {"CMA": proc.processing_cma_dp, "CMAbatch": proc.processing_cmabatch_dp, "CMAflex": proc.processing_cmaflex_dp}[loss_type]
+    mod, sps, M, batch_len, N_frame_max, nf = common
+    loc_s, loc_v, loc_r = {}, {}, {}
+    for i, c in shard_cells(cells, rank, world):
+        s, v, r = fn(mod, sps, c["SNR"], c["nu"], M, c["theta_diff"], c["theta"], c["lr_optim"], batch_len, N_frame_max, nf, kw["flex_step"],
+                     kw["channel"], kw["symb_rate"], kw["tau_cd"], kw["tau_pmd"], np.asarray(kw["phiIQ"], dtype=np.complex64), kw["N_lrhalf"],
+                     device=dev, verbose=False, datagen="gpu", seed=c["seed"])
+        loc_s[i], loc_v[i], loc_r[i] = s, v, r
+    n = len(cells)
+    out = (gather_cell_results(loc_s, n, (4, num_frames), rank, world, group, dev), gather_cell_results(loc_v, n, (2, num_frames), rank, world, group, dev),
+           gather_cell_results(loc_r, n, (2,), rank, world, group, dev))
+    return out if rank == 0 else None
+
+
+def save_mat(path, SER, Var_est, var_real, *, SNR_vec, nu_vec, theta_diff_vec, theta_vec, M_vec, lr_optim_vec, batch_len_vec, symb_rate_vec,
+             flex_step_vec):
+    """The .mat file of Eval_run_DP.py:99-114: one struct 'dict' with the result arrays and the parameter lists under the same keys."""
+    from scipy import io
+    io.savemat(path, {"dict": {"SER": SER.cpu().numpy(), "Var_est": Var_est.cpu().numpy(), "var_real": var_real.cpu().numpy(),
+                               "SNR": list(SNR_vec), "nu": list(nu_vec), "theta_diff": list(theta_diff_vec), "theta": list(theta_vec),
+                               "M": list(M_vec), "lr": list(lr_optim_vec), "batch_len": list(batch_len_vec),
+                               "symb_rate": list(symb_rate_vec), "symb_step": list(flex_step_vec)}})
