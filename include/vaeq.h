@@ -207,6 +207,20 @@ int vaeq_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld
  * scratch: 4 doubles. */
 int vaeq_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx, const float *amp, const float *var,
                       float nu_sc, int32_t n_lev, int32_t N, int32_t *counts_out, float *ser_out, void *scratch, void *stream);
+/* Per-frame evaluation of n_runs independent runs at once (sweep engine): what func_VAELE_DP_MQAM_shaping.py:70-89 (seg_len =
+ * batch_len: the last shift[0] + n_cut symbols of every minibatch are dropped) and func_VAEflex_DP_MQAM_shaping.py:74-84 (seg_len = 0)
+ * do per run -- find_shift on out_train and find_shift_symb_full on out_const, roll by (r, -shift), cut, slice [edge : -edge-max|shift|],
+ * SER_IQflip and SER_constell_shaping -- with the roll / cut / slice as index arithmetic and the shifts kept on the device.
+ * q (R,2,2n,N), out (R,2,2,N), tx (R,2,2,N) float16 bits, run strides rs_* in elements; var (R,2) with run stride rs_var; nu_sc (R).
+ * align_out int32 (R,2,4) = {shift_x, shift_y, r, symbols evaluated} for the estimators {from q, from out};
+ * counts_out int32 (R,2,2,2,4) optional; ser_out float (R,4) = rows of SER_valid: constellation x, y, soft demapper x, y. */
+size_t vaeq_frame_eval_scratch_bytes(int32_t n_runs, int32_t n_shift);
+int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, const float *out, int64_t ld_out, int64_t rs_out,
+                         const uint16_t *tx, int64_t ld_tx, int64_t rs_tx, const float *amp, const float *var, int64_t rs_var,
+                         const float *nu_sc, int32_t n_lev, int32_t N, int32_t n_shift, int32_t n_runs, int32_t seg_len,
+                         int32_t edge, int32_t n_cut, int32_t *align_out, int32_t *counts_out, float *ser_out, void *scratch,
+                         void *stream);
+
 /* extension, not in the reference: achievable-rate estimate H(X)+E[log2 q(x_tx|y)] per pol (bit/2D symbol) */
 int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, const float *P, int32_t n_lev, int32_t N,
              float *gmi_out, void *scratch, void *stream);

@@ -153,7 +153,8 @@ def test_sweep_engine_equals_single_run_drivers():
              dict(SNR=17, nu=0.0270955, lr_optim=1e-3, theta=0.0, theta_diff=0.01, seed=5)]
     common = dict(symb_rate=90e9, tau_cd=-26e-24, tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=np.array([0.0314, 0.0314], dtype=np.complex64))
     for kind, fn, flex in (("VAE", processing_vaele_dp, 10), ("VAEflex", processing_vaeflex_dp, 20)):
-        ser, ve, var = sweep_vae_dp(cells, "64-QAM", 2, 25, 100, 2000, 3, flex_step=flex, channel="h0", N_lrhalf=2, kind=kind, **common)
+        ser, ve, var = sweep_vae_dp(cells, "64-QAM", 2, 25, 100, 2000, 3, flex_step=flex, channel="h0", N_lrhalf=2, kind=kind,
+                                    eval_mode="per_cell", **common)
         torch.cuda.synchronize()
         for r, c in enumerate(cells):
             s1, v1, var1 = fn("64-QAM", 2, c["SNR"], c["nu"], 25, c["theta_diff"], c["theta"], c["lr_optim"], 100, 2000, 3, flex, "h0",
@@ -178,3 +179,49 @@ def test_run_dp_sweep_end_to_end(tmp_path):
     sweep.save_mat(str(tmp_path / "s.mat"), SER, Var_est, var_real, SNR_vec=lists["SNR_vec"], nu_vec=lists["nu_vec"],
                    theta_diff_vec=lists["theta_diff_vec"], theta_vec=lists["theta_vec"], M_vec=lists["M_vec"], lr_optim_vec=lists["lr_optim_vec"],
                    batch_len_vec=lists["batch_len_vec"], symb_rate_vec=lists["symb_rate_vec"], flex_step_vec=lists["flex_step_vec"])
+
+
+@pytest.mark.parametrize("seg_len", [0, 100])
+def test_batched_frame_evaluation_equals_per_run_calls(seg_len):
+    """vaeq_frame_eval_runs (roll / cut / slice as index arithmetic, shifts on the device, all runs at once) against the
+    single-run sequence find_shift -> roll -> cut -> SER_IQflip / SER_constell_shaping, on runs with different time shifts,
+    a polarisation swap, different SNR and PCS."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    from vae_equalizer_b200.processing import _align
+    from vae_equalizer_b200.sweep import _score
+    R, N, n = 5, 3000, 8
+    gen = torch.Generator().manual_seed(3)
+    consts, outs, txs = [], [], []
+    for r in range(R):
+        k = O.init("h0", "64-QAM", "cpu", [0.0, 0.0270955, 0.05, 0.0, 0.0270955][r], 2, 25, [30, 24, 27, 21, 33][r])
+        amps, P = torch.tensor(k[4], dtype=torch.float32), torch.tensor(k[2], dtype=torch.float32)
+        tx = amps[torch.multinomial(P, 4 * N, True, generator=gen)].reshape(2, 2, N)
+        sh, swap = [(1, 0), (-3, -3), (0, 0), (4, 4), (2, -5)][r], [0, 1, 0, 1, 0][r]
+        y = tx + float(k[7][0].sqrt()) * torch.randn(2, 2, N, generator=gen)
+        y = torch.stack((y[0].roll(sh[0], -1), y[1].roll(sh[1], -1)))          # delay per pol ...
+        if swap:
+            y = y.roll(1, 0)                                                    # ... and crossed polarisations
+        consts.append(k)
+        outs.append(y)
+        txs.append(tx.to(torch.float16))
+    amp = consts[0][3].cuda()
+    out_const = torch.stack(outs).cuda().contiguous()
+    tx = torch.stack(txs).cuda().contiguous()
+    var = torch.stack([k[7] for k in consts]).cuda()
+    nu_sc = torch.tensor([k[6] for k in consts], dtype=torch.float32).cuda()
+    out_train = torch.stack([sfun.soft_dec(out_const[r], var[r], amp, float(nu_sc[r])) for r in range(R)])
+    ser, align, counts = sfun.frame_eval_runs(out_train, out_const, tx, amp, var, nu_sc, seg_len, return_counts=True)
+    torch.cuda.synchronize()
+    kind, B, m_max = ("VAE", seg_len, N // seg_len) if seg_len else ("VAEflex", 100, N)
+    for r in range(R):
+        sq, rq = sfun.find_shift(out_train[r], tx[r], 21, amp, 2)
+        so, ro = sfun.find_shift_symb_full(out_const[r], tx[r], 21)
+        sq, so = [int(v) for v in sq.tolist()], [int(v) for v in so.tolist()]
+        assert align[r, 0, :3].tolist() == [sq[0], sq[1], rq] and align[r, 1, :3].tolist() == [so[0], so[1], ro], r
+        s_q = _score(kind, "q", _align(out_train[r].clone(), sq, rq), tx[r], sq, B, m_max, 2, n, amp, consts[r])
+        s_c = _score(kind, "c", _align(out_const[r].clone(), so, ro), tx[r], so, B, m_max, 2, n, amp, (None,) * 6 + (float(nu_sc[r]), var[r]))
+        n_q, n_c = int(align[r, 0, 3]), int(align[r, 1, 3])
+        assert torch.equal(s_q.cpu(), ser[r, 2:].cpu()), (r, s_q, ser[r])                     # integer decisions: exact
+        assert float((s_c.cpu() - ser[r, :2].cpu()).abs().max()) <= 1.5 / n_c, (r, s_c, ser[r])   # norm sums are atomics: +-1 count
+        assert 0 < n_q <= N and 0 < n_c <= N
+    assert float(ser.max()) < 0.2                                                             # aligned correctly: a misaligned run scores ~0.98

@@ -88,6 +88,9 @@ PROTOTYPES = {
     "vaeq_find_shift": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vaeq_ser_iqflip": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_ser_constell": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vaeq_frame_eval_scratch_bytes": (_sz, [_i32, _i32]),
+    "vaeq_frame_eval_runs": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32,
+                                      _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vaeq_gmi": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_cma_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_cma": (C.c_int, [_i32, _vp, _i32, _f, _vp, _i32, _f, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),

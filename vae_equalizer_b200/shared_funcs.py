@@ -209,6 +209,35 @@ def find_shift_symb_full(rx, tx, N_shift, return_corr=False):
     return _find_shift(None, rx, tx, N_shift, None, return_corr)
 
 
+def frame_eval_runs(out_train, out_const, tx, amp_levels, var, nu_sc, seg_len, n_shift=21, edge=11, n_cut=10, return_counts=False):
+    """The per-frame evaluation of the VAE drivers (VAELE_DP:70-89 with seg_len = batch_len, VAEflex_DP:74-84 with seg_len = 0) for R
+    runs in one call and without a host sync: out_train (R,2,2n,N), out_const (R,2,2,N), tx (R,2,2,N) float16 (may be a view into
+    longer rows), var (R,2), nu_sc (R,).  Returns ser (R,4) [constellation x, y, soft demapper x, y] and align (R,2,4) int32
+    [shift_x, shift_y, r, symbols evaluated] for the estimators (from q, from out)."""
+    _require_cuda(out_train, "out_train")
+    _require_cuda(out_const, "out_const")
+    tx = _tx_bits(tx)
+    lib = _lib.load()
+    R, N, n = int(out_train.shape[0]), int(out_train.shape[-1]), int(amp_levels.numel())
+    dev = out_train.device
+    for t, name in ((out_train, "out_train"), (out_const, "out_const"), (tx, "tx")):
+        if t.dim() != 4 or t.shape[0] != R or t.shape[-1] != N or t.stride(3) != 1 or t.stride(1) != t.shape[2] * t.stride(2):
+            raise _lib.VaeqError(f"{name}: need (R,2,rows,N) with unit time stride and evenly strided rows, got {tuple(t.shape)} {t.stride()}")
+    var = torch.as_tensor(var, dtype=_F32, device=dev).reshape(R, 2).contiguous()
+    nu = torch.as_tensor(nu_sc, dtype=_F32, device=dev).reshape(R).contiguous()
+    amp = amp_levels.to(dev, _F32).contiguous()
+    align = torch.empty(R, 2, 4, dtype=torch.int32, device=dev)
+    counts = torch.empty(R, 2, 2, 2, 4, dtype=torch.int32, device=dev)
+    ser = torch.empty(R, 4, dtype=_F32, device=dev)
+    scr = _scratch(dev, int(lib.vaeq_frame_eval_scratch_bytes(R, int(n_shift))))
+    _lib.check(lib.vaeq_frame_eval_runs(out_train.data_ptr(), int(out_train.stride(2)), int(out_train.stride(0)),
+                                        out_const.data_ptr(), int(out_const.stride(2)), int(out_const.stride(0)),
+                                        tx.data_ptr(), int(tx.stride(2)), int(tx.stride(0)), amp.data_ptr(), var.data_ptr(), 2, nu.data_ptr(),
+                                        n, N, int(n_shift), R, int(seg_len), int(edge), int(n_cut), align.data_ptr(), counts.data_ptr(),
+                                        ser.data_ptr(), scr.data_ptr(), _lib.current_stream()), "vaeq_frame_eval_runs")
+    return (ser, align, counts) if return_counts else (ser, align)
+
+
 def GMI(q, tx, P):
     """EXTENSION (not in the reference): H(X) + E[log2 q(x_tx|y)] per pol, bit/2D-symbol."""
     _require_cuda(q, "q")

@@ -28,13 +28,15 @@ def _cell(c, key):
 
 def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, flex_step=None, channel="h0", symb_rate=90e9,
                  tau_cd=-26e-24, tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=(0.0314, 0.0314), N_lrhalf=None, *, kind="VAE",
-                 device=None, datagen="gpu", eval_every=1, verbose=False):
+                 device=None, datagen="gpu", eval_every=1, eval_mode="batched", verbose=False):
     """Train and score R = len(cells) independent runs in lockstep.
 
     cells: list of dicts with per-cell values: SNR, nu, lr_optim, theta, theta_diff, and optionally seed.
     datagen: "numpy" (the reference's host generator, per cell), "gpu" (device generator, per cell: a cell's data depends on
     its own seed only, so a cell gives the same result alone or in any batch) or "gpu_batched" (one batched generation for all
     cells per frame, seeded by the first cell's seed: fastest).
+    eval_mode: "batched" (default: vaeq_frame_eval_runs, all cells in 7 launches, no host sync) or "per_cell" (the single-run
+    drivers' own sequence of calls per cell: find_shift -> roll -> cut -> SER; the two agree to the last error count).
     kind: "VAE" (func_VAELE_DP_MQAM_shaping.py: non-overlapping minibatches) or "VAEflex" (func_VAEflex_DP_MQAM_shaping.py:
     window batch_len advanced by flex_step).  eval_every: score every k-th frame (and the last); unscored frames hold NaN.
     Returns (SER_valid (R,4,num_frames), Var_est (R,2,num_frames), var (R,2))."""
@@ -100,6 +102,17 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
                                                 keep_lo_in_dst=kd)
         Var_est[:, :, frame] = var_steps.mean(dim=2)
         if frame % eval_every and frame != num_frames - 1:
+            continue
+        if eval_mode == "batched":
+            if datagen == "gpu_batched":
+                tx_b4 = tx_b if kind == "VAE" else tx_b[:, :, :, batch_len // 2:m_max + batch_len // 2]
+            else:
+                tx_b4 = torch.stack(tx_all)
+            ser, _ = sfun.frame_eval_runs(out_train, out_const, tx_b4, amp_levels, var_all, nu_sc_all, batch_len if kind == "VAE" else 0,
+                                          n_cut=N_CUT)
+            SER_valid[:, :, frame] = ser
+            if verbose:
+                print(frame, "loss", loss_steps[:, -1].tolist(), "SER", SER_valid[:, :, frame].tolist())
             continue
         # pass 1: both shift searches of every cell, ONE host sync for all of them
         found = [(sfun._find_shift(out_train[r], None, tx_all[r], 21, amp_levels, False, sync=False),
