@@ -128,6 +128,10 @@ int vaeq_dp_dynamic_tiles(int32_t on);
 int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream);
 /* forward + backward: additionally gW, gh (must be non-NULL); parameters are NOT updated */
 int vaeq_dp_forward_backward(const vaeq_dp_desc *d, void *stream);
+/* loss_function_shaping (sf:92-137) as an operator on an ARBITRARY q: d->q (2,2n,B) is an INPUT here; outputs d->loss, d->var_est,
+ * d->gh = dL/dh_est (optional) and gq (2,2n,B, row stride ld_gq) = dL/dq (optional).  d->W / out / var / adam are not used. */
+int vaeq_dp_loss_from_q(const vaeq_dp_desc *d, float *gq, int64_t ld_gq, void *stream);
+
 /* forward + backward + Adam on both groups: lr_w for W (group 0), lr_h for h (group 1);
  * betas (0.9,0.999), eps 1e-8, no weight decay (torch defaults used at func_VAELE_DP_MQAM_shaping.py:28) */
 int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stream);

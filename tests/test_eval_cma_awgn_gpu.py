@@ -156,6 +156,29 @@ def test_operator_level_autograd_matches_oracle():
         assert rel(net.conv_w.weight, g["W"][s]) < 1e-4 and rel(h_est, g["h"][s]) < 1e-4
 
 
+@pytest.mark.parametrize("mod,M,B", [("64-QAM", 25, 100), ("16-QAM", 9, 700), ("4-QAM", 5, 64), ("64-QAM", 13, 1200)])
+def test_loss_function_shaping_on_arbitrary_q(mod, M, B):
+    """loss_function_shaping(q, rx, h_est, amp, P) as a plain operator on a q that did NOT come from this package's equalizer
+    (a softmax of random logits): loss, var_est, dL/dq and dL/dh_est against the CPU oracle's autograd (sf:92-137)."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", mod, "cpu", 0.0270955, 2, M, 20)
+    n = amp.numel()
+    gen = torch.Generator().manual_seed(B + M)
+    q0 = torch.softmax(3.0 * torch.randn(2, 2, n, B, generator=gen), dim=2).reshape(2, 2 * n, B)
+    rx = 0.7 * torch.randn(2, 2, 2 * B, generator=gen)
+    h0 = h_est.detach() + 0.05 * torch.randn(2, 2, 2, M, generator=gen)
+    Pt = torch.tensor(P, dtype=torch.float32)
+    qo, ho = q0.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+    lo, vo = O.elbo_loss(qo, rx, ho, amp, Pt)
+    lo.backward()
+    qd, hd = q0.cuda().requires_grad_(True), h0.cuda().requires_grad_(True)
+    loss, ve = sfun.loss_function_shaping(qd, rx.cuda(), hd, amp.cuda(), Pt.cuda())
+    (2.0 * loss).backward()                                  # also checks that the upstream gradient is applied
+    assert rel(loss, lo.detach()) < 1e-5 and rel(ve, vo) < 1e-5
+    assert rel(qd.grad / 2.0, qo.grad) < 1e-4 and rel(hd.grad / 2.0, ho.grad) < 1e-4
+    assert not ve.requires_grad
+
+
 def test_dropin_processing_runs_and_converges():
     """func_VAELE_DP_MQAM_shaping.processing with the Eval_run_DP defaults (shortened): the SER must fall the
     way SURVEY.md §8c reports for the reference (converged SER of a few 1e-2 at SNR 23 dB)."""

@@ -70,7 +70,9 @@ def rel(x, y):
 
 @pytest.mark.parametrize("mod,M,B,stride,n_steps,keep_lo,keep_n,kd,nu", FRAME_CASES + [("64-QAM", 63, 256, 256, 4, 0, 256, True, 0.0),
                                                                                  ("16-QAM", 3, 40, 8, 11, 16, 8, False, 0.0),
-                                                                                 ("64-QAM", 7, 130, 130, 5, 0, 130, True, 0.02)])
+                                                                                 ("64-QAM", 7, 130, 130, 5, 0, 130, True, 0.02),
+                                                                                 ("4-QAM", 63, 512, 512, 2, 0, 512, True, 0.0),     # largest shared-memory plan
+                                                                                 ("64-QAM", 25, 28, 28, 6, 0, 28, True, 0.0)])      # shortest useful minibatch
 def test_fast_persistent_frame_matches_stepped_frame(mod, M, B, stride, n_steps, keep_lo, keep_n, kd, nu):
     """dp_small.cu against the launch-by-launch path on the same frame: every step's loss / var_est, the kept q / out
     columns and the taps after the last step."""

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "vaeq_dp_dynamic_tiles": (C.c_int, [_i32]),
     "vaeq_dp_forward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_forward_backward": (C.c_int, [C.POINTER(DpDesc), _vp]),
+    "vaeq_dp_loss_from_q": (C.c_int, [C.POINTER(DpDesc), _vp, _i64, _vp]),
     "vaeq_dp_train_step": (C.c_int, [C.POINTER(DpDesc), _f, _f, _vp]),
     "vaeq_dp_train_frame": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
     "vaeq_dp_persistent_frames": (C.c_int, [_i32]),

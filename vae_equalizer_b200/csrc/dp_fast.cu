@@ -376,11 +376,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
             // x[2u + k - MH]: even k = 2a -> xe[u + a - HF], odd k = 2a+1 -> xo[u + a - HF]
 #pragma unroll 1
             for (int ph = 0; ph < 2; ++ph)
-#ifdef VAEQ_EXP_NOFIR
-                if (ph == 0) { const float4 xx = xe[pidx(i0 + FT_XOFF)]; for (int r = 0; r < FT_R; ++r) { y[r][0] = xx.x + r; y[r][1] = xx.y; y[r][2] = xx.z; y[r][3] = xx.w; } }
-#else
                 fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? FT_TAPV * NE : 0), ph ? NO : NE, y);
-#endif
             PT(2)
             // point-wise stage, rolled over the polarisation (code size); y / mom rotate by two components per pass
 #pragma unroll 1
@@ -402,11 +398,9 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                         mom[r][cq] = m1v[r];
                     }
                     if (owned) {
-#ifndef VAEQ_EXP_NOQ
 #pragma unroll
                         for (int l = 0; l < NL; ++l)
                             st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
-#endif
                         st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
                         st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
                         if (p.need_bwd) {

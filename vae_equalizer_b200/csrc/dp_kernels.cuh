@@ -45,6 +45,9 @@ struct DpK {
     float *gyrows;                // 4 rows: dL/dout
     float *srows;                 // 12 rows: [S1 | T2 | S3][component]: dL/dout = gE*S1 + gV*T2 + w*S3 (see dp_fast.cu)
     int need_bwd;                 // forward kernel also emits srows (skipped in forward-only mode)
+    int from_q;                   // generic kernels: q is an INPUT (operator-level loss on an arbitrary q), gq receives dL/dq
+    float *gq;
+    int64_t ld_gq;
     float *gpart;                 // [grid][16*M]
     float *gfinal;                // [16*M]: gW then gh
     float *loss_out, *var_est_out;

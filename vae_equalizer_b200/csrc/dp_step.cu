@@ -16,14 +16,6 @@
 
 namespace vaeq {
 
-#ifdef VAEQ_FRAME_TIMING
-__device__ unsigned long long g_ph[32];
-__device__ long long g_ph_last;
-#define PH(i) { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) { long long _n = clock64(); g_ph[i] += (unsigned long long)(_n - g_ph_last); g_ph_last = _n; } }
-#else
-#define PH(i)
-#endif
-
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -49,7 +41,6 @@ __device__ __forceinline__ void dp_fwd_body(const DpK &p, float *smem, int cta, 
     const DemapConst &c = *cst;
 
     float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
-    PH(0)
 
     for (int tile = cta; tile < p.ntiles; tile += ncta) {
         const int t0 = tile * T;
@@ -60,13 +51,43 @@ __device__ __forceinline__ void dp_fwd_body(const DpK &p, float *smem, int cta, 
             xs[r * XN + jj] = (s >= 0 && s < p.L) ? p.rx[(int64_t)r * p.ld_rx + s] : 0.f;
         }
         __syncthreads();
-        PH(1)
 
         // ---- FIR + demapper for the tile and its halo of H symbols each side -------------------
         for (int i = tid; i < tn + 2 * H; i += DP_NT) {
             const int u = t0 - H + i;
             float4 mom = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (u >= 0 && u < p.B) {
+            if (u >= 0 && u < p.B && p.from_q) {
+                // operator-level loss_function_shaping(q, ...) on a GIVEN q (sf:101-113): posterior moments and entropy only
+                const bool owned = (i >= H) && (i < H + tn);
+                const bool ent_on = owned && (u >= mh) && (u < p.B - mh);
+                float m1v[4];
+                float vloc[2] = {0.f, 0.f};
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    float q[NL], m1 = 0.f, m2 = 0.f;
+                    const float *qrow = p.q + (int64_t)(cc * NL) * p.ld_q + u;
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) {
+                        q[l] = qrow[(int64_t)l * p.ld_q];
+                        m1 = fmaf(c.amp[l], q[l], m1);
+                        m2 = fmaf(c.a2[l], q[l], m2);
+                    }
+                    m1v[cc] = m1;
+                    if (ent_on) accEnt += entropy_component<NL>(q, c);
+                    vloc[cc >> 1] += m2 - m1 * m1;
+                }
+                mom = make_float4(m1v[0], m1v[1], m1v[2], m1v[3]);
+                if (owned) {
+                    accV[0] += vloc[0];
+                    accV[1] += vloc[1];
+                    if (u < mh || u >= p.B - mh) {
+                        const int slot = (u < mh) ? u : mh + (u - (p.B - mh));
+                        p.edge_vs[slot] = vloc[0];
+                        p.edge_vs[2 * mh + slot] = vloc[1];
+                    }
+                    p.m1buf4[u] = mom;
+                }
+            } else if (u >= 0 && u < p.B) {
                 float y[4] = {0.f, 0.f, 0.f, 0.f};      // (p0 I, p0 Q, p1 I, p1 Q)
                 const float *x0 = xs + 2 * i;
                 for (int k = 0; k < M; ++k) {
@@ -120,7 +141,6 @@ __device__ __forceinline__ void dp_fwd_body(const DpK &p, float *smem, int cta, 
             m1s[i] = mom;
         }
         __syncthreads();
-        PH(2)
 
         // ---- estimated-channel convolution and residual for the owned samples (sf:123-134) -----
         for (int i = tid; i < tn; i += DP_NT) {
@@ -157,12 +177,10 @@ __device__ __forceinline__ void dp_fwd_body(const DpK &p, float *smem, int cta, 
             }
         }
         __syncthreads();
-        PH(3)
     }
 
     float v[5] = {accC[0], accC[1], accEnt, accV[0], accV[1]};
     block_sum<5>(v, red);
-    PH(4)
     if (tid == 0) {
         double *dst = p.part_fwd + (int64_t)cta * 8;
 #pragma unroll
@@ -290,7 +308,6 @@ __device__ __forceinline__ void dp_bwd_body(const DpK &p, float *smem, int cta, 
 
     // each thread owns up to two complex tap-gradient outputs: idx < 4M -> dh(chi,nu,j), else dW(o,in,k)
     float accR[2] = {0.f, 0.f}, accI[2] = {0.f, 0.f};
-    PH(8)
 
     for (int tile = cta; tile < p.ntiles; tile += ncta) {
         const int t0 = tile * T;
@@ -312,7 +329,6 @@ __device__ __forceinline__ void dp_bwd_body(const DpK &p, float *smem, int cta, 
             m1s[i] = (u >= 0 && u < p.B) ? p.m1buf4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        PH(9)
 
         for (int i = tid; i < tn; i += DP_NT) {
             const int u = t0 + i;
@@ -345,15 +361,30 @@ __device__ __forceinline__ void dp_bwd_body(const DpK &p, float *smem, int cta, 
                 const float *qrow = p.q + (int64_t)(cc * NL) * p.ld_q + u;
 #pragma unroll
                 for (int l = 0; l < NL; ++l) q[l] = qrow[(int64_t)l * p.ld_q];
-                const float y = p.out[(int64_t)cc * p.ld_out + u];
                 const float gV = (cc >> 1) ? gV1 : gV0;
                 const float g1 = gE[cc] - 2.f * m1v[cc] * gV;
+                if (p.from_q) {                                 // dL/dq_l = a_l dL/dE[x] + a_l^2 dL/dE[x^2] + d(-entropy)/dq_l
+                    gy[cc] = 0.f;
+                    if (p.gq != nullptr) {
+                        float *grow = p.gq + (int64_t)(cc * NL) * p.ld_gq + u;
+#pragma unroll
+                        for (int l = 0; l < NL; ++l) {
+                            float g = fmaf(c.amp[l], g1, c.a2[l] * gV);
+                            if (ent_on) {
+                                const float uu = __fdiv_rn(q[l], c.P[l]), t = uu + 1e-12f;
+                                g += logf(t) + __fdiv_rn(uu, t);
+                            }
+                            grow[(int64_t)l * p.ld_gq] = g;
+                        }
+                    }
+                    continue;
+                }
+                const float y = p.out[(int64_t)cc * p.ld_out + u];
                 gy[cc] = demap_backward<NL>(y, c.var[cc >> 1], c, q, g1, gV, ent_on);
             }
             gys[i] = make_float4(gy[0], gy[1], gy[2], gy[3]);
         }
         __syncthreads();
-        PH(10)
 
         // ---- tap gradients: one complex output per thread slot, summed over the owned samples ----
 #pragma unroll
@@ -390,7 +421,6 @@ __device__ __forceinline__ void dp_bwd_body(const DpK &p, float *smem, int cta, 
             }
         }
         __syncthreads();
-        PH(11)
     }
 
     float *gp = p.gpart + (int64_t)cta * 16 * M;            // layout: gW (2,4,M) then gh (2,2,2,M)
@@ -499,17 +529,6 @@ __device__ __forceinline__ T *byte_off(T *ptr, int64_t bytes) {
     return ptr ? reinterpret_cast<T *>(reinterpret_cast<char *>(ptr) + bytes) : nullptr;
 }
 
-#ifdef VAEQ_FRAME_TIMING
-__device__ unsigned long long g_frame_cycles[8];
-#define FT_T0 long long _ft = clock64(); unsigned long long _fa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define FT_P(i) { long long _n = clock64(); _fa[i] += (unsigned long long)(_n - _ft); _ft = _n; }
-#define FT_END if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 8; ++i) g_frame_cycles[i] = _fa[i];
-#else
-#define FT_T0
-#define FT_P(i)
-#define FT_END
-#endif
-
 template <int NL>
 __global__ void __launch_bounds__(DP_NT) k_dp_frame_small(DpK p, DpRunsK rs, int n_steps, int stride_sym, int keep_lo_in_dst,
                                                           float lr_w, float lr_h, int amsgrad) {
@@ -536,7 +555,6 @@ __global__ void __launch_bounds__(DP_NT) k_dp_frame_small(DpK p, DpRunsK rs, int
     const float *rx0 = p.rx;
     int *step_ptr = reinterpret_cast<int *>(p.adam + 48 * M);
 
-    FT_T0
     for (int m = 0; m < n_steps; ++m) {
         p.rx = rx0 + (int64_t)m * stride_sym * 2;
         p.keep_base = (int64_t)m * stride_sym + (keep_lo_in_dst ? p.keep_lo : 0);
@@ -544,20 +562,16 @@ __global__ void __launch_bounds__(DP_NT) k_dp_frame_small(DpK p, DpRunsK rs, int
         p.loss_out = rs.loss_steps ? rs.loss_steps + (int64_t)run * n_steps + m : nullptr;
         p.var_est_out = rs.var_steps ? rs.var_steps + (int64_t)run * 2 * n_steps + m : nullptr;
         p.var_est_stride = n_steps;
-        FT_P(0)
         dp_fwd_body<NL>(p, smem, 0, 1);
         __syncthreads();
-        FT_P(1)
         dp_fin_body(p, 1);
         __syncthreads();
-        FT_P(2)
         if (last && threadIdx.x < 3) {                       // the desc's loss / var_est keep the last step's values
             if (threadIdx.x == 0 && rs.loss_last) rs.loss_last[run] = p.scal[DP_LOSS_OFF];
             if (threadIdx.x > 0 && rs.var_last) rs.var_last[2 * run + threadIdx.x - 1] = p.scal[DP_VAREST_OFF + threadIdx.x - 1];
         }
         dp_bwd_body<NL>(p, smem, 0, 1);
         __syncthreads();
-        FT_P(3)
         // gradient "reduction" over the single partial + Adam: one THREAD per entry (same arithmetic as k_dp_adam's lane 0)
         const int step = *step_ptr + 1;
         if (threadIdx.x == 0) adam_bias(step, &bc1_sh, &bc2s_sh);
@@ -565,9 +579,7 @@ __global__ void __launch_bounds__(DP_NT) k_dp_frame_small(DpK p, DpRunsK rs, int
         for (int i = threadIdx.x; i < n; i += DP_NT) dp_adam_finish(p, i, (double)p.gpart[i], 1, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
         __syncthreads();
         if (threadIdx.x == 0) *step_ptr = step;
-        FT_P(4)
     }
-    FT_END
 }
 
 __global__ void k_adam_generic(float *param, const float *grad, float *state, int n, float lr, int amsgrad,
@@ -805,6 +817,37 @@ extern "C" int vaeq_dp_forward_backward(const vaeq_dp_desc *d, void *stream) {
     return dp_dispatch(dp_make_params(d), d->n_lev, DP_MODE_FWDBWD, 0.f, 0.f, 0, (cudaStream_t)stream);
 }
 
+// loss_function_shaping(q, rx, h_est, amp_levels, P) as an operator on an ARBITRARY q (sf:92-137): loss, var_est, and the
+// gradients w.r.t. q and h_est.  Generic kernels only (the fused fast path differentiates through the equalizer instead).
+extern "C" int vaeq_dp_loss_from_q(const vaeq_dp_desc *d, float *gq, int64_t ld_gq, void *stream) {
+    VAEQ_CHECK_ARG(d != nullptr, "desc is NULL");
+    VAEQ_CHECK_ARG(d->sps == 2, "sps=%d: only sps=2 is implemented", d->sps);
+    VAEQ_CHECK_ARG(d->M >= 1 && d->M <= VAEQ_MAX_TAPS && (d->M & 1), "M_est=%d must be odd and <= %d", d->M, VAEQ_MAX_TAPS);
+    VAEQ_CHECK_ARG(d->n_lev == 2 || d->n_lev == 4 || d->n_lev == 8, "n_lev=%d must be 2, 4 or 8", d->n_lev);
+    VAEQ_CHECK_ARG(d->B > 2 * (d->M / 2), "batch_len=%d must exceed M_est-1", d->B);
+    VAEQ_CHECK_ARG(d->rx && d->amp && d->P && d->h && d->q && d->loss && d->var_est, "NULL tensor pointer (rx, amp, P, h, q, loss, var_est)");
+    VAEQ_CHECK_ARG(d->ld_rx >= (int64_t)d->B * d->sps && d->ld_q >= d->B && (!gq || ld_gq >= d->B), "row stride smaller than the row");
+    VAEQ_CHECK_ARG(d->workspace != nullptr, "workspace is NULL");
+    if (d->workspace_bytes < vaeq_dp_workspace_bytes(d->B, d->M, d->n_lev)) {
+        set_error("workspace too small: %zu < %zu", d->workspace_bytes, vaeq_dp_workspace_bytes(d->B, d->M, d->n_lev));
+        return VAEQ_EWORKSPACE;
+    }
+    DpK p = dp_make_params(d);
+    p.from_q = 1;
+    p.gq = gq;
+    p.ld_gq = ld_gq;
+    p.qk = nullptr;
+    p.W = p.h;                                               // never dereferenced for its values: the FIR is skipped
+    p.var = p.amp;                                           // (the demapper constants are unused as well)
+    p.gW_out = nullptr;
+    const bool need_grads = gq != nullptr || d->gh != nullptr;
+    switch (d->n_lev) {
+        case 2: return dp_run<2>(p, need_grads ? DP_MODE_FWDBWD : DP_MODE_FWD, 0.f, 0.f, 0, (cudaStream_t)stream);
+        case 4: return dp_run<4>(p, need_grads ? DP_MODE_FWDBWD : DP_MODE_FWD, 0.f, 0.f, 0, (cudaStream_t)stream);
+        default: return dp_run<8>(p, need_grads ? DP_MODE_FWDBWD : DP_MODE_FWD, 0.f, 0.f, 0, (cudaStream_t)stream);
+    }
+}
+
 extern "C" int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stream) {
     int rc = dp_validate(d, true, true);
     if (rc) return rc;
@@ -862,16 +905,6 @@ static int dp_frame_persistent(const vaeq_dp_desc *d, const vaeq_dp_runs *runs, 
     return VAEQ_OK;
 }
 }  // namespace vaeq
-
-#ifdef VAEQ_FRAME_TIMING
-extern "C" int vaeq_debug_frame_cycles(unsigned long long *out8) {
-    return (int)cudaMemcpyFromSymbol(out8, vaeq::g_frame_cycles, 8 * sizeof(unsigned long long));
-}
-extern "C" int vaeq_debug_phase32(unsigned long long *out32, int reset) {
-    if (reset) { unsigned long long z[32] = {0}; return (int)cudaMemcpyToSymbol(vaeq::g_ph, z, sizeof(z)); }
-    return (int)cudaMemcpyFromSymbol(out32, vaeq::g_ph, 32 * sizeof(unsigned long long));
-}
-#endif
 
 extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
                                    float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream) {

@@ -127,16 +127,51 @@ def soft_dec(out, var, amp_levels, nu_sc):
     return q
 
 
+class _LossFromQ(torch.autograd.Function):
+    """loss_function_shaping as a plain operator: loss(q, h_est) for ANY q, with dL/dq and dL/dh_est from vaeq_dp_loss_from_q."""
+
+    @staticmethod
+    def forward(ctx, q, h, rx, amp, P):
+        lib = _lib.load()
+        dev = rx.device
+        q2, rx2 = q.detach().reshape(2, -1, q.shape[-1]).contiguous(), rx.detach().reshape(2, 2, -1).contiguous()
+        h2 = h.detach().contiguous()
+        n, B, M = int(amp.numel()), int(q2.shape[-1]), int(h2.shape[-1])
+        ws = torch.empty(int(lib.vaeq_dp_workspace_bytes(B, M, n)), dtype=torch.uint8, device=dev)
+        loss, var_est = torch.empty(1, dtype=_F32, device=dev), torch.empty(2, dtype=_F32, device=dev)
+        gq, gh = torch.empty_like(q2), torch.empty_like(h2)
+        d = _lib.DpDesc()
+        d.B, d.sps, d.M, d.n_lev = B, rx2.shape[-1] // B, M, n
+        d.rx, d.ld_rx = rx2.data_ptr(), int(rx2.stride(1))
+        d.amp, d.P, d.h = amp.data_ptr(), P.data_ptr(), h2.data_ptr()
+        d.q, d.ld_q = q2.data_ptr(), B
+        d.loss, d.var_est, d.gh = loss.data_ptr(), var_est.data_ptr(), gh.data_ptr()
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.vaeq_dp_loss_from_q(C.byref(d), gq.data_ptr(), B, _lib.current_stream()), "vaeq_dp_loss_from_q")
+        ctx.save_for_backward(gq.reshape(q.shape), gh.reshape(h.shape))
+        ctx.mark_non_differentiable(var_est)
+        return loss.reshape(()), var_est
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_var):
+        gq, gh = ctx.saved_tensors
+        return g_loss * gq, g_loss * gh, None, None, None
+
+
 def loss_function_shaping(q, rx, h_est, amp_levels, P):
-    """ELBO loss (sf:92-137): returns (loss, var_est (2,)); differentiable w.r.t. the taps of the
-    twoXtwoFIR that produced `q` and w.r.t. `h_est` (fused CUDA backward)."""
+    """ELBO loss (sf:92-137): returns (loss, var_est (2,)).
+
+    When `q` is the tensor returned by this package's twoXtwoFIR.forward for the minibatch `rx`, the fused CUDA step runs and the
+    gradients reach the equalizer taps and `h_est` without materialising dL/dq.  For any other q (any CUDA tensor (2,2n,B), e.g. a
+    posterior from another demapper) the loss is an ordinary autograd operator differentiable w.r.t. `q` and `h_est`."""
     src = _Q_SOURCES.get(q.data_ptr())
-    if src is None or src[5] != q.numel():
-        raise _lib.VaeqError("loss_function_shaping needs the q returned by twoXtwoFIR.forward of this package "
-                             "(the fused backward differentiates through the equalizer); arbitrary q is not supported")
+    if src is None or src[5] != q.numel() or src[1].data_ptr() != rx.data_ptr() or src[1].numel() != rx.numel():
+        _require_cuda(q, "q")
+        _require_cuda(rx, "rx")
+        amp = torch.as_tensor(amp_levels, dtype=_F32, device=rx.device).contiguous()
+        Pt = torch.as_tensor(P, dtype=_F32, device=rx.device).contiguous()
+        return _LossFromQ.apply(q, h_est, rx, amp, Pt)
     net, x, amp_src, var, nu_sc, _ = src
-    if x.data_ptr() != rx.data_ptr() or x.numel() != rx.numel():
-        raise _lib.VaeqError("loss_function_shaping: rx is not the minibatch q was computed from")
     Pt = torch.as_tensor(P, dtype=_F32, device=rx.device).contiguous()
     eq = net._engine(amp_src, var, nu_sc, P=Pt)
     loss, var_est = _FusedLoss.apply(net.conv_w.weight, h_est, eq, x.contiguous())
