@@ -510,7 +510,8 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_BWD1) k_dp_bwd1_fast(DpK p) {
     extern __shared__ __align__(16) float4 smem4[];
     float4 *ge = smem4, *go = ge + FT_ES;
     float4 *tapG = go + FT_ES;                               // 2 kappa_chi conj(h) taps for dE_q: [phase][lag][FT_TAPV]
-    float *PSg = reinterpret_cast<float *>(tapG + FT_TAPV * (NE + NO));   // (2, M+1)
+    float4 *sst = tapG + FT_TAPV * (NE + NO);                // [12][FT_NT]: this thread's S1/T2/S3 float4s, landed by cp.async
+    float *PSg = reinterpret_cast<float *>(sst + 12 * FT_NT);         // (2, M+1)
     const int tid = threadIdx.x;
     const float kap0 = p.scal[DP_KAPPA_OFF], kap1 = p.scal[DP_KAPPA_OFF + 1];
 
@@ -545,6 +546,11 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_BWD1) k_dp_bwd1_fast(DpK p) {
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
+        if (owned) {                                         // backward coefficients of MY four symbols: in flight during the e staging
+#pragma unroll                                               // and the FIR-like loop below, read back by the same thread (no barrier)
+            for (int k = 0; k < 12; ++k) cp_async16(sst + k * FT_NT + tid, p.srows + (int64_t)k * p.B + u0);
+        }
+        cp_async_commit();
         {   // stage the residual e for the tile and its halo (gD = 2 kappa e: the factor sits in the taps)
             float4 er[8];
 #pragma unroll
@@ -571,6 +577,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_BWD1) k_dp_bwd1_fast(DpK p) {
                 const int u = u0 + r;
                 entw[r] = (u >= MH && u < p.B - MH) ? LN2 : 0.f;
             }
+            cp_async_wait_all();
 #pragma unroll 1
             for (int pol = 0; pol < 2; ++pol) {
                 float gV[FT_R];
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_BWD1) k_dp_bwd1_fast(DpK p) {
                 for (int cq = 0; cq < 2; ++cq) {
                     const int cc = 2 * pol + cq;
                     // dL/dout = dL/dE_q * S1 + dL/dVar * T2 + w * S3 with the coefficients the forward pass left in srows
-                    const float4 s1 = ld_row4(p.srows, p.B, cc, u0), t2 = ld_row4(p.srows, p.B, 4 + cc, u0), s3 = ld_row4(p.srows, p.B, 8 + cc, u0);
+                    const float4 s1 = sst[cc * FT_NT + tid], t2 = sst[(4 + cc) * FT_NT + tid], s3 = sst[(8 + cc) * FT_NT + tid];
                     float gy[FT_R];
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r)
@@ -731,7 +738,7 @@ static size_t fast_smem_fwd() {
 }
 template <int MH>
 static size_t fast_smem_bwd1() {
-    return (size_t)(2 * FT_ES + FT_TAPV * (2 * MH + 1)) * sizeof(float4) + sizeof(FastConst) + (2 * (2 * MH + 2) + 2) * sizeof(float) + 64;
+    return (size_t)(2 * FT_ES + FT_TAPV * (2 * MH + 1) + 12 * FT_NT) * sizeof(float4) + sizeof(FastConst) + (2 * (2 * MH + 2) + 2) * sizeof(float) + 64;
 }
 template <int MH, int FAM>
 static size_t fast_smem_taps() {
