@@ -625,21 +625,38 @@ struct Roles {
 // Each warp owns one role = (phase, lag half) for the whole kernel (warps w and w+4 share a role and split the
 // symbol groups); its AMAX x 8 accumulators live in registers across all tiles of the persistent CTA.
 // ---------------------------------------------------------------------------------------------
+// The per-symbol operand g (dL/dout rows for dW, residual rows e for dh) is used by its SoA rows directly: a lane's four symbols
+// are one float4 per row, so the rows land in shared memory by cp.async exactly as they lie in HBM (double-buffered: the next
+// tile's rows are in flight while this tile is correlated) and are "transposed" by register naming only.  The sliding-window
+// operand needs one float4 per position: raw rows are staged by cp.async as well and re-laid-out smem -> smem at the top
+// of the next iteration (dW: rx phases; dh: E_q rows, by the owning thread, no barrier).
+constexpr int FT_GROW = FT_TE / 4;                      // float4 per staged g row
+template <int NROW>
+__device__ __forceinline__ void issue_g_rows(const float *rows, int64_t ld, int u0, bool owned, float4 *dst) {
+    if (owned) {
+#pragma unroll
+        for (int k = 0; k < NROW; ++k) cp_async16(dst + k * FT_GROW + threadIdx.x, rows + (int64_t)k * ld + u0);
+    }
+}
+
 template <int MH, int FAM>
 __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
-    constexpr int M = 2 * MH + 1, HF = MH / 2;
+    constexpr int M = 2 * MH + 1, HF = MH / 2, NG = FAM == 0 ? 4 : 8;
     using RL = Roles<MH>;
     extern __shared__ __align__(16) float4 smem4[];
-    // FAM 0: s0 = xe, s1 = xo (windows), g0 = g1 = gy.   FAM 1: s0 = s1 = E_q (window), g0 = gD even, g1 = gD odd
+    // FAM 0: s0 = xe, s1 = xo (windows), raw = next tile's rx rows, grow = dL/dout rows (4).
+    // FAM 1: s0 = s1 = E_q window, raw = next tile's E_q rows (4 x FT_GROW, own slots), grow = residual rows (8: even | odd phase).
     float4 *s0 = smem4, *s1 = FAM == 0 ? s0 + FT_XS : s0;
-    float4 *g0 = FAM == 0 ? s1 + FT_XS : s0 + FT_ES, *g1 = FAM == 0 ? g0 : g0 + FT_ES;
-    float *red = reinterpret_cast<float *>((FAM == 0 ? g0 : g1) + FT_ES);
+    float4 *raw = FAM == 0 ? s1 + FT_XS : s0 + FT_ES;
+    float4 *grow = raw + (FAM == 0 ? FT_RAW : 4 * FT_GROW);  // [2][NG][FT_GROW]
+    float *red = reinterpret_cast<float *>(grow + 2 * NG * FT_GROW);
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, role = wid & 3, ph = role >> 1;
     const int a0 = (role & 1) ? (ph ? RL::A0o : RL::A0e) : 0;
     const int n_real = role == 0 ? RL::A0e : role == 1 ? RL::A1e : role == 2 ? RL::A0o : RL::A1o;
-    const float4 *win = ph ? s1 : s0, *gsrc = ph ? g1 : g0;
-    const int c0 = (FAM == 0 ? FT_XOFF - HF : -HF + ph) + a0;
-    const float kap0 = FAM ? p.scal[DP_KAPPA_OFF] : 0.f, kap1 = FAM ? p.scal[DP_KAPPA_OFF + 1] : 0.f;
+    const float4 *win = ph ? s1 : s0;
+    const int c0 = (FAM == 0 ? FT_XOFF - HF : -HF + ph) + a0, grow0 = FAM == 0 ? 0 : 4 * ph;
+    const float *grows_g = FAM == 0 ? p.gyrows : p.erows;
+    const int i0 = FT_R * tid;
 
     float2 acc2[RL::AMAX][4];
 #pragma unroll
@@ -647,60 +664,60 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc2[a][k] = make_float2(0.f, 0.f);
 
+    auto issue_tile = [&](int tile_i, int buf) {
+        const int t0 = p.sym_lo + tile_i * FT_T, u0 = t0 - FT_HP + i0;
+        const bool in_seq = (u0 >= 0) && (u0 < p.B);
+        const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
+        issue_g_rows<NG>(grows_g, p.B, u0, owned, grow + buf * NG * FT_GROW);
+        if (FAM == 0) {
+            issue_x_raw(p, t0, raw);                         // commits the group
+        } else {
+            if (in_seq) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cp_async16(raw + k * FT_GROW + tid, p.m1rows + (int64_t)k * p.B + u0);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) raw[k * FT_GROW + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            cp_async_commit();
+        }
+    };
+
     __shared__ int s_next;
+    int buf = 0;
+    if ((int)blockIdx.x < p.ntiles) issue_tile(blockIdx.x, 0);
+    cp_async_wait_all();
+    __syncthreads();
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles;) {
         const int t0 = p.sym_lo + tile * FT_T;
         tile_fetch_next(p, 2 + FAM, tile, &s_next);
-        {
-            const int i0 = FT_R * tid, u0 = t0 - FT_HP + i0;
-            const bool in_seq = (u0 >= 0) && (u0 < p.B);
-            const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.sym_hi);
-            if (FAM == 0) {
-                load_x_phases<true>(p, t0, s0, s1);
-                float4 gr[4];
+        if (FAM == 0) {
+            transpose_x_raw<true>(raw, s0, s1);
+        } else {
+            float4 mr[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) gr[k] = owned ? ld_row4(p.gyrows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 4; ++k) mr[k] = raw[k * FT_GROW + tid];
 #pragma unroll
-                for (int r = 0; r < FT_R; ++r) g0[5 * tid + r] = make_float4(f4c(gr[0], r), f4c(gr[1], r), f4c(gr[2], r), f4c(gr[3], r));
-            } else {
-                float4 er[8], mr[4];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) er[k] = owned ? ld_row4(p.erows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mr[k] = in_seq ? ld_row4(p.m1rows, p.B, k, u0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float f0 = 2.f * kap0, f1 = 2.f * kap1;
-#pragma unroll
-                for (int r = 0; r < FT_R; ++r) {
-                    g0[5 * tid + r] = make_float4(f0 * f4c(er[0], r), f0 * f4c(er[1], r), f1 * f4c(er[2], r), f1 * f4c(er[3], r));
-                    g1[5 * tid + r] = make_float4(f0 * f4c(er[4], r), f0 * f4c(er[5], r), f1 * f4c(er[6], r), f1 * f4c(er[7], r));
-                    s0[5 * tid + r] = make_float4(f4c(mr[0], r), f4c(mr[2], r), f4c(mr[1], r), f4c(mr[3], r));     // swizzled window
-                }
-            }
+            for (int r = 0; r < FT_R; ++r) s0[5 * tid + r] = make_float4(f4c(mr[0], r), f4c(mr[2], r), f4c(mr[1], r), f4c(mr[3], r));   // swizzled window
         }
         __syncthreads();
         const int tile_next = s_next;
-        if (tile_next < p.ntiles) {
-            const int64_t nu0 = p.sym_lo + (int64_t)tile_next * FT_T;
-            if (FAM == 0) {
-                prefetch_rows(p.rx, p.ld_rx, 4, 2 * (nu0 - FT_HP - FT_XOFF), 2 * FT_XN, p.L);
-                prefetch_rows(p.gyrows, p.B, 4, nu0, FT_T, p.B);
-            } else {
-                prefetch_rows(p.erows, p.B, 8, nu0, FT_T, p.B);
-                prefetch_rows(p.m1rows, p.B, 4, nu0 - FT_HP, FT_TE, p.B);
-            }
-        }
+        if (tile_next < p.ntiles) issue_tile(tile_next, buf ^ 1);       // lands while this tile is correlated
+        const float4 *gb = grow + (buf * NG + grow0) * FT_GROW;
 #pragma unroll 1
         for (int g = (wid >> 2); g < FT_NW; g += FT_NW / 4) {
             const int l = g * 32 + lane;                     // thread-slot whose 4 symbols this lane processes
             const int li0 = FT_R * l, uu0 = t0 - FT_HP + li0;
             if (!((uu0 >= 0) && (uu0 < p.sym_hi) && (li0 >= FT_HP) && (li0 < FT_HP + FT_T))) continue;   // halo slots own nothing
-            float4 gd[FT_R];
-#pragma unroll
-            for (int r = 0; r < FT_R; ++r) gd[r] = gsrc[5 * l + r];
+            const float4 r0 = gb[l], r1 = gb[FT_GROW + l], r2 = gb[2 * FT_GROW + l], r3 = gb[3 * FT_GROW + l];
+            const float4 gd[FT_R] = {make_float4(r0.x, r1.x, r2.x, r3.x), make_float4(r0.y, r1.y, r2.y, r3.y),
+                                     make_float4(r0.z, r1.z, r2.z, r3.z), make_float4(r0.w, r1.w, r2.w, r3.w)};
             corr4<RL::AMAX>(win, li0 + c0, gd, acc2);
         }
+        cp_async_wait_all();
         __syncthreads();
+        buf ^= 1;
         tile = tile_next;
     }
 
@@ -723,7 +740,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
 #pragma unroll
             for (int w = wid; w < FT_NW; w += 4) s += red[w * (RL::AMAX * 8) + idx];
             const int lag = a0 + a;
-            if (FAM == 1) dst[8 * M + ((o * 2 + i) * 2 + cidx) * M + (2 * MH - ph - 2 * lag)] = s;
+            if (FAM == 1) dst[8 * M + ((o * 2 + i) * 2 + cidx) * M + (2 * MH - ph - 2 * lag)] = 2.f * p.scal[DP_KAPPA_OFF + o] * s;   // gD = 2 kappa_chi e
             else dst[(o * 4 + 2 * cidx + i) * M + (2 * lag + ph)] = s;
         }
     }
@@ -742,7 +759,8 @@ static size_t fast_smem_bwd1() {
 }
 template <int MH, int FAM>
 static size_t fast_smem_taps() {
-    return (size_t)(FAM == 0 ? 2 * FT_XS + FT_ES : 3 * FT_ES) * sizeof(float4) + FT_NW * Roles<MH>::AMAX * 8 * sizeof(float) + 64;
+    return (size_t)(FAM == 0 ? 2 * FT_XS + FT_RAW + 2 * 4 * FT_GROW : FT_ES + 4 * FT_GROW + 2 * 8 * FT_GROW) * sizeof(float4) +
+           FT_NW * Roles<MH>::AMAX * 8 * sizeof(float) + 64;
 }
 
 template <typename K>
