@@ -1,0 +1,28 @@
+"""The reference's DEFAULT sweep (Eval_run_DP.py:17-49: 64-QAM, nu = 0, SNR 23 dB, M = 25, batch_len 100, lr in {2.5e-3, 2e-3, 3e-3},
+5 realisations, 170 frames of 10 000 symbols, theta drifting 0.06 pi per frame) through the batched sweep engine, wall-clocked.
+SURVEY.md §8c records what the unmodified reference converges to on this setting: SER_x/y ~ 2.5-3.5e-2 from frame 15 on, estimated
+SNR ~ 21.9 dB; the reference needs ~6 s per frame and cell on an 8-core host (15 cells x 170 frames ~ 4.3 h)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from vae_equalizer_b200 import sweep
+
+kw = dict(mod="64-QAM", sps=2, loss_type=os.environ.get("LOSS", "VAE"), channel="h0", nu_vec=[0], symb_rate_vec=[90e9], theta_vec=[np.pi / 10],
+          theta_diff_vec=[0.06 * np.pi], SNR_vec=[23], M_vec=[25], batch_len_vec=[100], flex_step_vec=[10], lr_optim_vec=[2.5e-3, 2e-3, 3e-3],
+          iter=5, N_lrhalf=170, num_frames=int(os.environ.get("FRAMES", 170)), N_frame_max=10000)
+sweep.run_dp_sweep(**{**kw, "num_frames": 2})          # warm-up (module load, cuFFT plans)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+SER, Var_est, var_real = sweep.run_dp_sweep(**kw)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+F = kw["num_frames"]
+print(f"loss_type={kw['loss_type']}: 15 cells x {F} frames x 10 000 symbols in {dt:.2f} s wall ({15 * F * 10000 / dt / 1e6:.1f} M symbols/s end to end)")
+S = SER[:, 0, 0, 0, 0, 0, :, 0, 0, 0, :, :]            # (4, lr, iter, frame)
+pm = 1.0                                               # 64-QAM unit mean power
+for l, lr in enumerate(kw["lr_optim_vec"]):
+    tail = S[:, l, :, max(15, F - 50):].mean(dim=(1, 2)).tolist()
+    snr = 10 * torch.log10(pm / Var_est[:, 0, 0, 0, 0, 0, l, 0, 0, 0, :, max(15, F - 50):].mean())      # VAELE_DP:68
+    print(f"  lr {lr:g}: SER constellation x/y {tail[0]:.4f} {tail[1]:.4f}, soft demapper x/y {tail[2]:.4f} {tail[3]:.4f} (mean of the last frames, 5 realisations); "
+          f"frame 0 SER {S[0, l, :, 0].mean():.3f}; SNR_est {float(snr):.1f} dB")
+sweep.save_mat("gpurun_out/default_sweep.mat", SER, Var_est, var_real, SNR_vec=kw["SNR_vec"], nu_vec=kw["nu_vec"], theta_diff_vec=kw["theta_diff_vec"],
+               theta_vec=kw["theta_vec"], M_vec=kw["M_vec"], lr_optim_vec=kw["lr_optim_vec"], batch_len_vec=kw["batch_len_vec"],
+               symb_rate_vec=kw["symb_rate_vec"], flex_step_vec=kw["flex_step_vec"])
