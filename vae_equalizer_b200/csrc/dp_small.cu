@@ -18,12 +18,23 @@
 
 namespace vaeq {
 
+#ifdef VAEQ_SMALL_TIMING
+__device__ unsigned long long g_small_cyc[16];
+#define ST_DECL long long _st = clock64(); unsigned long long _sa[16] = {0};
+#define ST(i) { __syncthreads(); long long _n = clock64(); _sa[i] += (unsigned long long)(_n - _st); _st = _n; }
+#define ST_END if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 16; ++i) g_small_cyc[i] = _sa[i];
+#else
+#define ST_DECL
+#define ST(i)
+#define ST_END
+#endif
+
 constexpr int SM_NT = 256;
 
 // shared-memory plan (offsets in floats); doubles first (8-byte aligned), then float4 arrays, then floats
 struct SmallLayout {
     int XA, XO, SA, SO;                     // phase-array lengths (float4) and zero margins of x and e
-    int dsc, xph, m1s, eph, gys, Wt, hD, hG, part4, cst, ys, srow, vsc, PSg, Wf, hf, adam, gfin, Ssh, hsq, red, scal, total;
+    int dsc, xph, m1s, eph, gys, Wt, hD, hG, part4, cst, srow, vsc, PS, Asum, edge, Wf, hf, adam, gfin, hsq, red, scal, total;
 };
 __host__ __device__ inline SmallLayout small_layout(int B, int M) {
     SmallLayout l;
@@ -38,34 +49,42 @@ __host__ __device__ inline SmallLayout small_layout(int B, int M) {
         off += (nfloats + 3) & ~3;          // keep 16-byte alignment throughout
         return o;
     };
-    l.dsc = take(2 * 12);                   // 12 doubles: tot[5], Esh[2], bc1, spare
-    l.xph = take(4 * 2 * l.XA);
+    l.dsc = take(2 * 4);                    // doubles: bc1 (Adam bias correction)
+    l.xph = take(2 * 4 * 2 * l.XA);         // double-buffered: the next step's window lands by cp.async during this step
     l.m1s = take(4 * B);
     l.eph = take(4 * 2 * l.SA);
     l.gys = take(4 * B);
     l.Wt = take(4 * 2 * M);
     l.hD = take(4 * 2 * M);
     l.hG = take(4 * 2 * M);
-    l.part4 = take(4 * SM_NT);
+    l.part4 = take(4 * 2 * SM_NT);
     l.cst = take((int)(sizeof(FastConst) / 4));
-    l.ys = take(4 * B);
     l.srow = take(12 * B);
     l.vsc = take(4 * B);
-    l.PSg = take(2 * (M + 1));
+    l.PS = take(4 * (M + 1));
+    l.Asum = take(4);
+    l.edge = take(2 * M);
     l.Wf = take(8 * M);
     l.hf = take(8 * M);
     l.adam = take(48 * M);
     l.gfin = take(16 * M);
-    l.Ssh = take(2 * M);
     l.hsq = take(4 * M);
-    l.red = take(5 * 32);
+    l.red = take(7 * 32);
     l.scal = take(8);
     l.total = off;
     return l;
 }
 
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+
+#ifndef SM_MINB
+#define SM_MINB 3          // 85 registers: 3 CTAs (runs) per SM; 98 registers uncapped = 2 CTAs, 64 = 4 CTAs with spills (profiles/r01b_experiments.txt)
+#endif
 template <int NL>
-__global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int n_steps, int stride_sym, int keep_lo_in_dst,
+__global__ void __launch_bounds__(SM_NT, SM_MINB) k_dp_frame_fast(DpK p, DpRunsK rs, int n_steps, int stride_sym, int keep_lo_in_dst,
                                                          float lr_w, float lr_h, int amsgrad) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -73,17 +92,18 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
     const SmallLayout lay = small_layout(B, M);
     const int XA = lay.XA, XO = lay.XO, SA = lay.SA, SO = lay.SO;
     double *dsc = reinterpret_cast<double *>(sm + lay.dsc);
-    float4 *xph = reinterpret_cast<float4 *>(sm + lay.xph);      // [2][XA]  rx phases {I0,Q0,I1,Q1}: xph[ph][a+XO] = rx[:, 2a+ph]
+    float4 *xph2 = reinterpret_cast<float4 *>(sm + lay.xph);     // [2 buffers][2 phases][XA]  rx {I0,Q0,I1,Q1}: [ph][a+XO] = rx[:, 2a+ph]
     float4 *m1s = reinterpret_cast<float4 *>(sm + lay.m1s);      // [B]      E_q[x] {p0 I, p0 Q, p1 I, p1 Q}
     float4 *eph = reinterpret_cast<float4 *>(sm + lay.eph);      // [2][SA]  residual D - rx {chi0 re, im, chi1 re, im} by sample phase
     float4 *gys = reinterpret_cast<float4 *>(sm + lay.gys);      // [B]      dL/dout
     float4 *Wt = reinterpret_cast<float4 *>(sm + lay.Wt);        // [o][k]   {wr<-p0, wi<-p0, wr<-p1, wi<-p1}
     float4 *hD = reinterpret_cast<float4 *>(sm + lay.hD);        // [chi][j] {h_chi,0 re, im, h_chi,1 re, im}
-    float4 *hG = reinterpret_cast<float4 *>(sm + lay.hG);        // [nu][j]  2 kappa_chi * {h_0,nu re, im, h_1,nu re, im}
+    float4 *hG = reinterpret_cast<float4 *>(sm + lay.hG);        // [nu][j]  {h_0,nu re, im, h_1,nu re, im}   (kappa applied at use)
     float4 *part4 = reinterpret_cast<float4 *>(sm + lay.part4);
     FastConst *cst = reinterpret_cast<FastConst *>(sm + lay.cst);
-    float *ys = sm + lay.ys, *srow = sm + lay.srow, *vsc = sm + lay.vsc, *PSg = sm + lay.PSg, *Wf = sm + lay.Wf, *hf = sm + lay.hf;
-    float *ad = sm + lay.adam, *gfin = sm + lay.gfin, *Ssh = sm + lay.Ssh, *hsq = sm + lay.hsq, *red = sm + lay.red, *scal = sm + lay.scal;
+    float *srow = sm + lay.srow, *vsc = sm + lay.vsc, *PS = sm + lay.PS, *Asum = sm + lay.Asum, *edge = sm + lay.edge;
+    float *Wf = sm + lay.Wf, *hf = sm + lay.hf, *ad = sm + lay.adam, *gfin = sm + lay.gfin, *hsq = sm + lay.hsq, *red = sm + lay.red;
+    float *scal = sm + lay.scal;
 
     // ---- this run's tensors (blockIdx.x = run) ---------------------------------------------------------------------
     const float *rx0 = p.rx + run * rs.rs_rx;
@@ -93,49 +113,93 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
     if (rs.lr_h) lr_h = rs.lr_h[run];
     const float nu_sc = rs.nu_sc ? rs.nu_sc[run] : p.nu_sc;
 
+    // the rx window of step m -> phase arrays of buffer m & 1: 4-byte cp.async scatter (4 rows -> one float4 per position);
+    // positions outside [0, L) are the FIR's zero padding, the same in every step: zeroed once below
+    auto issue_window = [&](int m) {
+        const float *rx = rx0 + (int64_t)m * stride_sym * 2;
+        float4 *dst = xph2 + (m & 1) * 2 * XA;
+        for (int idx = tid; idx < 2 * XA; idx += SM_NT) {
+            const int ph = idx >= XA, a = idx - ph * XA - XO, s = 2 * a + ph;
+            if (s >= 0 && s < L) {
+                float *d4 = reinterpret_cast<float *>(dst + idx);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) cp_async4(d4 + r, rx + r * p.ld_rx + s);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     for (int i = tid; i < 8 * M; i += SM_NT) {
         Wf[i] = Wg[i];
         hf[i] = hg[i];
     }
     for (int i = tid; i < 48 * M; i += SM_NT) ad[i] = adg[i];
     for (int i = tid; i < 2 * SA; i += SM_NT) eph[i] = make_float4(0.f, 0.f, 0.f, 0.f);     // margins stay zero for the whole frame
+    for (int i = tid; i < 4 * XA; i += SM_NT) xph2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     load_fast_const(cst, p.amp + run * rs.rs_amp, p.P + run * rs.rs_P, p.var + run * rs.rs_var, nu_sc, NL);
     const int step0 = *reinterpret_cast<const int *>(adg + 48 * M);
     const double width = (double)(L - Mh);
+    double b1t = 1.0, b2t = 1.0;                             // beta1^t, beta2^t at the step count the frame starts from
+    if (tid == 0) {
+        b1t = pow(0.9, (double)step0);
+        b2t = pow(0.999, (double)step0);
+    }
     __syncthreads();
+    if (n_steps > 0) issue_window(0);
     const FastConst &c = *cst;
 
+    ST_DECL
     for (int m = 0; m < n_steps; ++m) {
-        const float *rx = rx0 + (int64_t)m * stride_sym * 2;
         const int64_t keep_base = (int64_t)m * stride_sym + (keep_lo_in_dst ? p.keep_lo : 0);
         const bool last = m == n_steps - 1;
+        const float4 *xph = xph2 + (m & 1) * 2 * XA;
 
-        // ---- P0: tap tables from the master copies, rx window -> phase arrays (zero padded), Adam bias corrections ------
+        // ---- P0: tap tables from the master copies; |h|^2, its prefix sums over the taps and totals (warp scans) -----------
         for (int idx = tid; idx < 2 * M; idx += SM_NT) {
             const int o = idx / M, k = idx - o * M;
             Wt[idx] = make_float4(Wf[(o * 4 + 0) * M + k], Wf[(o * 4 + 2) * M + k], Wf[(o * 4 + 1) * M + k], Wf[(o * 4 + 3) * M + k]);
             hD[idx] = make_float4(hf[((o * 2 + 0) * 2 + 0) * M + k], hf[((o * 2 + 0) * 2 + 1) * M + k],
                                   hf[((o * 2 + 1) * 2 + 0) * M + k], hf[((o * 2 + 1) * 2 + 1) * M + k]);
+            hG[idx] = make_float4(hf[((0 * 2 + o) * 2 + 0) * M + k], hf[((0 * 2 + o) * 2 + 1) * M + k],
+                                  hf[((1 * 2 + o) * 2 + 0) * M + k], hf[((1 * 2 + o) * 2 + 1) * M + k]);
         }
-        for (int i = tid; i < 4 * M; i += SM_NT) {
-            const int cn = i / M, j = i - cn * M;
-            const float hr = hf[(cn * 2 + 0) * M + j], hi = hf[(cn * 2 + 1) * M + j];
-            hsq[i] = hr * hr + hi * hi;
+        if (wid >= 4) {                                      // warp 4 + cn: PS[cn][j] = sum_{j' < j} |h_cn,j'|^2, cn = chi * 2 + nu
+            const int cn = wid - 4;
+            float carry = 0.f;
+            if (lane == 0) PS[cn * (M + 1)] = 0.f;
+            for (int j0 = 0; j0 < M; j0 += 32) {
+                const int j = j0 + lane;
+                float v = 0.f;
+                if (j < M) {
+                    const float hr = hf[(cn * 2 + 0) * M + j], hi = hf[(cn * 2 + 1) * M + j];
+                    v = hr * hr + hi * hi;
+                    hsq[cn * M + j] = v;
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += t;
+                }
+                v += carry;
+                if (j < M) PS[cn * (M + 1) + j + 1] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+            if (lane == 0) Asum[cn] = carry;
         }
-        for (int idx = tid; idx < 2 * XA; idx += SM_NT) {
-            const int ph = idx >= XA, a = idx - ph * XA - XO, s = 2 * a + ph;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s >= 0 && s < L) v = make_float4(rx[s], rx[p.ld_rx + s], rx[2 * p.ld_rx + s], rx[3 * p.ld_rx + s]);
-            xph[idx] = v;
+        if (tid == 0) {                                      // Adam bias corrections 1 - beta^t: running products (pow once per frame)
+            b1t *= 0.9;
+            b2t *= 0.999;
+            dsc[0] = 1.0 - b1t;
+            scal[6] = sqrtf((float)(1.0 - b2t));
         }
-        if (tid == SM_NT - 1) {
-            float bc2s;
-            adam_bias(step0 + m + 1, &dsc[8], &bc2s);
-            scal[6] = bc2s;
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // this step's window (issued during the previous step)
         __syncthreads();
+        if (!last) issue_window(m + 1);                      // lands in the other buffer while this step computes
 
-        // ---- P1: butterfly FIR (sf:500-518), one (symbol, output pol) item per thread --------------------------------
+        ST(0)
+        // ---- P1: butterfly FIR (sf:500-518) + soft demapper, moments, entropy, backward coefficients (sf:511-523, 101-113):
+        //      one (symbol, output pol) item per thread, its two components demapped right away ------------------------------
+        float accEnt = 0.f, accV0 = 0.f, accV1 = 0.f;
         for (int it = tid; it < 2 * B; it += SM_NT) {
             const int o = it >= B, u = it - o * B;
             float reA = 0.f, reB = 0.f, imA = 0.f, imB = 0.f;
@@ -154,36 +218,36 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
                     imB = fmaf(w.z, x.w, imB); imB = fmaf(w.w, x.z, imB);
                 }
             }
-            ys[(2 * o) * B + u] = reA + reB;
-            ys[(2 * o + 1) * B + u] = imA + imB;
-        }
-        __syncthreads();
-
-        // ---- P2: soft demapper + moments + entropy + backward coefficients, one (symbol, component) item per thread ----
-        float accEnt = 0.f, accV0 = 0.f, accV1 = 0.f;
-        for (int it = tid; it < 4 * B; it += SM_NT) {
-            const int cc = it / B, u = it - cc * B, pol = cc >> 1;
-            const float y = ys[it];
-            float q[NL], m1, m2, ent, S1, S2, S3;
-            demap_fast<NL, true>(y, c.c2[pol], c.inv_var[pol], c, q, m1, m2, ent, S1, S2, S3);
-            if (qk != nullptr && u >= p.keep_lo && u < p.keep_lo + p.keep_n) {       // VAELE_DP:61-62 / VAEflex_DP:64-65
-                const int64_t col = keep_base + (u - p.keep_lo);
+            const float yc[2] = {reA + reB, imA + imB};
+            const bool keep = qk != nullptr && u >= p.keep_lo && u < p.keep_lo + p.keep_n;      // VAELE_DP:61-62 / VAEflex_DP:64-65
+            const int64_t col = keep_base + (u - p.keep_lo);
+            float vsum = 0.f;
 #pragma unroll
-                for (int l = 0; l < NL; ++l) qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = q[l];
-                outk[(int64_t)cc * p.ld_outk + col] = y;
+            for (int cq = 0; cq < 2; ++cq) {
+                const int cc = 2 * o + cq;
+                float q[NL], m1, m2, ent, S1, S2, S3;
+                demap_fast<NL, true>(yc[cq], c.c2[o], c.inv_var[o], c, q, m1, m2, ent, S1, S2, S3);
+                if (keep) {
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = q[l];
+                    outk[(int64_t)cc * p.ld_outk + col] = yc[cq];
+                }
+                reinterpret_cast<float *>(m1s + u)[cc] = m1;
+                srow[cc * B + u] = S1;
+                srow[(4 + cc) * B + u] = fmaf(-2.f * m1, S1, S2);
+                srow[(8 + cc) * B + u] = S3;
+                vsum += m2 - m1 * m1;                                                    // sf:113
+                if (u >= mh && u < B - mh) accEnt += ent;                                // sf:132: [mh:-mh] in SYMBOLS
             }
-            reinterpret_cast<float *>(m1s + u)[cc] = m1;
-            srow[cc * B + u] = S1;
-            srow[(4 + cc) * B + u] = fmaf(-2.f * m1, S1, S2);
-            srow[(8 + cc) * B + u] = S3;
-            const float v = m2 - m1 * m1;                                            // sf:113
-            vsc[it] = v;
-            if (pol) accV1 += v; else accV0 += v;
-            if (u >= mh && u < B - mh) accEnt += ent;                                // sf:132: [mh:-mh] in SYMBOLS
+            vsc[o * B + u] = vsum;                                                       // Var_I + Var_Q of pol o
+            if (o) accV1 += vsum; else accV0 += vsum;
         }
         __syncthreads();
 
-        // ---- P3: D = h * E_q on the valid samples, residual e = D - rx (sf:115-134), one (sample, rx pol) item per thread --
+        ST(1)
+        ST(2)
+        // ---- P3: D = h * E_q on the valid samples, residual e = D - rx (sf:115-134), one (sample, rx pol) item per thread;
+        //      then the edge sums of S_nu(j) = V_nu - edge_nu(j) (Var over source symbols outside Mh <= 2u+j < L, sf:128) --------
         float accC0 = 0.f, accC1 = 0.f;
         for (int it = tid; it < 2 * L; it += SM_NT) {
             const int chi = it >= L, s = it - chi * L;
@@ -210,70 +274,50 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
             const float e2 = er * er + ei * ei;
             if (chi) accC1 += e2; else accC0 += e2;
         }
-
-        // ---- P4: ELBO scalars (sf:131-137): C, loss, var_est, kappa = (L-Mh)/C, S_nu(j) ------------------------------------
-        {
-            float v[5] = {accC0, accC1, accEnt, accV0, accV1};
-            block_sum<5>(v, red);                                                    // has the barriers that publish eph
-            if (tid == 0) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) dsc[i] = (double)v[i];
-            }
-        }
-        __syncthreads();
-        for (int idx = tid; idx < 2 * M; idx += SM_NT) {                             // S_nu(j): Var sum over Mh <= 2u+j < L (sf:128)
+        float accB0 = 0.f, accB1 = 0.f;                          // sum_{nu,j} |h_chi,nu,j|^2 edge_nu(j); on the LAST 2M threads,
+        for (int idx = tid - (SM_NT - 2 * M); idx >= 0 && idx < 2 * M; idx += SM_NT) {      // which have the fewest D items above
             const int nu = idx / M, j = idx - nu * M;
-            double s = dsc[3 + nu];
             const int u_lo = (Mh - j + 1) >> 1, u_hi = (L - 1 - j) >> 1;
-            for (int u = 0; u < u_lo && u < B; ++u) s -= (double)(vsc[(2 * nu) * B + u] + vsc[(2 * nu + 1) * B + u]);
-            for (int u = u_hi + 1; u < B; ++u) s -= (double)(vsc[(2 * nu) * B + u] + vsc[(2 * nu + 1) * B + u]);
-            Ssh[idx] = (float)s;
+            float ed = 0.f;
+            for (int u = 0; u < u_lo && u < B; ++u) ed += vsc[nu * B + u];
+            for (int u = u_hi + 1; u < B; ++u) ed += vsc[nu * B + u];
+            edge[idx] = ed;
+            accB0 += hsq[idx] * ed;
+            accB1 += hsq[2 * M + idx] * ed;
         }
-        __syncthreads();
-        if (wid < 2) {                                                               // E_chi = sum |h|^2 S_nu(j)  (sf:129)
-            double E = 0.0;
-            for (int idx = lane; idx < 2 * M; idx += 32) E += (double)hsq[wid * 2 * M + idx] * (double)Ssh[idx];
-            E = warp_sum(E);
-            if (lane == 0) dsc[5 + wid] = E;
-        }
-        __syncthreads();
-        if (tid < 2) {
-            const int chi = tid;
-            const double C = dsc[chi] + dsc[5 + chi];                                // sf:133-134
-            const double term = width * log(C);                                      // sf:136
-            scal[chi] = (float)(width / C);                                          // kappa
-            const float ve = (float)(C / width);                                     // sf:137
-            if (rs.var_steps) rs.var_steps[((int64_t)run * 2 + chi) * n_steps + m] = ve;
-            if (last && rs.var_last) rs.var_last[2 * run + chi] = ve;
-            const double term1 = __shfl_sync(0x3u, term, 1);
-            if (chi == 0) {
-                const float loss = (float)((-dsc[2] + term) + term1);
-                if (rs.loss_steps) rs.loss_steps[(int64_t)run * n_steps + m] = loss;
-                if (last && rs.loss_last) rs.loss_last[run] = loss;
+
+        ST(3)
+        // ---- P4: ELBO scalars (sf:131-137): C = sum|e|^2 + sum_nu V_nu A_chi,nu - B_chi, loss, var_est, kappa = (L-Mh)/C ---------
+        {
+            float v[7] = {accC0, accC1, accEnt, accV0, accV1, accB0, accB1};
+            block_sum<7>(v, red);                                // its barriers also publish eph and edge; totals in ALL lanes of warp 0
+            if (tid < 2) {
+                const int chi = tid;
+                const double C = (double)v[chi] + ((double)v[3] * (double)Asum[chi * 2] + (double)v[4] * (double)Asum[chi * 2 + 1]) -
+                                 (double)v[5 + chi];                                 // sf:133-134
+                const double term = width * log(C);                                  // sf:136
+                scal[chi] = (float)(width / C);                                      // kappa
+                scal[2 + chi] = v[3 + chi];                                          // V_nu, for S_nu(j) in the Adam phase
+                const float ve = (float)(C / width);                                 // sf:137
+                if (rs.var_steps) rs.var_steps[((int64_t)run * 2 + chi) * n_steps + m] = ve;
+                if (last && rs.var_last) rs.var_last[2 * run + chi] = ve;
+                const double term1 = __shfl_sync(0x3u, term, 1);
+                if (chi == 0) {
+                    const float loss = (float)((-(double)v[2] + term) + term1);
+                    if (rs.loss_steps) rs.loss_steps[(int64_t)run * n_steps + m] = loss;
+                    if (last && rs.loss_last) rs.loss_last[run] = loss;
+                }
             }
         }
         __syncthreads();
         const float kap0 = scal[0], kap1 = scal[1];
-        for (int idx = tid; idx < 2 * M; idx += SM_NT) {                             // conj(h) taps of dL/dE_q, scaled by 2 kappa_chi
-            const int nu = idx / M, j = idx - nu * M;
-            hG[idx] = make_float4(2.f * kap0 * hf[((0 * 2 + nu) * 2 + 0) * M + j], 2.f * kap0 * hf[((0 * 2 + nu) * 2 + 1) * M + j],
-                                  2.f * kap1 * hf[((1 * 2 + nu) * 2 + 0) * M + j], 2.f * kap1 * hf[((1 * 2 + nu) * 2 + 1) * M + j]);
-        }
-        if (tid >= 32 && tid < 34) {                                                 // dL/dVar prefix sums over the taps
-            const int nu = tid - 32;
-            float a = 0.f;
-            PSg[nu * (M + 1)] = 0.f;
-            for (int j = 0; j < M; ++j) {
-                a += kap0 * hsq[(0 * 2 + nu) * M + j] + kap1 * hsq[(1 * 2 + nu) * M + j];
-                PSg[nu * (M + 1) + j + 1] = a;
-            }
-        }
-        __syncthreads();
 
-        // ---- P5: dL/dE_q = conj(h) (*) gD, then dL/dout = dL/dE_q S1 + dL/dVar T2 + w S3; one (symbol, tx pol) item per thread --
+        ST(4)
+        // ---- P5: dL/dE_q = conj(h) (*) gD with gD = 2 kappa_chi e, then dL/dout = dL/dE_q S1 + dL/dVar T2 + w S3;
+        //      one (symbol, tx pol) item per thread ----------------------------------------------------------------------------
         for (int it = tid; it < 2 * B; it += SM_NT) {
             const int nu = it >= B, u = it - nu * B;
-            float grA = 0.f, grB = 0.f, giA = 0.f, giB = 0.f;
+            float grA = 0.f, grB = 0.f, giA = 0.f, giB = 0.f;            // A: chi = 0 terms, B: chi = 1 terms
 #pragma unroll
             for (int ph = 0; ph < 2; ++ph) {
                 const int j0 = (mh + ph) & 1;                    // gD sample 2u - mh + j has phase ph for j = j0, j0+2, ...
@@ -289,87 +333,104 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
                     giB = fmaf(hh.z, e.w, giB); giB = fmaf(-hh.w, e.z, giB);
                 }
             }
+            const float gr = 2.f * (kap0 * grA + kap1 * grB), gi = 2.f * (kap0 * giA + kap1 * giB);
             const int jlo = max(0, Mh - 2 * u), jhi = min(M, L - 2 * u);
-            const float gV = PSg[nu * (M + 1) + jhi] - PSg[nu * (M + 1) + jlo];
+            const float gV = kap0 * (PS[(0 * 2 + nu) * (M + 1) + jhi] - PS[(0 * 2 + nu) * (M + 1) + jlo]) +
+                             kap1 * (PS[(1 * 2 + nu) * (M + 1) + jhi] - PS[(1 * 2 + nu) * (M + 1) + jlo]);
             const float entw = (u >= mh && u < B - mh) ? LN2 : 0.f;
             const int cc = 2 * nu;
-            const float gI = fmaf(grA + grB, srow[cc * B + u], fmaf(gV, srow[(4 + cc) * B + u], entw * srow[(8 + cc) * B + u]));
-            const float gQ = fmaf(giA + giB, srow[(cc + 1) * B + u], fmaf(gV, srow[(5 + cc) * B + u], entw * srow[(9 + cc) * B + u]));
+            const float gI = fmaf(gr, srow[cc * B + u], fmaf(gV, srow[(4 + cc) * B + u], entw * srow[(8 + cc) * B + u]));
+            const float gQ = fmaf(gi, srow[(cc + 1) * B + u], fmaf(gV, srow[(5 + cc) * B + u], entw * srow[(9 + cc) * B + u]));
             reinterpret_cast<float2 *>(gys + u)[nu] = make_float2(gI, gQ);
         }
         __syncthreads();
 
-        // ---- P6: tap gradients.  item < 2M: dW[o=0,1][in][k] = sum_u gy_o(u) conj(x_in[2u+k-mh]);
-        //          item >= 2M: dh[chi=0,1][nu][j] = 2 kappa_chi sum_v e_chi(2v+j-mh) conj(E_q,nu[v]).  The symbol range is cut
-        //          into `parts` chunks so that all threads work; partials are summed in fixed order (deterministic).
+        ST(5)
+        // ---- P6: tap gradients.  Warps 0-3: dW[o=0,1][in][k] = sum_u gy_o(u) conj(x_in[2u+k-mh]); warps 4-7:
+        //      dh[chi=0,1][nu][j] = 2 kappa_chi sum_v e_chi(2v+j-mh) conj(E_q,nu[v]) (warp-uniform roles).  A thread owns a PAIR of
+        //      neighbouring taps of one sample phase (k, k+2): their windows are one position apart, so one LDS.128 of the window
+        //      and one broadcast of the per-symbol operand feed 16 FMA (the phase was shared-memory-bandwidth bound with one tap
+        //      per thread).  The symbol range is cut into `parts` chunks so that all 128 threads of a family work; partials are
+        //      summed in fixed order (deterministic).
         {
-            const int items = 4 * M, parts = max(1, SM_NT / items), chunk = (B + parts - 1) / parts;
-            if (tid < items * parts) {
-                const int item = tid % items, part = tid / items;
-                const int u0 = part * chunk, u1 = min(B, u0 + chunk);
-                float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
-                if (item < 2 * M) {
-                    const int in = item / M, k = item - in * M;
-                    const int t = k - mh, ph = t & 1;
-                    const float4 *xb = xph + ph * XA + XO + ((t - ph) >> 1);
+            const int kf0 = mh & 1, kf1 = (mh + 1) & 1;                               // first tap of phase 0 / 1
+            const int np0 = (((M - kf0 + 1) >> 1) + 1) >> 1, np1 = (((M - kf1 + 1) >> 1) + 1) >> 1, nps = np0 + np1;
+            const int items = 2 * nps, parts = max(1, 128 / items), chunk = (B + parts - 1) / parts;
+            const int fam = wid >> 2, ft = tid & 127;
+            if (ft < items * parts) {
+                const int item = ft % items, part = ft / items;
+                const int sel = item / nps, q = item - sel * nps, ph = q >= np0, kA = (ph ? kf1 : kf0) + 4 * (ph ? q - np0 : q);
+                const int u0 = part * chunk, u1 = min(B, u0 + chunk), off = (kA - mh - ph) >> 1;
+                float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f, b0r = 0.f, b0i = 0.f, b1r = 0.f, b1i = 0.f;
+                if (fam == 0) {                                  // f = dL/dout {o0 re, im, o1 re, im}; window = rx of input pol sel
+                    const float2 *wb = reinterpret_cast<const float2 *>(xph + ph * XA + XO + off) + sel;     // (I, Q) of pol sel
+                    float2 wa = wb[2 * u0];
 #pragma unroll 4
                     for (int u = u0; u < u1; ++u) {
-                        const float4 x = xb[u], g = gys[u];
-                        const float a = in ? x.z : x.x, b = in ? x.w : x.y;
-                        a0r = fmaf(g.x, a, a0r); a0r = fmaf(g.y, b, a0r);
-                        a0i = fmaf(g.y, a, a0i); a0i = fmaf(-g.x, b, a0i);
-                        a1r = fmaf(g.z, a, a1r); a1r = fmaf(g.w, b, a1r);
-                        a1i = fmaf(g.w, a, a1i); a1i = fmaf(-g.z, b, a1i);
+                        const float2 wn = wb[2 * (u + 1)];
+                        const float4 f = gys[u];
+                        a0r = fmaf(f.x, wa.x, a0r); a0r = fmaf(f.y, wa.y, a0r); a0i = fmaf(f.y, wa.x, a0i); a0i = fmaf(-f.x, wa.y, a0i);
+                        a1r = fmaf(f.z, wa.x, a1r); a1r = fmaf(f.w, wa.y, a1r); a1i = fmaf(f.w, wa.x, a1i); a1i = fmaf(-f.z, wa.y, a1i);
+                        b0r = fmaf(f.x, wn.x, b0r); b0r = fmaf(f.y, wn.y, b0r); b0i = fmaf(f.y, wn.x, b0i); b0i = fmaf(-f.x, wn.y, b0i);
+                        b1r = fmaf(f.z, wn.x, b1r); b1r = fmaf(f.w, wn.y, b1r); b1i = fmaf(f.w, wn.x, b1i); b1i = fmaf(-f.z, wn.y, b1i);
+                        wa = wn;
                     }
-                } else {
-                    const int it2 = item - 2 * M, nu = it2 / M, j = it2 - nu * M;
-                    const int t = j - mh, ph = t & 1;
-                    const float4 *eb = eph + ph * SA + SO + ((t - ph) >> 1);
+                } else {                                         // window = residual e {chi0 re, im, chi1 re, im}; f = E_q of tx pol sel
+                    const float4 *wb = eph + ph * SA + SO + off;
+                    const float2 *fb = reinterpret_cast<const float2 *>(m1s) + sel;
+                    float4 wa = wb[u0];
 #pragma unroll 4
-                    for (int v = u0; v < u1; ++v) {
-                        const float4 e = eb[v], mm = m1s[v];
-                        const float a = nu ? mm.z : mm.x, b = nu ? mm.w : mm.y;
-                        a0r = fmaf(e.x, a, a0r); a0r = fmaf(e.y, b, a0r);
-                        a0i = fmaf(e.y, a, a0i); a0i = fmaf(-e.x, b, a0i);
-                        a1r = fmaf(e.z, a, a1r); a1r = fmaf(e.w, b, a1r);
-                        a1i = fmaf(e.w, a, a1i); a1i = fmaf(-e.z, b, a1i);
+                    for (int u = u0; u < u1; ++u) {
+                        const float4 wn = wb[u + 1];
+                        const float2 f = fb[2 * u];
+                        a0r = fmaf(wa.x, f.x, a0r); a0r = fmaf(wa.y, f.y, a0r); a0i = fmaf(wa.y, f.x, a0i); a0i = fmaf(-wa.x, f.y, a0i);
+                        a1r = fmaf(wa.z, f.x, a1r); a1r = fmaf(wa.w, f.y, a1r); a1i = fmaf(wa.w, f.x, a1i); a1i = fmaf(-wa.z, f.y, a1i);
+                        b0r = fmaf(wn.x, f.x, b0r); b0r = fmaf(wn.y, f.y, b0r); b0i = fmaf(wn.y, f.x, b0i); b0i = fmaf(-wn.x, f.y, b0i);
+                        b1r = fmaf(wn.z, f.x, b1r); b1r = fmaf(wn.w, f.y, b1r); b1i = fmaf(wn.w, f.x, b1i); b1i = fmaf(-wn.z, f.y, b1i);
+                        wa = wn;
                     }
                 }
-                part4[part * items + item] = make_float4(a0r, a0i, a1r, a1i);
+                part4[(fam * 128 + part * items + item) * 2] = make_float4(a0r, a0i, a1r, a1i);
+                part4[(fam * 128 + part * items + item) * 2 + 1] = make_float4(b0r, b0i, b1r, b1i);
             }
             __syncthreads();
-            if (tid < items) {
-                float4 s = part4[tid];
-                for (int part = 1; part < parts; ++part) {
-                    const float4 t4 = part4[part * items + tid];
-                    s.x += t4.x; s.y += t4.y; s.z += t4.z; s.w += t4.w;
-                }
-                if (tid < 2 * M) {
-                    const int in = tid / M, k = tid - in * M;
-                    gfin[(0 * 4 + in) * M + k] = s.x;
-                    gfin[(0 * 4 + 2 + in) * M + k] = s.y;
-                    gfin[(1 * 4 + in) * M + k] = s.z;
-                    gfin[(1 * 4 + 2 + in) * M + k] = s.w;
-                } else {
-                    const int it2 = tid - 2 * M, nu = it2 / M, j = it2 - nu * M;
-                    gfin[8 * M + ((0 * 2 + nu) * 2 + 0) * M + j] = 2.f * kap0 * s.x;
-                    gfin[8 * M + ((0 * 2 + nu) * 2 + 1) * M + j] = 2.f * kap0 * s.y;
-                    gfin[8 * M + ((1 * 2 + nu) * 2 + 0) * M + j] = 2.f * kap1 * s.z;
-                    gfin[8 * M + ((1 * 2 + nu) * 2 + 1) * M + j] = 2.f * kap1 * s.w;
+            if (ft < 2 * items) {                                // one thread per (item, tap of the pair)
+                const int item = ft >> 1, tb = ft & 1;
+                const int sel = item / nps, q = item - sel * nps, ph = q >= np0, kA = (ph ? kf1 : kf0) + 4 * (ph ? q - np0 : q);
+                const int kk = kA + 2 * tb;
+                if (kk < M) {
+                    float4 sacc = part4[(fam * 128 + item) * 2 + tb];
+                    for (int part = 1; part < parts; ++part) {
+                        const float4 t4 = part4[(fam * 128 + part * items + item) * 2 + tb];
+                        sacc.x += t4.x; sacc.y += t4.y; sacc.z += t4.z; sacc.w += t4.w;
+                    }
+                    if (fam == 0) {
+                        gfin[(0 * 4 + sel) * M + kk] = sacc.x;
+                        gfin[(0 * 4 + 2 + sel) * M + kk] = sacc.y;
+                        gfin[(1 * 4 + sel) * M + kk] = sacc.z;
+                        gfin[(1 * 4 + 2 + sel) * M + kk] = sacc.w;
+                    } else {
+                        gfin[8 * M + ((0 * 2 + sel) * 2 + 0) * M + kk] = 2.f * kap0 * sacc.x;
+                        gfin[8 * M + ((0 * 2 + sel) * 2 + 1) * M + kk] = 2.f * kap0 * sacc.y;
+                        gfin[8 * M + ((1 * 2 + sel) * 2 + 0) * M + kk] = 2.f * kap1 * sacc.z;
+                        gfin[8 * M + ((1 * 2 + sel) * 2 + 1) * M + kk] = 2.f * kap1 * sacc.w;
+                    }
                 }
             }
             __syncthreads();
         }
 
-        // ---- P7: E-term of dh, Adam on both parameter groups (VAELE_DP:28-31,66), one parameter per thread -----------------
+        ST(6)
+        // ---- P7: E-term of dh (2 kappa_chi h S_nu(j), S = V_nu - edge), Adam on both parameter groups (VAELE_DP:28-31,66) -----
         {
-            const double bc1 = dsc[8];
+            const double bc1 = dsc[0];
             const float bc2s = scal[6];
             for (int i = tid; i < 16 * M; i += SM_NT) {
                 float g = gfin[i];
                 if (i >= 8 * M) {
                     const int r = i - 8 * M, j = r % M, cn = r / (2 * M), chi = cn >> 1, nu = cn & 1;
-                    g = (float)((double)g + 2.0 * (double)(chi ? kap1 : kap0) * (double)hf[r] * (double)Ssh[nu * M + j]);
+                    const float S = scal[2 + nu] - edge[nu * M + j];
+                    g = (float)((double)g + 2.0 * (double)(chi ? kap1 : kap0) * (double)hf[r] * (double)S);
                 }
                 if (last) {
                     if (i < 8 * M) {
@@ -383,7 +444,9 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
             }
         }
         __syncthreads();
+        ST(7)
     }
+    ST_END
 
     // ---- write the trained state back -------------------------------------------------------------------------------
     for (int i = tid; i < 8 * M; i += SM_NT) {
@@ -393,6 +456,12 @@ __global__ void __launch_bounds__(SM_NT) k_dp_frame_fast(DpK p, DpRunsK rs, int 
     for (int i = tid; i < 48 * M; i += SM_NT) adg[i] = ad[i];
     if (tid == 0) *reinterpret_cast<int *>(adg + 48 * M) = step0 + n_steps;
 }
+
+#ifdef VAEQ_SMALL_TIMING
+}
+extern "C" int vaeq_debug_small_cycles(unsigned long long *out16) { return (int)cudaMemcpyFromSymbol(out16, vaeq::g_small_cyc, 16 * sizeof(unsigned long long)); }
+namespace vaeq {
+#endif
 
 size_t dp_small_smem(int B, int M) { return (size_t)small_layout(B, M).total * sizeof(float); }
 
