@@ -146,7 +146,7 @@ int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stre
 int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32_t stride_sym, int32_t keep_lo_in_dst,
                         float lr_w, float lr_h, float *loss_steps, float *var_est_steps, void *stream);
 
-/* Reference-size minibatches (batch_len <= 512, Eval_run_DP.py:38 uses 100): vaeq_dp_train_frame runs the whole frame in
+/* Reference-size minibatches (batch_len <= 1000, Eval_run_DP.py:38 uses 100): vaeq_dp_train_frame runs the whole frame in
  * ONE persistent launch: one CTA walks the sequential steps with taps, Adam state and all intermediates in shared memory
  * (dp_small.cu).  Testing hook vaeq_dp_persistent_frames(mode): 1 = that kernel (default); 0 = one set of launches per
  * step; 2 = the per-step kernels' own bodies inside one launch (bitwise identical to mode 0). */

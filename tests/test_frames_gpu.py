@@ -72,7 +72,9 @@ def rel(x, y):
                                                                                  ("16-QAM", 3, 40, 8, 11, 16, 8, False, 0.0),
                                                                                  ("64-QAM", 7, 130, 130, 5, 0, 130, True, 0.02),
                                                                                  ("4-QAM", 63, 512, 512, 2, 0, 512, True, 0.0),     # largest shared-memory plan
-                                                                                 ("64-QAM", 25, 28, 28, 6, 0, 28, True, 0.0)])      # shortest useful minibatch
+                                                                                 ("64-QAM", 25, 28, 28, 6, 0, 28, True, 0.0),       # shortest useful minibatch
+                                                                                 ("64-QAM", 25, 900, 900, 3, 0, 900, True, 0.0270955),   # between 512 and the fast path
+                                                                                 ("16-QAM", 13, 1000, 250, 4, 375, 250, False, 0.0)])
 def test_fast_persistent_frame_matches_stepped_frame(mod, M, B, stride, n_steps, keep_lo, keep_n, kd, nu):
     """dp_small.cu against the launch-by-launch path on the same frame: every step's loss / var_est, the kept q / out
     columns and the taps after the last step."""

@@ -82,7 +82,7 @@ struct DpRunsK {
 
 
 // dp_small.cu: persistent frame kernel for batch_len <= DP_SMALL_MAX_B (state and intermediates in shared memory)
-constexpr int DP_SMALL_MAX_B = 512;
+constexpr int DP_SMALL_MAX_B = 1000;   // ~200 KB of shared memory at M_est = 25; the fast path starts at 992
 size_t dp_small_smem(int B, int M);
 int dp_small_launch(const DpK &p, const DpRunsK &rs, int n_lev, int n_runs, int n_steps, int stride_sym, int keep_lo_in_dst,
                     float lr_w, float lr_h, int amsgrad, cudaStream_t st);

@@ -913,7 +913,10 @@ extern "C" int vaeq_dp_train_frame(const vaeq_dp_desc *d, int32_t n_steps, int32
     VAEQ_CHECK_ARG(n_steps >= 0 && stride_sym > 0, "bad n_steps/stride");
     VAEQ_CHECK_ARG(d->ld_rx >= ((int64_t)(n_steps - 1) * stride_sym + d->B) * d->sps, "frame shorter than the last window");
     if (n_steps == 0) return VAEQ_OK;
-    if (g_persistent_frames && d->B <= DP_TILE)
+    // mode 1 (dp_small.cu) covers batch_len up to DP_SMALL_MAX_B, i.e. up to where the register-blocked fast path takes over for
+    // single steps; mode 2 (generic bodies in one launch) needs the minibatch to be one tile
+    if ((g_persistent_frames == 1 && d->B <= DP_SMALL_MAX_B && dp_small_smem(d->B, d->M) <= 220 * 1024) ||
+        (g_persistent_frames == 2 && d->B <= DP_TILE))
         return dp_frame_persistent(d, nullptr, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, loss_steps, var_est_steps,
                                    (cudaStream_t)stream);
     DpK base = dp_make_params(d);
@@ -934,7 +937,8 @@ extern "C" int vaeq_dp_train_frame_runs(const vaeq_dp_desc *d, const vaeq_dp_run
                                         int32_t keep_lo_in_dst, float lr_w, float lr_h, float *loss_steps, float *var_est_steps,
                                         void *stream) {
     VAEQ_CHECK_ARG(d != nullptr && runs != nullptr && runs->n_runs >= 1, "desc / runs is NULL or n_runs < 1");
-    VAEQ_CHECK_ARG(d->B <= DP_TILE, "batched runs need batch_len <= %d (one CTA per run), got %d", DP_TILE, d->B);
+    VAEQ_CHECK_ARG(d->B <= (g_persistent_frames == 2 ? DP_TILE : DP_SMALL_MAX_B) && dp_small_smem(d->B, d->M) <= 220 * 1024,
+                   "batched runs need batch_len <= %d and a shared-memory plan <= 220 KB (one CTA per run), got batch_len %d", DP_SMALL_MAX_B, d->B);
     vaeq_dp_desc one = *d;
     one.workspace_bytes = d->workspace_bytes / (size_t)runs->n_runs;      // every run needs a full workspace
     int rc = dp_validate(&one, true, true);
