@@ -148,6 +148,12 @@ def test_run_dp_sweep_layout_and_mat_schema(tmp_path):
     v = float(SER[0, 2, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0])
     assert abs(v - (1000.0 * 26 + 10 * 2.0 + 25)) < 1.0
     assert float(Var_est[1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 2]) == np.float32(0.027) and float(var_real[0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]) == np.float32(0.3)
+    # resume: a second call with the same checkpoint directory recomputes nothing and returns the same arrays
+    ck = str(tmp_path / "ck")
+    a = sweep.run_dp_sweep(iter=2, num_frames=3, runner=runner, checkpoint_dir=ck, **lists)
+    n_calls = len(calls)
+    b = sweep.run_dp_sweep(iter=2, num_frames=3, runner=runner, checkpoint_dir=ck, **lists)
+    assert len(calls) == n_calls and all(torch.equal(x, y) for x, y in zip(a, b)) and torch.equal(a[0], SER)
     path = str(tmp_path / "sweep.mat")
     sweep.save_mat(path, SER, Var_est, var_real, SNR_vec=lists["SNR_vec"], nu_vec=lists["nu_vec"], theta_diff_vec=lists["theta_diff_vec"],
                    theta_vec=lists["theta_vec"], M_vec=lists["M_vec"], lr_optim_vec=lists["lr_optim_vec"], batch_len_vec=lists["batch_len_vec"],

@@ -180,12 +180,14 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
                  theta_diff_vec=(0.06 * np.pi,), SNR_vec=(23,), M_vec=(25,), batch_len_vec=(100,), flex_step_vec=(10,),
                  lr_optim_vec=(2.5e-3, 2e-3, 3e-3), iter=5, N_lrhalf=170, num_frames=170, N_frame_max=10000,
                  tau_pmd=0.1e-12 * np.sqrt(1000), tau_cd=-26e-24, phiIQ=(0.0314, 0.0314), *, device=None, datagen="gpu_batched",
-                 eval_every=1, rank=0, world=1, group=None, runner=None, verbose=False):
+                 eval_every=1, rank=0, world=1, group=None, runner=None, verbose=False, checkpoint_dir=None):
     """Eval_run_DP.py's ten nested loops (RUN_DP:68-95) as batched run sets.  Cells that share (M, batch_len, flex_step, symb_rate)
     train in the same persistent launch; with world > 1 every rank takes a round-robin share of each set.  Returns the
     reference's result arrays on rank 0 (None elsewhere):
         SER (4, SNR, symb_rate, nu, theta_diff, M, lr, batch_len, flex_step, theta, iter, num_frames), Var_est (2, ...), var_real (2, ..., 1)
-    loss_type 'VAE' / 'VAEflex' use the batched engine; the CMA variants have a per-symbol tap recurrence and run cell by cell."""
+    loss_type 'VAE' / 'VAEflex' use the batched engine; the CMA variants have a per-symbol tap recurrence and run cell by cell.
+    checkpoint_dir: rank 0 writes each finished run set there (one .npz per set, keyed by the set's parameters); a restarted sweep
+    loads what it finds instead of recomputing (the reference only saves once, at the very end: RUN_DP:99-114)."""
     vecs = dict(SNR=list(SNR_vec), symb_rate=list(symb_rate_vec), nu=list(nu_vec), theta_diff=list(theta_diff_vec), M=list(M_vec),
                 lr_optim=list(lr_optim_vec), batch_len=list(batch_len_vec), flex_step=list(flex_step_vec), theta=list(theta_vec))
     shape = tuple(len(vecs[a]) for a in AXES) + (iter,)
@@ -201,6 +203,19 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
     for (M, batch_len, flex_step, symb_rate), members in groups.items():
         cells = [c for _, c in members]
         common = (mod, sps, M, batch_len, N_frame_max, num_frames)
+        ck = None
+        if checkpoint_dir is not None:
+            import os
+            os.makedirs(checkpoint_dir, exist_ok=True)
+            ck = os.path.join(checkpoint_dir, f"{loss_type}_{mod}_M{M}_B{batch_len}_F{flex_step}_R{symb_rate:g}_n{len(cells)}_f{num_frames}.npz")
+            if os.path.exists(ck):                                   # every rank skips the set; rank 0 restores it
+                if rank == 0:
+                    z = np.load(ck)
+                    for k, (idx, _) in enumerate(members):
+                        SER[(slice(None),) + idx] = torch.from_numpy(z["ser"][k]).to(dev)
+                        Var_est[(slice(None),) + idx] = torch.from_numpy(z["ve"][k]).to(dev)
+                        var_real[(slice(None),) + idx + (0,)] = torch.from_numpy(z["var"][k]).to(dev)
+                continue
         kw = dict(flex_step=flex_step, channel=channel, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ, N_lrhalf=N_lrhalf)
         if runner is not None:                                       # test hook: stands for sweep_vae_dp_sharded
             res = runner(cells, *common, **kw)
@@ -212,6 +227,8 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
         if res is None:
             continue
         ser, ve, var = res
+        if ck is not None and rank == 0:
+            np.savez(ck, ser=ser.cpu().numpy(), ve=ve.cpu().numpy(), var=var.cpu().numpy())
         for k, (idx, _) in enumerate(members):
             SER[(slice(None),) + idx] = ser[k].to(dev)
             Var_est[(slice(None),) + idx] = ve[k].to(dev)
