@@ -36,8 +36,8 @@ N_LEV = 8
 ALG_BYTES_PER_SYMBOL = 4 * 2 * (2 * SPS + 2 * N_LEV + 2)        # read rx once, write q and out once = 176 B
 ALG_FLOP_PER_SYMBOL = 5 * 32 * M_EST + 1000                      # 5 tap contractions + point-wise work
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (k_dp_fwd_fast<8,12>) at batch_len 2^22 from the
-# `ncu --set full` capture summarised in profiles/r01b_ncu_full_summary.json: 137.2 MB read + 969.2 MB written = 263.8 B/symbol
-FWD_DRAM_BYTES_PER_SYMBOL = (137.16e6 + 969.189e6) / (1 << 22)
+# `ncu --set full` capture summarised in profiles/r01c_ncu_full_summary.json: 137.2 MB read + 967.1 MB written = 263.3 B/symbol
+FWD_DRAM_BYTES_PER_SYMBOL = (137.168e6 + 967.142e6) / (1 << 22)
 CPU_SAMPLE_LOG2 = 17
 
 
@@ -346,7 +346,7 @@ def ours_arm(args, rank, local_rank, world):
     step_gbs = B * ALG_BYTES_PER_SYMBOL * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (FWD_DRAM_BYTES_PER_SYMBOL * B if names[dom] == "k_dp_fwd" and M_EST == 25 else None),
-                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01b_ncu_full_summary.json, scaled to this batch_len)",
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01c_ncu_full_summary.json, scaled to this batch_len)",
                 "peak_source": peak_src, "alg_bytes_per_symbol": ALG_BYTES_PER_SYMBOL,
                 "alg_bytes_per_launch": B * ALG_BYTES_PER_SYMBOL,
                 "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,

@@ -29,7 +29,7 @@ namespace vaeq {
 constexpr int FT_NT = FT_NT_DEF;           // threads per CTA.  Every tile is load -> barrier -> FIR -> point-wise -> barrier -> ...,
                                            // so what hides one CTA's load / barrier phases is the OTHER CTAs of the SM: four
                                            // 128-thread CTAs per SM interleave better than two of 256 (0.664 -> 0.627 ms per step,
-                                           // profiles/r01b_*), one of 512 is worst (0.782 vs 0.744, profiles/r01_cta_imbalance.txt).
+                                           // profiles/r01c_*), one of 512 is worst (0.782 vs 0.744, profiles/r01_cta_imbalance.txt).
                                            // The tap-gradient kernels need >= 4 warps (one per role), so 128 is the floor.
 constexpr int FT_NW = FT_NT / 32;          // warps per CTA
 constexpr int FT_CTAS_PER_SM = 512 / FT_NT;   // 128 registers per thread either way
@@ -234,7 +234,7 @@ __device__ __forceinline__ void load_x_phases(const DpK &p, int t0, float4 *xe, 
 // The raw rows (4 rows x 2*FT_XN samples, as they lie in HBM) are copied into a staging buffer while the current tile is being
 // computed; at the top of the next iteration they are transposed smem -> smem into the even/odd phase arrays.  This takes
 // the HBM/L2 load latency (8.6 % of the forward kernel's stall samples sat on the first use of the tile loader's LDG,
-// profiles/r01b_*) off the critical path without holding the tile in registers.
+// profiles/r01c_*) off the critical path without holding the tile in registers.
 constexpr int FT_RAWROW = FT_XN / 2;                    // float4 per raw row
 constexpr int FT_RAW = 4 * FT_RAWROW;                   // float4 of the staging buffer
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
