@@ -155,8 +155,10 @@ int vaeq_dp_persistent_frames(int32_t mode);
 /* The same frame for n_runs INDEPENDENT runs in one launch, one CTA per run -- the sweep cells of Eval_run_DP.py:68-95
  * (SNR x realisation x lr ...) that share batch_len, M_est and n_lev.  Every tensor of the desc addresses run 0; run r
  * is found rs_* ELEMENTS further (0 = shared by all runs).  d->loss (n_runs), d->var_est (n_runs,2), d->gW (n_runs,2,4,M),
- * d->gh (n_runs,2,2,2,M) get a leading run dimension; d->workspace holds n_runs x vaeq_dp_workspace_bytes(B,M,n_lev);
+ * d->gh (n_runs,2,2,2,M) get a leading run dimension; d->workspace holds vaeq_dp_runs_workspace_bytes(B,M,n_lev,n_runs) (the
+ * default kernel keeps all scratch in shared memory: 256 bytes; testing mode 2 needs a full workspace per run);
  * loss_steps (n_runs,n_steps), var_est_steps (n_runs,2,n_steps).  nu_sc / lr_w / lr_h: optional per-run device arrays. */
+size_t vaeq_dp_runs_workspace_bytes(int32_t B, int32_t M, int32_t n_lev, int32_t n_runs);
 typedef struct vaeq_dp_runs {
     int32_t n_runs;
     int64_t rs_rx, rs_amp, rs_P, rs_var, rs_W, rs_h, rs_adam, rs_q, rs_out, rs_q_keep, rs_out_keep;

@@ -658,6 +658,8 @@ static DpWsLayout dp_ws_layout(int B, int M) {
 }
 
 static bool g_dynamic_tiles = true;
+static int g_persistent_frames = 1;   // 0: per-step launches, 1: dp_small.cu (default), 2: generic bodies in one launch
+static int g_persistent_frames_mode() { return g_persistent_frames; }
 
 static int dp_validate(const vaeq_dp_desc *d, bool need_grads, bool need_adam) {
     VAEQ_CHECK_ARG(d != nullptr, "desc is NULL");
@@ -795,6 +797,11 @@ extern "C" size_t vaeq_dp_workspace_bytes(int32_t B, int32_t M, int32_t n_lev) {
 
 extern "C" size_t vaeq_adam_state_floats(int32_t M) { return (size_t)48 * M + 4; }
 
+extern "C" size_t vaeq_dp_runs_workspace_bytes(int32_t B, int32_t M, int32_t n_lev, int32_t n_runs) {
+    if (B <= 0 || M <= 0 || n_runs <= 0) return 0;
+    return g_persistent_frames_mode() == 2 ? (size_t)n_runs * vaeq_dp_workspace_bytes(B, M, n_lev) : 256;
+}
+
 extern "C" int vaeq_dp_dynamic_tiles(int32_t on) {
     g_dynamic_tiles = on != 0;
     return VAEQ_OK;
@@ -855,7 +862,6 @@ extern "C" int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h,
                        (cudaStream_t)stream);
 }
 
-static int g_persistent_frames = 1;   // 0: per-step launches, 1: dp_small.cu (default), 2: generic bodies in one launch
 
 extern "C" int vaeq_dp_persistent_frames(int32_t mode) {
     VAEQ_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
@@ -940,7 +946,13 @@ extern "C" int vaeq_dp_train_frame_runs(const vaeq_dp_desc *d, const vaeq_dp_run
     VAEQ_CHECK_ARG(d->B <= (g_persistent_frames == 2 ? DP_TILE : DP_SMALL_MAX_B) && dp_small_smem(d->B, d->M) <= 220 * 1024,
                    "batched runs need batch_len <= %d and a shared-memory plan <= 220 KB (one CTA per run), got batch_len %d", DP_SMALL_MAX_B, d->B);
     vaeq_dp_desc one = *d;
-    one.workspace_bytes = d->workspace_bytes / (size_t)runs->n_runs;      // every run needs a full workspace
+    static char dummy_ws;                                    // dp_small.cu keeps everything in shared memory: no workspace
+    if (g_persistent_frames == 2) {
+        one.workspace_bytes = d->workspace_bytes / (size_t)runs->n_runs;  // the generic bodies need a full workspace per run
+    } else {
+        one.workspace = d->workspace ? d->workspace : &dummy_ws;
+        one.workspace_bytes = vaeq_dp_workspace_bytes(d->B, d->M, d->n_lev);
+    }
     int rc = dp_validate(&one, true, true);
     if (rc) return rc;
     VAEQ_CHECK_ARG(n_steps >= 0 && stride_sym > 0, "bad n_steps/stride");

@@ -226,8 +226,7 @@ class DPEqualizerRuns:
         if not (out_train.is_contiguous() and out_const.is_contiguous()):
             raise _lib.VaeqError("out_train / out_const must be contiguous")
         if self._B != B:
-            self._ws_one = int(self.lib.vaeq_dp_workspace_bytes(B, self.M, self.n_lev))
-            self._ws = torch.empty(R * self._ws_one, dtype=torch.uint8, device=dev)
+            self._ws = torch.empty(int(self.lib.vaeq_dp_runs_workspace_bytes(B, self.M, self.n_lev, R)), dtype=torch.uint8, device=dev)
             self._q = torch.empty(R, 2, 2 * self.n_lev, B, dtype=_F32, device=dev)
             self._out = torch.empty(R, 2, 2, B, dtype=_F32, device=dev)
             self._B = B
