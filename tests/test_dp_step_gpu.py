@@ -247,3 +247,82 @@ def test_static_tiles_are_bitwise_reproducible_and_dynamic_agrees():
     a, b, d = run(0), run(0), run(1)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2]
     assert rel(d[0], a[0]) < 1e-5 and rel(d[1], a[1]) < 1e-5 and abs(d[2] - a[2]) / abs(a[2]) < 1e-6
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE size (batch_len = 2^22, the bench workload): size-independent properties instead of a CPU oracle
+# -------------------------------------------------------------------------------------------------
+def _bench_case():
+    from vae_equalizer_b200.datagen import generate_data_gpu
+    M, B = 25, 1 << 22
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rx = generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, "cuda", 99)[0]
+    gen = torch.Generator().manual_seed(17)
+    W0 = O.dirac_taps(M) + 0.02 * torch.randn(2, 4, M, generator=gen)
+    h0 = h_est.detach() + 0.02 * torch.randn(2, 2, 2, M, generator=gen)
+    return M, B, rx, dict(amp=amp, P=torch.tensor(P, dtype=torch.float32), var=var, nu_sc=nu_sc), W0, h0
+
+
+def test_full_size_fast_path_against_generic_kernels():
+    """At the bench size the register-blocked kernels must agree with the generic ones (reference operation order, IEEE division,
+    expf / logf), which are the ones pinned to the oracle at small sizes: loss, var_est, gradients, a strided sample of q / out."""
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    M, B, rx, c, W0, h0 = _bench_case()
+    res = {}
+    for tag, force in (("fast", 0), ("generic", 1)):
+        lib.vaeq_dp_force_generic(force)
+        try:
+            eq = DPEqualizer(M, 2, c["amp"], c["P"], c["var"], c["nu_sc"], W0=W0, h0=h0)
+            q, out, loss, ve, gW, gh = eq.forward_backward(rx)
+            torch.cuda.synchronize()
+            res[tag] = (q[:, :, ::997].cpu(), out[:, :, ::997].cpu(), float(loss), ve.cpu(), gW.cpu(), gh.cpu())
+        finally:
+            lib.vaeq_dp_force_generic(0)
+    f, g = res["fast"], res["generic"]
+    assert float((f[1] - g[1]).abs().max()) < 5e-6 and float((f[0] - g[0]).abs().max()) < 5e-5
+    assert abs(f[2] - g[2]) / abs(g[2]) < 1e-5 and rel(f[3], g[3]) < 1e-5
+    assert rel(f[4], g[4]) < 1e-4 and rel(f[5], g[5]) < 1e-4
+
+
+def test_full_size_polarisation_swap_symmetry():
+    """Exchanging the two polarisations everywhere (rx rows, equalizer outputs / inputs, channel estimate, demapper variances)
+    must exchange the outputs and leave the loss unchanged: checks every index of the 2x2 butterfly at the bench size."""
+    from vae_equalizer_b200.dp import DPEqualizer
+    M, B, rx, c, W0, h0 = _bench_case()
+    var = torch.tensor([float(c["var"][0]), 1.3 * float(c["var"][1])])                  # make the two pols distinguishable
+    eq = DPEqualizer(M, 2, c["amp"], c["P"], var, c["nu_sc"], W0=W0, h0=h0)
+    q, out, loss, ve, gW, gh = [t.clone() for t in eq.forward_backward(rx)]
+    # W (o, [Re<-p0, Re<-p1, Im<-p0, Im<-p1], k): swap o and the input pol; h (chi, nu, c, k): swap chi and nu
+    Ws = W0.flip(0)[:, [1, 0, 3, 2], :].contiguous()
+    hs = h0.flip(0).flip(1).contiguous()
+    eqs = DPEqualizer(M, 2, c["amp"], c["P"], var.flip(0), c["nu_sc"], W0=Ws, h0=hs)
+    q2, out2, loss2, ve2, gW2, gh2 = eqs.forward_backward(rx.flip(0).contiguous())
+    torch.cuda.synchronize()
+    assert float((out2.flip(0)[:, :, ::499] - out[:, :, ::499]).abs().max()) < 2e-6
+    assert float((q2.flip(0)[:, :, ::499] - q[:, :, ::499]).abs().max()) < 2e-5
+    assert abs(float(loss2) - float(loss)) / abs(float(loss)) < 1e-6 and rel(ve2.flip(0), ve) < 1e-6
+    assert rel(gW2.flip(0)[:, [1, 0, 3, 2], :], gW) < 1e-4 and rel(gh2.flip(0).flip(1), gh) < 1e-4
+
+
+def test_full_size_gradient_is_the_derivative_of_the_loss():
+    """Directional finite difference of the fused loss at the bench size against the fused gradient (both parameter groups)."""
+    from vae_equalizer_b200.dp import DPEqualizer
+    M, B, rx, c, W0, h0 = _bench_case()
+    eq = DPEqualizer(M, 2, c["amp"], c["P"], c["var"], c["nu_sc"], W0=W0, h0=h0)
+    _, _, _, _, gW, gh = eq.forward_backward(rx)
+    gW, gh = gW.cpu().double(), gh.cpu().double()
+    gen = torch.Generator().manual_seed(5)
+    for which in ("W", "h"):
+        d = torch.randn((2, 4, M) if which == "W" else (2, 2, 2, M), generator=gen)
+        d = d / d.norm()
+        eps = 2e-3
+        vals = []
+        for sgn in (+1, -1):
+            e2 = DPEqualizer(M, 2, c["amp"], c["P"], c["var"], c["nu_sc"], W0=W0 + sgn * eps * d if which == "W" else W0,
+                             h0=h0 + sgn * eps * d if which == "h" else h0)
+            vals.append(float(e2.forward(rx)[2]))
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        an = float(((gW if which == "W" else gh) * d.double()).sum())
+        assert abs(fd - an) / abs(an) < 2e-2, (which, fd, an)
