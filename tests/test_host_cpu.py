@@ -116,6 +116,13 @@ def test_batched_frame_generator_matches_single_generator():
     a, ta, _ = generate_data_gpu(1500, amps, 200, P, 2, 0.3, "cpu", 7)
     b, tb, _ = generate_frames_gpu(1500, amps, [200], P, 2, [0.3], "cpu", 7)
     assert torch.equal(ta, tb[0]) and float((a - b[0]).abs().max()) < 5e-6
+    # the drawn symbols follow the PCS pmf (sf:75-76) and the noise-free signal has the constellation's unit power (rotation, CD and
+    # PMD are all-pass, the RRC pulse has unit energy)
+    _, tbig, _ = generate_frames_gpu(40000, amps, [200], P, 2, [0.3], "cpu", 3)
+    lv = torch.tensor(amps, dtype=torch.float32)
+    cnt = torch.stack([(tbig.float().reshape(-1) - a_).abs().lt(1e-2).float().mean() for a_ in lv])
+    assert float((cnt - torch.tensor(P, dtype=torch.float32)).abs().max()) < 6e-3
+    assert abs(float((a ** 2).sum(dim=(0, 1)).mean()) - pm) < 0.05 * pm
     rx, tx, sig = generate_frames_gpu(3000, amps, [23, 13, 23], np.stack([P, P, P]), 2, [0.3, 0.3, 1.0], "cpu", 11)
     assert rx.shape == (3, 2, 2, 6000) and tx.shape == (3, 2, 2, 3000) and tx.dtype == torch.float16
     assert abs(float(sig[1] / sig[0]) - 10 ** 0.5) < 0.05 * 10 ** 0.5          # 10 dB lower SNR -> sqrt(10) more noise

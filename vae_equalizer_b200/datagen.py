@@ -76,28 +76,11 @@ def generate_data_shaping(N, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_c
 
 def generate_data_gpu(N, amps, SNR, P, sps, theta, device, seed, symb_rate=90e9, tau_cd=-26e-24,
                       tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=(0.0314, 0.0314)):
-    """Device-side generator with the same signal model (channel 'h0'); statistics, not bits, match."""
-    g = torch.Generator(device=device).manual_seed(int(seed))
-    n_conv = N + 1 + 4 * PULSE_SPAN
-    idx = torch.multinomial(torch.as_tensor(P, dtype=torch.float32, device=device), 4 * n_conv, True, generator=g).view(4, n_conv)
-    lev = torch.as_tensor(amps, dtype=torch.float32, device=device)[idx]
-    sym = torch.complex(lev[0::2], lev[1::2])
-    up = torch.zeros(2, sps * (n_conv - 1) + 1, dtype=torch.complex64, device=device)
-    up[:, ::sps] = sym
-    pulse = torch.as_tensor(rrcfir(PULSE_SPAN, sps, ROLLOFF), device=device).to(torch.complex64)
-    n_fft = up.shape[1] + pulse.numel() - 1
-    shaped = torch.fft.ifft(torch.fft.fft(up, n_fft) * torch.fft.fft(pulse, n_fft))[:, pulse.numel() - 1: up.shape[1]]
-    H, e_cd = jones_response(shaped.shape[1], symb_rate, sps, tau_cd, tau_pmd, np.asarray(phiIQ, dtype=np.complex64), theta)
-    Ht = [[torch.as_tensor(np.asarray(H[a][b] * e_cd), device=device).to(torch.complex64) for b in range(2)] for a in range(2)]
-    X = torch.fft.fft(shaped, dim=1)
-    sig = torch.fft.ifft(torch.stack((Ht[0][0] * X[0] + Ht[0][1] * X[1], Ht[1][0] * X[0] + Ht[1][1] * X[1])), dim=1)
-    sigma_n = torch.sqrt(torch.mean(sig.abs() ** 2) * sps / 2 / 10 ** (SNR / 10))
-    noise = torch.complex(torch.randn(sig.shape, device=device, generator=g), torch.randn(sig.shape, device=device, generator=g))
-    sig = (sig + sigma_n * noise)[:, :sps * N]
-    rx = torch.stack((sig.real, sig.imag), dim=1).to(torch.float32).contiguous()
-    sl = slice(PULSE_SPAN, N + PULSE_SPAN)
-    tx = torch.stack((lev[0::2][:, sl], lev[1::2][:, sl]), dim=1).to(torch.float16).contiguous()
-    return rx, tx, float(sigma_n)
+    """Device-side generator with the same signal model (channel 'h0'); statistics, not bits, match the host generator.
+    One run of generate_frames_gpu (cached channel terms, no per-call host FFT-grid work)."""
+    rx, tx, sigma_n = generate_frames_gpu(N, amps, [SNR], np.asarray(P)[None], sps, [theta], device, seed, symb_rate=symb_rate,
+                                          tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ)
+    return rx[0], tx[0], float(sigma_n[0])
 
 
 _GPU_CACHE: dict = {}
