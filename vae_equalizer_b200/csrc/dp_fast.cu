@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
     __syncthreads();
     const FastConst &c = *cst;
 
-    float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV[2] = {0.f, 0.f};
+    float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV0 = 0.f, accV1 = 0.f;   // scalars: accV[pol] in the rolled pol loop lived in local memory
     const int i0 = FT_R * tid;                               // local index of this thread's first symbol
     PT_DECL
     __shared__ int s_next;
@@ -362,12 +362,12 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.chi);
         const bool counted = owned && (u0 >= p.sym_lo) && (u0 < p.sym_hi);   // sums only over this rank's symbols
-        float mom[FT_R][4];
+        // posterior means go straight to the shared E_q window (float2 half per polarisation pass): they are not held in
+        // registers across the point-wise stage, which sits at the 128-register cap
+        if (!in_seq) {
 #pragma unroll
-        for (int r = 0; r < FT_R; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mom[r][k] = 0.f;
-        if (in_seq) {
+            for (int r = 0; r < FT_R; ++r) m1s[5 * tid + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
             float y[FT_R][4];
 #pragma unroll
             for (int r = 0; r < FT_R; ++r)
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
             for (int ph = 0; ph < 2; ++ph)
                 fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? FT_TAPV * NE : 0), ph ? NO : NE, y);
             PT(2)
-            // point-wise stage, rolled over the polarisation (code size); y / mom rotate by two components per pass
+            // point-wise stage, rolled over the polarisation (code size); y rotates by two components per pass
 #pragma unroll 1
             for (int pol = 0; pol < 2; ++pol) {
                 float vs[FT_R];
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                         if (counted && u >= MH && u < p.B - MH) accEnt += ent;                // sf:132
                         const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
                         vs[r] = cq ? vs[r] + v : v;
-                        mom[r][cq] = m1v[r];
+                        reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1v[r];
                     }
                     if (owned) {
 #pragma unroll
@@ -423,10 +423,12 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                     }
                 }
                 if (counted) {
+                    const float vsum = (vs[0] + vs[1]) + (vs[2] + vs[3]);
+                    accV0 += pol ? 0.f : vsum;
+                    accV1 += pol ? vsum : 0.f;
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r) {
                         const int u = u0 + r;
-                        accV[pol] += vs[r];
                         if (u < MH || u >= p.B - MH) {
                             const int slot = (u < MH) ? u : MH + (u - (p.B - MH));
                             p.edge_vs[2 * MH * pol + slot] = vs[r];
@@ -438,14 +440,10 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                     float t;
                     t = y[r][0]; y[r][0] = y[r][2]; y[r][2] = t;
                     t = y[r][1]; y[r][1] = y[r][3]; y[r][3] = t;
-                    t = mom[r][0]; mom[r][0] = mom[r][2]; mom[r][2] = t;
-                    t = mom[r][1]; mom[r][1] = mom[r][3]; mom[r][3] = t;
                 }
             }
         }
         PT(3)
-#pragma unroll
-        for (int r = 0; r < FT_R; ++r) m1s[5 * tid + r] = make_float4(mom[r][0], mom[r][1], mom[r][2], mom[r][3]);
         __syncthreads();
         PT(4)
 
@@ -488,7 +486,7 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
     }
     PT_FLUSH
 
-    float v[5] = {accC[0], accC[1], accEnt, accV[0], accV[1]};
+    float v[5] = {accC[0], accC[1], accEnt, accV0, accV1};
     block_sum<5>(v, red);
     if (tid == 0) {
         double *dst = p.part_fwd + (int64_t)blockIdx.x * 8;
