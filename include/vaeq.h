@@ -202,7 +202,9 @@ int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var, const floa
  * ---------------------------------------------------------------------------------------------- */
 /* find_shift (sf:290-314) when q != NULL (E = sum_l amp_l q_I[l]), find_shift_symb_full (sf:316-338)
  * when q == NULL (E = out[:,0,:]).  corr_out (2 comp,2 eq-pol,2 tx-pol,n_shift) |correlations|,
- * shift_out int16 (2) = n_shift/2 - argmax, r_out int32 (1) in {0,1}.  scratch: n_shift*8 doubles. */
+ * shift_out int16 (2) = n_shift/2 - argmax, r_out int32 (1) in {0,1}.  n_shift <= 64.
+ * scratch: vaeq_find_shift_scratch_bytes(n_shift) (per-CTA partial correlations, summed in fixed order). */
+size_t vaeq_find_shift_scratch_bytes(int32_t n_shift);
 int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, int64_t ld_out, const uint16_t *tx, int64_t ld_tx,
                     const float *amp, int32_t n_lev, int32_t N, int32_t n_shift, float *corr_out, int16_t *shift_out,
                     int32_t *r_out, void *scratch, void *stream);

@@ -87,6 +87,7 @@ PROTOTYPES = {
     "vaeq_dp_split_update": (C.c_int, [C.POINTER(DpDesc), _vp, _f, _f, _vp]),
     "vaeq_adam_update": (C.c_int, [_vp, _vp, _vp, _i32, _f, _i32, _vp, _i32, _vp]),
     "vaeq_soft_dec": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i32, _i32, _vp, _i64, _vp]),
+    "vaeq_find_shift_scratch_bytes": (_sz, [_i32]),
     "vaeq_find_shift": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vaeq_ser_iqflip": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_ser_constell": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp]),

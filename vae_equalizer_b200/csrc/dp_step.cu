@@ -618,6 +618,57 @@ __global__ void k_soft_dec(const float *out, int64_t ld_out, const float *var, c
     }
 }
 
+// Bandwidth version for 16-byte aligned rows and N % 4 == 0: a thread owns 4 consecutive symbols (float4 loads / streaming float4
+// stores, 512 B per warp instruction).  The logit z keeps the reference's operation order and roundings -- ((y-a)^2 * 0.5) / var
+// + nu_sc a^2 (sf:521) -- with the division by the per-polarisation constant var done as x*r + one fused residual correction
+// (r = RN(1/var); q0 = RN(x r); q = RN(q0 + RN(x - q0 var) r): Markstein's correction, the correctly rounded quotient except
+// for rare last-bit cases), so hard decisions (argmin z) follow the precise kernel; exp and the normalisation use ex2.approx
+// and one reciprocal per component (|dq| < 3e-7).  The precise kernel above took 586 us at N = 2^22 (0.16 of the HBM roofline: 64 IEEE divisions and 32 expf
+// per symbol); this one is bound by the q stores.
+__device__ __forceinline__ float div_by_const(float x, float c, float rc) {
+    const float q0 = x * rc;
+    return fmaf(fmaf(-q0, c, x), rc, q0);
+}
+template <int NL>
+__global__ void __launch_bounds__(256) k_soft_dec_vec(const float *__restrict__ out, int64_t ld_out, const float *var, const float *amp,
+                                                      float nu_sc, int N, float *__restrict__ q, int64_t ld_q) {
+    __shared__ DemapConst cst;
+    load_demap_const(&cst, amp, nullptr, var, nu_sc, NL);
+    __syncthreads();
+    const int n4 = N >> 2;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += gridDim.x * blockDim.x) {
+        const int64_t u = 4 * (int64_t)g;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const float v = cst.var[cc >> 1], rv = 1.f / v;
+            const float4 y4 = ldg_stream(reinterpret_cast<const float4 *>(out + (int64_t)cc * ld_out + u));
+            const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+            float pq[4][NL], r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float z[NL], zmin = 3.0e38f;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const float d = y[k] - cst.amp[l];
+                    z[l] = __fadd_rn(div_by_const(__fmul_rn(__fmul_rn(d, d), 0.5f), v, rv), cst.nua2[l]);
+                    zmin = fminf(zmin, z[l]);
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    pq[k][l] = ex2_approx((zmin - z[l]) * LOG2E);
+                    s += pq[k][l];
+                }
+                r[k] = rcp_approx(s);
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+                stg_stream(reinterpret_cast<float4 *>(q + (int64_t)(cc * NL + l) * ld_q + u),
+                           make_float4(pq[0][l] * r[0], pq[1][l] * r[1], pq[2][l] * r[2], pq[3][l] * r[3]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1067,8 +1118,21 @@ extern "C" int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var,
                              int32_t n_lev, int32_t N, float *q, int64_t ld_q, void *stream) {
     VAEQ_CHECK_ARG(out && var && amp && q && N > 0, "bad soft_dec arguments");
     VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
-    const int nt = 256, grid = min((N + nt - 1) / nt, sm_count() * 8);
+    const int nt = 256;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (N % 4 == 0) && (ld_out % 4 == 0) && (ld_q % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(q)) % 16 == 0);
+    if (vec) {
+        const int gridv = min((N / 4 + nt - 1) / nt, sm_count() * 8);
+        ktime_begin(VAEQ_K_EVAL, st);
+        if (n_lev == 2) k_soft_dec_vec<2><<<gridv, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+        else if (n_lev == 4) k_soft_dec_vec<4><<<gridv, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+        else k_soft_dec_vec<8><<<gridv, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
+        ktime_end(VAEQ_K_EVAL, st);
+        VAEQ_LAUNCH_CHECK("k_soft_dec_vec");
+        return VAEQ_OK;
+    }
+    const int grid = min((N + nt - 1) / nt, sm_count() * 8);
     ktime_begin(VAEQ_K_EVAL, st);
     if (n_lev == 2) k_soft_dec<2><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
     else if (n_lev == 4) k_soft_dec<4><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);

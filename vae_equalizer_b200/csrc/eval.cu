@@ -2,79 +2,92 @@
 // All are single-pass HBM scans (q: 128 B/symbol at 64-QAM, out: 16 B, tx: 8 B as float16) with integer
 // error COUNTS returned next to the float SER so that "bit-exact SER counts" is checkable.
 #include "common.cuh"
+#include "shift_corr.cuh"
 
 namespace vaeq {
 
 constexpr int EV_NT = 256;
-constexpr int EV_CHUNKS = 32;          // partial sums per shift (find_shift scratch = n_shift*8*EV_CHUNKS doubles)
+constexpr int EV_CHUNKS = 592;         // at most this many CTAs / partial blocks in find_shift (scratch = EV_CHUNKS*n_shift*8 doubles)
 
 __device__ __forceinline__ float tx_level(uint16_t bits, float scale) {
     // round(scale*tx.float()+scale), two fp32 roundings then round-half-even like torch.round (sf:198, sf:239)
     return rintf(__fadd_rn(__fmul_rn(scale, half_bits_to_float(bits)), scale));
 }
 
+// V consecutive symbols per thread (V = 4: 16-byte float / 8-byte float16 loads when rows and N allow, else V = 1): the scans
+// are HBM-bound and one 4-byte load per row and thread left them at 0.3-0.56 of the roofline (profiles/r01d_eval_cma.txt)
+template <int V>
+__device__ __forceinline__ void ld_f32(const float *p, float (&v)[V]) {
+    if constexpr (V == 4) {
+        const float4 x = __ldcs(reinterpret_cast<const float4 *>(p));
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int V>
+__device__ __forceinline__ void ld_f16(const uint16_t *p, float (&v)[V]) {
+    if constexpr (V == 4) {
+        const uint2 x = __ldcs(reinterpret_cast<const uint2 *>(p));
+        v[0] = half_bits_to_float((uint16_t)(x.x & 0xffffu)); v[1] = half_bits_to_float((uint16_t)(x.x >> 16));
+        v[2] = half_bits_to_float((uint16_t)(x.y & 0xffffu)); v[3] = half_bits_to_float((uint16_t)(x.y >> 16));
+    } else {
+        v[0] = half_bits_to_float(*p);
+    }
+}
+__device__ __forceinline__ float tx_level_f(float x, float scale) { return rintf(__fadd_rn(__fmul_rn(scale, x), scale)); }
+static bool ev_vec_ok(const void *a, int64_t ld_a, const void *tx, int64_t ld_tx, int N) {
+    return (N % 4 == 0) && (ld_a % 4 == 0) && (ld_tx % 4 == 0) && (reinterpret_cast<uintptr_t>(a) % 16 == 0) &&
+           (reinterpret_cast<uintptr_t>(tx) % 8 == 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // find_shift / find_shift_symb_full
 // ---------------------------------------------------------------------------------------------
-// grid (n_shift, EV_CHUNKS): block (i, c) accumulates, over its slice of t, the 8 sums
-//   S[comp][b][a] = sum_t tx[a][comp][t] * E[b][(t - (i - half)) mod N]          (sf:300-304, circular roll)
-template <bool FROM_Q>
-__global__ void __launch_bounds__(EV_NT) k_shift_corr(const float *q, int64_t ld_q, const float *out, int64_t ld_out,
+// grid (chunks): CTA c scans its contiguous range of t once for ALL shifts (shift_corr.cuh) and writes part[c][i][k],
+//   S[comp][b][a] = sum_t tx[a][comp][t] * E[b][(t - (i - half)) mod N]          (sf:300-304, circular roll), k = comp*4 + b*2 + a
+template <bool FROM_Q, int NPASS>
+__global__ void __launch_bounds__(SC_NT, FROM_Q ? 2 : SC_MINB) k_shift_corr(const float *q, int64_t ld_q, const float *out, int64_t ld_out,
                                                       const uint16_t *tx, int64_t ld_tx, const float *amp, int n_lev,
-                                                      int N, int n_shift, double *part) {
-    __shared__ double red[8 * 32];
-    const int i = blockIdx.x, chunk = blockIdx.y, half = n_shift / 2;
-    const int64_t per = ((int64_t)N + gridDim.y - 1) / gridDim.y;
-    const int64_t t_lo = chunk * per, t_hi = min((int64_t)N, t_lo + per);
-    float a_l[VAEQ_MAX_LEVELS];
-#pragma unroll
-    for (int l = 0; l < VAEQ_MAX_LEVELS; ++l) a_l[l] = (FROM_Q && l < n_lev) ? amp[l] : 0.f;
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t t = t_lo + threadIdx.x; t < t_hi; t += EV_NT) {
-        int64_t src = (t - (i - half)) % N;
-        if (src < 0) src += N;
-        float E[2];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            if (FROM_Q) {
-                float e = 0.f;                                            // E_q[x_I] = sum_l a_l q_I[l]  (sf:297)
-                for (int l = 0; l < n_lev; ++l) e += a_l[l] * q[(int64_t)(b * 2 * n_lev + l) * ld_q + src];
-                E[b] = e;
-            } else {
-                E[b] = out[(int64_t)(b * 2) * ld_out + src];             // rx[:,0,:]  (sf:321)
-            }
-        }
-#pragma unroll
-        for (int comp = 0; comp < 2; ++comp)
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const float x = half_bits_to_float(tx[(int64_t)(a * 2 + comp) * ld_tx + t]);
-                acc[comp * 4 + 0 * 2 + a] += (double)(x * E[0]);
-                acc[comp * 4 + 1 * 2 + a] += (double)(x * E[1]);
-            }
-    }
-    block_sum<8>(acc, red);
-    if (threadIdx.x == 0) {
-        double *dst = part + ((int64_t)i * gridDim.y + chunk) * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dst[k] = acc[k];
-    }
+                                                      int N, int n_shift, int64_t per, double *part) {
+    __shared__ ShiftSmem sm;
+    const int64_t t_lo = (int64_t)blockIdx.x * per, t_hi = min((int64_t)N, t_lo + per);
+    shift_corr_range<FROM_Q, NPASS>(sm, q, ld_q, out, ld_out, tx, ld_tx, amp, n_lev, N, n_shift, t_lo, t_hi,
+                             part + (int64_t)blockIdx.x * n_shift * 8);
 }
 
-// one thread: reduce chunks, then torch.max / argmax logic of sf:303-314 (first index wins ties)
-__global__ void k_shift_decide(const double *part, int n_shift, int chunks, float *corr_out, int16_t *shift_out, int *r_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int half = n_shift / 2;
+// one CTA: thread = (chunk group g, idx = (i, k)); consecutive threads read consecutive doubles of a partial block (coalesced),
+// a group sums chunks g, g + ng, ...; the groups are then added in fixed order; thread 0 replays the torch.max / argmax logic of
+// sf:303-314 (first index wins ties)
+__global__ void __launch_bounds__(1024) k_shift_decide(const double *part, int n_shift, int chunks, float *corr_out, int16_t *shift_out, int *r_out) {
+    __shared__ float v_s[8][SC_MAXSHIFT];
+    __shared__ double ps[1024];
+    const int half = n_shift / 2, nidx = n_shift * 8, lanes = (nidx + 31) & ~31, ng = max(1, (int)blockDim.x / lanes);
+    const int il = threadIdx.x % lanes, gq = threadIdx.x / lanes;
+    double s = 0.0;
+    if (gq < ng && il < nidx) {
+#pragma unroll 4
+        for (int c = gq; c < chunks; c += ng) s += part[(int64_t)c * nidx + il];
+    }
+    ps[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < nidx) {
+        double t = 0.0;
+        for (int g = 0; g < ng; ++g) t += ps[g * lanes + threadIdx.x];
+        const int i = threadIdx.x >> 3, k = threadIdx.x & 7;
+        const float v = fabsf((float)t);
+        v_s[k][i] = v;
+        if (corr_out) corr_out[k * n_shift + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     float cmax[8];
     int cind[8];
     for (int k = 0; k < 8; ++k) {                            // k = comp*4 + b*2 + a
         cmax[k] = -1.f;
         cind[k] = 0;
         for (int i = 0; i < n_shift; ++i) {
-            double s = 0.0;
-            for (int c = 0; c < chunks; ++c) s += part[((int64_t)i * chunks + c) * 8 + k];
-            const float v = fabsf((float)s);
-            if (corr_out) corr_out[k * n_shift + i] = v;
+            const float v = v_s[k][i];
             if (v > cmax[k]) {
                 cmax[k] = v;
                 cind[k] = i;
@@ -113,7 +126,7 @@ __device__ __forceinline__ void count_hypotheses(int (&cnt)[8], float DI, float 
     }
 }
 
-template <int NL>
+template <int NL, int V>
 __global__ void __launch_bounds__(EV_NT) k_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx,
                                                       int N, int *counts) {
     __shared__ int red[16 * 32];
@@ -121,35 +134,43 @@ __global__ void __launch_bounds__(EV_NT) k_ser_iqflip(const float *q, int64_t ld
     int cnt[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) cnt[k] = 0;
-    for (int64_t t = (int64_t)blockIdx.x * EV_NT + threadIdx.x; t < N; t += (int64_t)gridDim.x * EV_NT) {
+    for (int64_t t = ((int64_t)blockIdx.x * EV_NT + threadIdx.x) * V; t < N; t += (int64_t)gridDim.x * EV_NT * V) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            int d[2];
+            int d[2][V];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {                     // torch.argmax: first maximal index
-                float best = q[(int64_t)(p * 2 * NL + c * NL) * ld_q + t];
-                int bi = 0;
+                float best[V], v[V];
+                ld_f32<V>(q + (int64_t)(p * 2 * NL + c * NL) * ld_q + t, best);
+#pragma unroll
+                for (int k = 0; k < V; ++k) d[c][k] = 0;
 #pragma unroll
                 for (int l = 1; l < NL; ++l) {
-                    const float v = q[(int64_t)(p * 2 * NL + c * NL + l) * ld_q + t];
-                    if (v > best) {
-                        best = v;
-                        bi = l;
-                    }
-                }
-                d[c] = bi;
-            }
-            const float dI = (float)d[0], dQ = (float)d[1];
-            const float hI[4] = {dI, S - dI, S - dQ, dQ};     // 0, pi, pi/2, 3pi/2  (sf:201-219)
-            const float hQ[4] = {dQ, S - dQ, dI, S - dI};
-            const float DI = tx_level(tx[(int64_t)(p * 2 + 0) * ld_tx + t], scale);
-            const float DQ = tx_level(tx[(int64_t)(p * 2 + 1) * ld_tx + t], scale);
-            int c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            count_hypotheses(c8, DI, DQ, S, hI, hQ);
+                    ld_f32<V>(q + (int64_t)(p * 2 * NL + c * NL + l) * ld_q + t, v);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {                     // counts[flip][pol][rot]
-                cnt[(0 * 2 + p) * 4 + r] += c8[r];
-                cnt[(1 * 2 + p) * 4 + r] += c8[4 + r];
+                    for (int k = 0; k < V; ++k)
+                        if (v[k] > best[k]) {
+                            best[k] = v[k];
+                            d[c][k] = l;
+                        }
+                }
+            }
+            float xI[V], xQ[V];
+            ld_f16<V>(tx + (int64_t)(p * 2 + 0) * ld_tx + t, xI);
+            ld_f16<V>(tx + (int64_t)(p * 2 + 1) * ld_tx + t, xQ);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float dI = (float)d[0][k], dQ = (float)d[1][k];
+                const float hI[4] = {dI, S - dI, S - dQ, dQ};     // 0, pi, pi/2, 3pi/2  (sf:201-219)
+                const float hQ[4] = {dQ, S - dQ, dI, S - dI};
+                const float DI = tx_level_f(xI[k], scale), DQ = tx_level_f(xQ[k], scale);
+                int c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                count_hypotheses(c8, DI, DQ, S, hI, hQ);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {                     // counts[flip][pol][rot]
+                    cnt[(0 * 2 + p) * 4 + r] += c8[r];
+                    cnt[(1 * 2 + p) * 4 + r] += c8[4 + r];
+                }
             }
         }
     }
@@ -183,17 +204,24 @@ __global__ void k_ser_min(const int *counts, int N, float *ser_out) {
 // ---------------------------------------------------------------------------------------------
 // SER from the constellation with PCS-aware thresholds (sf:225-287)
 // ---------------------------------------------------------------------------------------------
+template <int V>
 __global__ void __launch_bounds__(EV_NT) k_constell_norms(const float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx,
                                                           int N, double *sums) {
     __shared__ double red[2 * 32];
     double acc[2] = {0.0, 0.0};
-    for (int64_t t = (int64_t)blockIdx.x * EV_NT + threadIdx.x; t < N; t += (int64_t)gridDim.x * EV_NT) {
+    for (int64_t t = ((int64_t)blockIdx.x * EV_NT + threadIdx.x) * V; t < N; t += (int64_t)gridDim.x * EV_NT * V) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const float a = half_bits_to_float(tx[(int64_t)(p * 2) * ld_tx + t]), b = half_bits_to_float(tx[(int64_t)(p * 2 + 1) * ld_tx + t]);
-            const float x = rx[(int64_t)(p * 2) * ld_rx + t], y = rx[(int64_t)(p * 2 + 1) * ld_rx + t];
-            acc[0] += (double)sqrtf(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));
-            acc[1] += (double)sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+            float a[V], b[V], x[V], y[V];
+            ld_f16<V>(tx + (int64_t)(p * 2) * ld_tx + t, a);
+            ld_f16<V>(tx + (int64_t)(p * 2 + 1) * ld_tx + t, b);
+            ld_f32<V>(rx + (int64_t)(p * 2) * ld_rx + t, x);
+            ld_f32<V>(rx + (int64_t)(p * 2 + 1) * ld_rx + t, y);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                acc[0] += (double)sqrtf(__fadd_rn(__fmul_rn(a[k], a[k]), __fmul_rn(b[k], b[k])));
+                acc[1] += (double)sqrtf(__fadd_rn(__fmul_rn(x[k], x[k]), __fmul_rn(y[k], y[k])));
+            }
         }
     }
     block_sum<2>(acc, red);
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(EV_NT) k_constell_norms(const float *rx, int64
     }
 }
 
-template <int NL>
+template <int NL, int V>
 __global__ void __launch_bounds__(EV_NT) k_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx,
                                                         const float *amp, const float *var, float nu_sc, int N,
                                                         const double *sums, int *counts) {
@@ -223,25 +251,42 @@ __global__ void __launch_bounds__(EV_NT) k_ser_constell(float *rx, int64_t ld_rx
     int cnt[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) cnt[k] = 0;
-    for (int64_t t = (int64_t)blockIdx.x * EV_NT + threadIdx.x; t < N; t += (int64_t)gridDim.x * EV_NT) {
+    for (int64_t t = ((int64_t)blockIdx.x * EV_NT + threadIdx.x) * V; t < N; t += (int64_t)gridDim.x * EV_NT * V) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             float *pI = rx + (int64_t)(p * 2) * ld_rx + t, *pQ = rx + (int64_t)(p * 2 + 1) * ld_rx + t;
-            const float yI = __fmul_rn(*pI, g), yQ = __fmul_rn(*pQ, g);
-            *pI = yI;                                         // in-place rescale, visible to the caller (sf:242)
-            *pQ = yQ;
-            const float DI = tx_level(tx[(int64_t)(p * 2) * ld_tx + t], scale), DQ = tx_level(tx[(int64_t)(p * 2 + 1) * ld_tx + t], scale);
-            const float DQf = S - DQ;
-            const int iI = min(max((int)DI, 0), NL - 1), iQ = min(max((int)DQ, 0), NL - 1), iQf = min(max((int)DQf, 0), NL - 1);
-            const float hI[4] = {yI, -yI, -yQ, yQ};           // sf:245-262
-            const float hQ[4] = {yQ, -yQ, yI, -yI};
+            float yI[V], yQ[V], xI[V], xQ[V];
+            ld_f32<V>(pI, yI);
+            ld_f32<V>(pQ, yQ);
+            ld_f16<V>(tx + (int64_t)(p * 2) * ld_tx + t, xI);
+            ld_f16<V>(tx + (int64_t)(p * 2 + 1) * ld_tx + t, xQ);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const bool okI = (lo[iI] <= hI[r]) && (hI[r] < hi[iI]);
-                const bool okQ = (lo[iQ] <= hQ[r]) && (hQ[r] < hi[iQ]);
-                const bool okQf = (lo[iQf] <= hQ[r]) && (hQ[r] < hi[iQf]);
-                cnt[(0 * 2 + p) * 4 + r] += !(okI && okQ);
-                cnt[(1 * 2 + p) * 4 + r] += !(okI && okQf);
+            for (int k = 0; k < V; ++k) {
+                yI[k] = __fmul_rn(yI[k], g);
+                yQ[k] = __fmul_rn(yQ[k], g);
+            }
+            if constexpr (V == 4) {                           // in-place rescale, visible to the caller (sf:242)
+                *reinterpret_cast<float4 *>(pI) = make_float4(yI[0], yI[1], yI[2], yI[3]);
+                *reinterpret_cast<float4 *>(pQ) = make_float4(yQ[0], yQ[1], yQ[2], yQ[3]);
+            } else {
+                *pI = yI[0];
+                *pQ = yQ[0];
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float DI = tx_level_f(xI[k], scale), DQ = tx_level_f(xQ[k], scale);
+                const float DQf = S - DQ;
+                const int iI = min(max((int)DI, 0), NL - 1), iQ = min(max((int)DQ, 0), NL - 1), iQf = min(max((int)DQf, 0), NL - 1);
+                const float hI[4] = {yI[k], -yI[k], -yQ[k], yQ[k]};           // sf:245-262
+                const float hQ[4] = {yQ[k], -yQ[k], yI[k], -yI[k]};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool okI = (lo[iI] <= hI[r]) && (hI[r] < hi[iI]);
+                    const bool okQ = (lo[iQ] <= hQ[r]) && (hQ[r] < hi[iQ]);
+                    const bool okQf = (lo[iQf] <= hQ[r]) && (hQ[r] < hi[iQf]);
+                    cnt[(0 * 2 + p) * 4 + r] += !(okI && okQ);
+                    cnt[(1 * 2 + p) * 4 + r] += !(okI && okQf);
+                }
             }
         }
     }
@@ -264,18 +309,24 @@ __global__ void __launch_bounds__(EV_NT) k_ser_constell(float *rx, int64_t ld_rx
 // ---------------------------------------------------------------------------------------------
 // extension (not in the reference): GMI-style achievable rate from the posteriors
 // ---------------------------------------------------------------------------------------------
-template <int NL>
+template <int NL, int V>
 __global__ void __launch_bounds__(EV_NT) k_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, int N, double *sums) {
     __shared__ double red[2 * 32];
     const float scale = (float)((NL - 1) / 2.0);
     double acc[2] = {0.0, 0.0};
-    for (int64_t t = (int64_t)blockIdx.x * EV_NT + threadIdx.x; t < N; t += (int64_t)gridDim.x * EV_NT) {
+    for (int64_t t = ((int64_t)blockIdx.x * EV_NT + threadIdx.x) * V; t < N; t += (int64_t)gridDim.x * EV_NT * V) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const int iI = min(max((int)tx_level(tx[(int64_t)(p * 2) * ld_tx + t], scale), 0), NL - 1);
-            const int iQ = min(max((int)tx_level(tx[(int64_t)(p * 2 + 1) * ld_tx + t], scale), 0), NL - 1);
-            const float qi = q[(int64_t)(p * 2 * NL + iI) * ld_q + t], qq = q[(int64_t)(p * 2 * NL + NL + iQ) * ld_q + t];
-            acc[p] += log2((double)fmaxf(qi, 1e-30f)) + log2((double)fmaxf(qq, 1e-30f));
+            float xI[V], xQ[V];
+            ld_f16<V>(tx + (int64_t)(p * 2) * ld_tx + t, xI);
+            ld_f16<V>(tx + (int64_t)(p * 2 + 1) * ld_tx + t, xQ);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int iI = min(max((int)tx_level_f(xI[k], scale), 0), NL - 1);
+                const int iQ = min(max((int)tx_level_f(xQ[k], scale), 0), NL - 1);
+                const float qi = q[(int64_t)(p * 2 * NL + iI) * ld_q + t + k], qq = q[(int64_t)(p * 2 * NL + NL + iQ) * ld_q + t + k];
+                acc[p] += log2((double)fmaxf(qi, 1e-30f)) + log2((double)fmaxf(qq, 1e-30f));
+            }
         }
     }
     block_sum<2>(acc, red);
@@ -292,11 +343,15 @@ __global__ void k_gmi_fin(const double *sums, const float *P, int n_lev, int N, 
     }
 }
 
-static int ev_grid(int N) { return max(1, min((N + EV_NT - 1) / EV_NT, sm_count() * 8)); }
+static int ev_grid(int N, int V = 1) { return max(1, min((N / V + EV_NT - 1) / EV_NT, sm_count() * 8)); }
 
 }  // namespace vaeq
 
 using namespace vaeq;
+
+extern "C" size_t vaeq_find_shift_scratch_bytes(int32_t n_shift) {
+    return n_shift > 0 ? (size_t)EV_CHUNKS * n_shift * 8 * sizeof(double) : 0;
+}
 
 extern "C" int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, int64_t ld_out, const uint16_t *tx,
                                int64_t ld_tx, const float *amp, int32_t n_lev, int32_t N, int32_t n_shift, float *corr_out,
@@ -305,14 +360,19 @@ extern "C" int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, i
     VAEQ_CHECK_ARG(tx && shift_out && r_out && scratch && N > 0 && n_shift > 0 && n_shift <= 64, "bad find_shift arguments");
     VAEQ_CHECK_ARG(!q || (amp && n_lev >= 1 && n_lev <= VAEQ_MAX_LEVELS), "bad amp / n_lev");
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunks = (int)min((int64_t)EV_CHUNKS, ((int64_t)N + 4095) / 4096);
-    dim3 grid(n_shift, chunks);
+    const int64_t tiles = ((int64_t)N + SC_T - 1) / SC_T;
+    const int chunks = (int)min((int64_t)min(EV_CHUNKS, 4 * sm_count()), tiles);
+    const int64_t per = (tiles + chunks - 1) / chunks * SC_T;
+    const int grid = (int)(((int64_t)N + per - 1) / per);
     double *part = static_cast<double *>(scratch);
-    if (q) k_shift_corr<true><<<grid, EV_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, part);
-    else k_shift_corr<false><<<grid, EV_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, part);
+    const bool one = n_shift <= 32;
+    if (q && one) k_shift_corr<true, 1><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
+    else if (q) k_shift_corr<true, 2><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
+    else if (one) k_shift_corr<false, 1><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);
+    else k_shift_corr<false, 2><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);
     ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_shift_corr");
-    k_shift_decide<<<1, 32, 0, st>>>(part, n_shift, chunks, corr_out, shift_out, r_out);
+    k_shift_decide<<<1, 1024, 0, st>>>(part, n_shift, grid, corr_out, shift_out, r_out);
     ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_shift_decide");
     return VAEQ_OK;
@@ -324,10 +384,13 @@ extern "C" int vaeq_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx,
     VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
     cudaStream_t st = (cudaStream_t)stream;
     VAEQ_CUDA(cudaMemsetAsync(counts_out, 0, 16 * sizeof(int), st));
-    const int grid = ev_grid(N);
-    if (n_lev == 2) k_ser_iqflip<2><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
-    else if (n_lev == 4) k_ser_iqflip<4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
-    else k_ser_iqflip<8><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
+    const bool vec = ev_vec_ok(q, ld_q, tx, ld_tx, N);
+    const int grid = ev_grid(N, vec ? 4 : 1);
+#define EV_CASE(NL_)                                                                                         \
+    if (vec) k_ser_iqflip<NL_, 4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);                \
+    else k_ser_iqflip<NL_, 1><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
+    if (n_lev == 2) { EV_CASE(2) } else if (n_lev == 4) { EV_CASE(4) } else { EV_CASE(8) }
+#undef EV_CASE
     ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_iqflip");
     k_ser_min<<<1, 32, 0, st>>>(counts_out, N, ser_out);
@@ -345,13 +408,17 @@ extern "C" int vaeq_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, i
     double *sums = static_cast<double *>(scratch);
     VAEQ_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
     VAEQ_CUDA(cudaMemsetAsync(counts_out, 0, 16 * sizeof(int), st));
-    const int grid = ev_grid(N);
-    k_constell_norms<<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, N, sums);
+    const bool vec = ev_vec_ok(rx, ld_rx, tx, ld_tx, N);
+    const int grid = ev_grid(N, vec ? 4 : 1);
+    if (vec) k_constell_norms<4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, N, sums);
+    else k_constell_norms<1><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, N, sums);
     ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_constell_norms");
-    if (n_lev == 2) k_ser_constell<2><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
-    else if (n_lev == 4) k_ser_constell<4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
-    else k_ser_constell<8><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
+#define EV_CASE(NL_)                                                                                                          \
+    if (vec) k_ser_constell<NL_, 4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);      \
+    else k_ser_constell<NL_, 1><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
+    if (n_lev == 2) { EV_CASE(2) } else if (n_lev == 4) { EV_CASE(4) } else { EV_CASE(8) }
+#undef EV_CASE
     ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_constell");
     k_ser_min<<<1, 32, 0, st>>>(counts_out, N, ser_out);
@@ -367,10 +434,13 @@ extern "C" int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_
     cudaStream_t st = (cudaStream_t)stream;
     double *sums = static_cast<double *>(scratch);
     VAEQ_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
-    const int grid = ev_grid(N);
-    if (n_lev == 2) k_gmi<2><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
-    else if (n_lev == 4) k_gmi<4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
-    else k_gmi<8><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
+    const bool vec = ev_vec_ok(q, ld_q, tx, ld_tx, N);
+    const int grid = ev_grid(N, vec ? 4 : 1);
+#define EV_CASE(NL_)                                                                        \
+    if (vec) k_gmi<NL_, 4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);            \
+    else k_gmi<NL_, 1><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
+    if (n_lev == 2) { EV_CASE(2) } else if (n_lev == 4) { EV_CASE(4) } else { EV_CASE(8) }
+#undef EV_CASE
     ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_gmi");
     k_gmi_fin<<<1, 32, 0, st>>>(sums, P, n_lev, N, gmi_out);

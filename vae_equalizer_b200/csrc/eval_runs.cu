@@ -8,6 +8,7 @@
 // stay on the device, so a frame of a sweep needs no host synchronisation and 7 launches for all runs instead of ~40 small
 // launches and two syncs per run.  The arithmetic per element is that of eval.cu (same decisions, same counts).
 #include "common.cuh"
+#include "shift_corr.cuh"
 
 namespace vaeq {
 
@@ -23,7 +24,7 @@ struct EvalRunsK {
     const float *nu_sc;                          // (R)
     int n_lev, N, n_shift, n_runs;
     int seg_len, edge, n_cut;                    // seg_len = batch_len (VAE-LE minibatch cut) or 0 (VAE-flex); edge = 11; n_cut = 10
-    double *part;                                // [R][2][n_shift][ER_CHUNKS][8]
+    double *part;                                // [R][2][ER_CHUNKS][n_shift][8]
     int *align;                                  // [R][2][4]: shift_0, shift_1, r, n_eval      (estimator 0: from q, 1: from out)
     double *norms;                               // [R][2]: sum |tx|, sum |rx| over the evaluated region (estimator 1)
     int *counts;                                 // [R][2][16]
@@ -46,62 +47,45 @@ __device__ __forceinline__ int er_wrap(int t, int N) {
     return t < 0 ? t + N : t;
 }
 
-// ---- shift search, both estimators, all runs: grid (n_shift, ER_CHUNKS, 2 R) -----------------------------------------------
-__global__ void __launch_bounds__(ER_NT) k_er_shift_corr(EvalRunsK p) {
-    __shared__ double red[8 * 32];
-    const int i = blockIdx.x, chunk = blockIdx.y, run = blockIdx.z >> 1, est = blockIdx.z & 1, half = p.n_shift / 2, N = p.N;
-    const int per = (N + ER_CHUNKS - 1) / ER_CHUNKS, t_lo = chunk * per, t_hi = min(N, t_lo + per);
+// ---- shift search, both estimators, all runs: grid (ER_CHUNKS, 2 R); a CTA scans its range of t once for all shifts ------------
+template <int NPASS>
+__global__ void __launch_bounds__(SC_NT, SC_MINB) k_er_shift_corr(EvalRunsK p) {
+    __shared__ ShiftSmem sm;
+    const int chunk = blockIdx.x, run = blockIdx.y >> 1, est = blockIdx.y & 1, N = p.N;
+    const int per = ((N + ER_CHUNKS - 1) / ER_CHUNKS + SC_SLICE - 1) / SC_SLICE * SC_SLICE;
+    const int64_t t_lo = min((int64_t)N, (int64_t)chunk * per), t_hi = min((int64_t)N, t_lo + per);
     const float *q = p.q + run * p.rs_q, *out = p.out + run * p.rs_out;
     const uint16_t *tx = p.tx + run * p.rs_tx;
-    float a_l[VAEQ_MAX_LEVELS];
-#pragma unroll
-    for (int l = 0; l < VAEQ_MAX_LEVELS; ++l) a_l[l] = (est == 0 && l < p.n_lev) ? p.amp[l] : 0.f;
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t_lo + threadIdx.x; t < t_hi; t += ER_NT) {
-        const int src = er_wrap(t - (i - half), N);
-        float E[2];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            if (est == 0) {
-                float e = 0.f;                                            // E_q[x_I] = sum_l a_l q_I[l]  (sf:297)
-                for (int l = 0; l < p.n_lev; ++l) e += a_l[l] * q[(int64_t)(b * 2 * p.n_lev + l) * p.ld_q + src];
-                E[b] = e;
-            } else {
-                E[b] = out[(int64_t)(b * 2) * p.ld_out + src];           // rx[:,0,:]  (sf:321)
-            }
-        }
-#pragma unroll
-        for (int comp = 0; comp < 2; ++comp)
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const float x = half_bits_to_float(tx[(int64_t)(a * 2 + comp) * p.ld_tx + t]);
-                acc[comp * 4 + 0 * 2 + a] += (double)(x * E[0]);
-                acc[comp * 4 + 1 * 2 + a] += (double)(x * E[1]);
-            }
-    }
-    block_sum<8>(acc, red);
-    if (threadIdx.x == 0) {
-        double *dst = p.part + ((((int64_t)run * 2 + est) * p.n_shift + i) * ER_CHUNKS + chunk) * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dst[k] = acc[k];
-    }
+    double *dst = p.part + ((((int64_t)run * 2 + est) * ER_CHUNKS + chunk) * p.n_shift) * 8;
+    if (est == 0) shift_corr_range<true, NPASS>(sm, q, p.ld_q, nullptr, 0, tx, p.ld_tx, p.amp, p.n_lev, N, p.n_shift, t_lo, t_hi, dst);
+    else shift_corr_range<false, NPASS>(sm, nullptr, 0, out, p.ld_out, tx, p.ld_tx, nullptr, 0, N, p.n_shift, t_lo, t_hi, dst);
 }
 
-// one thread per (run, estimator): torch.max / argmax logic of sf:303-314 (first index wins ties), then the cut geometry
-__global__ void k_er_shift_decide(EvalRunsK p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 2 * p.n_runs) return;
-    const int run = idx >> 1, est = idx & 1, half = p.n_shift / 2;
-    const double *part = p.part + ((int64_t)run * 2 + est) * p.n_shift * ER_CHUNKS * 8;
+// one warp per (run, estimator): lanes sum the chunk partials of consecutive (i, k) (coalesced), lane 0 replays the torch.max / argmax
+// logic of sf:303-314 (first index wins ties), then the cut geometry
+constexpr int ER_DEC_NT = 128;
+__global__ void __launch_bounds__(ER_DEC_NT) k_er_shift_decide(EvalRunsK p) {
+    __shared__ float v_s[ER_DEC_NT / 32][8][SC_MAXSHIFT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int idx = blockIdx.x * (ER_DEC_NT / 32) + w;
+    if (idx >= 2 * p.n_runs) return;                         // whole warps leave together; no block-wide barrier below
+    const int run = idx >> 1, est = idx & 1, half = p.n_shift / 2, nidx = p.n_shift * 8;
+    const double *part = p.part + ((int64_t)run * 2 + est) * ER_CHUNKS * nidx;
+    for (int j = lane; j < nidx; j += 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < ER_CHUNKS; ++c) s += part[(int64_t)c * nidx + j];
+        v_s[w][j & 7][j >> 3] = fabsf((float)s);
+    }
+    __syncwarp();
+    if (lane != 0) return;
     float cmax[8];
     int cind[8];
     for (int k = 0; k < 8; ++k) {
         cmax[k] = -1.f;
         cind[k] = 0;
         for (int i = 0; i < p.n_shift; ++i) {
-            double s = 0.0;
-            for (int c = 0; c < ER_CHUNKS; ++c) s += part[((int64_t)i * ER_CHUNKS + c) * 8 + k];
-            const float v = fabsf((float)s);
+            const float v = v_s[w][k][i];
             if (v > cmax[k]) {
                 cmax[k] = v;
                 cind[k] = i;
@@ -326,8 +310,9 @@ extern "C" int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, 
     __VA_ARGS__;                                \
     ktime_end(VAEQ_K_EVAL, st);                 \
     VAEQ_LAUNCH_CHECK(name);
-    ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<<<dim3(n_shift, ER_CHUNKS, 2 * n_runs), ER_NT, 0, st>>>(p))
-    ER_LAUNCH("k_er_shift_decide", k_er_shift_decide<<<(2 * n_runs + 127) / 128, 128, 0, st>>>(p))
+    if (n_shift <= 32) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<1><<<dim3(ER_CHUNKS, 2 * n_runs), SC_NT, 0, st>>>(p)) }
+    else { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<2><<<dim3(ER_CHUNKS, 2 * n_runs), SC_NT, 0, st>>>(p)) }
+    ER_LAUNCH("k_er_shift_decide", k_er_shift_decide<<<(2 * n_runs + ER_DEC_NT / 32 - 1) / (ER_DEC_NT / 32), ER_DEC_NT, 0, st>>>(p))
     if (n_lev == 2) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<2><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
     else if (n_lev == 4) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<4><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
     else { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<8><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }

@@ -220,7 +220,8 @@ def _find_shift(q, out, tx, N_shift, amp_levels, return_corr, sync=True):
     corr = torch.empty(2, 2, 2, N_shift, dtype=_F32, device=dev)
     shift = torch.empty(2, dtype=torch.int16, device=dev)
     r = torch.empty(1, dtype=torch.int32, device=dev)
-    scr = _scratch(dev)
+    lib = _lib.load()
+    scr = _scratch(dev, int(lib.vaeq_find_shift_scratch_bytes(int(N_shift))))
     n = 0 if q is None else q.shape[1] // 2
     _lib.check(lib.vaeq_find_shift(None if q is None else q.data_ptr(), 0 if q is None else _rows(q, "q"),
                                    None if out is None else out.data_ptr(), 0 if out is None else _rows(out, "rx"),
