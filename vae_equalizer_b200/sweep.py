@@ -48,7 +48,13 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
         raise KeyError(kind)
     N_lrhalf = num_frames if N_lrhalf is None else N_lrhalf
     phiIQ = np.asarray(phiIQ, dtype=np.complex64)
-    consts = [sfun.init(channel, mod, device, _cell(c, "nu"), sps, M_est, _cell(c, "SNR")) for c in cells]
+    init_cache = {}                                                      # cells of a sweep share few (nu, SNR) pairs: sf.init once per pair
+    consts = []
+    for c in cells:
+        key = (float(_cell(c, "nu")), float(_cell(c, "SNR")))
+        if key not in init_cache:
+            init_cache[key] = sfun.init(channel, mod, device, key[0], sps, M_est, key[1])
+        consts.append(init_cache[key])
     h_channel, amp_levels, amps, pol = consts[0][1], consts[0][3], consts[0][4], consts[0][5]
     num_lev = int(amp_levels.numel())
     P_all = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in consts])
