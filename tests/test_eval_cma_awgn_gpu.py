@@ -210,3 +210,64 @@ def test_dropin_awgn_runs():
     from vae_equalizer_b200 import processing as pr
     SER = pr.processing_vaele_awgn("16-QAM", 2, 20, 0, 25, 5e-3, 350, 5000, 1200, 40, 10, "h1", rng=np.random.default_rng(1), verbose=False)
     assert SER.shape == (4,) and torch.isfinite(SER).all() and float(SER[-1]) < float(SER[0]) + 1e-6
+
+
+@pytest.mark.parametrize("N,n_shift", [(64, 21), (516, 21), (1003, 21), (20000, 41), (4100, 64), (300000, 21)])
+def test_find_shift_one_pass_kernel_against_oracle(N, n_shift):
+    """csrc/shift_corr.cuh: tiles, circular wrap at both ends, vector and scalar staging, one and two shift passes."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    gen = torch.Generator().manual_seed(N + n_shift)
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, 25, 18)
+    idx = torch.randint(0, 8, (2, 2, N), generator=gen)
+    tx = amp[idx].to(torch.float16)
+    true_shift = (3, -2)
+    out = amp[idx] + 0.08 * torch.randn(2, 2, N, generator=gen)
+    out = torch.stack((out[1].roll(true_shift[0], -1), out[0].roll(true_shift[1], -1)))      # crossed polarisations, shifted
+    q = O.soft_demap(out, var, amp, nu_sc)
+    so, ro, co = O.find_shift(q, tx, n_shift, amp, 2, return_corr=True)
+    s, r, c_q = sfun.find_shift(q.cuda(), tx.cuda(), n_shift, amp.cuda(), 2, return_corr=True)
+    assert s.tolist() == so.tolist() and r == ro and rel(c_q, co) < 2e-5
+    sq, rq = so.tolist(), ro
+    so, ro, co = O.find_shift_symb_full(out, tx, n_shift, return_corr=True)
+    s, r, c = sfun.find_shift_symb_full(out.cuda(), tx.cuda(), n_shift, return_corr=True)
+    assert s.tolist() == so.tolist() and r == ro and rel(c, co) < 2e-5
+    # a view with a misaligned base takes the scalar staging path: same decisions, same correlations to rounding
+    big_q, big_o, big_t = torch.zeros(2, 16, N + 5).cuda(), torch.zeros(2, 2, N + 5).cuda(), torch.zeros(2, 2, N + 5, dtype=torch.float16).cuda()
+    big_q[:, :, 1:N + 1], big_o[:, :, 1:N + 1], big_t[:, :, 1:N + 1] = q.cuda(), out.cuda(), tx.cuda()
+    s2, r2, c2 = sfun.find_shift(big_q[:, :, 1:N + 1], big_t[:, :, 1:N + 1], n_shift, amp.cuda(), 2, return_corr=True)
+    assert s2.tolist() == sq and r2 == rq and rel(c2, c_q) < 1e-6
+    s3, r3 = sfun.find_shift_symb_full(big_o[:, :, 1:N + 1], big_t[:, :, 1:N + 1], n_shift)
+    assert s3.tolist() == so.tolist() and r3 == ro
+
+
+def test_vector_and_scalar_scan_paths_agree():
+    """4-symbols-per-thread kernels (aligned rows) against the one-symbol kernels (misaligned views of the same data)."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    gen = torch.Generator().manual_seed(11)
+    N = 200000
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, 25, 17)
+    idx = torch.randint(0, 8, (2, 2, N), generator=gen)
+    tx = amp[idx].to(torch.float16).cuda()
+    out = ((amp[idx] + 0.06 * torch.randn(2, 2, N, generator=gen)) * 0.93).cuda()
+    ampc, varc = amp.cuda(), var.cuda()
+    big_o, big_t = torch.zeros(2, 2, N + 8, device="cuda"), torch.zeros(2, 2, N + 8, dtype=torch.float16, device="cuda")
+    big_o[:, :, 3:N + 3], big_t[:, :, 3:N + 3] = out, tx
+    vo, vt = big_o[:, :, 3:N + 3], big_t[:, :, 3:N + 3]
+    q_vec = sfun.soft_dec(out, varc, ampc, nu_sc)                       # vector kernel
+    big_q = torch.zeros(2, 16, N + 8, device="cuda")
+    q_sca = big_q[:, :, 3:N + 3]
+    q_sca.copy_(q_vec)                                                  # same values behind a misaligned view
+    q_prec = sfun.soft_dec(out[:, :, :N - 1].contiguous(), varc, ampc, nu_sc)     # N - 1 is odd: the precise one-symbol kernel
+    assert float((q_prec - q_vec[:, :, :N - 1]).abs().max()) < 1e-6
+    assert torch.equal(q_prec.reshape(2, 2, 8, -1).argmax(2), q_vec[:, :, :N - 1].reshape(2, 2, 8, -1).argmax(2))
+    qo = O.soft_demap(out.cpu(), var, amp, nu_sc)
+    assert float((qo - q_vec.cpu()).abs().max()) < 2e-5
+    _, c_vec = sfun.SER_IQflip(q_vec, tx, return_counts=True)
+    _, c_sca = sfun.SER_IQflip(q_sca, vt, return_counts=True)
+    assert torch.equal(c_vec, c_sca)
+    g_vec, g_sca = sfun.GMI(q_vec, tx, P), sfun.GMI(q_sca, vt, P)
+    assert float((g_vec - g_sca).abs().max()) < 1e-6
+    r1, r2 = out.clone(), vo                                              # r2 rescaled in place inside big_o
+    s1, c1 = sfun.SER_constell_shaping(r1, tx, ampc, nu_sc, varc, return_counts=True)
+    s2, c2 = sfun.SER_constell_shaping(r2, vt, ampc, nu_sc, varc, return_counts=True)
+    assert torch.equal(c1, c2) and torch.equal(s1, s2) and torch.equal(r1, big_o[:, :, 3:N + 3])
