@@ -326,3 +326,33 @@ def test_full_size_gradient_is_the_derivative_of_the_loss():
         fd = (vals[0] - vals[1]) / (2 * eps)
         an = float(((gW if which == "W" else gh) * d.double()).sum())
         assert abs(fd - an) / abs(an) < 2e-2, (which, fd, an)
+
+
+def test_graph_replay_equals_plain_steps():
+    """DPEqualizer.capture_steps: replaying the CUDA graph of two consecutive steps continues training exactly like plain calls
+    (the Adam step counter lives on the device)."""
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    M, B = 25, 1 << 15
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rxs = [O.generate_data_shaping(B, amps, 23, h_ch, P, 2, 90e9, 2, -26e-24, 0.1e-12 * np.sqrt(1000), np.array([0.0314, 0.0314], dtype=np.complex64),
+                                   np.pi / 10, "cpu", rng=np.random.default_rng(5 + i))[0].cuda() for i in range(2)]
+    Pt = torch.tensor(P, dtype=torch.float32)
+    lib.vaeq_dp_dynamic_tiles(0)                         # static tiles: bitwise reproducible partial sums
+    try:
+        a, b = DPEqualizer(M, 2, amp, Pt, var, nu_sc), DPEqualizer(M, 2, amp, Pt, var, nu_sc)
+        qa, oa = torch.empty(2, 16, B, device="cuda"), torch.empty(2, 2, B, device="cuda")
+        qb, ob = torch.empty_like(qa), torch.empty_like(oa)
+        for eq, q, o in ((a, qa, oa), (b, qb, ob)):
+            eq.train_step(rxs[0], 2.5e-3, 2.5e-3, q=q, out=o)            # first call: workspaces, kernel attributes
+        g = b.capture_steps(rxs, 2.5e-3, 2.5e-3, q=qb, out=ob)
+        for _ in range(3):
+            g.replay()
+            for rx in rxs:
+                a.train_step(rx, 2.5e-3, 2.5e-3, q=qa, out=oa)
+        torch.cuda.synchronize()
+        assert torch.equal(a.W, b.W) and torch.equal(a.h, b.h) and torch.equal(qa, qb) and torch.equal(a.loss, b.loss)
+        assert int(a.step_count()) == int(b.step_count()) == 7
+    finally:
+        lib.vaeq_dp_dynamic_tiles(1)
