@@ -36,8 +36,8 @@ N_LEV = 8
 ALG_BYTES_PER_SYMBOL = 4 * 2 * (2 * SPS + 2 * N_LEV + 2)        # read rx once, write q and out once = 176 B
 ALG_FLOP_PER_SYMBOL = 5 * 32 * M_EST + 1000                      # 5 tap contractions + point-wise work
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (k_dp_fwd_fast<8,12>) at batch_len 2^22 from the
-# `ncu --set full` capture summarised in profiles/r01c_ncu_full_summary.json: 137.2 MB read + 967.1 MB written = 263.3 B/symbol
-FWD_DRAM_BYTES_PER_SYMBOL = (137.168e6 + 967.142e6) / (1 << 22)
+# `ncu --set full` capture summarised in profiles/r01d_ncu_full_summary.json: 134.3 MB read + 948.1 MB written = 258.1 B/symbol
+FWD_DRAM_BYTES_PER_SYMBOL = (134.274e6 + 948.072e6) / (1 << 22)
 CPU_SAMPLE_LOG2 = 17
 
 
@@ -316,7 +316,7 @@ def ours_arm(args, rank, local_rank, world):
         # the sweep engine end to end (configs[4]): per frame batched data generation + one training launch + batched evaluation
         from vae_equalizer_b200 import sweep as _sweep
         cells = [dict(SNR=15 + 2 * (i % 8), nu=NU, lr_optim=LR, theta=np.pi / 10, theta_diff=0.06 * np.pi, seed=i) for i in range(296)]
-        _sweep.sweep_vae_dp(cells[:4], MOD, SPS, M_EST, Bs, Bs * ns, 1, kind="VAE", datagen="gpu_batched", device=dev)
+        _sweep.sweep_vae_dp(cells, MOD, SPS, M_EST, Bs, Bs * ns, 1, kind="VAE", datagen="gpu_batched", device=dev)   # warm-up at full size (allocator, cuFFT plans)
         torch.cuda.synchronize()
         tw = time.perf_counter()
         ser_s, _, _ = _sweep.sweep_vae_dp(cells, MOD, SPS, M_EST, Bs, Bs * ns, 4, kind="VAE", datagen="gpu_batched", device=dev)
@@ -370,7 +370,7 @@ def ours_arm(args, rank, local_rank, world):
     step_gbs = B * ALG_BYTES_PER_SYMBOL * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (FWD_DRAM_BYTES_PER_SYMBOL * B if names[dom] == "k_dp_fwd" and M_EST == 25 else None),
-                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01c_ncu_full_summary.json, scaled to this batch_len)",
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01d_ncu_full_summary.json, scaled to this batch_len)",
                 "peak_source": peak_src, "alg_bytes_per_symbol": ALG_BYTES_PER_SYMBOL,
                 "alg_bytes_per_launch": B * ALG_BYTES_PER_SYMBOL,
                 "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
