@@ -251,6 +251,27 @@ size_t vaeq_cpe_scratch_bytes(int32_t N);
 int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Synthetic test signal on the device, n_runs independent runs per call (generate_data_shaping sf:65-90, channel 'h0'; the
+ * reference's generator is unseeded, parity is statistical).  The host side (vae_equalizer_b200/datagen.py) runs
+ *   vaeq_gen_levels -> vaeq_gen_pulse -> FFT -> vaeq_gen_jones -> IFFT -> vaeq_gen_noise
+ * with the two DFTs of the dispersion step (sf:40, 54) on cuFFT.  Random numbers are Philox4x32-10 outputs keyed by
+ * (seed, run, row, position): a run's data does not depend on the batch it is generated in.
+ * ---------------------------------------------------------------------------------------------- */
+/* sf:75-76, 89: lev (n_runs,4,n_conv) float rows [pol0 I, pol0 Q, pol1 I, pol1 Q] drawn from amps (n_lev) with pmf P (n_runs,n_lev);
+ * tx (n_runs,2,2,N) float16 bit patterns = lev[:, :, tx_off : tx_off + N] */
+int vaeq_gen_levels(const float *amps, const float *P, int32_t n_lev, int32_t n_conv, int32_t N, int32_t tx_off, uint64_t seed,
+                    float *lev, uint16_t *tx, int32_t n_runs, void *stream);
+/* sf:77-80 (simulate_channel sf:56-63 with a one-tap channel): zero insertion by sps = 2 and 'valid' convolution with the pulse h
+ * (n_pulse taps, even); shaped (n_runs,2,2*n_conv - n_pulse) complex64, 16-byte aligned */
+int vaeq_gen_pulse(const float *lev, const float *h, int32_t n_pulse, int32_t n_conv, float *shaped, int32_t n_runs, void *stream);
+/* sf:41-53 in the frequency domain, in place: X (n_runs,2,n) complex64 spectra; Pcd = exp_pmd*exp_cd, Picd = exp_cd/exp_pmd (n) complex64;
+ * theta (n_runs) rotation angles; phi0, phi1 the IQ phases (exp_phiIQ = exp(-j phi), sf:44) */
+int vaeq_gen_jones(float *X, const float *Pcd, const float *Picd, const float *theta, float phi0, float phi1, int32_t n, int32_t n_runs,
+                   void *stream);
+/* sf:83-88: rx (n_runs,2,2,L) float32 = Re/Im of sig[:, :, :L] + sigma[run] * N(0,1); sig (n_runs,2,n) complex64, L <= n */
+int vaeq_gen_noise(const float *sig, const float *sigma, uint64_t seed, int32_t n, int32_t L, float *rx, int32_t n_runs, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * AWGN single-polarisation VAE-LE step: twoFIR.forward (AWGN_channel/func_VAELE_MQAM_shaping.py:214-231)
  * + loss_function (:63-95) + backward + Adam(amsgrad=True) (:283-306)
  * ---------------------------------------------------------------------------------------------- */

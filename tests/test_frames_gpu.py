@@ -229,3 +229,62 @@ def test_batched_frame_evaluation_equals_per_run_calls(seg_len):
         assert float((s_c.cpu() - ser[r, :2].cpu()).abs().max()) <= 1.5 / n_c, (r, s_c, ser[r])   # norm sums are atomics: +-1 count
         assert 0 < n_q <= N and 0 < n_c <= N
     assert float(ser.max()) < 0.2                                                             # aligned correctly: a misaligned run scores ~0.98
+
+
+def test_cuda_data_generator_against_the_torch_formulation():
+    """csrc/datagen.cu (vaeq_gen_levels / _pulse / _jones / _noise): the noise-free signal equals the torch.fft formulation fed with
+    the same amplitude levels; the levels follow the run's pmf; the noise is white, unit-variance Gaussian scaled by sigma_n;
+    a run's data does not depend on the batch it is generated in."""
+    from vae_equalizer_b200 import datagen as dg
+    N, sps = 6000, 2
+    c64 = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, 25, 23)
+    c0 = O.init("h0", "64-QAM", "cpu", 0.0, 2, 25, 23)
+    amps, P = c64[4], np.stack([np.asarray(c64[2]), np.asarray(c0[2]), np.asarray(c64[2])]).astype(np.float32)
+    snr, theta = [23.0, 13.0, 30.0], [0.3, 1.0, -0.7]
+    args = (90e9, -26e-24, 0.1e-12 * np.sqrt(1000), np.array([0.0314, 0.0314], dtype=np.complex64))
+    Pt = torch.as_tensor(P, device="cuda")
+    rx, tx, sigma, lev, sig = dg._generate_frames_cuda(N, amps, snr, Pt, theta, torch.device("cuda"), 41, *args, return_parts=True)
+    assert rx.shape == (3, 2, 2, sps * N) and tx.shape == (3, 2, 2, N) and tx.dtype == torch.float16
+    # tx is the slice of the drawn levels the reference returns (sf:89)
+    for p in range(2):
+        for c in range(2):
+            assert torch.equal(tx[:, p, c], lev[:, 2 * p + c, dg.PULSE_SPAN:dg.PULSE_SPAN + N].to(torch.float16))
+    # deterministic part against the torch.fft formulation on the same levels
+    sig_t = dg._frames_torch_from_levels(lev, N, sps, theta, *args)
+    assert sig_t.shape == sig.shape
+    assert float((sig - sig_t).abs().max()) < 3e-5 * float(sig_t.abs().max())
+    # sigma_n (sf:83)
+    pw = (sig_t.abs() ** 2).mean(dim=(1, 2)).cpu().numpy()
+    assert np.allclose(sigma.cpu().numpy(), np.sqrt(pw * sps / 2 / 10 ** (np.asarray(snr) / 10)), rtol=1e-4)
+    # the levels follow the pmf of the run
+    a = np.asarray(amps, dtype=np.float32)
+    for r in range(3):
+        x = lev[r].cpu().numpy().ravel()
+        cnt = np.array([(x == a[l]).sum() for l in range(len(a))])
+        assert cnt.sum() == x.size
+        exp = P[r] / P[r].sum() * x.size
+        assert np.all(np.abs(cnt - exp) < 5 * np.sqrt(exp) + 1)
+    # noise: zero mean, unit variance, Gaussian kurtosis, I/Q and neighbouring samples uncorrelated
+    clean = torch.stack((sig.real, sig.imag), dim=2)[..., :sps * N]
+    z = ((rx - clean) / sigma[:, None, None, None]).double()
+    n_el = z[0].numel()
+    for r in range(3):
+        zr = z[r]
+        assert abs(float(zr.mean())) < 5 / np.sqrt(n_el) and abs(float(zr.var()) - 1) < 5 * np.sqrt(2 / n_el)
+        assert abs(float((zr ** 4).mean()) - 3) < 0.2
+        assert abs(float((zr[:, 0] * zr[:, 1]).mean())) < 5 / np.sqrt(n_el / 2)
+        assert abs(float((zr[..., 1:] * zr[..., :-1]).mean())) < 5 / np.sqrt(n_el)
+    # same seed -> same data; run 0 alone = run 0 of the batch; another seed differs
+    rx2, tx2, _ = dg.generate_frames_gpu(N, amps, snr, P, sps, theta, "cuda", 41, *args)
+    rx1, tx1, _ = dg.generate_frames_gpu(N, amps, snr[:1], P[:1], sps, theta[:1], "cuda", 41, *args)
+    rx3, _, _ = dg.generate_frames_gpu(N, amps, snr, P, sps, theta, "cuda", 42, *args)
+    assert torch.equal(rx2, rx) and torch.equal(tx2, tx) and torch.equal(rx1[0], rx[0]) and torch.equal(tx1[0], tx[0])
+    assert not torch.equal(rx3, rx)
+    # and the statistics of the full signal agree with the torch generator on the GPU
+    dg._FORCE_TORCH = True
+    try:
+        rxt, txt, sgt = dg.generate_frames_gpu(N, amps, snr, P, sps, theta, "cuda", 41, *args)
+    finally:
+        dg._FORCE_TORCH = False
+    assert np.allclose(sgt.cpu().numpy(), sigma.cpu().numpy(), rtol=0.05)
+    assert np.allclose(rxt.double().var(dim=(1, 2, 3)).cpu().numpy(), rx.double().var(dim=(1, 2, 3)).cpu().numpy(), rtol=0.05)

@@ -61,7 +61,7 @@ class AwgnDesc(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/vaeq.h declares
-_i32, _i64, _f, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+_i32, _i64, _f, _vp, _sz, _u64 = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t, C.c_uint64
 PROTOTYPES = {
     "vaeq_abi_version": (C.c_int, []),
     "vaeq_last_error": (C.c_char_p, []),
@@ -98,6 +98,10 @@ PROTOTYPES = {
     "vaeq_cma_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_cma": (C.c_int, [_i32, _vp, _i32, _f, _vp, _i32, _f, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "vaeq_cpe_scratch_bytes": (_sz, [_i32]),
+    "vaeq_gen_levels": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _u64, _vp, _vp, _i32, _vp]),
+    "vaeq_gen_pulse": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+    "vaeq_gen_jones": (C.c_int, [_vp, _vp, _vp, _vp, _f, _f, _i32, _i32, _vp]),
+    "vaeq_gen_noise": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _i32, _vp]),
     "vaeq_cpe": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "vaeq_awgn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_adam_state_floats_awgn": (_sz, [_i32]),
