@@ -106,6 +106,22 @@ def _cached_channel_terms(n_up, symb_rate, sps, tau_cd, tau_pmd, device):
     return hit
 
 
+def _per_run(v, R, dev):
+    """Per-run parameter as a float32 device tensor (R,); a tensor already on the device is used as it is."""
+    if torch.is_tensor(v):
+        return v.to(dev, torch.float32).reshape(-1).expand(R).contiguous()
+    return torch.as_tensor(np.broadcast_to(np.asarray(v, dtype=np.float64), (R,)).copy(), dtype=torch.float32, device=dev)
+
+
+def _cached_amps(amps, dev):
+    a = np.ascontiguousarray(np.asarray(amps, dtype=np.float32))
+    key = ("amps", a.tobytes(), str(dev))
+    hit = _GPU_CACHE.get(key)
+    if hit is None:
+        hit = _GPU_CACHE[key] = torch.as_tensor(a, device=dev)
+    return hit
+
+
 _FORCE_TORCH = False      # tests: run the torch.fft formulation on the GPU as the checker of the CUDA kernels
 
 
@@ -116,9 +132,8 @@ def _generate_frames_cuda(N, amps, SNR, P, theta, dev, seed, symb_rate, tau_cd, 
     lib = _lib.load()
     sps, R, n_lev = 2, int(P.shape[0]), int(P.shape[1])
     f32 = torch.float32
-    snr = torch.as_tensor(np.broadcast_to(np.asarray(SNR, dtype=np.float64), (R,)).copy(), dtype=f32, device=dev)
-    th = torch.as_tensor(np.broadcast_to(np.asarray(theta, dtype=np.float64), (R,)).copy(), dtype=f32, device=dev)
-    amps_t = torch.as_tensor(np.asarray(amps), dtype=f32, device=dev).contiguous()
+    snr, th = _per_run(SNR, R, dev), _per_run(theta, R, dev)      # device tensors pass through: no host->device copy (and no sync) per frame
+    amps_t = _cached_amps(amps, dev)
     n_conv = N + 1 + 4 * PULSE_SPAN
     n_up = sps * (n_conv - 1) + 1
     terms = _cached_channel_terms(n_up, symb_rate, sps, tau_cd, tau_pmd, dev)
@@ -182,14 +197,13 @@ def generate_frames_gpu(N, amps, SNR, P, sps, theta, device, seed, symb_rate=90e
     seed for the batch.  Same signal model as generate_data_gpu (channel 'h0'); returns rx (R,2,2,sps*N) f32,
     tx (R,2,2,N) f16, sigma_n (R,)."""
     dev = torch.device(device)
-    P = torch.as_tensor(np.asarray(P), dtype=torch.float32, device=dev)
+    P = P.to(dev, torch.float32) if torch.is_tensor(P) else torch.as_tensor(np.asarray(P), dtype=torch.float32, device=dev)
     if P.dim() == 1:
         P = P[None]
     R = P.shape[0]
     if dev.type == "cuda" and sps == 2 and not _FORCE_TORCH:
         return _generate_frames_cuda(N, amps, SNR, P, theta, dev, seed, symb_rate, tau_cd, tau_pmd, phiIQ)
-    snr = torch.as_tensor(np.broadcast_to(np.asarray(SNR, dtype=np.float64), (R,)).copy(), dtype=torch.float32, device=dev)
-    th = torch.as_tensor(np.broadcast_to(np.asarray(theta, dtype=np.float64), (R,)).copy(), dtype=torch.float32, device=dev)
+    snr, th = _per_run(SNR, R, dev), _per_run(theta, R, dev)
     g = torch.Generator(device=dev).manual_seed(int(seed))
     n_conv = N + 1 + 4 * PULSE_SPAN
     idx = torch.multinomial(P, 4 * n_conv, True, generator=g).view(R, 4, n_conv)

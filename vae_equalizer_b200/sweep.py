@@ -48,25 +48,28 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
         raise KeyError(kind)
     N_lrhalf = num_frames if N_lrhalf is None else N_lrhalf
     phiIQ = np.asarray(phiIQ, dtype=np.complex64)
-    init_cache = {}                                                      # cells of a sweep share few (nu, SNR) pairs: sf.init once per pair
-    consts = []
+    init_cache, uniq, which = {}, [], []                                 # cells of a sweep share few (nu, SNR) pairs: sf.init once per pair
     for c in cells:
         key = (float(_cell(c, "nu")), float(_cell(c, "SNR")))
         if key not in init_cache:
-            init_cache[key] = sfun.init(channel, mod, device, key[0], sps, M_est, key[1])
-        consts.append(init_cache[key])
+            init_cache[key] = len(uniq)
+            uniq.append(sfun.init(channel, mod, device, key[0], sps, M_est, key[1]))
+        which.append(init_cache[key])
+    consts = [uniq[i] for i in which]
     h_channel, amp_levels, amps, pol = consts[0][1], consts[0][3], consts[0][4], consts[0][5]
     num_lev = int(amp_levels.numel())
-    P_all = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in consts])
-    var_all = torch.stack([k[7].to(torch.float32).cpu() for k in consts])
-    nu_sc_all = torch.tensor([k[6] for k in consts], dtype=torch.float32)
+    widx = torch.tensor(which, dtype=torch.long)
+    P_all = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in uniq])[widx]
+    var_all = torch.stack([k[7].to(torch.float32).cpu() for k in uniq])[widx]
+    nu_sc_all = torch.tensor([k[6] for k in uniq], dtype=torch.float32)[widx]
     pow_mean = [k[8] for k in consts]
-    lr0 = torch.tensor([float(_cell(c, "lr_optim")) for c in cells], dtype=torch.float32)
+    lr0 = torch.tensor([float(_cell(c, "lr_optim")) for c in cells], dtype=torch.float32).to(device)     # on the device: no copy / sync per frame
     theta = [float(c.get("theta", 0.0)) for c in cells]
     theta_diff = [float(c.get("theta_diff", 0.0)) for c in cells]
     seeds = [int(c.get("seed", i)) for i, c in enumerate(cells)]
     rngs = [np.random.default_rng(s) for s in seeds]
     eqr = DPEqualizerRuns(R, M_est, sps, amp_levels, P_all, var_all, nu_sc_all, device=device)
+    amp_dev, var_dev, nu_dev = amp_levels.to(device, torch.float32), var_all.to(device), nu_sc_all.to(device)     # evaluation constants: on the device once
 
     if kind == "VAE":
         m_max = N_frame_max // batch_len
@@ -81,7 +84,7 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
 
     SER_valid = torch.full((R, 4, num_frames), float("nan"), device=device, dtype=torch.float32)
     Var_est = torch.empty(R, pol, num_frames, device=device, dtype=torch.float32)
-    rx_all = torch.empty(R, 2, 2, sps * N_frame, device=device, dtype=torch.float32)
+    rx_all = None if datagen == "gpu_batched" else torch.empty(R, 2, 2, sps * N_frame, device=device, dtype=torch.float32)
     out_train = torch.empty(R, pol, 2 * num_lev, N_keep, device=device, dtype=torch.float32)
     out_const = torch.empty(R, pol, 2, N_keep, device=device, dtype=torch.float32)
     lr_w = lr0
@@ -92,11 +95,17 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
         if datagen == "gpu_batched":                                     # all cells' frames in one batched launch sequence
             if len(h_channel) != 1:
                 raise sfun._lib.VaeqError("datagen='gpu_batched' implements the optical channel 'h0' only")
-            rx_b, tx_b, _ = generate_frames_gpu(N_frame, amps, [c["SNR"] for c in cells], P_all, sps, theta, device,
+            if frame == 0:                                               # per-run parameters live on the device: no copy / sync per frame
+                snr_dev = torch.tensor([float(c["SNR"]) for c in cells], dtype=torch.float32, device=device)
+                theta_dev = torch.tensor(theta, dtype=torch.float64, device=device)
+                theta_diff_dev = torch.tensor(theta_diff, dtype=torch.float64, device=device)
+                P_dev = P_all.to(device)
+            rx_b, tx_b, _ = generate_frames_gpu(N_frame, amps, snr_dev, P_dev, sps, theta_dev.to(torch.float32), device,
                                                 seeds[0] * 100003 + frame, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ)
-            rx_all.copy_(rx_b)
-            tx_all = [tx_b[r] if kind == "VAE" else tx_b[r][:, :, batch_len // 2:m_max + batch_len // 2] for r in range(R)]
-            theta = [t + d for t, d in zip(theta, theta_diff)]
+            rx_all = rx_b
+            if eval_mode != "batched":
+                tx_all = [tx_b[r] if kind == "VAE" else tx_b[r][:, :, batch_len // 2:m_max + batch_len // 2] for r in range(R)]
+            theta_dev = theta_dev + theta_diff_dev                       # VAELE_DP:47 theta drift per frame
         else:
             for r in range(R):
                 rx, tx, _ = _make_frame(datagen, N_frame, amps, cells[r]["SNR"], h_channel, consts[r][2], pol, symb_rate, sps, tau_cd,
@@ -114,7 +123,7 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
                 tx_b4 = tx_b if kind == "VAE" else tx_b[:, :, :, batch_len // 2:m_max + batch_len // 2]
             else:
                 tx_b4 = torch.stack(tx_all)
-            ser, _ = sfun.frame_eval_runs(out_train, out_const, tx_b4, amp_levels, var_all, nu_sc_all, batch_len if kind == "VAE" else 0,
+            ser, _ = sfun.frame_eval_runs(out_train, out_const, tx_b4, amp_dev, var_dev, nu_dev, batch_len if kind == "VAE" else 0,
                                           n_cut=N_CUT)
             SER_valid[:, :, frame] = ser
             if verbose:
