@@ -196,6 +196,11 @@ int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, f
 int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var, const float *amp, float nu_sc,
                   int32_t n_lev, int32_t N, float *q, int64_t ld_q, void *stream);
 
+/* soft_dec for n_runs independent runs in one launch (sweep engine): out (n_runs,2,2,N), q (n_runs,2,2*n_lev,N) contiguous,
+ * var (n_runs,2), nu_sc (n_runs); per run the arithmetic of vaeq_soft_dec */
+int vaeq_soft_dec_runs(const float *out, const float *var, const float *amp, const float *nu_sc, int32_t n_lev, int32_t N,
+                       int32_t n_runs, float *q, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * evaluation: shift search and SER estimators (sf:188-338).  tx is the reference's float16
  * data_tensor (2,2,N) (sf:89), passed as uint16_t bit patterns.
@@ -229,6 +234,21 @@ int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, const float
                          int32_t edge, int32_t n_cut, int32_t *align_out, int32_t *counts_out, float *ser_out, void *scratch,
                          void *stream);
 
+/* vaeq_frame_eval_runs with a choice of estimators (which: bit 0 = from q, bit 1 = from out; the pointer of an unselected one may be
+ * NULL, its rows of align_out / counts_out / ser_out are left untouched) and, optionally, the rescale factor mean|tx| / mean|rx| of
+ * sf:242 per run (scale_out, estimator from out).  The CMA drivers (CMA_DP:39-52) evaluate in two steps: estimator from out on the CPE
+ * output, then soft_dec of the aligned and partially rescaled copy (vaeq_cma_align_rescale) and the estimator from q on it. */
+int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_q, const float *out, int64_t ld_out, int64_t rs_out,
+                            const uint16_t *tx, int64_t ld_tx, int64_t rs_tx, const float *amp, const float *var, int64_t rs_var,
+                            const float *nu_sc, int32_t n_lev, int32_t N, int32_t n_shift, int32_t n_runs, int32_t seg_len,
+                            int32_t edge, int32_t n_cut, int32_t which, int32_t *align_out, int32_t *counts_out, float *ser_out,
+                            float *scale_out, void *scratch, void *stream);
+/* CMA_DP:42-48 for all runs: oc (n_runs,2,2,N) = out rolled by (r, -shift) per run (align = align_out of the call above, estimator
+ * from out) with the evaluated slice [edge, N - edge - max|shift|) multiplied by scale[run] -- what SER_constell_shaping leaves behind
+ * in the view the drivers pass (sf:242) and soft_dec then reads */
+int vaeq_cma_align_rescale(const float *out, int64_t ld_out, int64_t rs_out, const int32_t *align, const float *scale, int32_t N,
+                           int32_t edge, int32_t n_runs, float *oc, void *stream);
+
 /* extension, not in the reference: achievable-rate estimate H(X)+E[log2 q(x_tx|y)] per pol (bit/2D symbol) */
 int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, const float *P, int32_t n_lev, int32_t N,
              float *gmi_out, void *scratch, void *stream);
@@ -249,6 +269,9 @@ int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float *h, int32_
 /* CPE (sf:140-186): y (2,2,N) -> y_corr (2,2,N); scratch: vaeq_cpe_scratch_bytes(N) */
 size_t vaeq_cpe_scratch_bytes(int32_t N);
 int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream);
+/* the same for n_runs independent runs: y, y_corr (n_runs,2,2,N); scratch: vaeq_cpe_runs_scratch_bytes(N, n_runs) */
+size_t vaeq_cpe_runs_scratch_bytes(int32_t N, int32_t n_runs);
+int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Synthetic test signal on the device, n_runs independent runs per call (generate_data_shaping sf:65-90, channel 'h0'; the

@@ -288,3 +288,30 @@ def test_cuda_data_generator_against_the_torch_formulation():
         dg._FORCE_TORCH = False
     assert np.allclose(sgt.cpu().numpy(), sigma.cpu().numpy(), rtol=0.05)
     assert np.allclose(rxt.double().var(dim=(1, 2, 3)).cpu().numpy(), rx.double().var(dim=(1, 2, 3)).cpu().numpy(), rtol=0.05)
+
+
+@pytest.mark.parametrize("kind", ["CMA", "CMAbatch", "CMAflex"])
+def test_cma_sweep_engine_equals_single_run_drivers(kind):
+    """sweep.sweep_cma_dp (all cells per equalizer / CPE launch, batched CMA streams) against processing_cma*_dp cell by cell: a cell's
+    SER estimates are identical alone and inside a batch (datagen='gpu': its data depends on its own seed only)."""
+    from vae_equalizer_b200 import processing as pr, sweep
+    fn = {"CMA": pr.processing_cma_dp, "CMAbatch": pr.processing_cmabatch_dp, "CMAflex": pr.processing_cmaflex_dp}[kind]
+    lr = {"CMA": 1e-3, "CMAbatch": 1e-5, "CMAflex": 1e-6}[kind]
+    phiIQ = np.array([0.0314, 0.0314], dtype=np.complex64)
+    cells = [dict(SNR=20, nu=0.0270955, lr_optim=lr, theta=0.3, theta_diff=0.05, seed=3),
+             dict(SNR=24, nu=0.0, lr_optim=lr, theta=0.1, theta_diff=0.0, seed=4),
+             dict(SNR=22, nu=0.0270955, lr_optim=2 * lr, theta=-0.2, theta_diff=0.1, seed=5)]
+    M, B, N, F, step, half = 25, 100, 3000, 3, 20, 2
+    common = ("h0", 90e9, -26e-24, 0.1e-12 * np.sqrt(1000), phiIQ, half)
+    ser_b, ve_b, var_b = sweep.sweep_cma_dp(cells, "64-QAM", 2, M, B, N, F, step, *common, kind=kind, datagen="gpu")      # batched evaluation
+    assert ser_b.shape == (3, 4, F) and ve_b.shape == (3, 2, F) and float(ve_b.abs().max()) == 0.0
+    ser_p, _, _ = sweep.sweep_cma_dp(cells, "64-QAM", 2, M, B, N, F, step, *common, kind=kind, datagen="gpu", eval_mode="per_cell")
+    assert torch.equal(ser_p, ser_b), (ser_p.tolist(), ser_b.tolist())
+    for r, c in enumerate(cells):
+        s, v, var = fn("64-QAM", 2, c["SNR"], c["nu"], M, c["theta_diff"], c["theta"], c["lr_optim"], B, N, F, step, *common,
+                       verbose=False, datagen="gpu", seed=c["seed"])
+        assert torch.equal(s, ser_b[r]), (kind, r, s.tolist(), ser_b[r].tolist())
+        assert torch.equal(var.to(var_b.device), var_b[r])
+    # one batched generation for all cells: runs, finite, same shapes
+    ser_g, _, _ = sweep.sweep_cma_dp(cells, "64-QAM", 2, M, B, N, 2, step, *common, kind=kind, datagen="gpu_batched")
+    assert ser_g.shape == (3, 4, 2) and bool(torch.isfinite(ser_g).all())

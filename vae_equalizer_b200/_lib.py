@@ -94,6 +94,10 @@ PROTOTYPES = {
     "vaeq_frame_eval_scratch_bytes": (_sz, [_i32, _i32]),
     "vaeq_frame_eval_runs": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32,
                                       _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vaeq_frame_eval_runs_ex": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32,
+                                         _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vaeq_cma_align_rescale": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "vaeq_soft_dec_runs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "vaeq_gmi": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_cma_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_cma": (C.c_int, [_i32, _vp, _i32, _f, _vp, _i32, _f, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
@@ -103,6 +107,8 @@ PROTOTYPES = {
     "vaeq_gen_jones": (C.c_int, [_vp, _vp, _vp, _vp, _f, _f, _i32, _i32, _vp]),
     "vaeq_gen_noise": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _i32, _vp]),
     "vaeq_cpe": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "vaeq_cpe_runs_scratch_bytes": (_sz, [_i32, _i32]),
+    "vaeq_cpe_runs": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_awgn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_adam_state_floats_awgn": (_sz, [_i32]),
     "vaeq_awgn_forward": (C.c_int, [C.POINTER(AwgnDesc), _vp]),

@@ -237,8 +237,9 @@ __global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys
 // ---------------------------------------------------------------------------------------------
 constexpr int CPE_MA = 501;
 
-__global__ void k_cpe_pow4(const float *y, int N, float *p4) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
+// npol = 2 n_runs: the (n_runs,2,2,N) batch is npol independent (I, Q) row pairs
+__global__ void k_cpe_pow4(const float *y, int N, int npol, float *p4) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npol * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
         const int p = (int)(t / N), s = (int)(t - (int64_t)p * N);
         const float a = y[(int64_t)(2 * p) * N + s], b = y[(int64_t)(2 * p + 1) * N + s];
         const float a2 = a * a, b2 = b * b;
@@ -248,9 +249,9 @@ __global__ void k_cpe_pow4(const float *y, int N, float *p4) {
 }
 
 // phi[p][n] = atan2(ma_im, -ma_re)/4 with a zero-padded 501-tap moving average (sf:158-163)
-__global__ void k_cpe_phase(const float *p4, int N, float *phi) {
+__global__ void k_cpe_phase(const float *p4, int N, int npol, float *phi) {
     const float w = (float)(1.0 / CPE_MA);
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npol * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
         const int p = (int)(t / N), n = (int)(t - (int64_t)p * N);
         const float *re = p4 + (int64_t)(2 * p) * N, *im = p4 + (int64_t)(2 * p + 1) * N;
         float sr = 0.f, si = 0.f;
@@ -360,25 +361,31 @@ extern "C" int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float
     return VAEQ_OK;
 }
 
-extern "C" size_t vaeq_cpe_scratch_bytes(int32_t N) {
-    if (N <= 0) return 0;
-    return align_up((size_t)4 * N * sizeof(float), 256) + align_up((size_t)2 * N * sizeof(float), 256);
+extern "C" size_t vaeq_cpe_runs_scratch_bytes(int32_t N, int32_t n_runs) {
+    if (N <= 0 || n_runs <= 0) return 0;
+    return align_up((size_t)n_runs * 4 * N * sizeof(float), 256) + align_up((size_t)n_runs * 2 * N * sizeof(float), 256);
 }
+extern "C" size_t vaeq_cpe_scratch_bytes(int32_t N) { return vaeq_cpe_runs_scratch_bytes(N, 1); }
 
-extern "C" int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream) {
-    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1, "bad cpe arguments");
+extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream) {
+    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1 && n_runs > 0 && n_runs <= (1 << 20), "bad cpe arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    const int npol = 2 * n_runs;
     float *p4 = static_cast<float *>(scratch);
-    float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)4 * N * sizeof(float), 256));
-    const int grid = (int)std::min<int64_t>((2 * (int64_t)N + 255) / 256, (int64_t)sm_count() * 16);
-    k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, p4);
+    float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n_runs * 4 * N * sizeof(float), 256));
+    const int grid = (int)std::min<int64_t>((npol * (int64_t)N + 255) / 256, (int64_t)sm_count() * 16);
+    k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, npol, p4);
     ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_pow4");
-    k_cpe_phase<<<grid, 256, 0, st>>>(p4, N, phi);
+    k_cpe_phase<<<grid, 256, 0, st>>>(p4, N, npol, phi);
     ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_phase");
-    k_cpe_unwrap_rotate<<<2, 1024, 0, st>>>(y, phi, N, y_corr);
+    k_cpe_unwrap_rotate<<<npol, 1024, 0, st>>>(y, phi, N, y_corr);
     ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_unwrap_rotate");
     return VAEQ_OK;
+}
+
+extern "C" int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream) {
+    return vaeq_cpe_runs(y, N, 1, y_corr, scratch, stream);
 }

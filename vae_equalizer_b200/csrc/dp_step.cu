@@ -603,9 +603,11 @@ __global__ void k_adam_generic(float *param, const float *grad, float *state, in
 // ---------------------------------------------------------------------------------------------
 template <int NL>
 __global__ void k_soft_dec(const float *out, int64_t ld_out, const float *var, const float *amp, float nu_sc, int N,
-                           float *q, int64_t ld_q) {
+                           float *q, int64_t ld_q, const float *nu_runs = nullptr) {
     __shared__ DemapConst cst;
-    load_demap_const(&cst, amp, nullptr, var, nu_sc, NL);
+    out += (int64_t)blockIdx.y * 4 * ld_out;             // blockIdx.y = run of a batch (vaeq_soft_dec_runs)
+    q += (int64_t)blockIdx.y * 4 * NL * ld_q;
+    load_demap_const(&cst, amp, nullptr, var + 2 * blockIdx.y, nu_runs ? nu_runs[blockIdx.y] : nu_sc, NL);
     __syncthreads();
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < N; u += (int64_t)gridDim.x * blockDim.x) {
 #pragma unroll
@@ -631,9 +633,12 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
 }
 template <int NL>
 __global__ void __launch_bounds__(256) k_soft_dec_vec(const float *__restrict__ out, int64_t ld_out, const float *var, const float *amp,
-                                                      float nu_sc, int N, float *__restrict__ q, int64_t ld_q) {
+                                                      float nu_sc, int N, float *__restrict__ q, int64_t ld_q, const float *nu_runs = nullptr) {
+    // blockIdx.y = run of a batch (vaeq_soft_dec_runs): tensors advance by their size, var by 2, nu_sc comes from nu_runs
     __shared__ DemapConst cst;
-    load_demap_const(&cst, amp, nullptr, var, nu_sc, NL);
+    out += (int64_t)blockIdx.y * 4 * ld_out;
+    q += (int64_t)blockIdx.y * 4 * NL * ld_q;
+    load_demap_const(&cst, amp, nullptr, var + 2 * blockIdx.y, nu_runs ? nu_runs[blockIdx.y] : nu_sc, NL);
     __syncthreads();
     const int n4 = N >> 2;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += gridDim.x * blockDim.x) {
@@ -1139,5 +1144,32 @@ extern "C" int vaeq_soft_dec(const float *out, int64_t ld_out, const float *var,
     else k_soft_dec<8><<<grid, nt, 0, st>>>(out, ld_out, var, amp, nu_sc, N, q, ld_q);
     ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_soft_dec");
+    return VAEQ_OK;
+}
+
+// soft_dec for n_runs independent runs in one launch: out (n_runs,2,2,N), q (n_runs,2,2n,N) contiguous, var (n_runs,2), nu_sc (n_runs);
+// the arithmetic per run is that of vaeq_soft_dec (same kernels, blockIdx.y = run)
+extern "C" int vaeq_soft_dec_runs(const float *out, const float *var, const float *amp, const float *nu_sc, int32_t n_lev, int32_t N,
+                                  int32_t n_runs, float *q, void *stream) {
+    VAEQ_CHECK_ARG(out && var && amp && nu_sc && q && N > 0 && n_runs > 0 && n_runs <= 65535, "bad soft_dec_runs arguments");
+    VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
+    const int nt = 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(q)) % 16 == 0);
+    const int per = max(1, sm_count() * 8 / n_runs);
+    ktime_begin(VAEQ_K_EVAL, st);
+    if (vec) {
+        const dim3 grid(max(1, min((N / 4 + nt - 1) / nt, per)), n_runs);
+        if (n_lev == 2) k_soft_dec_vec<2><<<grid, nt, 0, st>>>(out, N, var, amp, 0.f, N, q, N, nu_sc);
+        else if (n_lev == 4) k_soft_dec_vec<4><<<grid, nt, 0, st>>>(out, N, var, amp, 0.f, N, q, N, nu_sc);
+        else k_soft_dec_vec<8><<<grid, nt, 0, st>>>(out, N, var, amp, 0.f, N, q, N, nu_sc);
+    } else {
+        const dim3 grid(max(1, min((N + nt - 1) / nt, per)), n_runs);
+        if (n_lev == 2) k_soft_dec<2><<<grid, nt, 0, st>>>(out, N, var, amp, 0.f, N, q, N, nu_sc);
+        else if (n_lev == 4) k_soft_dec<4><<<grid, nt, 0, st>>>(out, N, var, amp, 0.f, N, q, N, nu_sc);
+        else k_soft_dec<8><<<grid, nt, 0, st>>>(out, N, var, amp, 0.f, N, q, N, nu_sc);
+    }
+    ktime_end(VAEQ_K_EVAL, st);
+    VAEQ_LAUNCH_CHECK("k_soft_dec (runs)");
     return VAEQ_OK;
 }

@@ -29,6 +29,8 @@ struct EvalRunsK {
     double *norms;                               // [R][2]: sum |tx|, sum |rx| over the evaluated region (estimator 1)
     int *counts;                                 // [R][2][16]
     float *ser;                                  // [R][4]: constellation x, y, soft demapper x, y  (rows of SER_valid, VAELE_DP:79,89)
+    int which;                                   // bit 0: estimator from q, bit 1: estimator from out
+    float *scale;                                // optional [R]: the rescale factor mean|tx| / mean|rx| of sf:242 (estimator from out)
 };
 
 __device__ __forceinline__ float er_tx_level(uint16_t bits, float scale) {
@@ -52,6 +54,7 @@ template <int NPASS>
 __global__ void __launch_bounds__(SC_NT, SC_MINB) k_er_shift_corr(EvalRunsK p) {
     __shared__ ShiftSmem sm;
     const int chunk = blockIdx.x, run = blockIdx.y >> 1, est = blockIdx.y & 1, N = p.N;
+    if (!((p.which >> est) & 1)) return;
     const int per = ((N + ER_CHUNKS - 1) / ER_CHUNKS + SC_SLICE - 1) / SC_SLICE * SC_SLICE;
     const int64_t t_lo = min((int64_t)N, (int64_t)chunk * per), t_hi = min((int64_t)N, t_lo + per);
     const float *q = p.q + run * p.rs_q, *out = p.out + run * p.rs_out;
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(ER_DEC_NT) k_er_shift_decide(EvalRunsK p) {
     const int idx = blockIdx.x * (ER_DEC_NT / 32) + w;
     if (idx >= 2 * p.n_runs) return;                         // whole warps leave together; no block-wide barrier below
     const int run = idx >> 1, est = idx & 1, half = p.n_shift / 2, nidx = p.n_shift * 8;
+    if (!((p.which >> est) & 1)) return;
     const double *part = p.part + ((int64_t)run * 2 + est) * ER_CHUNKS * nidx;
     for (int j = lane; j < nidx; j += 32) {
         double s = 0.0;
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(ER_NT) k_er_ser_constell(EvalRunsK p) {
     __syncthreads();
     const double cnt2 = 2.0 * (double)n_eval;
     const float g = __fdiv_rn((float)(p.norms[2 * run] / cnt2), (float)(p.norms[2 * run + 1] / cnt2));      // sf:242
+    if (p.scale != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.scale[run] = g;
     const float S = (float)(NL - 1), scale = (float)((NL - 1) / 2.0);
     int cnt[16];
 #pragma unroll
@@ -263,12 +268,39 @@ __global__ void k_er_ser_min(EvalRunsK p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 4 * p.n_runs) return;
     const int run = idx >> 2, est = (idx >> 1) & 1, pol = idx & 1;
+    if (!((p.which >> est) & 1)) return;
     const int n_eval = p.align[((int64_t)run * 2 + est) * 4 + 3];
     const int *counts = p.counts + ((int64_t)run * 2 + est) * 16;
     float best = 3.0e38f;
     for (int f = 0; f < 2; ++f)
         for (int k = 0; k < 4; ++k) best = fminf(best, __fdiv_rn((float)counts[(f * 2 + pol) * 4 + k], (float)n_eval));
     p.ser[run * 4 + (est == 0 ? 2 : 0) + pol] = n_eval > 0 ? best : __int_as_float(0x7fc00000);
+}
+
+// ---- CMA drivers (CMA_DP:42-48): the aligned copy of the CPE output with the evaluated slice rescaled, all runs -------------------
+// oc[run][pol][c][t] = out[run][(pol - r) & 1][c][(t + shift[pol]) mod N] * (edge <= t < N - edge - max|shift| ? g_run : 1):
+// out.roll(r, 0), per-pol roll by -shift, and the in-place rescale SER_constell_shaping leaves in the slice it was given (sf:242),
+// which soft_dec then sees (CMA_DP:44,48).  align = the estimator-from-out rows of vaeq_frame_eval_runs, g = its scale_out.
+__global__ void __launch_bounds__(ER_NT) k_er_align_rescale(const float *out, int64_t ld_out, int64_t rs_out, const int *align, const float *scale,
+                                                            int N, int edge, float *oc) {
+    const int run = blockIdx.y;
+    const int *al = align + ((int64_t)run * 2 + 1) * 4;
+    const int sh[2] = {al[0], al[1]}, r = al[2], hi = N - edge - max(abs(al[0]), abs(al[1]));
+    const float g = scale[run];
+    const float *src = out + run * rs_out;
+    float *dst = oc + (int64_t)run * 4 * N;
+    for (int t = blockIdx.x * ER_NT + threadIdx.x; t < N; t += gridDim.x * ER_NT) {
+        const bool in = t >= edge && t < hi;
+#pragma unroll
+        for (int pol = 0; pol < 2; ++pol) {
+            const int sp = (pol - r) & 1, ts = er_wrap(t + sh[pol], N);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float v = src[(int64_t)(sp * 2 + c) * ld_out + ts];
+                dst[(int64_t)(pol * 2 + c) * N + t] = in ? __fmul_rn(v, g) : v;
+            }
+        }
+    }
 }
 
 }  // namespace vaeq
@@ -281,12 +313,13 @@ extern "C" size_t vaeq_frame_eval_scratch_bytes(int32_t n_runs, int32_t n_shift)
            align_up((size_t)n_runs * 2 * 16 * sizeof(int), 256);
 }
 
-extern "C" int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, const float *out, int64_t ld_out, int64_t rs_out,
-                                    const uint16_t *tx, int64_t ld_tx, int64_t rs_tx, const float *amp, const float *var, int64_t rs_var,
-                                    const float *nu_sc, int32_t n_lev, int32_t N, int32_t n_shift, int32_t n_runs, int32_t seg_len,
-                                    int32_t edge, int32_t n_cut, int32_t *align_out, int32_t *counts_out, float *ser_out, void *scratch,
-                                    void *stream) {
-    VAEQ_CHECK_ARG(q && out && tx && amp && var && nu_sc && align_out && ser_out && scratch, "NULL pointer");
+extern "C" int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_q, const float *out, int64_t ld_out, int64_t rs_out,
+                                       const uint16_t *tx, int64_t ld_tx, int64_t rs_tx, const float *amp, const float *var, int64_t rs_var,
+                                       const float *nu_sc, int32_t n_lev, int32_t N, int32_t n_shift, int32_t n_runs, int32_t seg_len,
+                                       int32_t edge, int32_t n_cut, int32_t which, int32_t *align_out, int32_t *counts_out, float *ser_out,
+                                       float *scale_out, void *scratch, void *stream) {
+    VAEQ_CHECK_ARG(which >= 1 && which <= 3, "which=%d: bit 0 = estimator from q, bit 1 = estimator from out", which);
+    VAEQ_CHECK_ARG((q || !(which & 1)) && (out || !(which & 2)) && tx && amp && var && nu_sc && align_out && ser_out && scratch, "NULL pointer");
     VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
     VAEQ_CHECK_ARG(N > 0 && n_runs > 0 && n_shift > 0 && n_shift <= 64 && edge >= 0 && n_cut >= 0, "bad sizes");
     VAEQ_CHECK_ARG(seg_len == 0 || (seg_len > 0 && N % seg_len == 0), "N=%d must be a multiple of seg_len=%d", N, seg_len);
@@ -301,7 +334,7 @@ extern "C" int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, 
     p.part = reinterpret_cast<double *>(ws);
     p.norms = reinterpret_cast<double *>(ws + part_b);
     p.counts = counts_out ? counts_out : reinterpret_cast<int *>(ws + part_b + norm_b);
-    p.align = align_out; p.ser = ser_out;
+    p.align = align_out; p.ser = ser_out; p.which = which; p.scale = scale_out;
     VAEQ_CUDA(cudaMemsetAsync(p.norms, 0, (size_t)n_runs * 2 * sizeof(double), st));
     VAEQ_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)n_runs * 2 * 16 * sizeof(int), st));
     const int blocks = max(1, min((N + ER_NT - 1) / ER_NT, max(1, sm_count() * 8 / n_runs)));
@@ -313,14 +346,39 @@ extern "C" int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, 
     if (n_shift <= 32) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<1><<<dim3(ER_CHUNKS, 2 * n_runs), SC_NT, 0, st>>>(p)) }
     else { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<2><<<dim3(ER_CHUNKS, 2 * n_runs), SC_NT, 0, st>>>(p)) }
     ER_LAUNCH("k_er_shift_decide", k_er_shift_decide<<<(2 * n_runs + ER_DEC_NT / 32 - 1) / (ER_DEC_NT / 32), ER_DEC_NT, 0, st>>>(p))
-    if (n_lev == 2) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<2><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
-    else if (n_lev == 4) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<4><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
-    else { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<8><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
-    ER_LAUNCH("k_er_constell_norms", k_er_constell_norms<<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p))
-    if (n_lev == 2) { ER_LAUNCH("k_er_ser_constell", k_er_ser_constell<2><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
-    else if (n_lev == 4) { ER_LAUNCH("k_er_ser_constell", k_er_ser_constell<4><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
-    else { ER_LAUNCH("k_er_ser_constell", k_er_ser_constell<8><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+    if (which & 1) {
+        if (n_lev == 2) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<2><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+        else if (n_lev == 4) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<4><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+        else { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<8><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+    }
+    if (which & 2) {
+        ER_LAUNCH("k_er_constell_norms", k_er_constell_norms<<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p))
+        if (n_lev == 2) { ER_LAUNCH("k_er_ser_constell", k_er_ser_constell<2><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+        else if (n_lev == 4) { ER_LAUNCH("k_er_ser_constell", k_er_ser_constell<4><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+        else { ER_LAUNCH("k_er_ser_constell", k_er_ser_constell<8><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
+    }
     ER_LAUNCH("k_er_ser_min", k_er_ser_min<<<(4 * n_runs + 127) / 128, 128, 0, st>>>(p))
 #undef ER_LAUNCH
+    return VAEQ_OK;
+}
+
+extern "C" int vaeq_frame_eval_runs(const float *q, int64_t ld_q, int64_t rs_q, const float *out, int64_t ld_out, int64_t rs_out,
+                                    const uint16_t *tx, int64_t ld_tx, int64_t rs_tx, const float *amp, const float *var, int64_t rs_var,
+                                    const float *nu_sc, int32_t n_lev, int32_t N, int32_t n_shift, int32_t n_runs, int32_t seg_len,
+                                    int32_t edge, int32_t n_cut, int32_t *align_out, int32_t *counts_out, float *ser_out, void *scratch,
+                                    void *stream) {
+    return vaeq_frame_eval_runs_ex(q, ld_q, rs_q, out, ld_out, rs_out, tx, ld_tx, rs_tx, amp, var, rs_var, nu_sc, n_lev, N, n_shift, n_runs,
+                                   seg_len, edge, n_cut, 3, align_out, counts_out, ser_out, nullptr, scratch, stream);
+}
+
+extern "C" int vaeq_cma_align_rescale(const float *out, int64_t ld_out, int64_t rs_out, const int32_t *align, const float *scale, int32_t N,
+                                      int32_t edge, int32_t n_runs, float *oc, void *stream) {
+    VAEQ_CHECK_ARG(out && align && scale && oc && N > 0 && edge >= 0 && n_runs > 0 && n_runs <= 32767, "bad align_rescale arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = max(1, min((N + ER_NT - 1) / ER_NT, max(1, sm_count() * 8 / n_runs)));
+    ktime_begin(VAEQ_K_EVAL, st);
+    k_er_align_rescale<<<dim3(blocks, n_runs), ER_NT, 0, st>>>(out, ld_out, rs_out, align, scale, N, edge, oc);
+    ktime_end(VAEQ_K_EVAL, st);
+    VAEQ_LAUNCH_CHECK("k_er_align_rescale");
     return VAEQ_OK;
 }

@@ -245,33 +245,71 @@ def find_shift_symb_full(rx, tx, N_shift, return_corr=False):
     return _find_shift(None, rx, tx, N_shift, None, return_corr)
 
 
-def frame_eval_runs(out_train, out_const, tx, amp_levels, var, nu_sc, seg_len, n_shift=21, edge=11, n_cut=10, return_counts=False):
+def frame_eval_runs(out_train, out_const, tx, amp_levels, var, nu_sc, seg_len, n_shift=21, edge=11, n_cut=10, return_counts=False, which=3,
+                    return_scale=False):
     """The per-frame evaluation of the VAE drivers (VAELE_DP:70-89 with seg_len = batch_len, VAEflex_DP:74-84 with seg_len = 0) for R
     runs in one call and without a host sync: out_train (R,2,2n,N), out_const (R,2,2,N), tx (R,2,2,N) float16 (may be a view into
     longer rows), var (R,2), nu_sc (R,).  Returns ser (R,4) [constellation x, y, soft demapper x, y] and align (R,2,4) int32
     [shift_x, shift_y, r, symbols evaluated] for the estimators (from q, from out)."""
-    _require_cuda(out_train, "out_train")
-    _require_cuda(out_const, "out_const")
+    ref = out_train if out_train is not None else out_const
+    if which not in (1, 2, 3) or (which & 1 and out_train is None) or (which & 2 and out_const is None):
+        raise _lib.VaeqError(f"which={which}: bit 0 needs out_train, bit 1 needs out_const")
+    _require_cuda(ref, "out_train / out_const")
     tx = _tx_bits(tx)
     lib = _lib.load()
-    R, N, n = int(out_train.shape[0]), int(out_train.shape[-1]), int(amp_levels.numel())
-    dev = out_train.device
+    R, N, n = int(ref.shape[0]), int(ref.shape[-1]), int(amp_levels.numel())
+    dev = ref.device
     for t, name in ((out_train, "out_train"), (out_const, "out_const"), (tx, "tx")):
+        if t is None:
+            continue
         if t.dim() != 4 or t.shape[0] != R or t.shape[-1] != N or t.stride(3) != 1 or t.stride(1) != t.shape[2] * t.stride(2):
             raise _lib.VaeqError(f"{name}: need (R,2,rows,N) with unit time stride and evenly strided rows, got {tuple(t.shape)} {t.stride()}")
     var = torch.as_tensor(var, dtype=_F32, device=dev).reshape(R, 2).contiguous()
     nu = torch.as_tensor(nu_sc, dtype=_F32, device=dev).reshape(R).contiguous()
     amp = amp_levels.to(dev, _F32).contiguous()
-    align = torch.empty(R, 2, 4, dtype=torch.int32, device=dev)
+    align = torch.zeros(R, 2, 4, dtype=torch.int32, device=dev)
     counts = torch.empty(R, 2, 2, 2, 4, dtype=torch.int32, device=dev)
-    ser = torch.empty(R, 4, dtype=_F32, device=dev)
+    ser = torch.full((R, 4), float("nan"), dtype=_F32, device=dev)
+    scale = torch.empty(R, dtype=_F32, device=dev) if return_scale else None
     scr = _scratch(dev, int(lib.vaeq_frame_eval_scratch_bytes(R, int(n_shift))))
-    _lib.check(lib.vaeq_frame_eval_runs(out_train.data_ptr(), int(out_train.stride(2)), int(out_train.stride(0)),
-                                        out_const.data_ptr(), int(out_const.stride(2)), int(out_const.stride(0)),
-                                        tx.data_ptr(), int(tx.stride(2)), int(tx.stride(0)), amp.data_ptr(), var.data_ptr(), 2, nu.data_ptr(),
-                                        n, N, int(n_shift), R, int(seg_len), int(edge), int(n_cut), align.data_ptr(), counts.data_ptr(),
-                                        ser.data_ptr(), scr.data_ptr(), _lib.current_stream()), "vaeq_frame_eval_runs")
+    qa = (out_train.data_ptr(), int(out_train.stride(2)), int(out_train.stride(0))) if out_train is not None else (None, 0, 0)
+    oa = (out_const.data_ptr(), int(out_const.stride(2)), int(out_const.stride(0))) if out_const is not None else (None, 0, 0)
+    _lib.check(lib.vaeq_frame_eval_runs_ex(*qa, *oa, tx.data_ptr(), int(tx.stride(2)), int(tx.stride(0)), amp.data_ptr(), var.data_ptr(), 2,
+                                           nu.data_ptr(), n, N, int(n_shift), R, int(seg_len), int(edge), int(n_cut), int(which), align.data_ptr(),
+                                           counts.data_ptr(), ser.data_ptr(), None if scale is None else scale.data_ptr(), scr.data_ptr(),
+                                           _lib.current_stream()), "vaeq_frame_eval_runs_ex")
+    if return_scale:
+        return (ser, align, counts, scale) if return_counts else (ser, align, scale)
     return (ser, align, counts) if return_counts else (ser, align)
+
+
+def soft_dec_runs(out, var, amp_levels, nu_sc):
+    """soft_dec (sf:529-542) for R independent runs in one launch: out (R,2,2,N), var (R,2), nu_sc (R,) -> q (R,2,2n,N)."""
+    _require_cuda(out, "out")
+    lib = _lib.load()
+    out = out.contiguous()
+    R, N, n = int(out.shape[0]), int(out.shape[-1]), int(amp_levels.numel())
+    dev = out.device
+    var = torch.as_tensor(var, dtype=_F32, device=dev).reshape(R, 2).contiguous()
+    nu = torch.as_tensor(nu_sc, dtype=_F32, device=dev).reshape(R).contiguous()
+    q = torch.empty(R, 2, 2 * n, N, dtype=_F32, device=dev)
+    _lib.check(lib.vaeq_soft_dec_runs(out.data_ptr(), var.data_ptr(), amp_levels.to(dev, _F32).contiguous().data_ptr(), nu.data_ptr(), n, N, R,
+                                      q.data_ptr(), _lib.current_stream()), "vaeq_soft_dec_runs")
+    return q
+
+
+def cma_align_rescale(out, align, scale, edge=11):
+    """CMA_DP:42-48 for R runs: out (R,2,2,N) rolled by (r, -shift) with the evaluated slice rescaled like SER_constell_shaping leaves it
+    (sf:242); align (R,2,4) int32 and scale (R,) from frame_eval_runs(..., which=2, return_scale=True)."""
+    _require_cuda(out, "out")
+    lib = _lib.load()
+    R, N = int(out.shape[0]), int(out.shape[-1])
+    if out.dim() != 4 or out.stride(3) != 1 or out.stride(1) != out.shape[2] * out.stride(2):
+        raise _lib.VaeqError(f"out: need (R,2,2,N) with unit time stride and evenly strided rows, got {tuple(out.shape)} {out.stride()}")
+    oc = torch.empty(R, 2, 2, N, dtype=_F32, device=out.device)
+    _lib.check(lib.vaeq_cma_align_rescale(out.data_ptr(), int(out.stride(2)), int(out.stride(0)), align.data_ptr(), scale.data_ptr(), N, int(edge), R,
+                                          oc.data_ptr(), _lib.current_stream()), "vaeq_cma_align_rescale")
+    return oc
 
 
 def GMI(q, tx, P):
@@ -291,19 +329,25 @@ def GMI(q, tx, P):
 # CMA baselines and CPE                                                         sf:140-186, sf:341-488
 # -------------------------------------------------------------------------------------------------
 def _cma(mode, Rx, R, h, lr, batchlen, symb_step, sps, train):
+    """Rx (2,2,N), h (2,2,2,M) like the reference -- or a batch of S independent streams: Rx (S,2,2,N), h (S,2,2,2,M), one launch
+    sequence for all of them (one warp / one CTA per stream); out and e then carry the leading stream dimension too."""
     _require_cuda(Rx, "Rx")
     _require_cuda(h, "h")
     if not (Rx.is_contiguous() and h.is_contiguous()):
         raise _lib.VaeqError("CMA: Rx and h must be contiguous")
+    batched = Rx.dim() == 4
+    if (batched and (h.dim() != 5 or h.shape[0] != Rx.shape[0])) or (not batched and (Rx.dim() != 3 or h.dim() != 4)):
+        raise _lib.VaeqError(f"CMA: need Rx (2,2,N) with h (2,2,2,M) or Rx (S,2,2,N) with h (S,2,2,2,M), got {tuple(Rx.shape)} {tuple(h.shape)}")
     lib = _lib.load()
+    S = int(Rx.shape[0]) if batched else 1
     N, M = int(Rx.shape[-1]), int(h.shape[-1])
     dev = Rx.device
-    out = torch.zeros(2, 2, N // sps, dtype=_F32, device=dev)
-    e = torch.empty(N // sps, 2, dtype=_F32, device=dev)
-    scr = torch.empty(int(lib.vaeq_cma_scratch_bytes(N, M, 1)), dtype=torch.uint8, device=dev)
+    out = torch.zeros((S, 2, 2, N // sps) if batched else (2, 2, N // sps), dtype=_F32, device=dev)
+    e = torch.empty((S, N // sps, 2) if batched else (N // sps, 2), dtype=_F32, device=dev)
+    scr = torch.empty(int(lib.vaeq_cma_scratch_bytes(N, M, S)), dtype=torch.uint8, device=dev)
     hd = h.detach()
     _lib.check(lib.vaeq_cma(mode, Rx.data_ptr(), N, float(R), hd.data_ptr(), M, float(lr), int(batchlen), int(symb_step),
-                            int(sps), 1 if train else 0, out.data_ptr(), e.data_ptr(), 1, scr.data_ptr(),
+                            int(sps), 1 if train else 0, out.data_ptr(), e.data_ptr(), S, scr.data_ptr(),
                             _lib.current_stream()), "vaeq_cma")
     return out, h, e
 
@@ -324,12 +368,13 @@ def CMAflex(Rx, R, h, lr, batchlen, symb_step, sps, eval):
 
 
 def CPE(y):
-    """Viterbi-Viterbi carrier phase estimation with unwrap (sf:140-186)."""
+    """Viterbi-Viterbi carrier phase estimation with unwrap (sf:140-186); y (2,2,N), or (S,2,2,N) for S independent runs in one call."""
     _require_cuda(y, "y")
     lib = _lib.load()
     y = y.contiguous()
     N = int(y.shape[-1])
+    S = int(y.shape[0]) if y.dim() == 4 else 1
     out = torch.empty_like(y)
-    scr = torch.empty(int(lib.vaeq_cpe_scratch_bytes(N)), dtype=torch.uint8, device=y.device)
-    _lib.check(lib.vaeq_cpe(y.data_ptr(), N, out.data_ptr(), scr.data_ptr(), _lib.current_stream()), "vaeq_cpe")
+    scr = torch.empty(int(lib.vaeq_cpe_runs_scratch_bytes(N, S)), dtype=torch.uint8, device=y.device)
+    _lib.check(lib.vaeq_cpe_runs(y.data_ptr(), N, S, out.data_ptr(), scr.data_ptr(), _lib.current_stream()), "vaeq_cpe_runs")
     return out

@@ -146,6 +146,108 @@ def sweep_vae_dp(cells, mod, sps, M_est, batch_len, N_frame_max, num_frames, fle
     return SER_valid, Var_est, var_all.to(device)
 
 
+def sweep_cma_dp(cells, mod, sps, M_est, batch_len, N_train_max, num_frames, flex_step=None, channel="h0", symb_rate=90e9,
+                 tau_cd=-26e-24, tau_pmd=0.1e-12 * np.sqrt(1000), phiIQ=(0.0314, 0.0314), N_lrhalf=None, *, kind="CMA", device=None,
+                 datagen="gpu", eval_mode="batched", verbose=False):
+    """The CMA / CMAbatch / CMAflex drivers (func_CMA_DP_MQAM_shaping.py:16-56 and siblings) for R = len(cells) independent cells
+    in lockstep.  The tap recurrence of a cell is sequential in the symbols, but cells are independent: per frame ONE equalizer
+    launch sequence covers all cells that share lr_optim (vaeq_cma n_runs: one warp / one CTA per cell) and ONE batched CPE
+    (vaeq_cpe_runs).  The evaluation (CMA_DP:39-52) is batched as well (eval_mode="batched": estimator from the CPE output ->
+    aligned, partially rescaled copy -> soft_dec -> estimator from q, 4 calls and no host sync for all cells) or replays the single-run
+    drivers' call sequence per cell (eval_mode="per_cell", two host syncs per frame); both give the same error counts.  A cell gives the same SER alone (processing_cma*_dp) or in any batch when
+    datagen="gpu" (its data depends on its own seed only); datagen="gpu_batched" generates all cells in one call (fastest).
+    Returns (SER_valid (R,4,num_frames), Var_est zeros (R,2,num_frames), var (R,2))."""
+    from .processing import _make_frame
+    device = _cuda_device(device)
+    R = len(cells)
+    if R == 0:
+        raise ValueError("no cells")
+    mode = {"CMA": 0, "CMAbatch": 1, "CMAflex": 2}[kind]
+    N_lrhalf = num_frames if N_lrhalf is None else N_lrhalf
+    phiIQ = np.asarray(phiIQ, dtype=np.complex64)
+    init_cache, consts = {}, []
+    for c in cells:
+        key = (float(_cell(c, "nu")), float(_cell(c, "SNR")))
+        if key not in init_cache:
+            init_cache[key] = sfun.init(channel, mod, device, key[0], sps, M_est, key[1])
+        consts.append(init_cache[key])
+    h_channel, amp_levels, amps, pol = consts[0][1], consts[0][3], consts[0][4], consts[0][5]
+    lrs = [float(_cell(c, "lr_optim")) for c in cells]
+    lr_groups = {}
+    for r, lr in enumerate(lrs):                                         # vaeq_cma takes one lr per call: one sub-batch per distinct lr
+        lr_groups.setdefault(lr, []).append(r)
+    theta = [float(c.get("theta", 0.0)) for c in cells]
+    theta_diff = [float(c.get("theta_diff", 0.0)) for c in cells]
+    seeds = [int(c.get("seed", i)) for i, c in enumerate(cells)]
+    rngs = [np.random.default_rng(s) for s in seeds]
+    h_est = consts[0][0].detach().to(device, torch.float32).unsqueeze(0).repeat(R, 1, 1, 1, 1).contiguous()      # Dirac init per cell (sf:583-585)
+    SER_valid = torch.empty(R, 4, num_frames, device=device, dtype=torch.float32)
+    Var_est = torch.zeros(R, pol, num_frames, device=device, dtype=torch.float32)
+    var_all = torch.stack([k[7].to(device, torch.float32) for k in consts])
+    nu_all = torch.tensor([float(k[6]) for k in consts], dtype=torch.float32, device=device)
+    lr_scale = 1.0
+    for frame in range(num_frames):
+        if frame % N_lrhalf == 0 and frame != 0:
+            lr_scale *= 0.5                                              # cumulative (CMA_DP:31-32)
+        if datagen == "gpu_batched":
+            if len(h_channel) != 1:
+                raise sfun._lib.VaeqError("datagen='gpu_batched' implements the optical channel 'h0' only")
+            P_all = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in consts])
+            rx_all, tx_all, _ = generate_frames_gpu(N_train_max, amps, [c["SNR"] for c in cells], P_all, sps, theta, device,
+                                                    seeds[0] * 100003 + frame, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ)
+        else:
+            fr = [_make_frame(datagen, N_train_max, amps, cells[r]["SNR"], h_channel, consts[r][2], pol, symb_rate, sps, tau_cd, tau_pmd,
+                              phiIQ, theta[r], device, rngs[r], seeds[r] * 100003 + frame) for r in range(R)]
+            rx_all, tx_all = torch.stack([f[0] for f in fr]), torch.stack([f[1] for f in fr])
+        theta = [t + d for t, d in zip(theta, theta_diff)]
+        out_all = torch.empty(R, 2, 2, rx_all.shape[-1] // sps, device=device, dtype=torch.float32)
+        for lr, members in lr_groups.items():
+            whole = len(members) == R
+            rx_g = rx_all if whole else rx_all[members].contiguous()
+            h_g = h_est if whole else h_est[members].contiguous()
+            out_g, h_g, _ = sfun._cma(mode, rx_g, 1, h_g, lr * lr_scale, batch_len, flex_step or 0, sps, True)
+            if whole:
+                out_all = out_g
+            else:
+                out_all[members] = out_g
+                h_est[members] = h_g
+        out_c = sfun.CPE(out_all[:, :, :, N_CUT:-N_CUT])                 # carrier phase estimation, all cells  (CMA_DP:39)
+        tx_c = tx_all[:, :, :, N_CUT:-N_CUT]
+        if eval_mode == "batched":
+            # CMA_DP:41-46: shift search on the CPE output, alignment as index arithmetic, SER from the constellation; the factor g of sf:242 comes back per cell
+            ser_c, al, g = sfun.frame_eval_runs(None, out_c, tx_c, amp_levels, var_all, nu_all, 0, which=2, return_scale=True)
+            # CMA_DP:44-48: soft_dec sees the aligned copy with the evaluated slice rescaled in place
+            q_all = sfun.soft_dec_runs(sfun.cma_align_rescale(out_c, al, g), var_all, amp_levels, nu_all)
+            ser_q, _ = sfun.frame_eval_runs(q_all, None, tx_c, amp_levels, var_all, nu_all, 0, which=1)      # CMA_DP:49-52
+            SER_valid[:, :2, frame] = ser_c[:, :2]
+            SER_valid[:, 2:, frame] = ser_q[:, 2:]
+            if verbose:
+                print(frame, "SER", SER_valid[:, :, frame].tolist())
+            continue
+        # evaluation, CMA_DP:41-52: the single-run sequence of calls per cell; shifts of all cells read back together
+        f1 = [sfun._find_shift(None, out_c[r], tx_c[r], 21, None, False, sync=False) for r in range(R)]
+        s1 = torch.stack([torch.cat((a.to(torch.int32), b)) for a, b in f1]).cpu().tolist()
+        q_al, f2 = [], []
+        for r in range(R):
+            sh, rr = s1[r][0:2], s1[r][2]
+            oc = _align(out_c[r], sh, rr)
+            tail = 11 + max(abs(sh[0]), abs(sh[1]))
+            # a VIEW is passed on purpose: the in-place rescale (sf:242) must be visible to soft_dec below (CMA_DP:44,48)
+            SER_valid[r, :2, frame] = sfun.SER_constell_shaping(oc[:, :, 11:-tail], tx_c[r][:, :, 11:-tail], amp_levels, consts[r][6], consts[r][7])
+            q = sfun.soft_dec(oc, consts[r][7], amp_levels, consts[r][6])
+            q_al.append(q)
+            f2.append(sfun._find_shift(q, None, tx_c[r], 21, amp_levels, False, sync=False))
+        s2 = torch.stack([torch.cat((a.to(torch.int32), b)) for a, b in f2]).cpu().tolist()
+        for r in range(R):
+            sh, rr = s2[r][0:2], s2[r][2]
+            qa = _align(q_al[r], sh, rr)
+            tail = 11 + max(abs(sh[0]), abs(sh[1]))
+            SER_valid[r, 2:, frame] = sfun.SER_IQflip(qa[:, :, 11:-tail], tx_c[r][:, :, 11:-tail])
+        if verbose:
+            print(frame, "SER", SER_valid[:, :, frame].tolist())
+    return SER_valid, Var_est, var_all
+
+
 def _score(kind, what, aligned, tx, sh, batch_len, m_max, pol, num_lev, amp_levels, const):
     """Cut the edges like the single-run drivers (VAELE_DP:73-89 / VAEflex_DP:74-84) and run the SER estimator."""
     tail = 11 + max(abs(sh[0]), abs(sh[1]))
@@ -200,7 +302,8 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
     train in the same persistent launch; with world > 1 every rank takes a round-robin share of each set.  Returns the
     reference's result arrays on rank 0 (None elsewhere):
         SER (4, SNR, symb_rate, nu, theta_diff, M, lr, batch_len, flex_step, theta, iter, num_frames), Var_est (2, ...), var_real (2, ..., 1)
-    loss_type 'VAE' / 'VAEflex' use the batched engine; the CMA variants have a per-symbol tap recurrence and run cell by cell.
+    loss_type 'VAE' / 'VAEflex' use the batched VAE engine (sweep_vae_dp), the CMA variants the batched CMA engine (sweep_cma_dp: a cell's tap
+    recurrence is sequential in the symbols, the cells of a set run side by side).
     checkpoint_dir: rank 0 writes each finished run set there (one .npz per set, keyed by the set's parameters); a restarted sweep
     loads what it finds instead of recomputing (the reference only saves once, at the very end: RUN_DP:99-114)."""
     vecs = dict(SNR=list(SNR_vec), symb_rate=list(symb_rate_vec), nu=list(nu_vec), theta_diff=list(theta_diff_vec), M=list(M_vec),
@@ -238,7 +341,7 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
             res = sweep_vae_dp_sharded(cells, *common, kind=loss_type, device=dev, datagen=datagen, eval_every=eval_every,
                                        verbose=verbose, rank=rank, world=world, group=group, **kw)
         else:
-            res = _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames)
+            res = _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames, datagen=datagen)
         if res is None:
             continue
         ser, ve, var = res
@@ -253,17 +356,17 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
     return SER, Var_est, var_real
 
 
-def _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames):
-    from . import processing as proc
+def _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames, datagen="gpu"):
+    """This rank's share of the cells of a CMA-family run set through the batched engine (sweep_cma_dp), gathered on rank 0."""
     from .parallel import gather_cell_results, shard_cells
-    fn = {"CMA": proc.processing_cma_dp, "CMAbatch": proc.processing_cmabatch_dp, "CMAflex": proc.processing_cmaflex_dp}[loss_type]
     mod, sps, M, batch_len, N_frame_max, nf = common
+    mine = shard_cells(cells, rank, world)
     loc_s, loc_v, loc_r = {}, {}, {}
-    for i, c in shard_cells(cells, rank, world):
-        s, v, r = fn(mod, sps, c["SNR"], c["nu"], M, c["theta_diff"], c["theta"], c["lr_optim"], batch_len, N_frame_max, nf, kw["flex_step"],
-                     kw["channel"], kw["symb_rate"], kw["tau_cd"], kw["tau_pmd"], np.asarray(kw["phiIQ"], dtype=np.complex64), kw["N_lrhalf"],
-                     device=dev, verbose=False, datagen="gpu", seed=c["seed"])
-        loc_s[i], loc_v[i], loc_r[i] = s, v, r
+    if mine:
+        s, v, r = sweep_cma_dp([c for _, c in mine], mod, sps, M, batch_len, N_frame_max, nf, kw["flex_step"], kw["channel"], kw["symb_rate"],
+                               kw["tau_cd"], kw["tau_pmd"], kw["phiIQ"], kw["N_lrhalf"], kind=loss_type, device=dev, datagen=datagen)
+        for k, (i, _) in enumerate(mine):
+            loc_s[i], loc_v[i], loc_r[i] = s[k], v[k], r[k]
     n = len(cells)
     out = (gather_cell_results(loc_s, n, (4, num_frames), rank, world, group, dev), gather_cell_results(loc_v, n, (2, num_frames), rank, world, group, dev),
            gather_cell_results(loc_r, n, (2,), rank, world, group, dev))
