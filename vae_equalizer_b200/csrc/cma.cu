@@ -248,19 +248,65 @@ __global__ void k_cpe_pow4(const float *y, int N, int npol, float *p4) {
     }
 }
 
-// phi[p][n] = atan2(ma_im, -ma_re)/4 with a zero-padded 501-tap moving average (sf:158-163)
-__global__ void k_cpe_phase(const float *p4, int N, int npol, float *phi) {
+// phi[p][n] = atan2(ma_im, -ma_re)/4 with a zero-padded 501-tap moving average (sf:158-163).
+// Every output keeps the reference's summation order (taps in ascending sample order, one fused multiply-add per tap), so the
+// phases are bit-identical to the one-output-per-thread loop this replaces; a thread owns CPE_OPT consecutive outputs whose windows
+// overlap, so one staged sample feeds CPE_OPT independent accumulator pairs (8x fewer loads, 16 independent chains instead of 2:
+// 1.83 -> 0.3 ms for 592 runs x 9980 symbols, profiles/r01d_sweep_and_datagen.txt).  grid (ceil(N / CPE_TILE), npol).
+constexpr int CPE_OPT = 8, CPE_PT = 128, CPE_TILE = CPE_OPT * CPE_PT, CPE_HALF = CPE_MA / 2, CPE_SPAN = CPE_TILE + 2 * CPE_HALF;
+__device__ __forceinline__ int cpe_pad(int i) { return i + (i >> 3); }       // lanes read 8 apart: +1 per 8 keeps them on distinct banks
+__global__ void __launch_bounds__(CPE_PT) k_cpe_phase(const float *p4, int N, int npol, float *phi) {
+    __shared__ float s_re[CPE_SPAN + CPE_SPAN / 8 + 1], s_im[CPE_SPAN + CPE_SPAN / 8 + 1];
     const float w = (float)(1.0 / CPE_MA);
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npol * (int64_t)N; t += (int64_t)gridDim.x * blockDim.x) {
-        const int p = (int)(t / N), n = (int)(t - (int64_t)p * N);
-        const float *re = p4 + (int64_t)(2 * p) * N, *im = p4 + (int64_t)(2 * p + 1) * N;
-        float sr = 0.f, si = 0.f;
-        const int lo = max(0, n - CPE_MA / 2), hi = min(N - 1, n + CPE_MA / 2);
-        for (int m = lo; m <= hi; ++m) {
-            sr = fmaf(re[m], w, sr);
-            si = fmaf(im[m], w, si);
+    const int p = blockIdx.y, blk0 = blockIdx.x * CPE_TILE, tid = threadIdx.x;
+    const float *re = p4 + (int64_t)(2 * p) * N, *im = p4 + (int64_t)(2 * p + 1) * N;
+    for (int i = tid; i < CPE_SPAN; i += CPE_PT) {
+        const int g = blk0 - CPE_HALF + i;
+        const bool ok = g >= 0 && g < N;
+        s_re[cpe_pad(i)] = ok ? re[g] : 0.f;
+        s_im[cpe_pad(i)] = ok ? im[g] : 0.f;
+    }
+    __syncthreads();
+    float sr[CPE_OPT], si[CPE_OPT];
+#pragma unroll
+    for (int k = 0; k < CPE_OPT; ++k) sr[k] = si[k] = 0.f;
+    const int i0 = CPE_OPT * tid;                                 // tile index of the first sample of output 0's window
+    const bool interior = blk0 - CPE_HALF >= 0 && blk0 + CPE_TILE + CPE_HALF <= N;
+    // output k (sample o = blk0 + i0 + k) sums tile indices i0 + k ... i0 + k + 2 CPE_HALF, i.e. steps j = k ... k + 2 CPE_HALF
+    auto step = [&](int j, bool check) {
+        const int i = i0 + j, g = blk0 - CPE_HALF + i;
+        const float xr = s_re[cpe_pad(i)], xi = s_im[cpe_pad(i)];
+        const bool in_seq = !check || (g >= 0 && g < N);          // the reference sums only over existing samples (lo / hi clipping)
+#pragma unroll
+        for (int k = 0; k < CPE_OPT; ++k) {
+            if (in_seq && j >= k && j <= k + 2 * CPE_HALF) {
+                sr[k] = fmaf(xr, w, sr[k]);
+                si[k] = fmaf(xi, w, si[k]);
+            }
         }
-        phi[(int64_t)p * N + n] = atan2f(si, -sr) * 0.25f;
+    };
+    if (interior) {
+#pragma unroll
+        for (int j = 0; j < CPE_OPT - 1; ++j) step(j, false);
+#pragma unroll 4
+        for (int j = CPE_OPT - 1; j <= 2 * CPE_HALF; ++j) {       // every output's window is open: no predicates
+            const int i = i0 + j;
+            const float xr = s_re[cpe_pad(i)], xi = s_im[cpe_pad(i)];
+#pragma unroll
+            for (int k = 0; k < CPE_OPT; ++k) {
+                sr[k] = fmaf(xr, w, sr[k]);
+                si[k] = fmaf(xi, w, si[k]);
+            }
+        }
+#pragma unroll
+        for (int j = 2 * CPE_HALF + 1; j < 2 * CPE_HALF + CPE_OPT; ++j) step(j, false);
+    } else {
+        for (int j = 0; j < 2 * CPE_HALF + CPE_OPT; ++j) step(j, true);
+    }
+#pragma unroll
+    for (int k = 0; k < CPE_OPT; ++k) {
+        const int o = blk0 + i0 + k;
+        if (o < N) phi[(int64_t)p * N + o] = atan2f(si[k], -sr[k]) * 0.25f;
     }
 }
 
@@ -368,7 +414,7 @@ extern "C" size_t vaeq_cpe_runs_scratch_bytes(int32_t N, int32_t n_runs) {
 extern "C" size_t vaeq_cpe_scratch_bytes(int32_t N) { return vaeq_cpe_runs_scratch_bytes(N, 1); }
 
 extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream) {
-    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1 && n_runs > 0 && n_runs <= (1 << 20), "bad cpe arguments");
+    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1 && n_runs > 0 && n_runs <= 32767, "bad cpe arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int npol = 2 * n_runs;
     float *p4 = static_cast<float *>(scratch);
@@ -377,7 +423,7 @@ extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y
     k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, npol, p4);
     ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_pow4");
-    k_cpe_phase<<<grid, 256, 0, st>>>(p4, N, npol, phi);
+    k_cpe_phase<<<dim3((N + CPE_TILE - 1) / CPE_TILE, npol), CPE_PT, 0, st>>>(p4, N, npol, phi);
     ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_phase");
     k_cpe_unwrap_rotate<<<npol, 1024, 0, st>>>(y, phi, N, y_corr);
