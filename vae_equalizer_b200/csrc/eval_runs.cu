@@ -13,7 +13,7 @@
 namespace vaeq {
 
 constexpr int ER_NT = 256;
-constexpr int ER_CHUNKS = 8;
+constexpr int ER_CHUNKS = 8;                     // at most this many CTAs (partial blocks) per run and estimator in the shift search
 
 struct EvalRunsK {
     const float *q; int64_t ld_q, rs_q;          // (R, 2, 2n, N)  out_train
@@ -29,6 +29,7 @@ struct EvalRunsK {
     double *norms;                               // [R][2]: sum |tx|, sum |rx| over the evaluated region (estimator 1)
     int *counts;                                 // [R][2][16]
     float *ser;                                  // [R][4]: constellation x, y, soft demapper x, y  (rows of SER_valid, VAELE_DP:79,89)
+    int chunks;                                  // CTAs per (run, estimator) of the shift search: few when there are many runs
     int which;                                   // bit 0: estimator from q, bit 1: estimator from out
     float *scale;                                // optional [R]: the rescale factor mean|tx| / mean|rx| of sf:242 (estimator from out)
 };
@@ -55,11 +56,11 @@ __global__ void __launch_bounds__(SC_NT, SC_MINB) k_er_shift_corr(EvalRunsK p) {
     __shared__ ShiftSmem sm;
     const int chunk = blockIdx.x, run = blockIdx.y >> 1, est = blockIdx.y & 1, N = p.N;
     if (!((p.which >> est) & 1)) return;
-    const int per = ((N + ER_CHUNKS - 1) / ER_CHUNKS + SC_SLICE - 1) / SC_SLICE * SC_SLICE;
+    const int per = ((N + p.chunks - 1) / p.chunks + SC_SLICE - 1) / SC_SLICE * SC_SLICE;
     const int64_t t_lo = min((int64_t)N, (int64_t)chunk * per), t_hi = min((int64_t)N, t_lo + per);
     const float *q = p.q + run * p.rs_q, *out = p.out + run * p.rs_out;
     const uint16_t *tx = p.tx + run * p.rs_tx;
-    double *dst = p.part + ((((int64_t)run * 2 + est) * ER_CHUNKS + chunk) * p.n_shift) * 8;
+    double *dst = p.part + ((((int64_t)run * 2 + est) * p.chunks + chunk) * p.n_shift) * 8;
     if (est == 0) shift_corr_range<true, NPASS>(sm, q, p.ld_q, nullptr, 0, tx, p.ld_tx, p.amp, p.n_lev, N, p.n_shift, t_lo, t_hi, dst);
     else shift_corr_range<false, NPASS>(sm, nullptr, 0, out, p.ld_out, tx, p.ld_tx, nullptr, 0, N, p.n_shift, t_lo, t_hi, dst);
 }
@@ -74,11 +75,10 @@ __global__ void __launch_bounds__(ER_DEC_NT) k_er_shift_decide(EvalRunsK p) {
     if (idx >= 2 * p.n_runs) return;                         // whole warps leave together; no block-wide barrier below
     const int run = idx >> 1, est = idx & 1, half = p.n_shift / 2, nidx = p.n_shift * 8;
     if (!((p.which >> est) & 1)) return;
-    const double *part = p.part + ((int64_t)run * 2 + est) * ER_CHUNKS * nidx;
+    const double *part = p.part + ((int64_t)run * 2 + est) * p.chunks * nidx;
     for (int j = lane; j < nidx; j += 32) {
         double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < ER_CHUNKS; ++c) s += part[(int64_t)c * nidx + j];
+        for (int c = 0; c < p.chunks; ++c) s += part[(int64_t)c * nidx + j];
         v_s[w][j & 7][j >> 3] = fabsf((float)s);
     }
     __syncwarp();
@@ -335,6 +335,8 @@ extern "C" int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_
     p.norms = reinterpret_cast<double *>(ws + part_b);
     p.counts = counts_out ? counts_out : reinterpret_cast<int *>(ws + part_b + norm_b);
     p.align = align_out; p.ser = ser_out; p.which = which; p.scale = scale_out;
+    // enough CTAs to fill the GPU, as few partial blocks as possible: every CTA pays a prologue and a fixed-order reduction
+    p.chunks = max(1, min(min(ER_CHUNKS, (N + 2 * SC_T - 1) / (2 * SC_T)), (4 * sm_count() + 2 * n_runs - 1) / (2 * n_runs)));
     VAEQ_CUDA(cudaMemsetAsync(p.norms, 0, (size_t)n_runs * 2 * sizeof(double), st));
     VAEQ_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)n_runs * 2 * 16 * sizeof(int), st));
     const int blocks = max(1, min((N + ER_NT - 1) / ER_NT, max(1, sm_count() * 8 / n_runs)));
@@ -343,8 +345,8 @@ extern "C" int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_
     __VA_ARGS__;                                \
     ktime_end(VAEQ_K_EVAL, st);                 \
     VAEQ_LAUNCH_CHECK(name);
-    if (n_shift <= 32) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<1><<<dim3(ER_CHUNKS, 2 * n_runs), SC_NT, 0, st>>>(p)) }
-    else { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<2><<<dim3(ER_CHUNKS, 2 * n_runs), SC_NT, 0, st>>>(p)) }
+    if (n_shift <= 32) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<1><<<dim3(p.chunks, 2 * n_runs), SC_NT, 0, st>>>(p)) }
+    else { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<2><<<dim3(p.chunks, 2 * n_runs), SC_NT, 0, st>>>(p)) }
     ER_LAUNCH("k_er_shift_decide", k_er_shift_decide<<<(2 * n_runs + ER_DEC_NT / 32 - 1) / (ER_DEC_NT / 32), ER_DEC_NT, 0, st>>>(p))
     if (which & 1) {
         if (n_lev == 2) { ER_LAUNCH("k_er_ser_iqflip", k_er_ser_iqflip<2><<<dim3(blocks, n_runs), ER_NT, 0, st>>>(p)) }
