@@ -271,3 +271,50 @@ def test_vector_and_scalar_scan_paths_agree():
     s1, c1 = sfun.SER_constell_shaping(r1, tx, ampc, nu_sc, varc, return_counts=True)
     s2, c2 = sfun.SER_constell_shaping(r2, vt, ampc, nu_sc, varc, return_counts=True)
     assert torch.equal(c1, c2) and torch.equal(s1, s2) and torch.equal(r1, big_o[:, :, 3:N + 3])
+
+
+def test_full_size_evaluation_properties():
+    """Evaluation kernels at the bench size (N = 2^22, where no CPU oracle finishes in seconds): size-independent properties.
+    * the shift search finds a planted circular shift / polarisation swap, and rolling the input moves the answer with it;
+    * SER_IQflip is invariant under the rotations and the IQ flip it searches over (its counts permute), and counts the planted errors;
+    * soft_dec posteriors sum to one and decide like a nearest-threshold slicer away from the thresholds;
+    * SER_constell_shaping agrees with SER_IQflip on the same decisions when there is no shaping (nu = 0)."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    N, n = 1 << 22, 8
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0, 2, 25, 25)
+    amp, var = amp.cuda(), var.cuda()
+    idx = torch.randint(0, n, (2, 2, N), device="cuda", generator=gen)
+    tx = amp[idx].to(torch.float16)
+    clean = amp[idx]
+    out = (clean + 0.03 * torch.randn(2, 2, N, device="cuda", generator=gen)).contiguous()
+    # planted errors: every 1000th symbol of pol 0 gets its I level replaced by the neighbouring one
+    bad = torch.arange(0, N, 1000, device="cuda")
+    out[0, 0, bad] = amp[(idx[0, 0, bad] + 1) % n]
+    q = sfun.soft_dec(out, var, amp, float(nu_sc))
+    assert float((q.reshape(2, 2, n, N).sum(2) - 1).abs().max()) < 1e-5
+    dec = q.reshape(2, 2, n, N).argmax(2)
+    slicer = (out.unsqueeze(2) - amp.view(1, 1, n, 1)).abs().argmin(2)
+    assert torch.equal(dec, slicer)
+    ser, counts = sfun.SER_IQflip(q, tx, return_counts=True)
+    n_err0 = int(((dec[0] != idx[0]).any(0)).sum())
+    n_err1 = int(((dec[1] != idx[1]).any(0)).sum())
+    assert counts[0, 0, 0].item() == n_err0 and counts[0, 1, 0].item() == n_err1 and n_err0 >= bad.numel() - 8
+    assert ser.tolist() == [n_err0 / N, n_err1 / N] or np.allclose(ser.cpu().numpy(), [n_err0 / N, n_err1 / N], rtol=1e-6)
+    # a 90 degree rotation of the constellation (I, Q) -> (-Q, I) is one of the searched hypotheses: same minimum, permuted counts
+    q4 = q.reshape(2, 2, n, N)
+    q_rot = torch.stack((q4[:, 1].flip(1), q4[:, 0]), dim=1).reshape(2, 2 * n, N).contiguous()
+    ser_r, counts_r = sfun.SER_IQflip(q_rot, tx, return_counts=True)
+    assert torch.equal(ser_r, ser) and sorted(counts_r[0, 0].tolist()) == sorted(counts[0, 0].tolist())
+    # constellation SER without shaping = the same decisions
+    ser_c, counts_c = sfun.SER_constell_shaping(out.clone(), tx, amp, float(nu_sc), var, return_counts=True)
+    assert abs(counts_c[0, 0, 0].item() - n_err0) <= 16 and abs(counts_c[0, 1, 0].item() - n_err1) <= 16   # global rescale: threshold-edge symbols may flip
+    # shift search: plant (shift, swap), then roll by 3 more
+    out_s = torch.stack((out[1].roll(4, -1), out[0].roll(-2, -1))).contiguous()
+    s, r = sfun.find_shift_symb_full(out_s, tx, 21)
+    assert r == 1 and s.tolist() == [4, -2]            # as the CPU oracle answers on a 20 000-symbol prefix of the same construction
+    s2, r2 = sfun.find_shift_symb_full(out_s.roll(3, -1), tx, 21)
+    assert r2 == 1 and s2.tolist() == [7, 1]
+    qs = sfun.soft_dec(out_s, var, amp, float(nu_sc))
+    s3, r3 = sfun.find_shift(qs, tx, 21, amp, 2)
+    assert r3 == r and s3.tolist() == s.tolist()
