@@ -192,9 +192,14 @@ def sweep_cma_dp(cells, mod, sps, M_est, batch_len, N_train_max, num_frames, fle
         if datagen == "gpu_batched":
             if len(h_channel) != 1:
                 raise sfun._lib.VaeqError("datagen='gpu_batched' implements the optical channel 'h0' only")
-            P_all = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in consts])
-            rx_all, tx_all, _ = generate_frames_gpu(N_train_max, amps, [c["SNR"] for c in cells], P_all, sps, theta, device,
+            if frame == 0:                                               # per-run generator parameters live on the device
+                P_dev = torch.stack([torch.as_tensor(k[2], dtype=torch.float32) for k in consts]).to(device)
+                snr_dev = torch.tensor([float(c["SNR"]) for c in cells], dtype=torch.float32, device=device)
+                theta_dev = torch.tensor(theta, dtype=torch.float64, device=device)
+                theta_diff_dev = torch.tensor(theta_diff, dtype=torch.float64, device=device)
+            rx_all, tx_all, _ = generate_frames_gpu(N_train_max, amps, snr_dev, P_dev, sps, theta_dev.to(torch.float32), device,
                                                     seeds[0] * 100003 + frame, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ)
+            theta_dev = theta_dev + theta_diff_dev
         else:
             fr = [_make_frame(datagen, N_train_max, amps, cells[r]["SNR"], h_channel, consts[r][2], pol, symb_rate, sps, tau_cd, tau_pmd,
                               phiIQ, theta[r], device, rngs[r], seeds[r] * 100003 + frame) for r in range(R)]
