@@ -1,3 +1,4 @@
+"""GPU time split of one frame of the batched CMA sweep engine (sweep.sweep_cma_dp, 592 cells; KIND = CMA | CMAbatch | CMAflex)."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch

@@ -1,3 +1,4 @@
+"""Device data generator (datagen.generate_frames_gpu), R runs x 10 000 symbols: wall time per call and the kernel list (torch profiler)."""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch

@@ -1,3 +1,4 @@
+"""Per-kernel GPU time of find_shift / find_shift_symb_full at N = 2^22 (torch profiler): correlation kernels vs the decide kernel."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import torch
