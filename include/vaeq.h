@@ -168,6 +168,10 @@ typedef struct vaeq_dp_runs {
 int vaeq_dp_train_frame_runs(const vaeq_dp_desc *d, const vaeq_dp_runs *runs, int32_t n_steps, int32_t stride_sym,
                              int32_t keep_lo_in_dst, float lr_w, float lr_h, float *loss_steps, float *var_est_steps,
                              void *stream);
+/* The persistent frame kernel exists for 3 runs per SM (80 registers, the faster one per run) and for 4 (64 registers); by default the
+ * library takes the fourth run per SM only when that saves a whole wave of CTAs (592 runs on 148 SMs).  Testing hook: 0 = automatic,
+ * 3 / 4 = force; both give bitwise identical results. */
+int vaeq_dp_frame_runs_per_sm(int32_t per_sm);
 
 /* Batch-split of ONE long minibatch across GPUs (the reference has no counterpart, it is what replaces
  * "one process, one device" for func_VAEflex_DP_MQAM_shaping.py at large batch_len).  Every rank holds the whole rx

@@ -315,3 +315,29 @@ def test_cma_sweep_engine_equals_single_run_drivers(kind):
     # one batched generation for all cells: runs, finite, same shapes
     ser_g, _, _ = sweep.sweep_cma_dp(cells, "64-QAM", 2, M, B, N, 2, step, *common, kind=kind, datagen="gpu_batched")
     assert ser_g.shape == (3, 4, 2) and bool(torch.isfinite(ser_g).all())
+
+
+def test_frame_kernel_three_and_four_runs_per_sm_are_bitwise_identical():
+    """k_dp_frame_fast is built for 3 and for 4 resident runs per SM (80 / 64 registers); the library picks by the number of CTA waves.
+    Same arithmetic: the results must not depend on the choice."""
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.datagen import generate_frames_gpu
+    from vae_equalizer_b200.dp import DPEqualizerRuns
+    lib = _lib.load()
+    R, B, n_steps, M = 5, 100, 12, 25
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rxs, _, _ = generate_frames_gpu(B * n_steps, amps, [23.0] * R, np.tile(np.asarray(P, dtype=np.float32)[None], (R, 1)), 2, [0.3] * R, "cuda", 9)
+    res = {}
+    try:
+        for per_sm in (3, 4):
+            _lib.check(lib.vaeq_dp_frame_runs_per_sm(per_sm), "vaeq_dp_frame_runs_per_sm")
+            eq = DPEqualizerRuns(R, M, 2, amp, torch.tensor(P, dtype=torch.float32), var, nu_sc, device="cuda")
+            ot, oc = torch.empty(R, 2, 16, B * n_steps, device="cuda"), torch.empty(R, 2, 2, B * n_steps, device="cuda")
+            loss, ve = eq.train_frame(rxs, B, B, n_steps, 2.5e-3, 2.5e-3, ot, oc, 0, B, keep_lo_in_dst=True)
+            torch.cuda.synchronize()
+            res[per_sm] = (eq.W.clone(), eq.h.clone(), ot, oc, loss.clone(), ve.clone())
+    finally:
+        _lib.check(lib.vaeq_dp_frame_runs_per_sm(0), "vaeq_dp_frame_runs_per_sm")
+    for a, b in zip(res[3], res[4]):
+        assert torch.equal(a, b)
+    assert lib.vaeq_dp_frame_runs_per_sm(5) != 0

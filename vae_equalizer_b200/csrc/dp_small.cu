@@ -83,8 +83,10 @@ __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) 
 #ifndef SM_MINB
 #define SM_MINB 3          // 85 registers: 3 CTAs (runs) per SM; 98 registers uncapped = 2 CTAs, 64 = 4 CTAs with spills (profiles/r01b_experiments.txt)
 #endif
-template <int NL>
-__global__ void __launch_bounds__(SM_NT, SM_MINB) k_dp_frame_fast(DpK p, DpRunsK rs, int n_steps, int stride_sym, int keep_lo_in_dst,
+// MINB = 3 (80 registers) is the faster kernel per run; MINB = 4 (64 registers, a few spills) is launched when a fourth run per SM saves a
+// whole wave of CTAs (e.g. 592 runs on 148 SMs: 444 + a tail of 148 at 3 per SM, one wave at 4 per SM), see dp_small_launch
+template <int NL, int MINB>
+__global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs, int n_steps, int stride_sym, int keep_lo_in_dst,
                                                          float lr_w, float lr_h, int amsgrad) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -463,28 +465,50 @@ extern "C" int vaeq_debug_small_cycles(unsigned long long *out16) { return (int)
 namespace vaeq {
 #endif
 
+static int g_small_per_sm = 0;       // vaeq_dp_frame_runs_per_sm: 0 = choose by waves, 3 / 4 = force that kernel (tests, A/B timing)
 size_t dp_small_smem(int B, int M) { return (size_t)small_layout(B, M).total * sizeof(float); }
 
 int dp_small_launch(const DpK &p, const DpRunsK &rs, int n_lev, int n_runs, int n_steps, int stride_sym, int keep_lo_in_dst,
                     float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
     const size_t smem = dp_small_smem(p.B, p.M);
-    static size_t set_smem[3] = {0, 0, 0};
-#define SMALL_CASE(NL_, IDX_)                                                                                              \
-    {                                                                                                                      \
-        if (smem > set_smem[IDX_]) {                                                                                       \
-            VAEQ_CUDA(cudaFuncSetAttribute(k_dp_frame_fast<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            set_smem[IDX_] = smem;                                                                                         \
-        }                                                                                                                  \
-        ktime_begin(VAEQ_K_DP_FRAME, st);                                                                                  \
-        k_dp_frame_fast<NL_><<<n_runs, SM_NT, smem, st>>>(p, rs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad); \
-        ktime_end(VAEQ_K_DP_FRAME, st);                                                                                    \
+    static size_t set_smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    // waves of CTAs at 3 and at 4 runs per SM (shared memory permitting): take the fourth run per SM only when it saves a wave
+    const int sms = sm_count(), w3 = (n_runs + SM_MINB * sms - 1) / (SM_MINB * sms), w4 = (n_runs + 4 * sms - 1) / (4 * sms);
+    const bool fits4 = 4 * (smem + 1024) <= (size_t)227 * 1024;
+    // measured (tools/time_frames.py): 592 runs 2.25 -> 2.08 ms per 100-step frame with the fourth run per SM; with two or more waves
+    // either way (1184 runs: 3.97 vs 4.06 ms) the 80-register kernel stays ahead
+    const bool four = fits4 && (g_small_per_sm == 4 || (g_small_per_sm == 0 && w4 < w3 && w4 == 1));
+#define SMALL_LAUNCH(NL_, IDX_, MB_, V_)                                                                                          \
+    {                                                                                                                             \
+        if (smem > set_smem[IDX_][V_]) {                                                                                          \
+            VAEQ_CUDA(cudaFuncSetAttribute(k_dp_frame_fast<NL_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+            set_smem[IDX_][V_] = smem;                                                                                            \
+        }                                                                                                                         \
+        ktime_begin(VAEQ_K_DP_FRAME, st);                                                                                         \
+        k_dp_frame_fast<NL_, MB_><<<n_runs, SM_NT, smem, st>>>(p, rs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad);  \
+        ktime_end(VAEQ_K_DP_FRAME, st);                                                                                           \
+    }
+#define SMALL_CASE(NL_, IDX_)                       \
+    {                                               \
+        if (four) SMALL_LAUNCH(NL_, IDX_, 4, 1)     \
+        else SMALL_LAUNCH(NL_, IDX_, SM_MINB, 0)    \
     }
     if (n_lev == 2) SMALL_CASE(2, 0)
     else if (n_lev == 4) SMALL_CASE(4, 1)
     else SMALL_CASE(8, 2)
+#undef SMALL_LAUNCH
 #undef SMALL_CASE
     VAEQ_LAUNCH_CHECK("k_dp_frame_fast");
     return VAEQ_OK;
 }
 
 }  // namespace vaeq
+
+extern "C" int vaeq_dp_frame_runs_per_sm(int32_t per_sm) {
+    if (per_sm != 0 && per_sm != 3 && per_sm != 4) {
+        vaeq::set_error("vaeq_dp_frame_runs_per_sm: %d is not 0 (automatic), 3 or 4", per_sm);
+        return VAEQ_EINVAL;
+    }
+    vaeq::g_small_per_sm = per_sm;
+    return VAEQ_OK;
+}
