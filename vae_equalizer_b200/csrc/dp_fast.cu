@@ -711,7 +711,9 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
             const float4 r0 = gb[l], r1 = gb[FT_GROW + l], r2 = gb[2 * FT_GROW + l], r3 = gb[3 * FT_GROW + l];
             const float4 gd[FT_R] = {make_float4(r0.x, r1.x, r2.x, r3.x), make_float4(r0.y, r1.y, r2.y, r3.y),
                                      make_float4(r0.z, r1.z, r2.z, r3.z), make_float4(r0.w, r1.w, r2.w, r3.w)};
-            corr4<RL::AMAX>(win, li0 + c0, gd, acc2);
+            // a role owns AMAX or AMAX - 1 lags (13 = 7 + 6, 12 = 6 + 6): the shorter roles skip the padded lag (warp-uniform branch)
+            if (RL::AMAX == 1 || n_real == RL::AMAX) corr4<RL::AMAX>(win, li0 + c0, gd, acc2);
+            else corr4<(RL::AMAX > 1 ? RL::AMAX - 1 : 1)>(win, li0 + c0, gd, reinterpret_cast<float2(&)[(RL::AMAX > 1 ? RL::AMAX - 1 : 1)][4]>(acc2));
         }
         cp_async_wait_all();
         __syncthreads();
