@@ -653,6 +653,9 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
     const int n_real = role == 0 ? RL::A0e : role == 1 ? RL::A1e : role == 2 ? RL::A0o : RL::A1o;
     const float4 *win = ph ? s1 : s0;
     const int c0 = (FAM == 0 ? FT_XOFF - HF : -HF + ph) + a0, grow0 = FAM == 0 ? 0 : 4 * ph;
+    constexpr int BASE = RL::AMAX - 1;                           // = MH / 2 lags per role; A0e = BASE + 1, A1e = A0o = A1o = BASE
+    static_assert(BASE >= 1 && RL::A0e == BASE + 1 && RL::A1e == BASE && RL::A0o == BASE && RL::A1o == BASE, "role split");
+    const int c0x = (FAM == 0 ? FT_XOFF - HF : -HF) + BASE;      // window offset of the shared lag (even phase, lag BASE)
     const float *grows_g = FAM == 0 ? p.gyrows : p.erows;
     const int i0 = FT_R * tid;
 
@@ -711,9 +714,20 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
             const float4 r0 = gb[l], r1 = gb[FT_GROW + l], r2 = gb[2 * FT_GROW + l], r3 = gb[3 * FT_GROW + l];
             const float4 gd[FT_R] = {make_float4(r0.x, r1.x, r2.x, r3.x), make_float4(r0.y, r1.y, r2.y, r3.y),
                                      make_float4(r0.z, r1.z, r2.z, r3.z), make_float4(r0.w, r1.w, r2.w, r3.w)};
-            // a role owns AMAX or AMAX - 1 lags (13 = 7 + 6, 12 = 6 + 6): the shorter roles skip the padded lag (warp-uniform branch)
-            if (RL::AMAX == 1 || n_real == RL::AMAX) corr4<RL::AMAX>(win, li0 + c0, gd, acc2);
-            else corr4<(RL::AMAX > 1 ? RL::AMAX - 1 : 1)>(win, li0 + c0, gd, reinterpret_cast<float2(&)[(RL::AMAX > 1 ? RL::AMAX - 1 : 1)][4]>(acc2));
+            // every role correlates BASE = MH/2 lags of its phase; the one lag left over (even phase, lag BASE: 13 = 6 + 1 + 6 even taps at
+            // M_est = 25) is shared out by symbol group, so all four roles do the same amount of work between two barriers
+            corr4<BASE>(win, li0 + c0, gd, reinterpret_cast<float2(&)[BASE][4]>(acc2));
+            if ((g & 3) == role) {
+                if (FAM == 1 && ph) {                        // dh: the even-phase residual rows for the shared lag
+                    const float4 *ge = grow + (buf * NG) * FT_GROW;
+                    const float4 e0 = ge[l], e1 = ge[FT_GROW + l], e2 = ge[2 * FT_GROW + l], e3 = ge[3 * FT_GROW + l];
+                    const float4 gx[FT_R] = {make_float4(e0.x, e1.x, e2.x, e3.x), make_float4(e0.y, e1.y, e2.y, e3.y),
+                                             make_float4(e0.z, e1.z, e2.z, e3.z), make_float4(e0.w, e1.w, e2.w, e3.w)};
+                    corr4<1>(s0, li0 + c0x, gx, reinterpret_cast<float2(&)[1][4]>(acc2[BASE]));
+                } else {
+                    corr4<1>(s0, li0 + c0x, gd, reinterpret_cast<float2(&)[1][4]>(acc2[BASE]));
+                }
+            }
         }
         cp_async_wait_all();
         __syncthreads();
@@ -737,8 +751,13 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB) k_dp_taps_fast(DpK p) {
         for (int idx = lane; idx < n_real * 8; idx += 32) {
             const int a = idx >> 3, k = idx & 7, oi = k >> 1, cidx = k & 1, o = oi >> 1, i = oi & 1;
             float s = 0.f;
+            if (a == BASE) {                                 // the shared lag (role 0 publishes it): partial sums of every warp, fixed order
 #pragma unroll
-            for (int w = wid; w < FT_NW; w += 4) s += red[w * (RL::AMAX * 8) + idx];
+                for (int w = 0; w < FT_NW; ++w) s += red[w * (RL::AMAX * 8) + idx];
+            } else {
+#pragma unroll
+                for (int w = wid; w < FT_NW; w += 4) s += red[w * (RL::AMAX * 8) + idx];
+            }
             const int lag = a0 + a;
             if (FAM == 1) dst[8 * M + ((o * 2 + i) * 2 + cidx) * M + (2 * MH - ph - 2 * lag)] = 2.f * p.scal[DP_KAPPA_OFF + o] * s;   // gD = 2 kappa_chi e
             else dst[(o * 4 + 2 * cidx + i) * M + (2 * lag + ph)] = s;
