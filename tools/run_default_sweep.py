@@ -8,19 +8,22 @@ import numpy as np, torch
 from vae_equalizer_b200 import sweep
 
 kw = dict(mod="64-QAM", sps=2, loss_type=os.environ.get("LOSS", "VAE"), channel="h0", nu_vec=[0], symb_rate_vec=[90e9], theta_vec=[np.pi / 10],
-          theta_diff_vec=[0.06 * np.pi], SNR_vec=[23], M_vec=[25], batch_len_vec=[100], flex_step_vec=[10], lr_optim_vec=[2.5e-3, 2e-3, 3e-3],
+          theta_diff_vec=[0.06 * np.pi], SNR_vec=[23], M_vec=[25], batch_len_vec=[100], flex_step_vec=[10],
+          lr_optim_vec=[float(v) for v in os.environ.get("LRS", "2.5e-3,2e-3,3e-3").split(",")],      # CMA family: e.g. LOSS=CMAbatch LRS=1e-5,2e-5,5e-6
           iter=5, N_lrhalf=170, num_frames=int(os.environ.get("FRAMES", 170)), N_frame_max=10000)
 sweep.run_dp_sweep(**{**kw, "num_frames": 2})          # warm-up (module load, cuFFT plans)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 SER, Var_est, var_real = sweep.run_dp_sweep(**kw)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 F = kw["num_frames"]
-print(f"loss_type={kw['loss_type']}: 15 cells x {F} frames x 10 000 symbols in {dt:.2f} s wall ({15 * F * 10000 / dt / 1e6:.1f} M symbols/s end to end)")
+n_cells = 5 * len(kw["lr_optim_vec"])
+print(f"loss_type={kw['loss_type']}: {n_cells} cells x {F} frames x 10 000 symbols in {dt:.2f} s wall ({n_cells * F * 10000 / dt / 1e6:.1f} M symbols/s end to end)")
 S = SER[:, 0, 0, 0, 0, 0, :, 0, 0, 0, :, :]            # (4, lr, iter, frame)
 pm = 1.0                                               # 64-QAM unit mean power
 for l, lr in enumerate(kw["lr_optim_vec"]):
     tail = S[:, l, :, max(15, F - 50):].mean(dim=(1, 2)).tolist()
-    snr = 10 * torch.log10(pm / Var_est[:, 0, 0, 0, 0, 0, l, 0, 0, 0, :, max(15, F - 50):].mean())      # VAELE_DP:68
+    ve = Var_est[:, 0, 0, 0, 0, 0, l, 0, 0, 0, :, max(15, F - 50):].mean()
+    snr = 10 * torch.log10(pm / ve) if float(ve) > 0 else torch.tensor(float("nan"))      # VAELE_DP:68; the CMA drivers report no variance estimate
     print(f"  lr {lr:g}: SER constellation x/y {tail[0]:.4f} {tail[1]:.4f}, soft demapper x/y {tail[2]:.4f} {tail[3]:.4f} (mean of the last frames, 5 realisations); "
           f"frame 0 SER {S[0, l, :, 0].mean():.3f}; SNR_est {float(snr):.1f} dB")
 sweep.save_mat("gpurun_out/default_sweep.mat", SER, Var_est, var_real, SNR_vec=kw["SNR_vec"], nu_vec=kw["nu_vec"], theta_diff_vec=kw["theta_diff_vec"],
