@@ -80,18 +80,32 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
     }
     const float lr2 = 2.f * lr;
     const int nsym_loop = (N + sps - 1) / sps;
-    for (int ks = 0; ks < nsym_loop; ++ks) {
-        float yI[2][2], yQ[2][2];                                               // [slot][in pol]
+    // the window of symbol ks + 1 does not depend on the tap recurrence: it is loaded one iteration ahead, so that the
+    // L2 latency of the loads is not part of the per-symbol dependency chain (one warp per run has nothing else to hide it)
+    float nI[2][2], nQ[2][2];                                                   // [slot][in pol]
+    auto load_window = [&](int ks) {
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
             const int k = lane + 32 * sl, s = ks * sps - mh + k;
             const bool ok = (k < M) && (s >= 0) && (s < N);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                yI[sl][i] = ok ? r.y[(int64_t)(2 * i) * N + s] : 0.f;
-                yQ[sl][i] = ok ? r.y[(int64_t)(2 * i + 1) * N + s] : 0.f;
+                nI[sl][i] = ok ? r.y[(int64_t)(2 * i) * N + s] : 0.f;
+                nQ[sl][i] = ok ? r.y[(int64_t)(2 * i + 1) * N + s] : 0.f;
             }
         }
+    };
+    load_window(0);
+    for (int ks = 0; ks < nsym_loop; ++ks) {
+        float yI[2][2], yQ[2][2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                yI[sl][i] = nI[sl][i];
+                yQ[sl][i] = nQ[sl][i];
+            }
+        if (ks + 1 < nsym_loop) load_window(ks + 1);
         float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl)
