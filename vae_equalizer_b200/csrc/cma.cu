@@ -62,13 +62,15 @@ __device__ __forceinline__ int cma_out_index(int ks, int sps, int mh, int Nsym) 
 // ---------------------------------------------------------------------------------------------
 // CMA: per-symbol update.  One warp per run; lane l owns taps k = l and k = l + 32.
 // ---------------------------------------------------------------------------------------------
+// NSLOT = 1 for M <= 32 (every reference setting uses M = 25): no second, all-zero tap slot to multiply, update and load for
+template <int NSLOT>
 __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, float *h, float *out, float *e, int N, int M,
                                                    int sps, float R, float lr, int train) {
     const int lane = threadIdx.x, mh = M / 2, Nsym = N / sps;
     const CmaRun r = cma_run_ptrs(Rx, ys, h, out, e, blockIdx.x, N, M, Nsym);
-    float hr[2][2][2], hi[2][2][2];                                              // [tap slot][o][i]
+    float hr[NSLOT][2][2], hi[NSLOT][2][2];                                              // [tap slot][o][i]
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
+    for (int sl = 0; sl < NSLOT; ++sl) {
         const int k = lane + 32 * sl;
 #pragma unroll
         for (int o = 0; o < 2; ++o)
@@ -82,10 +84,10 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
     const int nsym_loop = (N + sps - 1) / sps;
     // the window of symbol ks + 1 does not depend on the tap recurrence: it is loaded one iteration ahead, so that the
     // L2 latency of the loads is not part of the per-symbol dependency chain (one warp per run has nothing else to hide it)
-    float nI[2][2], nQ[2][2];                                                   // [slot][in pol]
+    float nI[NSLOT][2], nQ[NSLOT][2];                                                   // [slot][in pol]
     auto load_window = [&](int ks) {
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int sl = 0; sl < NSLOT; ++sl) {
             const int k = lane + 32 * sl, s = ks * sps - mh + k;
             const bool ok = (k < M) && (s >= 0) && (s < N);
 #pragma unroll
@@ -97,9 +99,9 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
     };
     load_window(0);
     for (int ks = 0; ks < nsym_loop; ++ks) {
-        float yI[2][2], yQ[2][2];
+        float yI[NSLOT][2], yQ[NSLOT][2];
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
+        for (int sl = 0; sl < NSLOT; ++sl)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 yI[sl][i] = nI[sl][i];
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
         if (ks + 1 < nsym_loop) load_window(ks + 1);
         float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
+        for (int sl = 0; sl < NSLOT; ++sl)
 #pragma unroll
             for (int o = 0; o < 2; ++o)
 #pragma unroll
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
         }
         if (train) {
 #pragma unroll
-            for (int sl = 0; sl < 2; ++sl)
+            for (int sl = 0; sl < NSLOT; ++sl)
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
                     const float f = lr2 * err[o];
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
     }
     if (train) {
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int sl = 0; sl < NSLOT; ++sl) {
             const int k = lane + 32 * sl;
             if (k < M) {
 #pragma unroll
@@ -410,7 +412,8 @@ extern "C" int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float
     ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cma_scale");
     if (mode == VAEQ_CMA_SAMPLE) {
-        k_cma_sample<<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
+        if (M <= 32) k_cma_sample<1><<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
+        else k_cma_sample<2><<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
         ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_sample");
     } else {
