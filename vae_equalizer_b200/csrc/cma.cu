@@ -170,10 +170,19 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
 // ---------------------------------------------------------------------------------------------
 // CMAbatch / CMAflex: one CTA per run, segment-parallel.
 // ---------------------------------------------------------------------------------------------
+// STAGED: the sample window of a chunk of symbols (equalize stage) and the window, outputs and errors of an update are staged in
+// shared memory first, so the sequential per-thread loops (25 taps per symbol; batchlen symbols per tap gradient) run on shared-memory
+// latency instead of a global round trip per step.  Same operations in the same order: results are bit-identical to the
+// unstaged form, which remains for windows that do not fit (batchlen > CMA_WCAP).
+constexpr int CMA_WCAP = 1024;                                                   // largest update window (symbols) held in shared memory
+template <bool STAGED>
 __global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys, float *h, float *out, float *e, int N, int M,
                                                       int sps, float R, float lr, int train, int mode, int batchlen,
-                                                      int symb_step) {
-    extern __shared__ float hs[];                                                // (2,2,2,M) taps of this run
+                                                      int symb_step, int ycap) {
+    extern __shared__ float hs[];                                                // (2,2,2,M) taps of this run | staging buffers
+    float *ybuf = hs + 8 * M;                                                    // [4][ycap] samples
+    float *obuf = ybuf + 4 * ycap;                                               // [4][batchlen] equalizer outputs of the update window
+    float *ebuf = obuf + (STAGED ? 4 * batchlen : 0);                            // [batchlen][2] errors
     const int tid = threadIdx.x, mh = M / 2, Nsym = N / sps;
     const CmaRun r = cma_run_ptrs(Rx, ys, h, out, e, blockIdx.x, N, M, Nsym);
     for (int i = tid; i < 8 * M; i += CMA_NT) hs[i] = r.h[i];
@@ -196,47 +205,79 @@ __global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys
             k_fire = ((lo + symb_step - 1) / symb_step) * symb_step;
         }
         const int k_end = min(k_fire, k_last);                                   // inclusive
-        // ---- equalize symbols k_cur..k_end with the current taps ------------------------------
-        for (int k = k_cur + tid; k <= k_end; k += CMA_NT) {
-            const int ks = k + off;
-            float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
-            for (int m = 0; m < M; ++m) {
-                const int s = ks * sps - mh + m;
-                if (s < 0 || s >= N) continue;
+        // ---- equalize symbols k_cur..k_end with the current taps, CMA_NT symbols at a time ------------------------------
+        for (int kc = k_cur; kc <= k_end; kc += CMA_NT) {
+            const int kc_hi = min(kc + CMA_NT - 1, k_end);
+            const int s_base = (kc + off) * sps - mh, ns = (kc_hi - kc) * sps + M;
+            if (STAGED) {
+                for (int j = tid; j < 4 * ns; j += CMA_NT) {
+                    const int row = j / ns, jj = j - row * ns, sidx = s_base + jj;
+                    ybuf[row * ycap + jj] = (sidx >= 0 && sidx < N) ? r.y[(int64_t)row * N + sidx] : 0.f;
+                }
+                __syncthreads();
+            }
+            const int k = kc + tid;
+            if (k <= kc_hi) {
+                const int ks = k + off;
+                float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
+                for (int m = 0; m < M; ++m) {
+                    const int s = ks * sps - mh + m;
+                    if (s < 0 || s >= N) continue;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float a = r.y[(int64_t)(2 * i) * N + s], b = r.y[(int64_t)(2 * i + 1) * N + s];
+                    for (int i = 0; i < 2; ++i) {
+                        const float a = STAGED ? ybuf[(2 * i) * ycap + (s - s_base)] : r.y[(int64_t)(2 * i) * N + s];
+                        const float b = STAGED ? ybuf[(2 * i + 1) * ycap + (s - s_base)] : r.y[(int64_t)(2 * i + 1) * N + s];
 #pragma unroll
-                    for (int o = 0; o < 2; ++o) {
-                        const float wr = hs[((o * 2 + i) * 2 + 0) * M + m], wi = hs[((o * 2 + i) * 2 + 1) * M + m];
-                        oI[o] += a * wr - b * wi;
-                        oQ[o] += a * wi + b * wr;
+                        for (int o = 0; o < 2; ++o) {
+                            const float wr = hs[((o * 2 + i) * 2 + 0) * M + m], wi = hs[((o * 2 + i) * 2 + 1) * M + m];
+                            oI[o] += a * wr - b * wi;
+                            oQ[o] += a * wi + b * wr;
+                        }
                     }
                 }
+                const int kk = k < 0 ? k + Nsym : k;
+                if (kk >= 0 && kk < Nsym) {
+                    r.out[0 * Nsym + kk] = oI[0];
+                    r.out[1 * Nsym + kk] = oQ[0];
+                    r.out[2 * Nsym + kk] = oI[1];
+                    r.out[3 * Nsym + kk] = oQ[1];
+                    r.e[2 * kk + 0] = R - oI[0] * oI[0] - oQ[0] * oQ[0];
+                    r.e[2 * kk + 1] = R - oI[1] * oI[1] - oQ[1] * oQ[1];
+                }
             }
-            const int kk = k < 0 ? k + Nsym : k;
-            if (kk >= 0 && kk < Nsym) {
-                r.out[0 * Nsym + kk] = oI[0];
-                r.out[1 * Nsym + kk] = oQ[0];
-                r.out[2 * Nsym + kk] = oI[1];
-                r.out[3 * Nsym + kk] = oQ[1];
-                r.e[2 * kk + 0] = R - oI[0] * oI[0] - oQ[0] * oQ[0];
-                r.e[2 * kk + 1] = R - oI[1] * oI[1] - oQ[1] * oQ[1];
-            }
+            __syncthreads();                                                     // outputs visible to the update; ybuf free again
         }
-        __syncthreads();
         // ---- tap update from the window [k_fire - batchlen, k_fire) ------------------------------
         if (train && k_fire <= k_last) {
+            const int kap0 = k_fire - batchlen, sw_base = (kap0 + off) * sps - mh, nsw = (batchlen - 1) * sps + M;
+            if (STAGED) {
+                for (int j = tid; j < 4 * nsw; j += CMA_NT) {
+                    const int row = j / nsw, jj = j - row * nsw, sidx = sw_base + jj;
+                    ybuf[row * ycap + jj] = (sidx >= 0 && sidx < N) ? r.y[(int64_t)row * N + sidx] : 0.f;
+                }
+                for (int j = tid; j < 4 * batchlen; j += CMA_NT) {
+                    const int row = j / batchlen, kap = kap0 + (j - row * batchlen);
+                    obuf[j] = (kap >= 0 && kap < Nsym) ? r.out[row * Nsym + kap] : 0.f;
+                }
+                for (int j = tid; j < 2 * batchlen; j += CMA_NT) {
+                    const int kap = kap0 + (j >> 1);
+                    ebuf[j] = (kap >= 0 && kap < Nsym) ? r.e[2 * kap + (j & 1)] : 0.f;
+                }
+                __syncthreads();
+            }
             for (int idx = tid; idx < 8 * M; idx += CMA_NT) {
                 const int m = idx % M, oic = idx / M, c = oic & 1, oi = oic >> 1, i = oi & 1, o = oi >> 1;
                 float acc = 0.f;
-                for (int kap = k_fire - batchlen; kap < k_fire; ++kap) {
+                for (int kap = kap0; kap < k_fire; ++kap) {
                     const int ks = kap + off, s = ks * sps - mh + m;
                     if (kap < 0 || s < 0 || s >= N) continue;                    // kap < 0 would read torch.empty garbage in the reference
-                    const float a = r.y[(int64_t)(2 * i) * N + s], b = r.y[(int64_t)(2 * i + 1) * N + s];
-                    const float vI = r.out[(2 * o) * Nsym + kap], vQ = r.out[(2 * o + 1) * Nsym + kap];
+                    const int w = kap - kap0;
+                    const float a = STAGED ? ybuf[(2 * i) * ycap + (s - sw_base)] : r.y[(int64_t)(2 * i) * N + s];
+                    const float b = STAGED ? ybuf[(2 * i + 1) * ycap + (s - sw_base)] : r.y[(int64_t)(2 * i + 1) * N + s];
+                    const float vI = STAGED ? obuf[(2 * o) * batchlen + w] : r.out[(2 * o) * Nsym + kap];
+                    const float vQ = STAGED ? obuf[(2 * o + 1) * batchlen + w] : r.out[(2 * o + 1) * Nsym + kap];
                     const float inc = c ? (vQ * a - vI * b) : (vI * a + vQ * b);     // sf:414-422
-                    acc += r.e[2 * kap + o] * inc;
+                    acc += (STAGED ? ebuf[2 * w + o] : r.e[2 * kap + o]) * inc;
                 }
                 hs[idx] += lr2 * acc;                                            // sf:425-433
             }
@@ -417,7 +458,19 @@ extern "C" int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float
         ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_sample");
     } else {
-        k_cma_block<<<n_runs, CMA_NT, 8 * M * sizeof(float), st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step);
+        const bool staged = batchlen <= CMA_WCAP;
+        const int ycap = (std::max(CMA_NT, batchlen) - 1) * sps + M;            // samples per row of the staged window
+        const size_t smem = (size_t)(8 * M + (staged ? 4 * ycap + 6 * batchlen : 0)) * sizeof(float);
+        if (staged) {
+            static size_t set_smem = 0;
+            if (smem > set_smem) {
+                VAEQ_CUDA(cudaFuncSetAttribute(k_cma_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                set_smem = smem;
+            }
+            k_cma_block<true><<<n_runs, CMA_NT, smem, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step, ycap);
+        } else {
+            k_cma_block<false><<<n_runs, CMA_NT, smem, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step, 0);
+        }
         ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_block");
     }
