@@ -341,3 +341,17 @@ def test_frame_kernel_three_and_four_runs_per_sm_are_bitwise_identical():
     for a, b in zip(res[3], res[4]):
         assert torch.equal(a, b)
     assert lib.vaeq_dp_frame_runs_per_sm(5) != 0
+
+
+@pytest.mark.parametrize("kind", ["VAE", "VAEflex"])
+def test_single_run_drivers_fused_evaluation_equals_per_op(kind):
+    """processing_vaele_dp / processing_vaeflex_dp with eval_mode="fused" (one batched evaluation call per frame, no host sync) against the
+    reference's call-by-call evaluation: identical SER estimates."""
+    from vae_equalizer_b200 import processing as pr
+    phiIQ = np.array([0.0314, 0.0314], dtype=np.complex64)
+    fn = pr.processing_vaele_dp if kind == "VAE" else pr.processing_vaeflex_dp
+    args = ("64-QAM", 2, 22, 0.0270955, 25, 0.05, 0.3, 2.5e-3, 100, 3000 if kind == "VAE" else 1000, 3, 20, "h0", 90e9, -26e-24,
+            0.1e-12 * np.sqrt(1000), phiIQ, 2)
+    a = fn(*args, verbose=False, datagen="gpu", seed=6)
+    b = fn(*args, verbose=False, datagen="gpu", seed=6, eval_mode="fused")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])

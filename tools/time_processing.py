@@ -11,6 +11,10 @@ for dg in ("numpy", "gpu"):
     SER, Var_est, var = pr.processing_vaele_dp(*args, rng=np.random.default_rng(1), verbose=False, datagen=dg)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"VAE-LE DP processing, datagen={dg}: {dt / 30 * 1e3:.1f} ms per frame of 10000 symbols ({10000 * 30 / dt:.0f} symbols/s); final SER {SER[:, -1].tolist()}")
+torch.cuda.synchronize(); t0 = time.perf_counter()
+SER, Var_est, var = pr.processing_vaele_dp(*args, rng=np.random.default_rng(1), verbose=False, datagen="gpu", eval_mode="fused")
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"VAE-LE DP processing, datagen=gpu, eval_mode=fused: {dt / 30 * 1e3:.1f} ms per frame of 10000 symbols ({10000 * 30 / dt:.0f} symbols/s); final SER {SER[:, -1].tolist()}")
 flex = list(args); flex[9] = 2000; flex[10] = 5
 for dg in ("numpy", "gpu"):
     torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -55,9 +55,19 @@ def _print_frame(frame, loss, shift_h, r, snr_db, ser):
     print('\t\t\t\t\t\t\tSER_x = ', ser[2], '\tSER_y = ', ser[3], '\t(soft demapper)')
 
 
+def _eval_fused(out_train, out_const, data_tensor, amp_levels, var, nu_sc, seg_len):
+    """The per-frame evaluation of the VAE drivers in ONE call sequence without a host sync (vaeq_frame_eval_runs with a single run): the
+    same error counts as the find_shift -> roll -> cut -> SER_* sequence (tests/test_frames_gpu.py).  Returns (SER (4,), align (2,4) int32)."""
+    ser, al = sfun.frame_eval_runs(out_train.unsqueeze(0), out_const.unsqueeze(0), data_tensor.unsqueeze(0), amp_levels, var.reshape(1, 2),
+                                   torch.full((1,), float(nu_sc), device=out_train.device), seg_len, n_cut=N_CUT)
+    return ser[0], al[0]
+
+
 def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_frame_max, num_frames, flex_step,
-                        channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0):
-    """VAE-LE, non-overlapping minibatches (func_VAELE_DP_MQAM_shaping.py:17-95)."""
+                        channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0,
+                        eval_mode="per_op"):
+    """VAE-LE, non-overlapping minibatches (func_VAELE_DP_MQAM_shaping.py:17-95).  eval_mode="per_op" replays the reference's evaluation
+    call by call (two host syncs per frame for the detected shifts), "fused" evaluates the frame in one launch sequence without a sync."""
     device = _cuda_device(device)
     if verbose:
         print("We are using the following device for learning:", device)
@@ -82,6 +92,12 @@ def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, b
         SNR_est = pow_mean / torch.mean(var_est)
         Var_est[:, frame] = torch.mean(var_est, dim=1)
 
+        if eval_mode == "fused":
+            SER_valid[:, frame], al = _eval_fused(out_train, out_const, data_tensor, amp_levels, var, nu_sc, batch_len)
+            if verbose:
+                a = al.tolist()
+                _print_frame(frame, loss_steps[-1].item(), a[1][:2], a[1][2], (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
+            continue
         shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
         sh = [int(v) for v in shift.tolist()]
         out_train = _align(out_train, sh, r)
@@ -106,7 +122,8 @@ def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, b
 
 
 def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
-                          channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0):
+                          channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0,
+                          eval_mode="per_op"):
     """VAE-flex, sliding window advanced by flex_step (func_VAEflex_DP_MQAM_shaping.py:16-88)."""
     device = _cuda_device(device)
     if verbose:
@@ -135,6 +152,12 @@ def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
         SNR_est = pow_mean / torch.mean(var_est)
         Var_est[:, frame] = torch.mean(var_est, dim=1)
 
+        if eval_mode == "fused":
+            SER_valid[:, frame], al = _eval_fused(out_train, out_const, data_tensor, amp_levels, var, nu_sc, 0)
+            if verbose:
+                a = al.tolist()
+                _print_frame(frame, loss_steps[-1].item(), a[1][:2], a[1][2], (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
+            continue
         shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
         sh = [int(v) for v in shift.tolist()]
         out_train = _align(out_train, sh, r)
