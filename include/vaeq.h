@@ -132,6 +132,14 @@ int vaeq_dp_forward_backward(const vaeq_dp_desc *d, void *stream);
  * d->gh = dL/dh_est (optional) and gq (2,2n,B, row stride ld_gq) = dL/dq (optional).  d->W / out / var / adam are not used. */
 int vaeq_dp_loss_from_q(const vaeq_dp_desc *d, float *gq, int64_t ld_gq, void *stream);
 
+/* Backward of twoXtwoFIR.forward (sf:500-527) alone, for ARBITRARY upstream gradients: gq (2,2n,B) = dL/dq and / or gout (2,2,B) =
+ * dL/dout (either may be NULL) -> gW (2,4,M) = dL/dconv_w.weight.  q / out are the forward's outputs (needed when gq != NULL).  What
+ * autograd calls when a caller derives something else from q before differentiating; the fused step above does not use it. */
+size_t vaeq_eq_backward_scratch_bytes(int32_t B, int32_t M);
+int vaeq_eq_backward(const float *rx, int64_t ld_rx, const float *q, int64_t ld_q, const float *out, int64_t ld_out, const float *gq,
+                     int64_t ld_gq, const float *gout, int64_t ld_gout, const float *amp, const float *var, int32_t n_lev, int32_t B,
+                     int32_t M, float *gW, void *scratch, void *stream);
+
 /* forward + backward + Adam on both groups: lr_w for W (group 0), lr_h for h (group 1);
  * betas (0.9,0.999), eps 1e-8, no weight decay (torch defaults used at func_VAELE_DP_MQAM_shaping.py:28) */
 int vaeq_dp_train_step(const vaeq_dp_desc *d, float lr_w, float lr_h, void *stream);
@@ -221,7 +229,9 @@ int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, int64_t ld_o
 int vaeq_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, int32_t n_lev, int32_t N,
                     int32_t *counts_out, float *ser_out, void *stream);
 /* SER_constell_shaping + dec_on_bound (sf:225-287): rescales rx IN PLACE (sf:242) like the reference.
- * scratch: 4 doubles. */
+ * scratch: VAEQ_EVAL_SCRATCH_BYTES (per-CTA partial sums of the two norms, added in a fixed order: no floating-point
+ * atomics, so the scale factor and hence every count is bit-reproducible). */
+#define VAEQ_EVAL_SCRATCH_BYTES 65536
 int vaeq_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx, const float *amp, const float *var,
                       float nu_sc, int32_t n_lev, int32_t N, int32_t *counts_out, float *ser_out, void *scratch, void *stream);
 /* Per-frame evaluation of n_runs independent runs at once (sweep engine): what func_VAELE_DP_MQAM_shaping.py:70-89 (seg_len =
@@ -253,7 +263,8 @@ int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_q, const fl
 int vaeq_cma_align_rescale(const float *out, int64_t ld_out, int64_t rs_out, const int32_t *align, const float *scale, int32_t N,
                            int32_t edge, int32_t n_runs, float *oc, void *stream);
 
-/* extension, not in the reference: achievable-rate estimate H(X)+E[log2 q(x_tx|y)] per pol (bit/2D symbol) */
+/* extension, not in the reference: achievable-rate estimate H(X)+E[log2 q(x_tx|y)] per pol (bit/2D symbol);
+ * scratch: VAEQ_EVAL_SCRATCH_BYTES */
 int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_t ld_tx, const float *P, int32_t n_lev, int32_t N,
              float *gmi_out, void *scratch, void *stream);
 

@@ -156,6 +156,76 @@ def test_operator_level_autograd_matches_oracle():
         assert rel(net.conv_w.weight, g["W"][s]) < 1e-4 and rel(h_est, g["h"][s]) < 1e-4
 
 
+@pytest.mark.parametrize("mod,M,B", [("64-QAM", 25, 100), ("16-QAM", 9, 1300), ("4-QAM", 5, 64)])
+def test_equalizer_autograd_through_a_derived_q(mod, M, B):
+    """A q DERIVED from net(x) (here a clamp + mask, and a second loss on `out`) must differentiate into conv_w.weight like the
+    reference's nn.Module (sf:500-527): the fused shortcut does not apply, autograd goes through vaeq_dp_loss_from_q (dL/dq) and
+    vaeq_eq_backward (softmin + FIR backward for arbitrary upstream gradients).  Checked against the CPU oracle's autograd."""
+    import vae_equalizer_b200.shared_funcs as sfun
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", mod, "cpu", 0.0270955, 2, M, 12)
+    gen = torch.Generator().manual_seed(3 * B + M)
+    rx = 0.6 * torch.randn(2, 2, 2 * B, generator=gen)
+    W0 = torch.zeros(2, 4, M)
+    W0[0, 0, M // 2] = W0[1, 1, M // 2] = 1.0
+    W0 += 0.03 * torch.randn(2, 4, M, generator=gen)
+    h0 = h_est.detach() + 0.03 * torch.randn(2, 2, 2, M, generator=gen)
+    Pt = torch.tensor(P, dtype=torch.float32)
+    mask = (torch.rand(1, 1, B, generator=gen) > 0.2).float()
+
+    def objective(q, out, rx_, h, amp_, P_, lossfn):
+        qd = q.clamp(min=1e-6) * mask.to(q.device) + (1.0 - mask.to(q.device)) / q.shape[1] * 2
+        loss, ve = lossfn(qd, rx_, h, amp_, P_)
+        return loss + 3.0 * (out ** 2).sum(), ve
+
+    Wo, ho = W0.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+    qo, oo = O.equalizer_forward(rx, Wo, amp, var, nu_sc, 2)
+    lo, vo = objective(qo, oo, rx, ho, amp, Pt, O.elbo_loss)
+    lo.backward()
+    net = sfun.twoXtwoFIR(M, 2).cuda()
+    with torch.no_grad():
+        net.conv_w.weight.copy_(W0)
+    hd = h0.cuda().requires_grad_(True)
+    x = rx.cuda()
+    q, out = net(x, amp.cuda(), var.cuda(), nu_sc)
+    assert q.grad_fn is not None and out.grad_fn is not None
+    ld, vd = objective(q, out, x, hd, amp.cuda(), Pt.cuda(), sfun.loss_function_shaping)
+    ld.backward()
+    assert rel(ld.detach(), lo.detach()) < 1e-4 and rel(vd, vo) < 1e-4
+    assert rel(net.conv_w.weight.grad, Wo.grad) < 2e-4 and rel(hd.grad, ho.grad) < 2e-4
+    # and the unmodified q (through the .squeeze() view the reference drivers pass) still takes the fused path with the same result
+    net.zero_grad()
+    q2, _ = net(x, amp.cuda(), var.cuda(), nu_sc)
+    n_launch = sfun._lib.load().vaeq_launch_count(7)
+    l2, _ = sfun.loss_function_shaping(q2.squeeze(), x.squeeze(), hd, amp.cuda(), Pt.cuda())
+    l2.backward()
+    assert sfun._lib.load().vaeq_launch_count(7) == n_launch       # no vaeq_eq_backward launch: fused
+    Wf = W0.clone().requires_grad_(True)
+    qf, _ = O.equalizer_forward(rx, Wf, amp, var, nu_sc, 2)
+    lf, _ = O.elbo_loss(qf, rx, h0, amp, Pt)
+    lf.backward()
+    assert rel(l2.detach(), lf.detach()) < 1e-4 and rel(net.conv_w.weight.grad, Wf.grad) < 2e-4
+
+
+def test_calls_follow_the_tensors_device():
+    """Every Python entry runs on the device of its tensors, not on the caller's current device (two GPUs needed)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import vae_equalizer_b200.shared_funcs as sfun
+    from vae_equalizer_b200.dp import DPEqualizer
+    g = load("dp_step_16qam_M9_B64")
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(0):                               # current device stays 0 on purpose
+            eq = DPEqualizer(9, 2, T(g["amp"]), T(g["P"]), T(g["var"]), float(g["nu_sc"]), device=dev, W0=T(g["W0"]), h0=T(g["h0"]))
+            q, out, loss, ve, gW, gh = eq.forward_backward(T(g["rx"][0]).to(dev))
+            q2 = sfun.soft_dec(out, T(g["var"]).to(dev), T(g["amp"]).to(dev), float(g["nu_sc"]))
+            res.append((loss.cpu(), gW.cpu(), q2.cpu()))
+            assert q.device == torch.device(dev) and q2.device == torch.device(dev)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    with pytest.raises(sfun._lib.VaeqError):
+        sfun.soft_dec(out, T(g["var"]).to("cuda:0"), T(g["amp"]).to(dev), float(g["nu_sc"]))
+
+
 @pytest.mark.parametrize("mod,M,B", [("64-QAM", 25, 100), ("16-QAM", 9, 700), ("4-QAM", 5, 64), ("64-QAM", 13, 1200)])
 def test_loss_function_shaping_on_arbitrary_q(mod, M, B):
     """loss_function_shaping(q, rx, h_est, amp, P) as a plain operator on a q that did NOT come from this package's equalizer

@@ -161,6 +161,13 @@ def test_run_dp_sweep_layout_and_mat_schema(tmp_path):
     n_calls = len(calls)
     b = sweep.run_dp_sweep(iter=2, num_frames=3, runner=runner, checkpoint_dir=ck, **lists)
     assert len(calls) == n_calls and all(torch.equal(x, y) for x, y in zip(a, b)) and torch.equal(a[0], SER)
+    # a sweep with a different SNR list of the same length must NOT pick up the stale files (the signature differs): it recomputes
+    lists2 = dict(lists, SNR_vec=[10, 13, 16])
+    c = sweep.run_dp_sweep(iter=2, num_frames=3, runner=runner, checkpoint_dir=ck, **lists2)
+    assert len(calls) == n_calls + 2 and not torch.equal(c[0], a[0])
+    assert abs(float(c[0][0, 2, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0]) - (1000.0 * 16 + 10 * 2.0 + 25)) < 1.0
+    c2 = sweep.run_dp_sweep(iter=2, num_frames=3, runner=runner, checkpoint_dir=ck, N_lrhalf=50, **lists2)     # other setting, same lists
+    assert len(calls) == n_calls + 4 and torch.equal(c2[0], c[0])
     path = str(tmp_path / "sweep.mat")
     sweep.save_mat(path, SER, Var_est, var_real, SNR_vec=lists["SNR_vec"], nu_vec=lists["nu_vec"], theta_diff_vec=lists["theta_diff_vec"],
                    theta_vec=lists["theta_vec"], M_vec=lists["M_vec"], lr_optim_vec=lists["lr_optim_vec"], batch_len_vec=lists["batch_len_vec"],

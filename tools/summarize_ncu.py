@@ -14,6 +14,8 @@ WANT = {'duration_us': 'gpu__time_duration.sum', 'dram_read_MB': 'dram__bytes_re
         'stall_dispatch': 'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
         'stall_short_sb': 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio'}
 SCALE = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6, 'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}
+if len(sys.argv) < 3 or sys.argv[1].startswith('-'):
+    sys.exit(__doc__)
 tag, out = sys.argv[1], {}
 for arg in sys.argv[2:]:
     path, _, label = arg.partition(':')

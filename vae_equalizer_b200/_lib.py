@@ -5,6 +5,7 @@ There is NO CPU fallback: if the shared library is missing or a call fails this 
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -76,6 +77,8 @@ PROTOTYPES = {
     "vaeq_dp_forward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_forward_backward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_loss_from_q": (C.c_int, [C.POINTER(DpDesc), _vp, _i64, _vp]),
+    "vaeq_eq_backward_scratch_bytes": (_sz, [_i32, _i32]),
+    "vaeq_eq_backward": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_dp_train_step": (C.c_int, [C.POINTER(DpDesc), _f, _f, _vp]),
     "vaeq_dp_train_frame": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
     "vaeq_dp_persistent_frames": (C.c_int, [_i32]),
@@ -157,3 +160,32 @@ def ptr(t):
 def current_stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_guard(fn):
+    """Run `fn` with the CUDA device of its first device-bearing argument (a tensor, or an object with a `.device`) current.
+
+    libvaeq launches on the calling thread's current device and `current_stream()` is that device's stream, so every Python
+    entry that reaches the C ABI is wrapped: tensors of `cuda:1` are processed on `cuda:1` whatever the caller's current device is."""
+    import torch
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        for a in (*args, *kw.values()):
+            d = a if isinstance(a, torch.device) else getattr(a, "device", None)
+            if isinstance(d, torch.device) and d.type == "cuda":
+                if d.index is None or d.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(d):
+                    return fn(*args, **kw)
+        return fn(*args, **kw)
+
+    return wrapper
+
+
+def require_current_device(t, name="tensor"):
+    """Raise unless the CUDA tensor `t` lives on the current device (inside a device_guard: the device of the first argument)."""
+    import torch
+    if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise VaeqError(f"{name} lives on {t.device} but the call runs on cuda:{torch.cuda.current_device()}: all tensors of one "
+                        "call must be on the same device")

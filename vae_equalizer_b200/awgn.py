@@ -55,6 +55,7 @@ class AWGNEqualizer:
         d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         return d
 
+    @_lib.device_guard
     def _run(self, fn, name, rx, *extra):
         B = rx.shape[-1] // self.sps
         q = torch.empty(2 * self.n_lev, B, dtype=_F32, device=self.device)

@@ -272,12 +272,13 @@ static int awgn_launch(const vaeq_awgn_desc *d, int mode, float lr_w, float lr_h
     p.gyp = ws; ws += 2 * (size_t)d->B;
     p.gout = ws;
     p.mode = mode; p.lr_w = lr_w; p.lr_h = lr_h; p.amsgrad = 1;
+    ktime_begin(VAEQ_K_AWGN, st);
     switch (d->n_lev) {
         case 2: k_awgn_step<2><<<1, AW_NT, 0, st>>>(p); break;
         case 4: k_awgn_step<4><<<1, AW_NT, 0, st>>>(p); break;
         default: k_awgn_step<8><<<1, AW_NT, 0, st>>>(p); break;
     }
-    ktime_begin(VAEQ_K_AWGN, st); ktime_end(VAEQ_K_AWGN, st);
+    ktime_end(VAEQ_K_AWGN, st);
     VAEQ_LAUNCH_CHECK("k_awgn_step");
     return VAEQ_OK;
 }

@@ -445,33 +445,34 @@ extern "C" int vaeq_cma(int32_t mode, const float *Rx, int32_t N, float R, float
     cudaStream_t st = (cudaStream_t)stream;
     float *ys = static_cast<float *>(scratch);
     float *pw = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n_runs * 4 * N * sizeof(float), 256));
+    ktime_begin(VAEQ_K_CMA, st);
     k_cma_power<<<n_runs, CMA_NT, 0, st>>>(Rx, N, M / 2, pw);
-    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+    ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cma_power");
     const int64_t total = (int64_t)n_runs * 4 * N;
+    ktime_begin(VAEQ_K_CMA, st);
     k_cma_scale<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8), 256, 0, st>>>(Rx, N, pw, ys, n_runs);
-    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+    ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cma_scale");
     if (mode == VAEQ_CMA_SAMPLE) {
+        ktime_begin(VAEQ_K_CMA, st);
         if (M <= 32) k_cma_sample<1><<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
         else k_cma_sample<2><<<n_runs, 32, 0, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train);
-        ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+        ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_sample");
     } else {
         const bool staged = batchlen <= CMA_WCAP;
         const int ycap = (std::max(CMA_NT, batchlen) - 1) * sps + M;            // samples per row of the staged window
         const size_t smem = (size_t)(8 * M + (staged ? 4 * ycap + 6 * batchlen : 0)) * sizeof(float);
+        ktime_begin(VAEQ_K_CMA, st);
         if (staged) {
-            static size_t set_smem = 0;
-            if (smem > set_smem) {
-                VAEQ_CUDA(cudaFuncSetAttribute(k_cma_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                set_smem = smem;
-            }
+            static SmemAttrCache set_smem;
+            if (int rc = ensure_dyn_smem(k_cma_block<true>, smem, set_smem)) return rc;
             k_cma_block<true><<<n_runs, CMA_NT, smem, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step, ycap);
         } else {
             k_cma_block<false><<<n_runs, CMA_NT, smem, st>>>(Rx, ys, h, out, e, N, M, sps, R, lr, train, mode, batchlen, symb_step, 0);
         }
-        ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+        ktime_end(VAEQ_K_CMA, st);
         VAEQ_LAUNCH_CHECK("k_cma_block");
     }
     return VAEQ_OK;
@@ -490,14 +491,17 @@ extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y
     float *p4 = static_cast<float *>(scratch);
     float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n_runs * 4 * N * sizeof(float), 256));
     const int grid = (int)std::min<int64_t>((npol * (int64_t)N + 255) / 256, (int64_t)sm_count() * 16);
+    ktime_begin(VAEQ_K_CMA, st);
     k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, npol, p4);
-    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+    ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_pow4");
+    ktime_begin(VAEQ_K_CMA, st);
     k_cpe_phase<<<dim3((N + CPE_TILE - 1) / CPE_TILE, npol), CPE_PT, 0, st>>>(p4, N, npol, phi);
-    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+    ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_phase");
+    ktime_begin(VAEQ_K_CMA, st);
     k_cpe_unwrap_rotate<<<npol, 1024, 0, st>>>(y, phi, N, y_corr);
-    ktime_begin(VAEQ_K_CMA, st); ktime_end(VAEQ_K_CMA, st);
+    ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_unwrap_rotate");
     return VAEQ_OK;
 }

@@ -42,6 +42,27 @@ void ktime_end(int kind, cudaStream_t st);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) and occupancy-derived grids are PER DEVICE: every cache of
+// them is indexed by the calling thread's current device, like sm_count().
+constexpr int VAEQ_MAX_DEVICES = 64;
+static inline int cur_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= VAEQ_MAX_DEVICES) return 0;
+    return dev;
+}
+struct SmemAttrCache {
+    size_t set[VAEQ_MAX_DEVICES] = {0};
+};
+template <typename K>
+static inline int ensure_dyn_smem(K kern, size_t smem, SmemAttrCache &c) {
+    const int dev = cur_device();
+    if (smem > c.set[dev]) {
+        VAEQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c.set[dev] = smem;
+    }
+    return VAEQ_OK;
+}
+
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

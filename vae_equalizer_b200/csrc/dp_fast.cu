@@ -793,7 +793,8 @@ static int fast_prepare(K kern, size_t smem, int *grid) {
 
 template <int NL, int MH>
 static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
-    static int gF = 0, g1 = 0, g2 = 0, g3 = 0;
+    static int grids[VAEQ_MAX_DEVICES][4] = {{0}};           // occupancy-derived grids and the shared-memory attribute are per device
+    int &gF = grids[cur_device()][0], &g1 = grids[cur_device()][1], &g2 = grids[cur_device()][2], &g3 = grids[cur_device()][3];
     const size_t sf = fast_smem_fwd<MH>(), s1 = fast_smem_bwd1<MH>(), s2 = fast_smem_taps<MH, 0>(), s3 = fast_smem_taps<MH, 1>();
     if (!gF) {
         int rc;

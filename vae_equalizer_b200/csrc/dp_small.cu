@@ -471,7 +471,7 @@ size_t dp_small_smem(int B, int M) { return (size_t)small_layout(B, M).total * s
 int dp_small_launch(const DpK &p, const DpRunsK &rs, int n_lev, int n_runs, int n_steps, int stride_sym, int keep_lo_in_dst,
                     float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
     const size_t smem = dp_small_smem(p.B, p.M);
-    static size_t set_smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    static SmemAttrCache set_smem[3][2];
     // waves of CTAs at 3 and at 4 runs per SM (shared memory permitting): take the fourth run per SM only when it saves a wave
     const int sms = sm_count(), w3 = (n_runs + SM_MINB * sms - 1) / (SM_MINB * sms), w4 = (n_runs + 4 * sms - 1) / (4 * sms);
     const bool fits4 = 4 * (smem + 1024) <= (size_t)227 * 1024;
@@ -480,10 +480,7 @@ int dp_small_launch(const DpK &p, const DpRunsK &rs, int n_lev, int n_runs, int 
     const bool four = fits4 && (g_small_per_sm == 4 || (g_small_per_sm == 0 && w4 < w3 && w4 == 1));
 #define SMALL_LAUNCH(NL_, IDX_, MB_, V_)                                                                                          \
     {                                                                                                                             \
-        if (smem > set_smem[IDX_][V_]) {                                                                                          \
-            VAEQ_CUDA(cudaFuncSetAttribute(k_dp_frame_fast<NL_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-            set_smem[IDX_][V_] = smem;                                                                                            \
-        }                                                                                                                         \
+        if (int rc_ = ensure_dyn_smem(k_dp_frame_fast<NL_, MB_>, smem, set_smem[IDX_][V_])) return rc_;                           \
         ktime_begin(VAEQ_K_DP_FRAME, st);                                                                                         \
         k_dp_frame_fast<NL_, MB_><<<n_runs, SM_NT, smem, st>>>(p, rs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad);  \
         ktime_end(VAEQ_K_DP_FRAME, st);                                                                                           \

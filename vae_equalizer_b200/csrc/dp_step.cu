@@ -788,17 +788,12 @@ static int dp_launch_adam(const DpK &p, int nparts, int mode, float lr_w, float 
 
 template <int NL>
 static int dp_run(const DpK &p, int mode, float lr_w, float lr_h, int amsgrad, cudaStream_t st) {
-    static int grid_fwd[VAEQ_MAX_TAPS + 1] = {0}, grid_bwd[VAEQ_MAX_TAPS + 1] = {0};   // cached per M_est
-    static size_t set_f = 0, set_b = 0;
+    static int grid_fwd_c[VAEQ_MAX_DEVICES][VAEQ_MAX_TAPS + 1] = {{0}}, grid_bwd_c[VAEQ_MAX_DEVICES][VAEQ_MAX_TAPS + 1] = {{0}};   // cached per device and M_est
+    static SmemAttrCache set_f, set_b;
+    int *grid_fwd = grid_fwd_c[cur_device()], *grid_bwd = grid_bwd_c[cur_device()];
     const size_t sm_f = dp_fwd_smem(p.M, p.T, p.H, p.mh), sm_b = dp_bwd_smem(p.M, p.T, p.H, p.mh);
-    if (sm_f > set_f) {
-        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_fwd<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f));
-        set_f = sm_f;
-    }
-    if (sm_b > set_b) {
-        VAEQ_CUDA(cudaFuncSetAttribute(k_dp_bwd<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
-        set_b = sm_b;
-    }
+    if (int rc = ensure_dyn_smem(k_dp_fwd<NL>, sm_f, set_f)) return rc;
+    if (int rc = ensure_dyn_smem(k_dp_bwd<NL>, sm_b, set_b)) return rc;
     if (!grid_fwd[p.M]) {
         int per = 0;
         VAEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_dp_fwd<NL>, DP_NT, sm_f));
@@ -948,13 +943,10 @@ static int dp_frame_persistent(const vaeq_dp_desc *d, const vaeq_dp_runs *runs, 
     const int amsgrad = (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0;
     if (g_persistent_frames != 2)
         return dp_small_launch(p, rs, d->n_lev, n_runs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad, st);
-    static size_t set_smem[3] = {0, 0, 0};
+    static SmemAttrCache set_smem[3];
 #define FRAME_CASE(NL_, IDX_)                                                                                             \
     {                                                                                                                     \
-        if (smem > set_smem[IDX_]) {                                                                                      \
-            VAEQ_CUDA(cudaFuncSetAttribute(k_dp_frame_small<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            set_smem[IDX_] = smem;                                                                                        \
-        }                                                                                                                 \
+        if (int rc_ = ensure_dyn_smem(k_dp_frame_small<NL_>, smem, set_smem[IDX_])) return rc_;                           \
         ktime_begin(VAEQ_K_DP_FRAME, st);                                                                                 \
         k_dp_frame_small<NL_><<<n_runs, DP_NT, smem, st>>>(p, rs, n_steps, stride_sym, keep_lo_in_dst, lr_w, lr_h, amsgrad); \
         ktime_end(VAEQ_K_DP_FRAME, st);                                                                                   \

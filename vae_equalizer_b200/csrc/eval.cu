@@ -201,6 +201,28 @@ __global__ void k_ser_min(const int *counts, int N, float *ser_out) {
     }
 }
 
+
+// Sum of per-CTA partial pairs in a FIXED order (no floating-point atomics: the result is bit-reproducible for a given grid):
+// warp 0 strides over the partials, then a butterfly; the pair is broadcast through shared memory.  All threads must call.
+__device__ __forceinline__ void fixed_order_sum2(const double *part, int n, double *bc /* __shared__ [2] */, double &s0, double &s1) {
+    if (threadIdx.x < 32) {
+        double a = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < n; i += 32) {
+            a += part[2 * i];
+            b += part[2 * i + 1];
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (threadIdx.x == 0) {
+            bc[0] = a;
+            bc[1] = b;
+        }
+    }
+    __syncthreads();
+    s0 = bc[0];
+    s1 = bc[1];
+}
+
 // ---------------------------------------------------------------------------------------------
 // SER from the constellation with PCS-aware thresholds (sf:225-287)
 // ---------------------------------------------------------------------------------------------
@@ -225,18 +247,21 @@ __global__ void __launch_bounds__(EV_NT) k_constell_norms(const float *rx, int64
         }
     }
     block_sum<2>(acc, red);
-    if (threadIdx.x == 0) {
-        atomicAdd(&sums[0], acc[0]);
-        atomicAdd(&sums[1], acc[1]);
+    if (threadIdx.x == 0) {                                   // per-CTA partials, summed in fixed order by the consumer
+        sums[2 * blockIdx.x] = acc[0];
+        sums[2 * blockIdx.x + 1] = acc[1];
     }
 }
 
 template <int NL, int V>
 __global__ void __launch_bounds__(EV_NT) k_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx,
                                                         const float *amp, const float *var, float nu_sc, int N,
-                                                        const double *sums, int *counts) {
+                                                        const double *sums, int nparts, int *counts) {
     __shared__ int red[16 * 32];
     __shared__ float lo[NL], hi[NL];
+    __shared__ double bc[2];
+    double sum_tx, sum_rx;
+    fixed_order_sum2(sums, nparts, bc, sum_tx, sum_rx);
     if (threadIdx.x < NL) {
         const int l = threadIdx.x;
         // d = (1 + 2 nu_sc var[0]) (a_l + a_{l+1}) / 2, padded with -inf / +inf  (sf:234-236)
@@ -246,7 +271,7 @@ __global__ void __launch_bounds__(EV_NT) k_ser_constell(float *rx, int64_t ld_rx
     }
     __syncthreads();
     const double cnt2 = 2.0 * (double)N;
-    const float g = __fdiv_rn((float)(sums[0] / cnt2), (float)(sums[1] / cnt2));      // sf:242
+    const float g = __fdiv_rn((float)(sum_tx / cnt2), (float)(sum_rx / cnt2));      // sf:242
     const float S = (float)(NL - 1), scale = (float)((NL - 1) / 2.0);
     int cnt[16];
 #pragma unroll
@@ -331,19 +356,22 @@ __global__ void __launch_bounds__(EV_NT) k_gmi(const float *q, int64_t ld_q, con
     }
     block_sum<2>(acc, red);
     if (threadIdx.x == 0) {
-        atomicAdd(&sums[0], acc[0]);
-        atomicAdd(&sums[1], acc[1]);
+        sums[2 * blockIdx.x] = acc[0];
+        sums[2 * blockIdx.x + 1] = acc[1];
     }
 }
-__global__ void k_gmi_fin(const double *sums, const float *P, int n_lev, int N, float *gmi_out) {
+__global__ void k_gmi_fin(const double *sums, int nparts, const float *P, int n_lev, int N, float *gmi_out) {
+    __shared__ double bc[2];
+    double s[2];
+    fixed_order_sum2(sums, nparts, bc, s[0], s[1]);
     if (threadIdx.x < 2) {
         double H = 0.0;
         for (int l = 0; l < n_lev; ++l) H -= 2.0 * (double)P[l] * log2((double)P[l]);
-        gmi_out[threadIdx.x] = (float)(H + sums[threadIdx.x] / (double)N);
+        gmi_out[threadIdx.x] = (float)(H + s[threadIdx.x] / (double)N);
     }
 }
 
-static int ev_grid(int N, int V = 1) { return max(1, min((N / V + EV_NT - 1) / EV_NT, sm_count() * 8)); }
+static int ev_grid(int N, int V = 1) { return max(1, min(min((N / V + EV_NT - 1) / EV_NT, sm_count() * 8), (int)(VAEQ_EVAL_SCRATCH_BYTES / (2 * sizeof(double))))); }
 
 }  // namespace vaeq
 
@@ -366,14 +394,16 @@ extern "C" int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, i
     const int grid = (int)(((int64_t)N + per - 1) / per);
     double *part = static_cast<double *>(scratch);
     const bool one = n_shift <= 32;
+    ktime_begin(VAEQ_K_EVAL, st);
     if (q && one) k_shift_corr<true, 1><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
     else if (q) k_shift_corr<true, 2><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
     else if (one) k_shift_corr<false, 1><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);
     else k_shift_corr<false, 2><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_shift_corr");
+    ktime_begin(VAEQ_K_EVAL, st);
     k_shift_decide<<<1, 1024, 0, st>>>(part, n_shift, grid, corr_out, shift_out, r_out);
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_shift_decide");
     return VAEQ_OK;
 }
@@ -386,15 +416,17 @@ extern "C" int vaeq_ser_iqflip(const float *q, int64_t ld_q, const uint16_t *tx,
     VAEQ_CUDA(cudaMemsetAsync(counts_out, 0, 16 * sizeof(int), st));
     const bool vec = ev_vec_ok(q, ld_q, tx, ld_tx, N);
     const int grid = ev_grid(N, vec ? 4 : 1);
+    ktime_begin(VAEQ_K_EVAL, st);
 #define EV_CASE(NL_)                                                                                         \
     if (vec) k_ser_iqflip<NL_, 4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);                \
     else k_ser_iqflip<NL_, 1><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, counts_out);
     if (n_lev == 2) { EV_CASE(2) } else if (n_lev == 4) { EV_CASE(4) } else { EV_CASE(8) }
 #undef EV_CASE
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_iqflip");
+    ktime_begin(VAEQ_K_EVAL, st);
     k_ser_min<<<1, 32, 0, st>>>(counts_out, N, ser_out);
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_min");
     return VAEQ_OK;
 }
@@ -405,24 +437,26 @@ extern "C" int vaeq_ser_constell(float *rx, int64_t ld_rx, const uint16_t *tx, i
     VAEQ_CHECK_ARG(rx && tx && amp && var && counts_out && ser_out && scratch && N > 0, "bad ser_constell arguments");
     VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
     cudaStream_t st = (cudaStream_t)stream;
-    double *sums = static_cast<double *>(scratch);
-    VAEQ_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+    double *sums = static_cast<double *>(scratch);           // [grid][2] per-CTA partials (VAEQ_EVAL_SCRATCH_BYTES covers the largest grid)
     VAEQ_CUDA(cudaMemsetAsync(counts_out, 0, 16 * sizeof(int), st));
     const bool vec = ev_vec_ok(rx, ld_rx, tx, ld_tx, N);
     const int grid = ev_grid(N, vec ? 4 : 1);
+    ktime_begin(VAEQ_K_EVAL, st);
     if (vec) k_constell_norms<4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, N, sums);
     else k_constell_norms<1><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, N, sums);
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_constell_norms");
+    ktime_begin(VAEQ_K_EVAL, st);
 #define EV_CASE(NL_)                                                                                                          \
-    if (vec) k_ser_constell<NL_, 4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);      \
-    else k_ser_constell<NL_, 1><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, counts_out);
+    if (vec) k_ser_constell<NL_, 4><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, grid, counts_out);      \
+    else k_ser_constell<NL_, 1><<<grid, EV_NT, 0, st>>>(rx, ld_rx, tx, ld_tx, amp, var, nu_sc, N, sums, grid, counts_out);
     if (n_lev == 2) { EV_CASE(2) } else if (n_lev == 4) { EV_CASE(4) } else { EV_CASE(8) }
 #undef EV_CASE
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_constell");
+    ktime_begin(VAEQ_K_EVAL, st);
     k_ser_min<<<1, 32, 0, st>>>(counts_out, N, ser_out);
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_ser_min");
     return VAEQ_OK;
 }
@@ -432,19 +466,20 @@ extern "C" int vaeq_gmi(const float *q, int64_t ld_q, const uint16_t *tx, int64_
     VAEQ_CHECK_ARG(q && tx && P && gmi_out && scratch && N > 0, "bad gmi arguments");
     VAEQ_CHECK_ARG(n_lev == 2 || n_lev == 4 || n_lev == 8, "n_lev=%d must be 2, 4 or 8", n_lev);
     cudaStream_t st = (cudaStream_t)stream;
-    double *sums = static_cast<double *>(scratch);
-    VAEQ_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+    double *sums = static_cast<double *>(scratch);           // [grid][2] per-CTA partials (VAEQ_EVAL_SCRATCH_BYTES covers the largest grid)
     const bool vec = ev_vec_ok(q, ld_q, tx, ld_tx, N);
     const int grid = ev_grid(N, vec ? 4 : 1);
+    ktime_begin(VAEQ_K_EVAL, st);
 #define EV_CASE(NL_)                                                                        \
     if (vec) k_gmi<NL_, 4><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);            \
     else k_gmi<NL_, 1><<<grid, EV_NT, 0, st>>>(q, ld_q, tx, ld_tx, N, sums);
     if (n_lev == 2) { EV_CASE(2) } else if (n_lev == 4) { EV_CASE(4) } else { EV_CASE(8) }
 #undef EV_CASE
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_gmi");
-    k_gmi_fin<<<1, 32, 0, st>>>(sums, P, n_lev, N, gmi_out);
-    ktime_begin(VAEQ_K_EVAL, st); ktime_end(VAEQ_K_EVAL, st);
+    ktime_begin(VAEQ_K_EVAL, st);
+    k_gmi_fin<<<1, 32, 0, st>>>(sums, grid, P, n_lev, N, gmi_out);
+    ktime_end(VAEQ_K_EVAL, st);
     VAEQ_LAUNCH_CHECK("k_gmi_fin");
     return VAEQ_OK;
 }

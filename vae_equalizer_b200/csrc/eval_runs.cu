@@ -13,6 +13,7 @@
 namespace vaeq {
 
 constexpr int ER_NT = 256;
+constexpr int ER_NORM_EXTRA = 2048;           // bound of blocks-per-run x runs beyond n_runs (norm partials in the scratch)
 constexpr int ER_CHUNKS = 8;                     // at most this many CTAs (partial blocks) per run and estimator in the shift search
 
 struct EvalRunsK {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(ER_DEC_NT) k_er_shift_decide(EvalRunsK p) {
     const int tail = p.edge + max(abs(sh0), abs(sh1));
     int total = p.N;
     if (p.seg_len) {
-        const int keep = p.seg_len - sh0 - p.n_cut;                      // VAELE_DP:73-77
+        const int keep = min(p.seg_len, p.seg_len - sh0 - p.n_cut);      // VAELE_DP:73-77; torch's [:keep] slice clamps to the minibatch length
         total = keep > 0 ? (p.N / p.seg_len) * keep : 0;
     }
     int *al = p.align + ((int64_t)run * 2 + est) * 4;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(ER_NT) k_er_ser_iqflip(EvalRunsK p) {
     __shared__ int red[16 * 32];
     const int run = blockIdx.y, N = p.N;
     const int *al = p.align + ((int64_t)run * 2 + 0) * 4;
-    const int sh[2] = {al[0], al[1]}, r = al[2], n_eval = al[3], keep = p.seg_len ? p.seg_len - sh[0] - p.n_cut : 0;
+    const int sh[2] = {al[0], al[1]}, r = al[2], n_eval = al[3], keep = p.seg_len ? min(p.seg_len, p.seg_len - sh[0] - p.n_cut) : 0;
     const float *q = p.q + run * p.rs_q;
     const uint16_t *tx = p.tx + run * p.rs_tx;
     const float S = (float)(NL - 1), scale = (float)((NL - 1) / 2.0);
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(ER_NT) k_er_constell_norms(EvalRunsK p) {
     __shared__ double red[2 * 32];
     const int run = blockIdx.y, N = p.N;
     const int *al = p.align + ((int64_t)run * 2 + 1) * 4;
-    const int sh[2] = {al[0], al[1]}, r = al[2], n_eval = al[3], keep = p.seg_len ? p.seg_len - sh[0] - p.n_cut : 0;
+    const int sh[2] = {al[0], al[1]}, r = al[2], n_eval = al[3], keep = p.seg_len ? min(p.seg_len, p.seg_len - sh[0] - p.n_cut) : 0;
     const float *out = p.out + run * p.rs_out;
     const uint16_t *tx = p.tx + run * p.rs_tx;
     double acc[2] = {0.0, 0.0};
@@ -210,9 +211,10 @@ __global__ void __launch_bounds__(ER_NT) k_er_constell_norms(EvalRunsK p) {
         }
     }
     block_sum<2>(acc, red);
-    if (threadIdx.x == 0) {
-        atomicAdd(&p.norms[2 * run], acc[0]);
-        atomicAdd(&p.norms[2 * run + 1], acc[1]);
+    if (threadIdx.x == 0) {                                   // per-CTA partials [run][block][2], summed in fixed order by k_er_ser_constell
+        double *dst = p.norms + ((int64_t)run * gridDim.x + blockIdx.x) * 2;
+        dst[0] = acc[0];
+        dst[1] = acc[1];
     }
 }
 
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(ER_NT) k_er_ser_constell(EvalRunsK p) {
     __shared__ float lo[NL], hi[NL];
     const int run = blockIdx.y, N = p.N;
     const int *al = p.align + ((int64_t)run * 2 + 1) * 4;
-    const int sh[2] = {al[0], al[1]}, r = al[2], n_eval = al[3], keep = p.seg_len ? p.seg_len - sh[0] - p.n_cut : 0;
+    const int sh[2] = {al[0], al[1]}, r = al[2], n_eval = al[3], keep = p.seg_len ? min(p.seg_len, p.seg_len - sh[0] - p.n_cut) : 0;
     const float *out = p.out + run * p.rs_out;
     const uint16_t *tx = p.tx + run * p.rs_tx;
     if (threadIdx.x < NL) {
@@ -233,7 +235,23 @@ __global__ void __launch_bounds__(ER_NT) k_er_ser_constell(EvalRunsK p) {
     }
     __syncthreads();
     const double cnt2 = 2.0 * (double)n_eval;
-    const float g = __fdiv_rn((float)(p.norms[2 * run] / cnt2), (float)(p.norms[2 * run + 1] / cnt2));      // sf:242
+    __shared__ double bc[2];
+    double sum_tx = 0.0, sum_rx = 0.0;
+    if (threadIdx.x < 32) {                                   // fixed-order sum of the norm partials (no floating-point atomics)
+        const double *part = p.norms + (int64_t)run * gridDim.x * 2;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {
+            sum_tx += part[2 * i];
+            sum_rx += part[2 * i + 1];
+        }
+        sum_tx = warp_sum(sum_tx);
+        sum_rx = warp_sum(sum_rx);
+        if (threadIdx.x == 0) {
+            bc[0] = sum_tx;
+            bc[1] = sum_rx;
+        }
+    }
+    __syncthreads();
+    const float g = __fdiv_rn((float)(bc[0] / cnt2), (float)(bc[1] / cnt2));      // sf:242
     if (p.scale != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.scale[run] = g;
     const float S = (float)(NL - 1), scale = (float)((NL - 1) / 2.0);
     int cnt[16];
@@ -309,7 +327,7 @@ using namespace vaeq;
 
 extern "C" size_t vaeq_frame_eval_scratch_bytes(int32_t n_runs, int32_t n_shift) {
     if (n_runs <= 0 || n_shift <= 0) return 0;
-    return align_up((size_t)n_runs * 2 * n_shift * ER_CHUNKS * 8 * sizeof(double), 256) + align_up((size_t)n_runs * 2 * sizeof(double), 256) +
+    return align_up((size_t)n_runs * 2 * n_shift * ER_CHUNKS * 8 * sizeof(double), 256) + align_up(((size_t)n_runs + ER_NORM_EXTRA) * 2 * sizeof(double), 256) +
            align_up((size_t)n_runs * 2 * 16 * sizeof(int), 256);
 }
 
@@ -330,16 +348,15 @@ extern "C" int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_
     p.tx = tx; p.ld_tx = ld_tx; p.rs_tx = rs_tx; p.amp = amp; p.var = var; p.rs_var = rs_var; p.nu_sc = nu_sc;
     p.n_lev = n_lev; p.N = N; p.n_shift = n_shift; p.n_runs = n_runs; p.seg_len = seg_len; p.edge = edge; p.n_cut = n_cut;
     char *ws = static_cast<char *>(scratch);
-    const size_t part_b = align_up((size_t)n_runs * 2 * n_shift * ER_CHUNKS * 8 * sizeof(double), 256), norm_b = align_up((size_t)n_runs * 2 * sizeof(double), 256);
+    const size_t part_b = align_up((size_t)n_runs * 2 * n_shift * ER_CHUNKS * 8 * sizeof(double), 256), norm_b = align_up(((size_t)n_runs + ER_NORM_EXTRA) * 2 * sizeof(double), 256);
     p.part = reinterpret_cast<double *>(ws);
     p.norms = reinterpret_cast<double *>(ws + part_b);
     p.counts = counts_out ? counts_out : reinterpret_cast<int *>(ws + part_b + norm_b);
     p.align = align_out; p.ser = ser_out; p.which = which; p.scale = scale_out;
     // enough CTAs to fill the GPU, as few partial blocks as possible: every CTA pays a prologue and a fixed-order reduction
     p.chunks = max(1, min(min(ER_CHUNKS, (N + 2 * SC_T - 1) / (2 * SC_T)), (4 * sm_count() + 2 * n_runs - 1) / (2 * n_runs)));
-    VAEQ_CUDA(cudaMemsetAsync(p.norms, 0, (size_t)n_runs * 2 * sizeof(double), st));
     VAEQ_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)n_runs * 2 * 16 * sizeof(int), st));
-    const int blocks = max(1, min((N + ER_NT - 1) / ER_NT, max(1, sm_count() * 8 / n_runs)));
+    const int blocks = max(1, min((N + ER_NT - 1) / ER_NT, max(1, min(sm_count() * 8, ER_NORM_EXTRA) / n_runs)));     // n_runs * blocks <= n_runs + ER_NORM_EXTRA norm partials
 #define ER_LAUNCH(name, ...)                    \
     ktime_begin(VAEQ_K_EVAL, st);               \
     __VA_ARGS__;                                \

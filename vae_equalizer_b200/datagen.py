@@ -9,6 +9,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from ._lib import device_guard as _device_guard
+
 PULSE_SPAN, ROLLOFF = 8, 0.1          # sf:66-67
 
 
@@ -125,6 +127,7 @@ def _cached_amps(amps, dev):
 _FORCE_TORCH = False      # tests: run the torch.fft formulation on the GPU as the checker of the CUDA kernels
 
 
+@_device_guard
 def _generate_frames_cuda(N, amps, SNR, P, theta, dev, seed, symb_rate, tau_cd, tau_pmd, phiIQ, return_parts=False):
     """generate_frames_gpu on a CUDA device: the element-wise stages are the vaeq_gen_* kernels (csrc/datagen.cu), the two DFTs of the
     dispersion step are torch.fft (cuFFT).  6.6 -> ~3 ms for 592 runs x 10 000 symbols (profiles/r01d_*)."""

@@ -20,6 +20,7 @@ def _require_cuda(t: torch.Tensor, name: str):
         raise _lib.VaeqError(f"{name} must be a CUDA tensor: vae_equalizer_b200 has no CPU path")
     if t.dtype != _F32:
         raise _lib.VaeqError(f"{name} must be float32, got {t.dtype}")
+    _lib.require_current_device(t, name)
 
 
 class DPEqualizer:
@@ -103,6 +104,7 @@ class DPEqualizer:
         return q, out
 
     # -- the three entry points --------------------------------------------------------------------
+    @_lib.device_guard
     def forward(self, rx, q=None, out=None):
         """net(minibatch) + loss_function_shaping without gradients -> (q, out, loss(1), var_est(2))."""
         B = self._check_rx(rx)
@@ -112,6 +114,7 @@ class DPEqualizer:
         _lib.check(self.lib.vaeq_dp_forward(C.byref(d), _lib.current_stream()), "vaeq_dp_forward")
         return q, out, self.loss, self.var_est
 
+    @_lib.device_guard
     def forward_backward(self, rx, q=None, out=None):
         """As forward, plus gW (2,4,M) and gh (2,2,2,M); parameters untouched."""
         B = self._check_rx(rx)
@@ -121,6 +124,7 @@ class DPEqualizer:
         _lib.check(self.lib.vaeq_dp_forward_backward(C.byref(d), _lib.current_stream()), "vaeq_dp_forward_backward")
         return q, out, self.loss, self.var_est, self.gW, self.gh
 
+    @_lib.device_guard
     def train_step(self, rx, lr_w, lr_h=None, q=None, out=None):
         """One optimizer step (VAELE_DP:59-66).  lr_h defaults to lr_w."""
         B = self._check_rx(rx)
@@ -132,6 +136,7 @@ class DPEqualizer:
                    "vaeq_dp_train_step")
         return q, out, self.loss, self.var_est
 
+    @_lib.device_guard
     def capture_steps(self, rx_list, lr_w, lr_h=None, q=None, out=None):
         """CUDA graph of len(rx_list) consecutive train_step calls (one per rx tensor, in order): `g.replay()` re-issues the
         6 kernels of every step without the per-launch host work (profiles/r01d: 559 -> 547 us per step at batch_len 2^22).
@@ -148,6 +153,7 @@ class DPEqualizer:
         g.outputs = (q, out, self.loss, self.var_est)
         return g
 
+    @_lib.device_guard
     def train_frame(self, rx_frame, batch_len, stride_sym, n_steps, lr_w, lr_h, out_train, out_const, keep_lo, keep_n,
                     keep_lo_in_dst=False):
         """All minibatches of one frame (VAELE_DP:57-66 / VAEflex_DP:59-70).
@@ -167,6 +173,7 @@ class DPEqualizer:
         return loss_steps, var_steps
 
     # -- batch-split phases (vaeq_dp_split_*; the caller all-reduces `stats` and `grads` between them) ---------------
+    @_lib.device_guard
     def split_forward(self, rx, sym_lo, sym_hi, q, out):
         B = self._check_rx(rx)
         d = self._desc(rx, q, out, B)
@@ -177,6 +184,7 @@ class DPEqualizer:
                                                   _lib.current_stream()), "vaeq_dp_split_forward")
         return self._stats
 
+    @_lib.device_guard
     def split_backward(self, rx, sym_lo, sym_hi, q, out):
         B = self._check_rx(rx)
         d = self._desc(rx, q, out, B)
@@ -184,6 +192,7 @@ class DPEqualizer:
                                                    self._grads.data_ptr(), _lib.current_stream()), "vaeq_dp_split_backward")
         return self._grads
 
+    @_lib.device_guard
     def split_update(self, rx, q, out, lr_w, lr_h):
         B = self._check_rx(rx)
         d = self._desc(rx, q, out, B)
@@ -231,6 +240,7 @@ class DPEqualizerRuns:
         self._ws = None
         self._B = -1
 
+    @_lib.device_guard
     def train_frame(self, rx_frames, batch_len, stride_sym, n_steps, lr_w, lr_h, out_train, out_const, keep_lo, keep_n,
                     keep_lo_in_dst=False):
         """rx_frames (R,2,2,L_frame); out_train (R,2,2n,N_keep), out_const (R,2,2,N_keep); lr_w / lr_h: floats or (R,) tensors.

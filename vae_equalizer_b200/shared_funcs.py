@@ -11,6 +11,7 @@ SER_constell_shaping rescales its `rx` argument in place (sf:242).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -22,11 +23,6 @@ from .dp import DPEqualizer, _require_cuda
 
 _F32 = torch.float32
 EVAL_SCRATCH_BYTES = 1 << 16
-# q tensors handed out by twoXtwoFIR.forward, keyed by storage address, so that views of them
-# (the reference drivers pass `minibatch_output.squeeze()`) still find their source
-_Q_SOURCES: "dict[int, tuple]" = {}
-_Q_SOURCES_MAX = 64
-
 
 def _rows(t: torch.Tensor, name: str):
     """Check the (2, R, N) row-major-with-stride layout the C ABI takes and return the row stride."""
@@ -83,10 +79,9 @@ class _FusedLoss(torch.autograd.Function):
 class twoXtwoFIR(torch.nn.Module):
     """Complex-valued 2x2 butterfly FIR + soft demapper (sf:490-527).
 
-    forward(x, amp_levels, var, nu_sc) -> (q_est (2,2n,N), out (2,2,N)).  The returned q carries a
-    hidden reference to (self, x) so that loss_function_shaping(q, x, h_est, ...) can run the fused
-    forward+backward kernels and hand gradients for `conv_w.weight` and `h_est` to autograd without
-    materialising dL/dq."""
+    forward(x, amp_levels, var, nu_sc) -> (q_est (2,2n,N), out (2,2,N)), outputs of one autograd node (_EqualizerFn).
+    loss_function_shaping(q, x, h_est, ...) recognises an unmodified q of that node and runs the fused forward+backward
+    kernels, handing gradients for `conv_w.weight` and `h_est` to autograd without materialising dL/dq."""
 
     def __init__(self, M_est, sps):
         super().__init__()
@@ -95,26 +90,83 @@ class twoXtwoFIR(torch.nn.Module):
         self._eq = None
 
     def _engine(self, amp_levels, var, nu_sc, P=None):
+        """ONE DPEqualizer per (amp_levels, var, nu_sc): forward() needs no prior, loss_function_shaping() sets it in place, so the two
+        calls of a minibatch share the engine (and its workspace) instead of rebuilding it twice per step."""
         dev = self.conv_w.weight.device
-        key = (amp_levels.data_ptr(), var.data_ptr(), float(nu_sc), None if P is None else P.data_ptr())
+        key = (amp_levels.data_ptr(), amp_levels._version, var.data_ptr(), var._version, float(nu_sc))
         if self._eq is None or self._eq_key != key:
             n = amp_levels.numel()
-            Pq = torch.full((n,), 1.0 / n, dtype=_F32, device=dev) if P is None else P
-            self._eq = DPEqualizer(self.M_est, self.sps, amp_levels, Pq, var, float(nu_sc), device=dev)
+            self._eq = DPEqualizer(self.M_est, self.sps, amp_levels, torch.full((n,), 1.0 / n, dtype=_F32), var, float(nu_sc), device=dev)
             self._eq_key = key
+        if P is not None:
+            self._eq.P.copy_(P.reshape(-1))
         return self._eq
 
     def forward(self, x, amp_levels, var, nu_sc):
         _require_cuda(x, "x")
-        eq = self._engine(amp_levels, var, nu_sc)
-        eq.W.copy_(self.conv_w.weight.detach())
-        q, out, _, _ = eq.forward(x.contiguous())
-        if len(_Q_SOURCES) >= _Q_SOURCES_MAX:
-            _Q_SOURCES.pop(next(iter(_Q_SOURCES)))
-        _Q_SOURCES[q.data_ptr()] = (self, x, amp_levels, var, float(nu_sc), q.numel())
+        return _EqualizerFn.apply(self.conv_w.weight, x.contiguous(), self, amp_levels, var, float(nu_sc))
+
+
+class _EqualizerFn(torch.autograd.Function):
+    """net(x) = (q, out) as an autograd node.  loss_function_shaping recognises an unmodified q of this node (also through views such as
+    the `.squeeze()` the reference drivers apply, VAELE_DP:64) and runs the fused step; anything else derived from q / out differentiates
+    through `backward` below (vaeq_eq_backward: softmin + FIR backward for arbitrary upstream gradients)."""
+
+    @staticmethod
+    @_lib.device_guard
+    def forward(ctx, W, x, net, amp_levels, var, nu_sc):
+        eq = net._engine(amp_levels, var, nu_sc)
+        eq.W.copy_(W.detach())
+        q, out, _, _ = eq.forward(x)
+        ctx.net_ref, ctx.x, ctx.x_version = weakref.ref(net), x, x._version
+        ctx.consts = (amp_levels, var, nu_sc)
+        ctx.save_for_backward(q, out)
+        ctx.q_ptr, ctx.q_numel, ctx.q_version, ctx.M = q.data_ptr(), q.numel(), q._version, net.M_est
         return q, out
 
+    @staticmethod
+    @_lib.device_guard
+    def backward(ctx, gq, gout):
+        if gq is None and gout is None:
+            return (None,) * 6
+        q, out = ctx.saved_tensors
+        lib = _lib.load()
+        x, (amp, var, _) = ctx.x, ctx.consts
+        if x._version != ctx.x_version:
+            raise RuntimeError("twoXtwoFIR backward: the input minibatch was modified in place after the forward pass")
+        n, B, M = int(amp.numel()), int(q.shape[-1]), int(ctx.M)
+        dev = q.device
+        gq = None if gq is None else gq.to(_F32).contiguous()
+        gout = None if gout is None else gout.to(_F32).contiguous()
+        gW = torch.empty(2, 4, M, dtype=_F32, device=dev)
+        scr = torch.empty(int(lib.vaeq_eq_backward_scratch_bytes(B, M)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.vaeq_eq_backward(x.data_ptr(), int(x.stride(1)), q.data_ptr(), int(q.stride(1)), out.data_ptr(), int(out.stride(1)),
+                                        None if gq is None else gq.data_ptr(), B, None if gout is None else gout.data_ptr(), B,
+                                        amp.contiguous().data_ptr(), var.contiguous().data_ptr(), n, B, M, gW.data_ptr(), scr.data_ptr(),
+                                        _lib.current_stream()), "vaeq_eq_backward")
+        return gW, None, None, None, None, None
 
+
+_VIEW_NODES = ("SqueezeBackward", "UnsqueezeBackward", "ViewBackward", "AliasBackward", "ReshapeAliasBackward", "UnsafeViewBackward")
+
+
+def _equalizer_node(q):
+    """The _EqualizerFn node whose FIRST output `q` is (possibly through shape-only views), else None."""
+    fn = q.grad_fn
+    for _ in range(8):
+        if fn is None:
+            return None
+        if getattr(fn, "_forward_cls", None) is _EqualizerFn:
+            return fn
+        if not fn.name().startswith(_VIEW_NODES) or len(fn.next_functions) != 1:
+            return None
+        fn, nr = fn.next_functions[0]
+        if getattr(fn, "_forward_cls", None) is _EqualizerFn and nr != 0:
+            return None
+    return None
+
+
+@_lib.device_guard
 def soft_dec(out, var, amp_levels, nu_sc):
     """Soft demapper with the PCS correction term (sf:529-542)."""
     _require_cuda(out, "out")
@@ -131,6 +183,7 @@ class _LossFromQ(torch.autograd.Function):
     """loss_function_shaping as a plain operator: loss(q, h_est) for ANY q, with dL/dq and dL/dh_est from vaeq_dp_loss_from_q."""
 
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, q, h, rx, amp, P):
         lib = _lib.load()
         dev = rx.device
@@ -164,23 +217,28 @@ def loss_function_shaping(q, rx, h_est, amp_levels, P):
     When `q` is the tensor returned by this package's twoXtwoFIR.forward for the minibatch `rx`, the fused CUDA step runs and the
     gradients reach the equalizer taps and `h_est` without materialising dL/dq.  For any other q (any CUDA tensor (2,2n,B), e.g. a
     posterior from another demapper) the loss is an ordinary autograd operator differentiable w.r.t. `q` and `h_est`."""
-    src = _Q_SOURCES.get(q.data_ptr())
-    if src is None or src[5] != q.numel() or src[1].data_ptr() != rx.data_ptr() or src[1].numel() != rx.numel():
+    node = _equalizer_node(q)
+    net = node.net_ref() if node is not None else None
+    fused = (net is not None and q.data_ptr() == node.q_ptr and q.numel() == node.q_numel and q.is_contiguous()
+             and q._version == node.q_version and rx.data_ptr() == node.x.data_ptr() and rx.numel() == node.x.numel()
+             and node.x._version == node.x_version)
+    if not fused:
         _require_cuda(q, "q")
         _require_cuda(rx, "rx")
         amp = torch.as_tensor(amp_levels, dtype=_F32, device=rx.device).contiguous()
         Pt = torch.as_tensor(P, dtype=_F32, device=rx.device).contiguous()
         return _LossFromQ.apply(q, h_est, rx, amp, Pt)
-    net, x, amp_src, var, nu_sc, _ = src
+    x, (amp_src, var, nu_sc) = node.x, node.consts
     Pt = torch.as_tensor(P, dtype=_F32, device=rx.device).contiguous()
     eq = net._engine(amp_src, var, nu_sc, P=Pt)
-    loss, var_est = _FusedLoss.apply(net.conv_w.weight, h_est, eq, x.contiguous())
+    loss, var_est = _FusedLoss.apply(net.conv_w.weight, h_est, eq, x)
     return loss, var_est
 
 
 # -------------------------------------------------------------------------------------------------
 # evaluation                                                                    sf:188-338
 # -------------------------------------------------------------------------------------------------
+@_lib.device_guard
 def SER_IQflip(q, tx, return_counts=False):
     """SER from hard decisions argmax(q), min over 4 rotations x IQ flip per pol (sf:188-222)."""
     _require_cuda(q, "q")
@@ -194,6 +252,7 @@ def SER_IQflip(q, tx, return_counts=False):
     return (ser, counts) if return_counts else ser
 
 
+@_lib.device_guard
 def SER_constell_shaping(rx, tx, amp_levels, nu_sc, var, return_counts=False):
     """SER from the constellation with PCS-aware thresholds (sf:225-287).  Rescales `rx` IN PLACE (sf:242)."""
     _require_cuda(rx, "rx")
@@ -202,7 +261,7 @@ def SER_constell_shaping(rx, tx, amp_levels, nu_sc, var, return_counts=False):
     n, N = int(amp_levels.numel()), int(rx.shape[-1])
     counts = torch.empty(2, 2, 4, dtype=torch.int32, device=rx.device)
     ser = torch.empty(2, dtype=_F32, device=rx.device)
-    scr = _scratch(rx.device, 256)
+    scr = _scratch(rx.device)
     _lib.check(lib.vaeq_ser_constell(rx.data_ptr(), _rows(rx, "rx"), tx.data_ptr(), _rows(tx, "tx"),
                                      amp_levels.contiguous().data_ptr(), var.contiguous().data_ptr(), float(nu_sc), n, N,
                                      counts.data_ptr(), ser.data_ptr(), scr.data_ptr(), _lib.current_stream()),
@@ -210,6 +269,7 @@ def SER_constell_shaping(rx, tx, amp_levels, nu_sc, var, return_counts=False):
     return (ser, counts) if return_counts else ser
 
 
+@_lib.device_guard
 def _find_shift(q, out, tx, N_shift, amp_levels, return_corr, sync=True):
     lib = _lib.load()
     ref = q if q is not None else out
@@ -245,6 +305,7 @@ def find_shift_symb_full(rx, tx, N_shift, return_corr=False):
     return _find_shift(None, rx, tx, N_shift, None, return_corr)
 
 
+@_lib.device_guard
 def frame_eval_runs(out_train, out_const, tx, amp_levels, var, nu_sc, seg_len, n_shift=21, edge=11, n_cut=10, return_counts=False, which=3,
                     return_scale=False):
     """The per-frame evaluation of the VAE drivers (VAELE_DP:70-89 with seg_len = batch_len, VAEflex_DP:74-84 with seg_len = 0) for R
@@ -283,6 +344,7 @@ def frame_eval_runs(out_train, out_const, tx, amp_levels, var, nu_sc, seg_len, n
     return (ser, align, counts) if return_counts else (ser, align)
 
 
+@_lib.device_guard
 def soft_dec_runs(out, var, amp_levels, nu_sc):
     """soft_dec (sf:529-542) for R independent runs in one launch: out (R,2,2,N), var (R,2), nu_sc (R,) -> q (R,2,2n,N)."""
     _require_cuda(out, "out")
@@ -298,6 +360,7 @@ def soft_dec_runs(out, var, amp_levels, nu_sc):
     return q
 
 
+@_lib.device_guard
 def cma_align_rescale(out, align, scale, edge=11):
     """CMA_DP:42-48 for R runs: out (R,2,2,N) rolled by (r, -shift) with the evaluated slice rescaled like SER_constell_shaping leaves it
     (sf:242); align (R,2,4) int32 and scale (R,) from frame_eval_runs(..., which=2, return_scale=True)."""
@@ -312,6 +375,7 @@ def cma_align_rescale(out, align, scale, edge=11):
     return oc
 
 
+@_lib.device_guard
 def GMI(q, tx, P):
     """EXTENSION (not in the reference): H(X) + E[log2 q(x_tx|y)] per pol, bit/2D-symbol."""
     _require_cuda(q, "q")
@@ -319,7 +383,7 @@ def GMI(q, tx, P):
     n, N = q.shape[1] // 2, int(q.shape[-1])
     Pt = torch.as_tensor(P, dtype=_F32, device=q.device).contiguous()
     out = torch.empty(2, dtype=_F32, device=q.device)
-    scr = _scratch(q.device, 256)
+    scr = _scratch(q.device)
     _lib.check(lib.vaeq_gmi(q.data_ptr(), _rows(q, "q"), _tx_bits(tx).data_ptr(), _rows(tx, "tx"), Pt.data_ptr(), n, N,
                             out.data_ptr(), scr.data_ptr(), _lib.current_stream()), "vaeq_gmi")
     return out
@@ -328,6 +392,7 @@ def GMI(q, tx, P):
 # -------------------------------------------------------------------------------------------------
 # CMA baselines and CPE                                                         sf:140-186, sf:341-488
 # -------------------------------------------------------------------------------------------------
+@_lib.device_guard
 def _cma(mode, Rx, R, h, lr, batchlen, symb_step, sps, train):
     """Rx (2,2,N), h (2,2,2,M) like the reference -- or a batch of S independent streams: Rx (S,2,2,N), h (S,2,2,2,M), one launch
     sequence for all of them (one warp / one CTA per stream); out and e then carry the leading stream dimension too."""
@@ -367,6 +432,7 @@ def CMAflex(Rx, R, h, lr, batchlen, symb_step, sps, eval):
     return _cma(2, Rx, R, h, lr, batchlen, symb_step, sps, bool(eval))
 
 
+@_lib.device_guard
 def CPE(y):
     """Viterbi-Viterbi carrier phase estimation with unwrap (sf:140-186); y (2,2,N), or (S,2,2,N) for S independent runs in one call."""
     _require_cuda(y, "y")

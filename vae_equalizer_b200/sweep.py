@@ -326,18 +326,27 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
     for (M, batch_len, flex_step, symb_rate), members in groups.items():
         cells = [c for _, c in members]
         common = (mod, sps, M, batch_len, N_frame_max, num_frames)
-        ck = None
+        ck, sig = None, None
         if checkpoint_dir is not None:
             import os
             os.makedirs(checkpoint_dir, exist_ok=True)
-            ck = os.path.join(checkpoint_dir, f"{loss_type}_{mod}_M{M}_B{batch_len}_F{flex_step}_R{symb_rate:g}_n{len(cells)}_f{num_frames}.npz")
-            if os.path.exists(ck):                                   # every rank skips the set; rank 0 restores it
-                if rank == 0:
-                    z = np.load(ck)
+            # everything the set's results depend on: the file is only reused by a sweep with the same cells and settings
+            sig = _set_signature(loss_type=loss_type, mod=mod, sps=sps, channel=channel, M=M, batch_len=batch_len, flex_step=flex_step,
+                                 symb_rate=symb_rate, N_frame_max=N_frame_max, num_frames=num_frames, N_lrhalf=N_lrhalf, tau_cd=tau_cd,
+                                 tau_pmd=tau_pmd, phiIQ=list(phiIQ), datagen=datagen, eval_every=eval_every,
+                                 cells=[sorted(c.items()) for c in cells])
+            ck = os.path.join(checkpoint_dir, f"{loss_type}_{mod}_M{M}_B{batch_len}_F{flex_step}_R{symb_rate:g}_n{len(cells)}_f{num_frames}"
+                                              f"_{sig[:12]}.npz")
+            have = 0
+            if rank == 0 and os.path.exists(ck):
+                z = np.load(ck)
+                if "signature" in z.files and str(z["signature"]) == sig:
+                    have = 1
                     for k, (idx, _) in enumerate(members):
                         SER[(slice(None),) + idx] = torch.from_numpy(z["ser"][k]).to(dev)
                         Var_est[(slice(None),) + idx] = torch.from_numpy(z["ve"][k]).to(dev)
                         var_real[(slice(None),) + idx + (0,)] = torch.from_numpy(z["var"][k]).to(dev)
+            if _bcast_flag(have, rank, world, group, dev):           # rank 0 decides (the directory need not be shared); all ranks follow
                 continue
         kw = dict(flex_step=flex_step, channel=channel, symb_rate=symb_rate, tau_cd=tau_cd, tau_pmd=tau_pmd, phiIQ=phiIQ, N_lrhalf=N_lrhalf)
         if runner is not None:                                       # test hook: stands for sweep_vae_dp_sharded
@@ -351,7 +360,7 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
             continue
         ser, ve, var = res
         if ck is not None and rank == 0:
-            np.savez(ck, ser=ser.cpu().numpy(), ve=ve.cpu().numpy(), var=var.cpu().numpy())
+            np.savez(ck, ser=ser.cpu().numpy(), ve=ve.cpu().numpy(), var=var.cpu().numpy(), signature=np.array(sig))
         for k, (idx, _) in enumerate(members):
             SER[(slice(None),) + idx] = ser[k].to(dev)
             Var_est[(slice(None),) + idx] = ve[k].to(dev)
@@ -359,6 +368,33 @@ def run_dp_sweep(mod="64-QAM", sps=2, loss_type="VAE", channel="h0", nu_vec=(0,)
     if rank != 0:
         return None
     return SER, Var_est, var_real
+
+
+def _set_signature(**params):
+    """sha256 of a run set's full parameter dict (floats by repr, so 2.5e-3 and 0.0025 agree)."""
+    import hashlib
+    import json
+
+    def norm(x):
+        if isinstance(x, (list, tuple)):
+            return [norm(v) for v in x]
+        if isinstance(x, (float, np.floating)):
+            return repr(float(x))
+        if isinstance(x, (int, np.integer)):
+            return int(x)
+        return x
+    return hashlib.sha256(json.dumps({k: norm(v) for k, v in sorted(params.items())}, sort_keys=True).encode()).hexdigest()
+
+
+def _bcast_flag(flag, rank, world, group, dev):
+    """rank 0's decision on every rank (one tiny broadcast; a no-op for a single process)."""
+    import torch.distributed as dist
+    if world <= 1 or not (dist.is_available() and dist.is_initialized()):
+        return bool(flag)
+    on = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(flag)], dtype=torch.int32, device=on)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return bool(int(t.item()))
 
 
 def _cma_cells(loss_type, cells, common, kw, dev, rank, world, group, num_frames, datagen="gpu"):
