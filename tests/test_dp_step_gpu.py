@@ -252,15 +252,48 @@ def test_static_tiles_are_bitwise_reproducible_and_dynamic_agrees():
 # -------------------------------------------------------------------------------------------------
 # BASELINE size (batch_len = 2^22, the bench workload): size-independent properties instead of a CPU oracle
 # -------------------------------------------------------------------------------------------------
-def _bench_case():
+def _bench_case(B=1 << 22):
     from vae_equalizer_b200.datagen import generate_data_gpu
-    M, B = 25, 1 << 22
+    M = 25
     h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
     rx = generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, "cuda", 99)[0]
     gen = torch.Generator().manual_seed(17)
     W0 = O.dirac_taps(M) + 0.02 * torch.randn(2, 4, M, generator=gen)
     h0 = h_est.detach() + 0.02 * torch.randn(2, 2, 2, M, generator=gen)
     return M, B, rx, dict(amp=amp, P=torch.tensor(P, dtype=torch.float32), var=var, nu_sc=nu_sc), W0, h0
+
+
+@pytest.mark.parametrize("log2B", [20, 22])
+def test_bench_size_step_against_the_cpu_oracle(log2B):
+    """ONE step of the register-blocked path at 2^20 and at the bench size 2^22 against the CPU oracle (torch autograd through
+    oracle.equalizer_forward + oracle.elbo_loss, the restatement pinned to the reference's goldens): the FULL out and q tensors, loss,
+    var_est and both gradients -- the direct check at the size the metric is quoted on (the oracle needs ~5 / ~20 s and 2 / 8 GB)."""
+    import psutil
+    from vae_equalizer_b200.dp import DPEqualizer
+    if log2B == 22 and psutil.virtual_memory().available < 24 << 30:
+        pytest.skip("the 2^22 CPU oracle step needs ~8 GB of host memory")
+    M, B, rx, c, W0, h0 = _bench_case(1 << log2B)
+    eq = DPEqualizer(M, 2, c["amp"], c["P"], c["var"], c["nu_sc"], W0=W0, h0=h0)
+    q, out, loss, ve, gW, gh = eq.forward_backward(rx)
+    torch.cuda.synchronize()
+    Wo, ho = W0.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+    rx_c = rx.cpu()
+    qo, oo = O.equalizer_forward(rx_c, Wo, c["amp"], c["var"], c["nu_sc"], 2)
+    lo, vo = O.elbo_loss(qo, rx_c, ho, c["amp"], c["P"])
+    lo.backward()
+    d_out, d_q = float((out.cpu() - oo.detach()).abs().max()), float((q.cpu() - qo.detach()).abs().max())
+    e_l, e_v = abs(float(loss) - float(lo)) / abs(float(lo)), rel(ve, vo)
+    e_W, e_h = rel(gW, Wo.grad), rel(gh, ho.grad)
+    print(f"B=2^{log2B}: |out| {d_out:.2e} |q| {d_q:.2e} loss {e_l:.2e} var_est {e_v:.2e} gW {e_W:.2e} gh {e_h:.2e}")
+    assert d_out < 5e-6 and d_q < 5e-5
+    assert e_l < 1e-4 and e_v < 1e-4 and e_W < 1e-4 and e_h < 1e-4
+    # hard decisions of the whole minibatch: argmax over the I rows / Q rows of q (sf:201) must agree wherever the oracle's own
+    # top-2 margin exceeds the q tolerance (a tie within 5e-5 may legitimately fall either way)
+    n = c["amp"].numel()
+    qg, qc = q.cpu().reshape(2, 2, n, B), qo.detach().reshape(2, 2, n, B)
+    top2 = qc.topk(2, dim=2).values
+    clear = (top2[:, :, 0] - top2[:, :, 1]) > 1e-4
+    assert bool((qg.argmax(2)[clear] == qc.argmax(2)[clear]).all()) and float(clear.float().mean()) > 0.999
 
 
 def test_full_size_fast_path_against_generic_kernels():

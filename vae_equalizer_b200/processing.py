@@ -23,7 +23,15 @@ N_CUT = 10     # symbols cut per minibatch/frame edge (VAELE_DP:40, CMA_DP:26)
 
 def _make_frame(datagen, N, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd, phiIQ, theta, device, rng, frame_seed):
     """One frame of test signal.  datagen="numpy": the reference's host-side generator restated (sf:65-90);
-    datagen="gpu": the same signal model generated on the device (statistical, not bitwise, parity; channel 'h0' only)."""
+    datagen="gpu": the same signal model generated on the device (statistical, not bitwise, parity; channel 'h0' only);
+    datagen=<iterator of (rx (2,2,sps*N) float32, tx (2,2,N) float16)>: replay recorded frames (parity tests feed the frames the
+    reference's processing() was given, tests/golden/make_golden_drivers.py)."""
+    if hasattr(datagen, "__next__"):
+        rx, tx = next(datagen)
+        rx, tx = torch.as_tensor(rx, dtype=torch.float32).to(device).contiguous(), torch.as_tensor(tx, dtype=torch.float16).to(device).contiguous()
+        if tx.shape[-1] != N or rx.shape[-1] != sps * N:
+            raise sfun._lib.VaeqError(f"replayed frame has {tx.shape[-1]} symbols / {rx.shape[-1]} samples, the driver asked for {N} symbols")
+        return rx, tx, 0.0
     if datagen == "gpu":
         if len(h_channel) != 1:
             raise sfun._lib.VaeqError("datagen='gpu' implements the optical channel 'h0' only")
@@ -63,6 +71,55 @@ def _eval_fused(out_train, out_const, data_tensor, amp_levels, var, nu_sc, seg_l
     return ser[0], al[0]
 
 
+def eval_frame_vae(out_train, out_const, data_tensor, amp_levels, nu_sc, var, seg_len):
+    """The per-frame evaluation of the VAE drivers, call by call like the reference: VAELE_DP:70-89 with seg_len = batch_len (the last
+    shift[0] + N_cut symbols of every minibatch are dropped before the slice), VAEflex_DP:74-84 with seg_len = 0.
+    Returns (SER (4,) [constellation x, y, soft demapper x, y], (shift, r) of find_shift, (shift, r) of find_shift_symb_full)."""
+    pol, n2, N = out_train.shape
+    ser = torch.empty(4, device=out_train.device, dtype=torch.float32)
+
+    def cut(t, sh):
+        if not seg_len:
+            return t
+        keep = seg_len - sh[0] - N_CUT                 # VAELE_DP:73-77 (a slice bound: clamps to the minibatch, negative counts from its end)
+        return t.reshape(pol, t.shape[1], N // seg_len, seg_len)[:, :, :, :keep].reshape(pol, t.shape[1], -1)
+
+    shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
+    sh_q = [int(v) for v in shift.tolist()]
+    out_train = _align(out_train, sh_q, r)
+    tail = 11 + max(abs(sh_q[0]), abs(sh_q[1]))
+    ser[2:] = sfun.SER_IQflip(cut(out_train, sh_q)[:, :, 11:-tail], cut(data_tensor, sh_q)[:, :, 11:-tail])
+    shift, r2 = sfun.find_shift_symb_full(out_const, data_tensor, 21)
+    sh_c = [int(v) for v in shift.tolist()]
+    out_const = _align(out_const, sh_c, r2)
+    tail = 11 + max(abs(sh_c[0]), abs(sh_c[1]))
+    ser[:2] = sfun.SER_constell_shaping(cut(out_const, sh_c)[:, :, 11:-tail].detach().clone(), cut(data_tensor, sh_c)[:, :, 11:-tail],
+                                        amp_levels, nu_sc, var)
+    return ser, (sh_q, r), (sh_c, r2)
+
+
+def eval_frame_cma(out_const, data_tensor, amp_levels, nu_sc, var, pol=2):
+    """The per-frame evaluation of the CMA drivers (CMA_DP:39-52): CPE of the equalizer output without its N_cut edge symbols, alignment
+    from the constellation, SER_constell_shaping on a VIEW (its in-place rescale, sf:242, is what soft_dec then reads), soft demapper,
+    alignment from q, SER_IQflip.  Returns (SER (4,), (shift, r) from out, (shift, r) from q, out_const as soft_dec saw it)."""
+    ser = torch.empty(4, device=out_const.device, dtype=torch.float32)
+    out_const = sfun.CPE(out_const[:, :, N_CUT:-N_CUT])
+    data_tensor = data_tensor[:, :, N_CUT:-N_CUT]
+    shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
+    sh_c = [int(v) for v in shift.tolist()]
+    out_const = _align(out_const, sh_c, r)
+    tail = 11 + max(abs(sh_c[0]), abs(sh_c[1]))
+    # a VIEW is passed on purpose: the in-place rescale (sf:242) must be visible to soft_dec below (CMA_DP:44,48)
+    ser[:2] = sfun.SER_constell_shaping(out_const[:, :, 11:-tail], data_tensor[:, :, 11:-tail], amp_levels, nu_sc, var)
+    out_train = sfun.soft_dec(out_const, var, amp_levels, nu_sc)
+    shift, r2 = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
+    sh_q = [int(v) for v in shift.tolist()]
+    out_train = _align(out_train, sh_q, r2)
+    tail = 11 + max(abs(sh_q[0]), abs(sh_q[1]))
+    ser[2:] = sfun.SER_IQflip(out_train[:, :, 11:-tail], data_tensor[:, :, 11:-tail])
+    return ser, (sh_c, r), (sh_q, r2), out_const
+
+
 def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_frame_max, num_frames, flex_step,
                         channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0,
                         eval_mode="per_op"):
@@ -98,24 +155,7 @@ def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, b
                 a = al.tolist()
                 _print_frame(frame, loss_steps[-1].item(), a[1][:2], a[1][2], (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
             continue
-        shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
-        sh = [int(v) for v in shift.tolist()]
-        out_train = _align(out_train, sh, r)
-        keep = batch_len - sh[0] - N_CUT           # drop each minibatch's edge symbols (VAELE_DP:73-77)
-        q_cut = out_train.reshape(pol, 2 * num_lev, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2 * num_lev, -1)
-        d_cut = data_tensor.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
-        tail = 11 + max(abs(sh[0]), abs(sh[1]))
-        SER_valid[2:, frame] = sfun.SER_IQflip(q_cut[:, :, 11:-tail], d_cut[:, :, 11:-tail])
-
-        shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
-        sh = [int(v) for v in shift.tolist()]
-        out_const = _align(out_const, sh, r)
-        keep = batch_len - sh[0] - N_CUT
-        o_cut = out_const.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
-        d_cut = data_tensor.reshape(pol, 2, m_max, batch_len)[:, :, :, :keep].reshape(pol, 2, -1)
-        tail = 11 + max(abs(sh[0]), abs(sh[1]))
-        SER_valid[:2, frame] = sfun.SER_constell_shaping(o_cut[:, :, 11:-tail].detach().clone(), d_cut[:, :, 11:-tail],
-                                                         amp_levels, nu_sc, var)
+        SER_valid[:, frame], _, (sh, r) = eval_frame_vae(out_train, out_const, data_tensor, amp_levels, nu_sc, var, batch_len)
         if verbose:
             _print_frame(frame, loss_steps[-1].item(), sh, r, (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
     return SER_valid, Var_est, var
@@ -158,17 +198,7 @@ def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
                 a = al.tolist()
                 _print_frame(frame, loss_steps[-1].item(), a[1][:2], a[1][2], (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
             continue
-        shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
-        sh = [int(v) for v in shift.tolist()]
-        out_train = _align(out_train, sh, r)
-        tail = 11 + max(abs(sh[0]), abs(sh[1]))
-        SER_valid[2:, frame] = sfun.SER_IQflip(out_train[:, :, 11:-tail], data_tensor[:, :, 11:-tail])
-        shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
-        sh = [int(v) for v in shift.tolist()]
-        out_const = _align(out_const, sh, r)
-        tail = 11 + max(abs(sh[0]), abs(sh[1]))
-        SER_valid[:2, frame] = sfun.SER_constell_shaping(out_const[:, :, 11:-tail].detach().clone(), data_tensor[:, :, 11:-tail],
-                                                         amp_levels, nu_sc, var)
+        SER_valid[:, frame], _, (sh, r) = eval_frame_vae(out_train, out_const, data_tensor, amp_levels, nu_sc, var, 0)
         if verbose:
             _print_frame(frame, loss_steps[-1].item(), sh, r, (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
     return SER_valid, Var_est, var
@@ -197,24 +227,10 @@ def _processing_cma(kind, mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
         else:
             out_const, h_est, e = sfun.CMAflex(rx_tensor, R, h_est, lr_optim, batch_len, flex_step, sps, True)
         theta += theta_diff
-        out_const = sfun.CPE(out_const[:, :, N_CUT:-N_CUT])
-        data_tensor = data_tensor[:, :, N_CUT:-N_CUT]
-        shift, r = sfun.find_shift_symb_full(out_const, data_tensor, 21)
-        sh = [int(v) for v in shift.tolist()]
-        out_const = _align(out_const, sh, r)
-        tail = 11 + max(abs(sh[0]), abs(sh[1]))
-        # a VIEW is passed on purpose: the in-place rescale (sf:242) must be visible to soft_dec below (CMA_DP:44,48)
-        SER_valid[:2, frame] = sfun.SER_constell_shaping(out_const[:, :, 11:-tail], data_tensor[:, :, 11:-tail], amp_levels, nu_sc, var)
+        SER_valid[:, frame], (sh, r), _, _ = eval_frame_cma(out_const, data_tensor, amp_levels, nu_sc, var, pol)
         if verbose:
             print(frame, '\t\ttraining: loss = ', torch.sum(e).item(), '\tshift_x = ', sh[0], '\tshift_y = ', sh[1], '\tr = ', r)
             print('\t\t\t\t\t\t\tSER_x = ', SER_valid[0, frame].item(), '\tSER_y = ', SER_valid[1, frame].item(), '\t(constell. with shaping)')
-        out_train = sfun.soft_dec(out_const, var, amp_levels, nu_sc)
-        shift, r = sfun.find_shift(out_train, data_tensor, 21, amp_levels, pol)
-        sh = [int(v) for v in shift.tolist()]
-        out_train = _align(out_train, sh, r)
-        tail = 11 + max(abs(sh[0]), abs(sh[1]))
-        SER_valid[2:, frame] = sfun.SER_IQflip(out_train[:, :, 11:-tail], data_tensor[:, :, 11:-tail])
-        if verbose:
             print('\t\t\t\t\t\t\tSER_x = ', SER_valid[2, frame].item(), '\tSER_y = ', SER_valid[3, frame].item(), '\t(soft demapper)')
     return SER_valid, Var_est, var
 
