@@ -289,6 +289,26 @@ size_t vaeq_cpe_runs_scratch_bytes(int32_t N, int32_t n_runs);
 int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Single-polarisation CMA baseline of the AWGN module (AWGN_channel/func_CMA_MQAM_shaping.py, cm:)
+ * ---------------------------------------------------------------------------------------------- */
+/* CMA (cm:142-168): Rx (2,N) [I,Q], h (2,M) = Re / Im taps updated in place when train != 0, out (2,N/sps), e (N/sps); no power
+ * normalisation (unlike the DP version).  n_runs independent runs: every pointer strides by its tensor size per run. */
+int vaeq_cma_awgn(const float *Rx, int32_t N, float R, float *h, int32_t M, float lr, int32_t sps, int32_t train, float *out, float *e,
+                  int32_t n_runs, void *stream);
+/* CPE (cm:170-196): y (n_runs,2,N) -> y_corr, Viterbi-Viterbi WITHOUT unwrapping; scratch: vaeq_cpe_runs_scratch_bytes(N, n_runs) */
+int vaeq_cpe_awgn(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream);
+/* SER_CMA (cm:63-93): rx (2,N) rows with stride ld_rx, RESCALED IN PLACE by mean|tx| / mean|rx| (cm:73); nearest-level decisions;
+ * counts_out int32 (4) = symbol errors for the rotations 0, pi, and the two quarter turns; ser_out float (1) = min / N.
+ * scratch: VAEQ_EVAL_SCRATCH_BYTES */
+int vaeq_ser_cma(float *rx, int64_t ld_rx, const uint16_t *tx, int64_t ld_tx, const float *amp, int32_t n_lev, int32_t N,
+                 int32_t *counts_out, float *ser_out, void *scratch, void *stream);
+/* find_shift_symb (cm:127-140): correlation of tx[c, n_shift/2 : 1000] with rx[0, i : i + 1000 - n_shift/2], i < n_shift (NOT circular);
+ * corr_out float (2, n_shift) for c = I, Q; shift_out int32 (1) = argmax|corr_I| - n_shift/2, or the Q component's when
+ * max|corr_I| < 0.02 n_rx and max|corr_Q| >= max|corr_I| */
+int vaeq_find_shift_symb(const float *rx, int32_t n_rx, const uint16_t *tx, int64_t ld_tx, int32_t n_tx, int32_t n_shift, float *corr_out,
+                         int32_t *shift_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic test signal on the device, n_runs independent runs per call (generate_data_shaping sf:65-90, channel 'h0'; the
  * reference's generator is unseeded, parity is statistical).  The host side (vae_equalizer_b200/datagen.py) runs
  *   vaeq_gen_levels -> vaeq_gen_pulse -> FFT -> vaeq_gen_jones -> IFFT -> vaeq_gen_noise

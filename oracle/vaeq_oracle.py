@@ -602,6 +602,79 @@ def awgn_find_shift(q, tx, N_shift, amp):
 
 
 # --------------------------------------------------------------------------------------------
+# AWGN single-polarisation CMA module          AWGN_channel/func_CMA_MQAM_shaping.py (cm:)
+# --------------------------------------------------------------------------------------------
+def awgn_cma(Rx, R, h, lr, sps, train=True):
+    """CMA (cm:142-168): complex FIR h[0] + j h[1] over Rx (2,N), per-symbol tap update, no power normalisation.
+    Mutates h in place and returns it, like the reference.  The output index k = i//sps - mh is negative for the
+    first symbols and wraps to the end of out / e (cm:155)."""
+    M = h.shape[1]
+    mh = M // 2
+    N = Rx.shape[1]
+    y = F.pad(Rx.to(F32), (mh, mh)).numpy()
+    hh = h.detach().numpy().astype(np.float32).copy()
+    out = np.zeros((2, N // sps), dtype=np.float32)
+    e = np.zeros(N // sps, dtype=np.float32)
+    lr2, R = np.float32(2 * lr), np.float32(R)
+    for i in range(mh, N + mh, sps):
+        win = y[:, i - mh:i + mh + 1]
+        k = i // sps - mh
+        o0 = np.float32(np.dot(win[0], hh[0]) - np.dot(win[1], hh[1]))            # cm:157-158
+        o1 = np.float32(np.dot(win[0], hh[1]) + np.dot(win[1], hh[0]))
+        out[0, k], out[1, k] = o0, o1
+        e[k] = R - o0 * o0 - o1 * o1                                               # cm:160
+        if train:
+            f = lr2 * e[k]
+            hh[0] = hh[0] + f * (o0 * win[0] + o1 * win[1])                        # cm:163-164
+            hh[1] = hh[1] + f * (o1 * win[0] - o0 * win[1])
+    with torch.no_grad():
+        h.copy_(torch.from_numpy(hh))
+    return torch.from_numpy(out), h, torch.from_numpy(e)
+
+
+def awgn_cpe(y, M_ma=501):
+    """CPE of the AWGN module (cm:170-196): 4th power, 501-tap moving average, NO unwrapping."""
+    a, b = y[0], y[1]
+    a2, b2 = a ** 2, b ** 2
+    p4 = torch.stack((a2 ** 2 - 6 * a2 * b2 + b2 ** 2, 4 * (a2 * a * b - a * b2 * b))).unsqueeze(1)      # cm:180
+    ma = F.conv1d(p4, torch.full((1, 1, M_ma), 1 / M_ma, dtype=F32), padding=M_ma // 2)[:, 0, :]
+    phi = torch.atan2(ma[1], -ma[0]) / 4                                             # cm:189
+    c, s = torch.cos(phi), torch.sin(phi)
+    return torch.stack((a * c - b * s, b * c + a * s))                               # cm:193-194
+
+
+def awgn_ser_cma_counts(rx, tx, amp):
+    """Counts behind SER_CMA (cm:63-93): MUTATES rx (cm:73); nearest-level decisions, rotations 0, pi and the two quarter turns."""
+    n = amp.shape[0]
+    S = n - 1
+    N = tx.shape[1]
+    data = _tx_levels(tx, n)
+    rx *= torch.mean(torch.sqrt(tx[0].float() ** 2 + tx[1].float() ** 2)) / torch.mean(torch.sqrt(rx[0] ** 2 + rx[1] ** 2))
+    dI = torch.argmin(torch.abs(rx[0, :N] - amp.view(n, 1)), dim=0)
+    dQ = torch.argmin(torch.abs(rx[1, :N] - amp.view(n, 1)), dim=0)
+    rot = ((dI, dQ), (S - dI, S - dQ), (S - dQ, dI), (dQ, S - dI))
+    return torch.stack([((data[0] != a) | (data[1] != b)).sum() for a, b in rot]), N
+
+
+def awgn_ser_cma(rx, tx, amp):
+    counts, N = awgn_ser_cma_counts(rx, tx, amp)
+    return torch.min(counts.to(F32) / N)
+
+
+def awgn_find_shift_symb(rx, tx, N_shift):
+    """find_shift_symb (cm:127-140): non-circular correlation over the first 1000 symbols, I then Q fallback."""
+    half = N_shift // 2
+    mat = torch.stack([rx[0, i:1000 - half + i] for i in range(N_shift)], dim=1)
+    cI = tx[0, half:1000].float() @ mat
+    if torch.max(torch.abs(cI)) >= 0.02 * rx.shape[-1]:
+        return torch.argmax(torch.abs(cI)) - half
+    cQ = tx[1, half:1000].float() @ mat
+    if torch.max(torch.abs(cQ)) >= torch.max(torch.abs(cI)):
+        return torch.argmax(torch.abs(cQ)) - half
+    return torch.argmax(torch.abs(cI)) - half
+
+
+# --------------------------------------------------------------------------------------------
 # extension (NOT in the reference): GMI from the demapper posteriors
 # --------------------------------------------------------------------------------------------
 def gmi_from_posteriors(q, tx, P):

@@ -138,12 +138,13 @@ SNAPS = (10, 25, 50, 75, 100)
 def trajectory(name, mod="64-QAM", nu=0.0270955, SNR=23, M=25, B=100, steps=100, lr=2.5e-3, seed=77):
     """One VAE-LE frame of the Eval_run_DP.py defaults stepped by the reference's own modules (sf.twoXtwoFIR, sf.loss_function_shaping,
     torch.optim.Adam with the two parameter groups of VAELE_DP:28-31).  Recorded: loss / var_est of every step, the taps AND the Adam
-    moments after every step (teacher-forced step-by-step checks), and the taps of a second run of the SAME reference code with 8 host
-    threads instead of 1 at a few steps -- the trajectory is chaotic (Adam's m / sqrt(v) normalisation amplifies rounding noise of
-    near-zero gradients), so the reference's own spread between two thread counts is the yardstick for a free-running comparison."""
+    moments after every step (teacher-forced step-by-step checks), and the taps of two more runs of the SAME reference code at a few
+    steps: one with 8 host threads instead of 1, one whose input samples were moved by one float32 ulp at random.  The trajectory
+    is chaotic (Adam's m / sqrt(v) normalisation amplifies the rounding noise of near-zero gradients), so the reference's own spread
+    under such last-bit perturbations is the yardstick for a free-running comparison."""
     rx = None
 
-    def run(threads):
+    def run(threads, ulp_noise=False):
         nonlocal rx
         torch.set_num_threads(threads)
         h_est, h_channel, P, amp, amps, pol, nu_sc, var, pow_mean = sf.init("h0", mod, "cpu", nu, 2, M, SNR)
@@ -151,13 +152,17 @@ def trajectory(name, mod="64-QAM", nu=0.0270955, SNR=23, M=25, B=100, steps=100,
             rng = np.random.default_rng(seed)
             rx = O.generate_data_shaping(B * steps, amps, SNR, h_channel, P, pol, CHAN["symb_rate"], 2, CHAN["tau_cd"], CHAN["tau_pmd"], PHI_IQ,
                                          np.pi / 10, "cpu", rng=rng)[0]
+        x = rx
+        if ulp_noise:                                            # every second sample (at random) moved to the next float32
+            xn = npy(rx)
+            x = torch.from_numpy(np.where(np.random.default_rng(0).random(xn.shape) < 0.5, np.nextafter(xn, np.float32(np.inf)), xn).astype(np.float32))
         net = sf.twoXtwoFIR(M, 2)
         opt = torch.optim.Adam(net.parameters(), lr=lr)
         opt.add_param_group({"params": h_est})
         Pt = torch.tensor(P, dtype=torch.float32)
         rec = dict(loss=[], ve=[], W=[], h=[], mW=[], vW=[], mh=[], vh=[])
         for m in range(steps):
-            mb = rx[:, :, m * B * 2:(m + 1) * B * 2].contiguous()
+            mb = x[:, :, m * B * 2:(m + 1) * B * 2].contiguous()
             opt.zero_grad()
             q, out = net(mb, amp, var, nu_sc)
             loss, ve = sf.loss_function_shaping(q.squeeze(), mb.squeeze(), h_est, amp, Pt)
@@ -172,6 +177,7 @@ def trajectory(name, mod="64-QAM", nu=0.0270955, SNR=23, M=25, B=100, steps=100,
 
     a, consts, q_last, out_last = run(1)
     b = run(8)[0]
+    c = run(1, ulp_noise=True)[0]
     torch.set_num_threads(1)
     out = dict(rx=npy(rx), lr=np.float64(lr), B=np.int64(B), M=np.int64(M), loss=np.asarray(a["loss"], np.float32), var_est=np.stack(a["ve"]),
                W_steps=np.stack(a["W"]), h_steps=np.stack(a["h"]), mW_steps=np.stack(a["mW"]), vW_steps=np.stack(a["vW"]),
@@ -180,12 +186,14 @@ def trajectory(name, mod="64-QAM", nu=0.0270955, SNR=23, M=25, B=100, steps=100,
     for k in SNAPS:
         out[f"W_{k}"], out[f"h_{k}"] = a["W"][k - 1], a["h"][k - 1]
         out[f"W8_{k}"], out[f"h8_{k}"] = b["W"][k - 1], b["h"][k - 1]
+        out[f"Wn_{k}"], out[f"hn_{k}"] = c["W"][k - 1], c["h"][k - 1]
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
     def rel(x, y):
         return float(np.abs(np.asarray(x, np.float64) - np.asarray(y, np.float64)).max() / np.abs(y).max())
     print(name, "loss[0], loss[-1]", a["loss"][0], a["loss"][-1], "reference 1 vs 8 threads, taps W/h:",
-          [(k, f"{rel(b['W'][k - 1], a['W'][k - 1]):.1e}", f"{rel(b['h'][k - 1], a['h'][k - 1]):.1e}") for k in SNAPS])
+          [(k, f"{rel(b['W'][k - 1], a['W'][k - 1]):.1e}", f"{rel(b['h'][k - 1], a['h'][k - 1]):.1e}") for k in SNAPS],
+          "reference with 1-ulp input noise:", [(k, f"{rel(c['W'][k - 1], a['W'][k - 1]):.1e}", f"{rel(c['h'][k - 1], a['h'][k - 1]):.1e}") for k in SNAPS])
 
 
 if __name__ == "__main__":

@@ -185,10 +185,11 @@ def test_hundred_steps_teacher_forced_against_the_reference(persistent):
 
 @pytest.mark.parametrize("persistent", [0, 1, 2])
 def test_hundred_step_free_running_trajectory_against_the_reference(persistent):
-    """The same 100 steps free-running.  This trajectory is chaotic: the reference run with 8 host threads instead of 1 (same code,
-    same data) drifts from itself by 1e-7 / 2e-6 / 9e-5 / 4e-3 / 3e-2 in the taps after 10 / 25 / 50 / 75 / 100 steps (recorded in
-    the fixture: W8_k, h8_k) because Adam's m / sqrt(v) turns the rounding noise of near-zero gradients into full-size steps.  So the
-    1e-4 gate holds over the first 25 steps, and beyond that the bound is 10 x the reference's own spread at the same step."""
+    """The same 100 steps free-running.  This trajectory is chaotic: the reference run on inputs moved by ONE float32 ulp (same code)
+    drifts from itself by 9e-7 / 1e-5 / 7e-4 / 1e-2 / 4e-2 in the taps after 10 / 25 / 50 / 75 / 100 steps, with 8 host threads instead
+    of 1 by 1e-7 / 2e-6 / 9e-5 / 4e-3 / 3e-2 (both recorded in the fixture: Wn_k, hn_k, W8_k, h8_k) because Adam's m / sqrt(v) turns the
+    rounding noise of near-zero gradients into full-size steps.  So the 1e-4 gate holds over the first 25 steps, and beyond that the
+    bound is 10 x the reference's own spread at the same step (measured on B200: ours stays within 3-4 x, profiles/r02_parity.txt)."""
     from vae_equalizer_b200 import _lib
     from vae_equalizer_b200.dp import DPEqualizer
     g = load("traj_vaele_64qam_M25_B100_100steps")
@@ -205,7 +206,8 @@ def test_hundred_step_free_running_trajectory_against_the_reference(persistent):
             eq.train_frame(rx[:, :, 2 * B * lo:], B, B, hi - lo, float(g["lr"]), float(g["lr"]), ot[:, :, B * lo:], oc[:, :, B * lo:], 0, B,
                            keep_lo_in_dst=True)
             eW, eh = rel(eq.W.cpu().numpy(), g[f"W_{hi}"]), rel(eq.h.cpu().numpy(), g[f"h_{hi}"])
-            sW, sh = rel(g[f"W8_{hi}"], g[f"W_{hi}"]), rel(g[f"h8_{hi}"], g[f"h_{hi}"])
+            sW = max(rel(g[f"W8_{hi}"], g[f"W_{hi}"]), rel(g[f"Wn_{hi}"], g[f"W_{hi}"]))
+            sh = max(rel(g[f"h8_{hi}"], g[f"h_{hi}"]), rel(g[f"hn_{hi}"], g[f"h_{hi}"]))
             report.append((hi, eW, eh, sW, sh))
             lo = hi
     finally:

@@ -113,6 +113,10 @@ PROTOTYPES = {
     "vaeq_cpe": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "vaeq_cpe_runs_scratch_bytes": (_sz, [_i32, _i32]),
     "vaeq_cpe_runs": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "vaeq_cma_awgn": (C.c_int, [_vp, _i32, _f, _vp, _i32, _f, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "vaeq_cpe_awgn": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "vaeq_ser_cma": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vaeq_find_shift_symb": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "vaeq_awgn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vaeq_adam_state_floats_awgn": (_sz, [_i32]),
     "vaeq_awgn_forward": (C.c_int, [C.POINTER(AwgnDesc), _vp]),

@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(CPE_PT) k_cpe_phase(const float *p4, int N, in
 }
 
 // one CTA per pol: running counts of +/- jumps of the WRAPPED phase (sf:164-169), then derotation (sf:182-185)
-__global__ void __launch_bounds__(1024) k_cpe_unwrap_rotate(const float *y, const float *phi, int N, float *out) {
+__global__ void __launch_bounds__(1024) k_cpe_unwrap_rotate(const float *y, const float *phi, int N, float *out, int unwrap) {
     __shared__ int wsum[2][32];
     __shared__ int carry[2];
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(1024) k_cpe_unwrap_rotate(const float *y, cons
         const int n = base + tid;
         // flag at n: jump between n-1 and n  (phi[i+1:] is shifted when diff[i] crosses +-pi/4)
         int fp = 0, fn = 0;
-        if (n < N && n >= 1) {
+        if (unwrap && n < N && n >= 1) {                                         // unwrap == 0: the AWGN module's CPE (no unwrapping)
             const float d = __fsub_rn(ph[n], ph[n - 1]);
             fp = d > pi4;
             fn = d < -pi4;
@@ -484,12 +484,11 @@ extern "C" size_t vaeq_cpe_runs_scratch_bytes(int32_t N, int32_t n_runs) {
 }
 extern "C" size_t vaeq_cpe_scratch_bytes(int32_t N) { return vaeq_cpe_runs_scratch_bytes(N, 1); }
 
-extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream) {
-    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1 && n_runs > 0 && n_runs <= 32767, "bad cpe arguments");
+// npol independent complex sequences y (npol,2,N): 4th power, 501-tap moving average, phase (/4), optional unwrap, derotation
+static int cpe_launch(const float *y, int N, int npol, int unwrap, float *y_corr, void *scratch, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    const int npol = 2 * n_runs;
     float *p4 = static_cast<float *>(scratch);
-    float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n_runs * 4 * N * sizeof(float), 256));
+    float *phi = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)npol * 2 * N * sizeof(float), 256));
     const int grid = (int)std::min<int64_t>((npol * (int64_t)N + 255) / 256, (int64_t)sm_count() * 16);
     ktime_begin(VAEQ_K_CMA, st);
     k_cpe_pow4<<<grid, 256, 0, st>>>(y, N, npol, p4);
@@ -500,10 +499,21 @@ extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y
     ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_phase");
     ktime_begin(VAEQ_K_CMA, st);
-    k_cpe_unwrap_rotate<<<npol, 1024, 0, st>>>(y, phi, N, y_corr);
+    k_cpe_unwrap_rotate<<<npol, 1024, 0, st>>>(y, phi, N, y_corr, unwrap);
     ktime_end(VAEQ_K_CMA, st);
     VAEQ_LAUNCH_CHECK("k_cpe_unwrap_rotate");
     return VAEQ_OK;
+}
+
+extern "C" int vaeq_cpe_runs(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream) {
+    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1 && n_runs > 0 && n_runs <= 32767, "bad cpe arguments");
+    return cpe_launch(y, N, 2 * n_runs, 1, y_corr, scratch, stream);
+}
+
+// CPE of the AWGN module (AWGN_channel/func_CMA_MQAM_shaping.py:170-196): single polarisation y (n_runs,2,N), NO unwrapping
+extern "C" int vaeq_cpe_awgn(const float *y, int32_t N, int32_t n_runs, float *y_corr, void *scratch, void *stream) {
+    VAEQ_CHECK_ARG(y && y_corr && scratch && N > 1 && n_runs > 0 && n_runs <= 65535, "bad cpe arguments");
+    return cpe_launch(y, N, n_runs, 0, y_corr, scratch, stream);
 }
 
 extern "C" int vaeq_cpe(const float *y, int32_t N, float *y_corr, void *scratch, void *stream) {

@@ -301,3 +301,47 @@ def processing_vaele_awgn(mod, sps, SNR, nu, M_est, lr_optim, batch_len, N_valid
             if verbose:
                 print(epoch, loss.item(), shift, '\t\t\t\t\t\tSER = ', SER_valid[epoch // epe].item())
     return SER_valid
+
+
+# -------------------------------------------------------------------------------------------------
+# AWGN single-polarisation CMA baseline (AWGN_channel/func_CMA_MQAM_shaping.py:201-256)
+# -------------------------------------------------------------------------------------------------
+def processing_cma_awgn(mod, sps, SNR, nu, M_est, lr_optim, N_valid, N_train, num_epochs, epe, channel, *, device=None, rng=None,
+                        verbose=True, datagen=None):
+    """The reference's positional signature and return value (SER_valid float32 [num_epochs // epe]).  Per epoch one CMA pass over a
+    fresh training frame; every `epe` epochs a validation frame: CMA without updates -> CPE (no unwrap) -> find_shift_symb -> SER_CMA.
+    `datagen`: optional iterator of (rx (2,sps*N) float32, tx (2,N) float16) frames in the order the reference draws them (replay)."""
+    from . import awgn_cma as cm
+    device = _cuda_device(device)
+    if verbose:
+        print("We are using the following device for learning:", device)
+    if channel not in ("h1", "h2"):
+        raise KeyError(f"AWGN driver knows channels h1/h2, got {channel!r}")       # cm:205-208
+    h_channel = upsampled_channel(channel, sps)
+    M = (len(h_channel) - 1) // sps + 1
+    amps, P, _, _ = awgn_constants(mod, nu, SNR)
+    amp_levels = torch.tensor(amps, device=device, dtype=torch.float32)
+    num_lev = int(amp_levels.numel())
+    h_est = torch.zeros(2, M_est, device=device, dtype=torch.float32)              # cm:233-235
+    h_est[0, M_est // 2] = 1.0
+    SER_valid = torch.empty(num_epochs // epe, device=device, dtype=torch.float32)
+
+    def frame(N):
+        if datagen is not None:
+            rx, tx = next(datagen)
+            return (torch.as_tensor(rx, dtype=torch.float32).to(device).contiguous(), torch.as_tensor(tx, dtype=torch.float16).to(device).contiguous())
+        return generate_data(N, M, amps, SNR, h_channel, sps, device, P, rng=rng)
+
+    R = 1
+    for epoch in range(num_epochs):
+        rx_tensor, _ = frame(N_train)
+        _, h_est, e = cm.CMA(rx_tensor, R, h_est, lr_optim, sps, True)
+        if epoch % epe == 0:
+            rx_v, data_v = frame(N_valid)
+            out_v, h_est, _ = cm.CMA(rx_v, R, h_est, lr_optim, sps, False)
+            out_cpe = cm.CPE(out_v)
+            shift = int(cm.find_shift_symb(out_cpe, data_v, 21))
+            SER_valid[epoch // epe] = cm.SER_CMA(out_cpe[:, 11 + shift:-11], data_v[:, 11:-11 - shift], sps, amp_levels, num_lev, device)
+            if verbose:
+                print(epoch, torch.mean(torch.abs(e)).item(), shift, '\t\t\t\t\t\tSER = ', SER_valid[epoch // epe].item())
+    return SER_valid
