@@ -124,6 +124,10 @@ int vaeq_dp_force_generic(int32_t on);
  * loss / gradients (summation order of the per-CTA partials); 0 = static striding, bitwise reproducible. */
 int vaeq_dp_dynamic_tiles(int32_t on);
 
+/* Backward pass of the fast path: != 0 runs it as ONE warp-specialised launch (dp_bwd_fused.cu: TMA bulk loads, dL/dout
+ * never leaves the SM), 0 (default) = the three kernels of dp_fast.cu (dL/dout rows, dW, dh). */
+int vaeq_dp_fused_backward(int32_t on);
+
 /* forward only: q, out, loss, var_est  (net(minibatch) + loss_function_shaping, no grad) */
 int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream);
 /* forward + backward: additionally gW, gh (must be non-NULL); parameters are NOT updated */
