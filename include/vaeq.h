@@ -128,6 +128,12 @@ int vaeq_dp_dynamic_tiles(int32_t on);
  * never leaves the SM), 0 (default) = the three kernels of dp_fast.cu (dL/dout rows, dW, dh). */
 int vaeq_dp_fused_backward(int32_t on);
 
+/* Tap gradients of the fast path: != 0 (default) computes both correlations (dW, dh) on tcgen05 tensor cores as block outer products
+ * with a 3 x tf32 split and fp32 accumulation in TMEM (dp_taps_tc.cu: 116 us instead of 168 us per 2^22 symbols, agreement with the
+ * CUDA-core kernels 3e-7 ... 6e-6 relative, bitwise reproducible); 0 = the two CUDA-core correlation kernels of dp_fast.cu.  This
+ * departs from the hot path's stated "no tensor cores" design and was adopted on measurement (profiles/r02_tc_taps.txt). */
+int vaeq_dp_tc_taps(int32_t on);
+
 /* forward only: q, out, loss, var_est  (net(minibatch) + loss_function_shaping, no grad) */
 int vaeq_dp_forward(const vaeq_dp_desc *d, void *stream);
 /* forward + backward: additionally gW, gh (must be non-NULL); parameters are NOT updated */

@@ -13,8 +13,9 @@ h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = init("h0", "64-QAM", "cpu
 rxs = [generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, "cuda", 1 + i)[0] for i in range(3)]
 q = torch.empty(2, 16, B, device="cuda"); out = torch.empty(2, 2, B, device="cuda")
 NK = 11
-for fused in [int(a) for a in (sys.argv[1:] or ["1", "0"])]:
-    lib.vaeq_dp_fused_backward(fused)
+for fused in [int(a) for a in (sys.argv[1:] or ["2", "1", "0"])]:      # 2: tensor-core tap gradients, 1: fused CUDA-core backward, 0: three kernels
+    lib.vaeq_dp_fused_backward(1 if fused == 1 else 0)
+    lib.vaeq_dp_tc_taps(1 | int(os.environ.get('TC_DEBUG', 0)) if fused == 2 else 0)
     eq = DPEqualizer(M, 2, amp, P, var, nu_sc)
     for i in range(4):
         eq.train_step(rxs[i % 3], 2.5e-3, 2.5e-3, q=q, out=out)
@@ -34,6 +35,7 @@ for fused in [int(a) for a in (sys.argv[1:] or ["1", "0"])]:
     lib.vaeq_kernel_timing_read(ms, cnt)
     lib.vaeq_kernel_timing(0)
     per = {k: ms[k] / cnt[k] * 1e3 for k in range(NK) if cnt[k]}
-    print(f"fused_backward={fused}: step {plain * 1e3:.1f} us plain launches ({B / plain / 1e6:.2f} G symbols/s); kernels (us, by kind id): "
+    print(f"backward mode {fused}: step {plain * 1e3:.1f} us plain launches ({B / plain / 1e6:.2f} G symbols/s); kernels (us, by kind id): "
           + ", ".join(f"{k}: {v:.1f}" for k, v in per.items()) + f"; loss {float(eq.loss):.6g}")
 lib.vaeq_dp_fused_backward(0)
+lib.vaeq_dp_tc_taps(1)

@@ -19,6 +19,7 @@
 // (every (symbol, lag) pair counted once, partitioned by the position of the per-symbol operand).  DRAM: e 32 + E_q 16 +
 // S 48 + rx 32 = 128 B per symbol.  Reference: loss.backward() of loss_function_shaping sf:92-137 through twoXtwoFIR.forward sf:500-527.
 #include "dp_fast.cuh"
+#include "tma.cuh"
 
 namespace vaeq {
 
@@ -34,36 +35,6 @@ constexpr int FB_ES = FB_EN + FB_EN / 4 + 4;                // padded float4 len
 constexpr int FB_GS = FB_TE + FB_TE / 4 + 4;
 constexpr int FB_NBAR = 16;
 constexpr int FB_RB = 3;                                    // stages of the E_q / rx ring (consumed one tile later than the residual ring)
-
-// ---- mbarrier / TMA bulk copy (PTX) -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}" ::"r"(smem_u32(b)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- FIR-like contraction over a SWIZZLED window {re_0, re_1, im_0, im_1} (3-multiplication form, see dp_fast.cuh) -------------
 //     P1[r][o] += (tr_{o,0}, tr_{o,1}) * (re_0 + im_0, re_1 + im_1)
@@ -161,30 +132,6 @@ __device__ __forceinline__ void corr4m(const float4 *__restrict__ win, int q, co
     }
 }
 
-// producer: stage `nrows` row segments [start, start+len) of rows `src + r*ld` (clamped to [0, limit), the rest zero-filled) into
-// dst + r*len; the bytes the bulk copies will deliver are announced first (rows_bytes).
-__device__ __forceinline__ uint32_t rows_bytes(int nrows, int64_t start, int len, int64_t limit) {
-    const int64_t c0 = start < 0 ? 0 : start, c1 = start + len > limit ? limit : start + len;
-    return c1 > c0 ? (uint32_t)(nrows * (c1 - c0) * 4) : 0u;
-}
-__device__ __forceinline__ void rows_zero_fill(float *dst, int nrows, int64_t start, int len, int64_t limit, int lane) {
-    const int64_t c0 = start < 0 ? 0 : start, c1 = start + len > limit ? limit : start + len;
-    if (c0 == start && c1 == start + len) return;
-    const int n0 = c1 > c0 ? (int)(c0 - start) : len, n1 = c1 > c0 ? (int)(c1 - start) : len;   // keep [n0, n1)
-    for (int r = 0; r < nrows; ++r) {
-        for (int i = lane; i < n0; i += 32) dst[r * len + i] = 0.f;
-        for (int i = n1 + lane; i < len; i += 32) dst[r * len + i] = 0.f;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void rows_issue(float *dst, const float *src, int64_t ld, int nrows, int64_t start, int len, int64_t limit,
-                                           uint64_t *bar) {
-    const int64_t c0 = start < 0 ? 0 : start, c1 = start + len > limit ? limit : start + len;
-    if (c1 <= c0) return;
-    const uint32_t bytes = (uint32_t)((c1 - c0) * 4);
-    for (int r = 0; r < nrows; ++r) bulk_g2s(dst + r * len + (c0 - start), src + (int64_t)r * ld + c0, bytes, bar);
-}
-
 template <int MH>
 __global__ void __launch_bounds__(FB_NT, 1) k_dp_bwd_fused(DpK p) {
     constexpr int M = 2 * MH + 1, HF = MH / 2, NE = MH + 1, NO = MH, BASE = MH / 2, AMAX = BASE + 1;
@@ -248,18 +195,18 @@ __global__ void __launch_bounds__(FB_NT, 1) k_dp_bwd_fused(DpK p) {
             const int sa = it & 1, sb = it % FB_RB;
             const int64_t s0 = (int64_t)p.sym_lo + (int64_t)tile * FB_T - FB_HP;
             float *de = eraw + sa * 8 * FB_EN, *ds = sraw + sa * 12 * FB_TE, *dm = m1raw + sb * 4 * FB_TE, *dx = xraw + sb * 4 * 2 * FB_TE;
-            rows_zero_fill(de, 8, s0 - FB_EX, FB_EN, p.B, lane);
-            rows_zero_fill(ds, 12, s0, FB_TE, p.B, lane);
-            rows_zero_fill(dm, 4, s0, FB_TE, p.B, lane);
-            rows_zero_fill(dx, 4, 2 * s0, 2 * FB_TE, p.L, lane);
+            rows_zero_fill(de, 8, s0 - FB_EX, FB_EN, 0, p.B, lane);
+            rows_zero_fill(ds, 12, s0, FB_TE, 0, p.B, lane);
+            rows_zero_fill(dm, 4, s0, FB_TE, 0, p.B, lane);
+            rows_zero_fill(dx, 4, 2 * s0, 2 * FB_TE, 0, p.L, lane);
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(fullA + sa, rows_bytes(8, s0 - FB_EX, FB_EN, p.B) + rows_bytes(12, s0, FB_TE, p.B));
-                rows_issue(de, p.erows, p.B, 8, s0 - FB_EX, FB_EN, p.B, fullA + sa);
-                rows_issue(ds, p.srows, p.B, 12, s0, FB_TE, p.B, fullA + sa);
-                mbar_arrive_expect_tx(fullB + sb, rows_bytes(4, s0, FB_TE, p.B) + rows_bytes(4, 2 * s0, 2 * FB_TE, p.L));
-                rows_issue(dm, p.m1rows, p.B, 4, s0, FB_TE, p.B, fullB + sb);
-                rows_issue(dx, p.rx, p.ld_rx, 4, 2 * s0, 2 * FB_TE, p.L, fullB + sb);
+                mbar_arrive_expect_tx(fullA + sa, rows_bytes(8, s0 - FB_EX, FB_EN, 0, p.B) + rows_bytes(12, s0, FB_TE, 0, p.B));
+                rows_issue(de, p.erows, p.B, 8, s0 - FB_EX, FB_EN, 0, p.B, fullA + sa);
+                rows_issue(ds, p.srows, p.B, 12, s0, FB_TE, 0, p.B, fullA + sa);
+                mbar_arrive_expect_tx(fullB + sb, rows_bytes(4, s0, FB_TE, 0, p.B) + rows_bytes(4, 2 * s0, 2 * FB_TE, 0, p.L));
+                rows_issue(dm, p.m1rows, p.B, 4, s0, FB_TE, 0, p.B, fullB + sb);
+                rows_issue(dx, p.rx, p.ld_rx, 4, 2 * s0, 2 * FB_TE, 0, p.L, fullB + sb);
             }
         };
         if (wid == 2 * FB_NA && (int)blockIdx.x < nt) produce(blockIdx.x, 0);

@@ -630,7 +630,7 @@ static int fast_prepare(K kern, size_t smem, int *grid) {
     return VAEQ_OK;
 }
 
-extern bool g_fused_bwd;
+extern bool g_fused_bwd, g_tc_taps;
 template <int NL, int MH>
 static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
     static int grids[VAEQ_MAX_DEVICES][4] = {{0}};           // occupancy-derived grids and the shared-memory attribute are per device
@@ -668,6 +668,10 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
     k_dp_bwd1_fast<NL, MH><<<gb1, FT_NT, s1, st>>>(p);
     ktime_end(VAEQ_K_DP_BWD, st);
     VAEQ_LAUNCH_CHECK("k_dp_bwd1_fast");
+    if (g_tc_taps) {
+        int rc = VAEQ_OK;
+        if (dp_taps_tc_launch(p, st, grid_bwd_out, &rc)) return rc;
+    }
     ktime_begin(VAEQ_K_DP_BWD2, st);
     k_dp_taps_fast<MH, 0><<<gt, FT_NT, s2, st>>>(p);
     ktime_end(VAEQ_K_DP_BWD2, st);
@@ -681,6 +685,8 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
 }
 
 bool g_fused_bwd = false;   // until the fused launch beats the three kernels (profiles/r02_fused_backward.txt)
+
+bool g_tc_taps = true;      // both tap-gradient correlations on tcgen05 (dp_taps_tc.cu); false = the two CUDA-core correlation kernels
 
 // returns 1 if the fast path ran (and *grid_bwd_out is the number of gradient partials), 0 if not applicable
 int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bwd_out, int *rc) {
@@ -708,6 +714,13 @@ int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bw
 
 extern "C" int vaeq_dp_fused_backward(int32_t on) {
     vaeq::g_fused_bwd = on != 0;
+    return VAEQ_OK;
+}
+
+namespace vaeq { extern int g_tc_debug; }
+extern "C" int vaeq_dp_tc_taps(int32_t on) {
+    vaeq::g_tc_taps = on != 0;
+    vaeq::g_tc_debug = on & ~1;
     return VAEQ_OK;
 }
 

@@ -71,6 +71,8 @@ int dp_launch_fin(const DpK &p, int nparts, cudaStream_t st);
 int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bwd_out, int *rc);
 // dp_bwd_fused.cu: the fast path's backward pass as one launch; returns 0 if M_est does not qualify
 int dp_bwd_fused_launch(const DpK &p, cudaStream_t st, int *nparts, int *rc);
+// dp_taps_tc.cu: dW and dh on tcgen05 (after k_dp_bwd1_fast); returns 0 if M_est does not qualify
+int dp_taps_tc_launch(const DpK &p, cudaStream_t st, int *nparts, int *rc);
 constexpr int DP_MODE_SPLIT_FWD = 3, DP_MODE_SPLIT_BWD = 4;   // forward kernel only / backward kernels only (no fin, no adam)
 
 // batched independent runs of the frame kernels (vaeq_dp_train_frame_runs): blockIdx.x = run
