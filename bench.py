@@ -38,6 +38,7 @@ ALG_FLOP_PER_SYMBOL = 5 * 32 * M_EST + 1000
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (k_dp_fwd_fast<8,12>) at batch_len 2^22 from the
 # `ncu --set full` capture summarised in profiles/r01d_ncu_full_summary.json: 134.3 MB read + 948.1 MB written = 258.1 B/symbol
 FWD_DRAM_BYTES_PER_SYMBOL = (134.274e6 + 948.072e6) / (1 << 22)
+TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_dp_fwd_fast<8,12>, profiles/r01d_ncu_full_summary.json, scaled to this batch_len"
 CPU_SAMPLE_LOG2 = 17
 
 
@@ -221,6 +222,28 @@ def ours_arm(args, rank, local_rank, world):
     ms = e0.elapsed_time(e1)
     clocks = sampler.finish()
     launches = launches_per_step * K
+    # ---- sustained leg: the same graph replayed for >= 1 s (the K-step region above lasts milliseconds), with its own clock record ----
+    sustained = None
+    if not args.no_sustained:
+        n_rep = max(1, int(np.ceil(args.sustained_seconds * 1e3 / (ms / K * NB))))
+        s_sampler = ClockSampler(_nvml_index(local_rank))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s_sampler.start()
+        s0.record()
+        for _ in range(n_rep):
+            graph.replay()
+        s1.record()
+        while not s1.query():
+            time.sleep(0.002)
+        barrier()
+        s_ms = s0.elapsed_time(s1)
+        ts = torch.tensor([s_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sustained = {"value": world * B * NB * n_rep / (float(ts.item()) * 1e-3), "unit": UNIT, "steps": NB * n_rep, "seconds": float(ts.item()) * 1e-3,
+                     "ms_per_step": float(ts.item()) / (NB * n_rep), "clocks": s_sampler.finish(),
+                     "note": "same CUDA graph as the timed region, replayed back to back; max over ranks"}
     # ---- the same K steps as plain launches, and once more with the library's per-kernel event pairs on the launching stream
     # (12 event records per step: they cost ~30 us per step, so they stay out of the region `value` is taken from) ------------------
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -370,7 +393,7 @@ def ours_arm(args, rank, local_rank, world):
     step_gbs = B * ALG_BYTES_PER_SYMBOL * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (FWD_DRAM_BYTES_PER_SYMBOL * B if names[dom] == "k_dp_fwd" and M_EST == 25 else None),
-                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01d_ncu_full_summary.json, scaled to this batch_len)",
+                "traffic_unit": "bytes per launch", "traffic_source": TRAFFIC_SOURCE + " -- taken from that ncu capture, NOT measured in this run",
                 "peak_source": peak_src, "alg_bytes_per_symbol": ALG_BYTES_PER_SYMBOL,
                 "alg_bytes_per_launch": B * ALG_BYTES_PER_SYMBOL,
                 "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
@@ -390,6 +413,12 @@ def ours_arm(args, rank, local_rank, world):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{done} steps x 2^{CPU_SAMPLE_LOG2} symbols (first 2^{CPU_SAMPLE_LOG2} symbols of the workload), "
                          f"oracle/vaeq_oracle.py DPTrainer on torch CPU, {dt:.1f} s"}
+        other = {}
+        for b_cpu, n_cpu in ((100, 60), (10000, 20)):        # the reference's own batch_len and a mid size
+            rx_b = rx_dev[0][:, :, :SPS * b_cpu].cpu().contiguous()
+            r_b, d_b, t_b, _ = cpu_step_rate(rx_b, cst, n_cpu, 2, max_seconds=8.0)
+            other[str(b_cpu)] = {"value": r_b, "unit": UNIT, "steps": d_b, "seconds": t_b}
+        cpu["other_batch_len"] = other
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
@@ -409,10 +438,13 @@ def ours_arm(args, rank, local_rank, world):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    # extra legs live under `config` (the driver keeps the nested objects of the contract keys)
+    if sustained is not None:
+        line["config"]["sustained"] = sustained
     if split is not None:
-        line["batch_split"] = split
+        line["config"]["batch_split"] = split
     if small is not None:
-        line["reference_batch_len"] = small
+        line["config"]["reference_batch_len"] = small
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -429,6 +461,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the batch_len = 100 persistent-frame leg")
     ap.add_argument("--no-split", action="store_true", help="skip the batch-split (configs[2]) leg at N > 1")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 1 s sustained leg")
+    ap.add_argument("--sustained-seconds", type=float, default=1.5)
     ap.add_argument("--m-est", type=int, default=M_EST, help="equalizer / channel-estimate taps (default 25 = the BASELINE config; "
                     "5, 9, 13 show the HBM-bound regime, SURVEY.md §8d)")
     args = ap.parse_args()

@@ -463,3 +463,82 @@ def test_tensor_core_tap_gradients_against_the_cuda_core_kernels(M, mod, B):
     e_W, e_h = rel(res[1][0], res[0][0]), rel(res[1][1], res[0][1])
     print(f"tcgen05 vs CUDA-core tap gradients, M={M} {mod} B={B}: gW {e_W:.2e} gh {e_h:.2e}")
     assert e_W < 2e-5 and e_h < 2e-5
+
+
+@pytest.mark.parametrize("M,mod,B", [(25, "64-QAM", 1 << 20), (25, "64-QAM", 2016), (25, "64-QAM", 5 * 496 + 4), (25, "16-QAM", 49600),
+                                     (13, "64-QAM", 30000), (9, "64-QAM", 12348), (5, "64-QAM", 7936), (25, "4-QAM", 4000)])
+def test_tensor_core_forward_against_the_cuda_core_forward(M, mod, B):
+    """The forward kernel with the butterfly FIR and the channel convolution on tcgen05 (dp_fwd_tc.cu: Hankel operands, tf32 hi + lo
+    split, fp32 accumulation in TMEM) against k_dp_fwd_fast on the same inputs: out / q / loss / var_est / gradients inside the step
+    tolerances of DESIGN.md section 2 (both are then also compared with the reference goldens and the CPU oracle by the other tests)."""
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.datagen import generate_data_gpu
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", mod, "cpu", 0.0270955 if mod == "64-QAM" else 0.0, 2, M, 23)
+    rx = generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, "cuda", 7)[0]
+    gen = torch.Generator().manual_seed(3)
+    W0 = O.dirac_taps(M) + 0.02 * torch.randn(2, 4, M, generator=gen)
+    h0 = h_est.detach() + 0.02 * torch.randn(2, 2, 2, M, generator=gen)
+    res = {}
+    lib.vaeq_dp_dynamic_tiles(0)
+    try:
+        for tc in (1, 0):
+            lib.vaeq_dp_tc_forward(tc)
+            eq = DPEqualizer(M, 2, amp, torch.tensor(P, dtype=torch.float32), var, nu_sc, W0=W0, h0=h0)
+            r = eq.forward_backward(rx)
+            torch.cuda.synchronize()
+            res[tc] = [t.cpu().clone() for t in r]
+            if tc:
+                again = eq.forward_backward(rx)
+                torch.cuda.synchronize()
+                assert all(torch.equal(a.cpu(), b) for a, b in zip(again, res[1]))                         # static tiles: bitwise reproducible
+    finally:
+        lib.vaeq_dp_tc_forward(0)
+        lib.vaeq_dp_dynamic_tiles(1)
+    (q1, o1, l1, v1, gW1, gh1), (q0, o0, l0, v0, gW0, gh0) = res[1], res[0]
+    e_o, e_q = float((o1 - o0).abs().max()), float((q1 - q0).abs().max())
+    e_l, e_v, e_W, e_h = rel(l1, l0), rel(v1, v0), rel(gW1, gW0), rel(gh1, gh0)
+    print(f"tcgen05 vs CUDA-core forward, M={M} {mod} B={B}: out {e_o:.2e} q {e_q:.2e} loss {e_l:.2e} var_est {e_v:.2e} gW {e_W:.2e} gh {e_h:.2e}")
+    assert e_o < 2e-6 and e_q < 5e-5 and e_l < 1e-5 and e_v < 1e-5 and e_W < 1e-4 and e_h < 1e-4
+
+
+def _fir_float64(rx, W, M):
+    """The 2x2 butterfly FIR (sf:500-518) in float64 on the GPU: stride-2 correlation of the real-expanded channels."""
+    mh = (M - 1) // 2
+    x = rx.double().reshape(1, 4, -1)                                    # rows: pol0 I, pol0 Q, pol1 I, pol1 Q
+    Wd = W.double()
+    w = torch.zeros(4, 4, M, dtype=torch.float64, device=rx.device)
+    for o in range(2):
+        for i in range(2):
+            tr, ti = Wd[o, i], Wd[o, 2 + i]
+            w[2 * o, 2 * i], w[2 * o, 2 * i + 1] = tr, -ti               # Re = tr xr - ti xi
+            w[2 * o + 1, 2 * i], w[2 * o + 1, 2 * i + 1] = ti, tr        # Im = ti xr + tr xi
+    return torch.nn.functional.conv1d(x, w, stride=2, padding=mh)[0].reshape(2, 2, -1)
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+def test_forward_out_error_against_float64(tc):
+    """Equalizer output of both forward kernels against the same FIR in float64 at 2^20 symbols: the absolute error that the q
+    tolerance (5e-5, amplified ~50x from out) and the decision parity rest on.  Gate: max 2e-6, rms 3e-7."""
+    from vae_equalizer_b200 import _lib
+    from vae_equalizer_b200.datagen import generate_data_gpu
+    from vae_equalizer_b200.dp import DPEqualizer
+    lib = _lib.load()
+    M, B = 25, 1 << 20
+    h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = O.init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
+    rx = generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, "cuda", 7)[0]
+    gen = torch.Generator().manual_seed(3)
+    W0 = O.dirac_taps(M) + 0.05 * torch.randn(2, 4, M, generator=gen)
+    lib.vaeq_dp_tc_forward(tc)
+    try:
+        eq = DPEqualizer(M, 2, amp, torch.tensor(P, dtype=torch.float32), var, nu_sc, W0=W0)
+        q, out, loss, ve = eq.forward(rx)
+        torch.cuda.synchronize()
+    finally:
+        lib.vaeq_dp_tc_forward(0)
+    ref = _fir_float64(rx, W0.cuda(), M)
+    err = out.double() - ref
+    e_max, e_rms, bias = float(err.abs().max()), float(err.pow(2).mean().sqrt()), float((err * ref.sign()).mean())
+    print(f"forward kernel tc={tc}: out vs float64: max {e_max:.2e} rms {e_rms:.2e} mean error along sign(out) {bias:+.2e}")
+    assert e_max < 2e-6 and e_rms < 3e-7

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "vaeq_dp_dynamic_tiles": (C.c_int, [_i32]),
     "vaeq_dp_fused_backward": (C.c_int, [_i32]),
     "vaeq_dp_tc_taps": (C.c_int, [_i32]),
+    "vaeq_dp_tc_forward": (C.c_int, [_i32]),
     "vaeq_dp_forward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_forward_backward": (C.c_int, [C.POINTER(DpDesc), _vp]),
     "vaeq_dp_loss_from_q": (C.c_int, [C.POINTER(DpDesc), _vp, _i64, _vp]),

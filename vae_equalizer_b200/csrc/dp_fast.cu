@@ -140,14 +140,6 @@ __device__ __forceinline__ void tile_fetch_next(const DpK &p, int k, int cur, in
     if (threadIdx.x == 0) *s_next = p.dyn ? atomicAdd(p.tile_ctr + k, 1) + (int)gridDim.x : cur + (int)gridDim.x;
 }
 
-// SoA row helpers: 4 consecutive symbols of one row as a float4
-__device__ __forceinline__ float4 ld_row4(const float *base, int64_t ld, int row, int u) {
-    return __ldg(reinterpret_cast<const float4 *>(base + (int64_t)row * ld + u));
-}
-__device__ __forceinline__ void st_row4(float *base, int64_t ld, int row, int u, float4 v) {
-    *reinterpret_cast<float4 *>(base + (int64_t)row * ld + u) = v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -630,7 +622,7 @@ static int fast_prepare(K kern, size_t smem, int *grid) {
     return VAEQ_OK;
 }
 
-extern bool g_fused_bwd, g_tc_taps;
+extern bool g_fused_bwd, g_tc_taps, g_tc_fwd;
 template <int NL, int MH>
 static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
     static int grids[VAEQ_MAX_DEVICES][4] = {{0}};           // occupancy-derived grids and the shared-memory attribute are per device
@@ -649,13 +641,18 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
     const int gf = min(min(gF, DP_GRID_CAP), nt_f), gb1 = min(min(g1, DP_GRID_CAP), nt_b), gt = min(min(g2, DP_GRID_CAP), nt_b);
     if (mode != DP_MODE_SPLIT_BWD) {
         p.ntiles = nt_f;
-        ktime_begin(VAEQ_K_DP_FWD, st);
-        k_dp_fwd_fast<NL, MH><<<gf, FT_NT, sf, st>>>(p);
-        ktime_end(VAEQ_K_DP_FWD, st);
-        VAEQ_LAUNCH_CHECK("k_dp_fwd_fast");
-        *grid_bwd_out = gf;                                  // split forward: number of forward partials
+        int nparts_f = gf, rc_f = VAEQ_OK;
+        if (g_tc_fwd && dp_fwd_tc_launch(p, NL, st, &nparts_f, &rc_f)) {
+            if (rc_f) return rc_f;
+        } else {
+            ktime_begin(VAEQ_K_DP_FWD, st);
+            k_dp_fwd_fast<NL, MH><<<gf, FT_NT, sf, st>>>(p);
+            ktime_end(VAEQ_K_DP_FWD, st);
+            VAEQ_LAUNCH_CHECK("k_dp_fwd_fast");
+        }
+        *grid_bwd_out = nparts_f;                            // split forward: number of forward partials
         if (mode == DP_MODE_SPLIT_FWD) return VAEQ_OK;
-        const int rc = dp_launch_fin(p, gf, st);
+        const int rc = dp_launch_fin(p, nparts_f, st);
         if (rc) return rc;
     }
     if (mode == DP_MODE_FWD) return VAEQ_OK;
@@ -686,6 +683,9 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
 
 bool g_fused_bwd = false;   // until the fused launch beats the three kernels (profiles/r02_fused_backward.txt)
 
+bool g_tc_fwd = false;      // forward kernel with the FIR and the channel convolution on tcgen05 (dp_fwd_tc.cu): measured, not faster than
+                            // k_dp_fwd_fast at equal accuracy (profiles/r02_tc_forward.txt) -> opt-in through vaeq_dp_tc_forward(1)
+
 bool g_tc_taps = true;      // both tap-gradient correlations on tcgen05 (dp_taps_tc.cu); false = the two CUDA-core correlation kernels
 
 // returns 1 if the fast path ran (and *grid_bwd_out is the number of gradient partials), 0 if not applicable
@@ -714,6 +714,11 @@ int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bw
 
 extern "C" int vaeq_dp_fused_backward(int32_t on) {
     vaeq::g_fused_bwd = on != 0;
+    return VAEQ_OK;
+}
+
+extern "C" int vaeq_dp_tc_forward(int32_t on) {
+    vaeq::g_tc_fwd = on != 0;
     return VAEQ_OK;
 }
 

@@ -32,6 +32,14 @@ __host__ __device__ constexpr int fdiv4(int c) { return c >= 0 ? c / 4 : -((3 - 
 __host__ __device__ constexpr int poff(int c) { return c + fdiv4(c); }
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 2); }
 __device__ __forceinline__ float f4c(const float4 &v, int r) { return r == 0 ? v.x : r == 1 ? v.y : r == 2 ? v.z : v.w; }
+// SoA row helpers: 4 consecutive symbols of one row as a float4
+__device__ __forceinline__ float4 ld_row4(const float *base, int64_t ld, int row, int u) {
+    return __ldg(reinterpret_cast<const float4 *>(base + (int64_t)row * ld + u));
+}
+__device__ __forceinline__ void st_row4(float *base, int64_t ld, int row, int u, float4 v) {
+    *reinterpret_cast<float4 *>(base + (int64_t)row * ld + u) = v;
+}
+
 constexpr int FT_XS = FT_XN + FT_XN / 4 + 4;   // padded lengths (float4)
 constexpr int FT_ES = FT_TE + FT_TE / 4 + 4;
 

@@ -73,6 +73,8 @@ int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bw
 int dp_bwd_fused_launch(const DpK &p, cudaStream_t st, int *nparts, int *rc);
 // dp_taps_tc.cu: dW and dh on tcgen05 (after k_dp_bwd1_fast); returns 0 if M_est does not qualify
 int dp_taps_tc_launch(const DpK &p, cudaStream_t st, int *nparts, int *rc);
+// dp_fwd_tc.cu: the fast path's forward kernel with the FIR and the channel convolution on tcgen05; returns 0 if (n_lev, M_est) is not built
+int dp_fwd_tc_launch(const DpK &p, int n_lev, cudaStream_t st, int *nparts, int *rc);
 constexpr int DP_MODE_SPLIT_FWD = 3, DP_MODE_SPLIT_BWD = 4;   // forward kernel only / backward kernels only (no fin, no adam)
 
 // batched independent runs of the frame kernels (vaeq_dp_train_frame_runs): blockIdx.x = run
