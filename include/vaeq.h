@@ -214,6 +214,30 @@ int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi,
 int vaeq_dp_split_backward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, const double *stats_in, float *grads_out,
                            void *stream);
 int vaeq_dp_split_update(const vaeq_dp_desc *d, const float *grads_in, float lr_w, float lr_h, void *stream);
+/* q / out of the three calls above and of vaeq_dp_split_step_peer are touched in the columns [max(0, sym_lo - 16), min(B, sym_hi + 16))
+ * only, so a rank may pass a buffer that holds just those columns, its base pointers shifted back by the first column; d->q_keep /
+ * d->out_keep (if set) receive the kept columns [keep_lo, keep_lo + keep_n) that lie inside [sym_lo, sym_hi), at column u - keep_lo;
+ * with them set, d->q = d->out = NULL is allowed: the window's q / out are then not written at all (the VAE-flex frame loop keeps the
+ * middle flex_step symbols of every window and nothing else, func_VAEflex_DP_MQAM_shaping.py:64-67).
+ *
+ * The same step with BOTH reductions done by the library itself over NVLink peer memory instead of two host-issued all-reduces: every
+ * rank allocates a slot of vaeq_peer_slot_bytes(M) bytes, zero-initialised, in memory all peers can address (CUDA IPC / VMM, e.g.
+ * torch.distributed._symmetric_memory) and passes the `world` peer-mapped pointers in rank order (slot[rank] = its own) plus two
+ * zero-initialised int32 counters in its own device memory.  One call = forward, exchange of the ELBO sums, loss / kappa, backward,
+ * exchange of the 16 M gradient floats, replicated Adam: 8 launches, no host synchronisation, graph-capturable.  An exchange is a PUSH:
+ * a rank stores its partial into its own compartment of EVERY peer's slot, fences, raises that compartment's epoch word in every slot,
+ * then polls the epoch words of its own slot (local memory) and adds the compartments in rank order -- bit-identical on every rank, one
+ * NVLink store latency whatever the number of ranks.  All ranks must make the same sequence of calls; a peer that does not show up
+ * within 20 s traps the kernel. */
+#define VAEQ_MAX_PEERS 8
+typedef struct vaeq_peer_comm {
+    int32_t rank, world;
+    void *slot[VAEQ_MAX_PEERS];
+    int32_t *epoch;
+} vaeq_peer_comm;
+size_t vaeq_peer_slot_bytes(int32_t M);
+int vaeq_dp_split_step_peer(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, const vaeq_peer_comm *comm, float lr_w, float lr_h,
+                            void *stream);
 
 /* generic Adam update on n floats (torch.optim.Adam single-tensor semantics); state = [m|v|vmax] (3n floats),
  * step_count is a device int32 incremented by the call when bump_step != 0 */

@@ -68,3 +68,57 @@ def test_gloo_world2_shard_gather_allreduce():
     assert full1 is None and full0 == [1500.0, 1501.0, 1502.0, 1700.0, 1701.0, 1702.0, 1900.0, 1901.0, 1902.0]
     assert st0 == st1 == [3.0, 30.0]
     assert rg0 == (0, 8 * par.TILE) and rg1 == (8 * par.TILE, 16 * par.TILE)
+
+
+def test_kept_owner_ranges_tile_the_kept_section():
+    for B, world, stride in ((496 * 64, 2, 496 * 32), (1 << 22, 8, 1 << 21), (496 * 12, 5, 496 * 6), (4032, 3, 1000)):
+        keep_lo = (B - stride) // 2
+        parts = par.kept_owner_ranges(B, world, keep_lo, stride)
+        assert len(parts) == world and sum(b - a for a, b in parts) == stride
+        nonempty = [(a, b) for a, b in parts if b > a]
+        assert nonempty[0][0] == 0 and nonempty[-1][1] == stride
+        assert all(b == c for (_, b), (c, _) in zip(nonempty, nonempty[1:]))
+
+
+class _FakeEq:
+    device, sps, M, n_lev = torch.device("cpu"), 2, 25, 8
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, stride, n_steps = 496 * 8, 496 * 4, 3
+        keep_lo = (B - stride) // 2
+        bs = par.BatchSplitDP(_FakeEq(), None, "nccl")             # host logic only: ranges, kept-column exchange
+        lo, hi, col0, n = bs.local_columns(B)
+        ot, oc = torch.zeros(2, 16, n_steps * stride), torch.zeros(2, 2, n_steps * stride)
+        a, b = par.kept_owner_ranges(B, world, keep_lo, stride)[rank]
+        for m in range(n_steps):                                   # what the forward kernel leaves: this rank's part of every kept section
+            cols = torch.arange(m * stride + a, m * stride + b, dtype=torch.float32)
+            ot[:, :, m * stride + a:m * stride + b] = cols
+            oc[:, :, m * stride + a:m * stride + b] = -cols
+        bs.gather_kept(B, stride, n_steps, ot, oc, keep_lo, stride, dst=0)
+        full = torch.arange(n_steps * stride, dtype=torch.float32)
+        ok = bool((ot == full).all() and (oc == -full).all()) if rank == 0 else True
+        q.put((rank, ok, (lo, hi, col0, n)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_kept_columns():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1]
+    assert res[0][2] == (0, 496 * 4, 0, 496 * 4 + 16) and res[1][2] == (496 * 4, 496 * 8, 496 * 4 - 16, 496 * 4 + 16)

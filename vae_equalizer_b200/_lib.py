@@ -48,6 +48,11 @@ class DpRuns(C.Structure):
     ]
 
 
+class PeerComm(C.Structure):
+    """Mirror of `struct vaeq_peer_comm`: peer-mapped slot pointers of the batch-split ranks (vaeq_dp_split_step_peer)."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("slot", C.c_void_p * 8), ("epoch", C.c_void_p)]
+
+
 class AwgnDesc(C.Structure):
     """Mirror of `struct vaeq_awgn_desc`."""
     _fields_ = [
@@ -92,6 +97,8 @@ PROTOTYPES = {
     "vaeq_dp_split_forward": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _vp, _vp]),
     "vaeq_dp_split_backward": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, _vp, _vp, _vp]),
     "vaeq_dp_split_update": (C.c_int, [C.POINTER(DpDesc), _vp, _f, _f, _vp]),
+    "vaeq_peer_slot_bytes": (_sz, [_i32]),
+    "vaeq_dp_split_step_peer": (C.c_int, [C.POINTER(DpDesc), _i32, _i32, C.POINTER(PeerComm), _f, _f, _vp]),
     "vaeq_adam_update": (C.c_int, [_vp, _vp, _vp, _i32, _f, _i32, _vp, _i32, _vp]),
     "vaeq_soft_dec": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i32, _i32, _vp, _i64, _vp]),
     "vaeq_find_shift_scratch_bytes": (_sz, [_i32]),

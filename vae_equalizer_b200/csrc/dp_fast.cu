@@ -229,25 +229,36 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
                         reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1v[r];
                     }
                     if (owned) {
+                        if (p.q != nullptr) {                // NULL in the frame loops that only keep a section of every window
 #pragma unroll
-                        for (int l = 0; l < NL; ++l)
-                            st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
-                        st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
+                            for (int l = 0; l < NL; ++l)
+                                st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
+                            st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
+                        }
                         st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
                         if (p.need_bwd) {
                             st_row4(p.srows, p.B, cc, u0, make_float4(s1v[0], s1v[1], s1v[2], s1v[3]));
                             st_row4(p.srows, p.B, 4 + cc, u0, make_float4(t2v[0], t2v[1], t2v[2], t2v[3]));
                             st_row4(p.srows, p.B, 8 + cc, u0, make_float4(s3v[0], s3v[1], s3v[2], s3v[3]));
                         }
-                        if (p.qk != nullptr) {
+                        if (p.qk != nullptr && counted) {    // batch-split: the rank that counts a symbol keeps it
+                            const int k0 = u0 - p.keep_lo;
+                            if (p.keep_vec && k0 >= 0 && k0 + FT_R <= p.keep_n) {            // all four symbols kept, 16-byte aligned destination
+                                const int64_t col = p.keep_base + k0;
+#pragma unroll
+                                for (int l = 0; l < NL; ++l)
+                                    *reinterpret_cast<float4 *>(p.qk + (int64_t)(cc * NL + l) * p.ld_qk + col) = make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]);
+                                *reinterpret_cast<float4 *>(p.outk + (int64_t)cc * p.ld_outk + col) = make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]);
+                            } else if (k0 > -FT_R && k0 < p.keep_n) {
 #pragma unroll 1
-                            for (int r = 0; r < FT_R; ++r) {
-                                const int u = u0 + r;
-                                if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
-                                    const int64_t col = p.keep_base + (u - p.keep_lo);
-                                    for (int l = 0; l < NL; ++l)
-                                        p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
-                                    p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
+                                for (int r = 0; r < FT_R; ++r) {
+                                    const int u = u0 + r;
+                                    if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
+                                        const int64_t col = p.keep_base + (u - p.keep_lo);
+                                        for (int l = 0; l < NL; ++l)
+                                            p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
+                                        p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
+                                    }
                                 }
                             }
                         }
@@ -637,6 +648,8 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
         g2 = g3 = min(g2, g3);                               // both write the same per-CTA partial slots
     }
     p.T = FT_T;
+    p.keep_vec = p.qk != nullptr && p.keep_lo % 4 == 0 && p.keep_base % 4 == 0 && p.ld_qk % 4 == 0 && p.ld_outk % 4 == 0 &&
+                 (reinterpret_cast<uintptr_t>(p.qk) | reinterpret_cast<uintptr_t>(p.outk)) % 16 == 0;
     const int nt_f = (p.chi - p.clo + FT_T - 1) / FT_T, nt_b = (p.sym_hi - p.sym_lo + FT_T - 1) / FT_T;
     const int gf = min(min(gF, DP_GRID_CAP), nt_f), gb1 = min(min(g1, DP_GRID_CAP), nt_b), gt = min(min(g2, DP_GRID_CAP), nt_b);
     if (mode != DP_MODE_SPLIT_BWD) {
@@ -690,7 +703,8 @@ bool g_tc_taps = true;      // both tap-gradient correlations on tcgen05 (dp_tap
 
 // returns 1 if the fast path ran (and *grid_bwd_out is the number of gradient partials), 0 if not applicable
 int dp_try_fast(const DpK &p, int n_lev, int mode, cudaStream_t st, int *grid_bwd_out, int *rc) {
-    const bool aligned = (p.B % 4 == 0) && (p.ld_rx % 4 == 0) && (p.ld_q % 4 == 0) && (p.ld_out % 4 == 0) &&
+    const bool no_q = p.q == nullptr;                        // frame loops of the batch-split: only the kept columns are wanted
+    const bool aligned = (p.B % 4 == 0) && (p.ld_rx % 4 == 0) && (no_q || ((p.ld_q % 4 == 0) && (p.ld_out % 4 == 0))) &&
                          ((reinterpret_cast<uintptr_t>(p.rx) | reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.out)) % 16 == 0);
     if (!aligned || p.B < 2 * FT_T) return 0;                // small batches: the generic kernels (one tile) are as good
     if ((p.sym_lo | p.sym_hi | p.clo | p.chi) % 4 != 0) return 0;

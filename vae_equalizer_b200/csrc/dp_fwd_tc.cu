@@ -297,25 +297,36 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
                         *reinterpret_cast<float *>(qlo + off) = tf32_lo_part(m1v[r]);
                     }
                     if (owned) {
+                        if (p.q != nullptr) {                // NULL in the frame loops that only keep a section of every window
 #pragma unroll
-                        for (int l = 0; l < NL; ++l)
-                            st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
-                        st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
+                            for (int l = 0; l < NL; ++l)
+                                st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
+                            st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
+                        }
                         st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
                         if (p.need_bwd) {
                             st_row4(p.srows, p.B, cc, u0, make_float4(s1v[0], s1v[1], s1v[2], s1v[3]));
                             st_row4(p.srows, p.B, 4 + cc, u0, make_float4(t2v[0], t2v[1], t2v[2], t2v[3]));
                             st_row4(p.srows, p.B, 8 + cc, u0, make_float4(s3v[0], s3v[1], s3v[2], s3v[3]));
                         }
-                        if (p.qk != nullptr) {
+                        if (p.qk != nullptr && counted) {    // batch-split: the rank that counts a symbol keeps it
+                            const int k0 = u0 - p.keep_lo;
+                            if (p.keep_vec && k0 >= 0 && k0 + FT_R <= p.keep_n) {            // all four symbols kept, 16-byte aligned destination
+                                const int64_t col = p.keep_base + k0;
+#pragma unroll
+                                for (int l = 0; l < NL; ++l)
+                                    *reinterpret_cast<float4 *>(p.qk + (int64_t)(cc * NL + l) * p.ld_qk + col) = make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]);
+                                *reinterpret_cast<float4 *>(p.outk + (int64_t)cc * p.ld_outk + col) = make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]);
+                            } else if (k0 > -FT_R && k0 < p.keep_n) {
 #pragma unroll 1
-                            for (int r = 0; r < FT_R; ++r) {
-                                const int u = u0 + r;
-                                if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
-                                    const int64_t col = p.keep_base + (u - p.keep_lo);
-                                    for (int l = 0; l < NL; ++l)
-                                        p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
-                                    p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
+                                for (int r = 0; r < FT_R; ++r) {
+                                    const int u = u0 + r;
+                                    if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
+                                        const int64_t col = p.keep_base + (u - p.keep_lo);
+                                        for (int l = 0; l < NL; ++l)
+                                            p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
+                                        p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
+                                    }
                                 }
                             }
                         }

@@ -34,6 +34,7 @@ struct DpK {
     int64_t ld_outk;
     int keep_lo, keep_n;
     int64_t keep_base;            // destination column of symbol keep_lo
+    int keep_vec;                 // fast path: keep_lo, keep_base, the keep strides and pointers allow float4 stores of four kept symbols
     double *part_fwd;             // [grid][8]: C0, C1, entropy, sum Var pol0, sum Var pol1
     float *edge_vs;               // [2][2*mh]: Var_I+Var_Q of the first mh and last mh symbols
     float *scal;

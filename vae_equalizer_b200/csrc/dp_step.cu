@@ -717,14 +717,18 @@ static bool g_dynamic_tiles = true;
 static int g_persistent_frames = 1;   // 0: per-step launches, 1: dp_small.cu (default), 2: generic bodies in one launch
 static int g_persistent_frames_mode() { return g_persistent_frames; }
 
-static int dp_validate(const vaeq_dp_desc *d, bool need_grads, bool need_adam) {
+// cols_qout >= 0: q / out need only hold that many columns per row (batch-split ranks pass buffers of their own columns)
+static int dp_validate(const vaeq_dp_desc *d, bool need_grads, bool need_adam, int64_t cols_qout = -1) {
     VAEQ_CHECK_ARG(d != nullptr, "desc is NULL");
     VAEQ_CHECK_ARG(d->sps == 2, "sps=%d: only sps=2 is implemented (every reference driver uses 2)", d->sps);
     VAEQ_CHECK_ARG(d->M >= 1 && d->M <= VAEQ_MAX_TAPS && (d->M & 1), "M_est=%d must be odd and <= %d", d->M, VAEQ_MAX_TAPS);
     VAEQ_CHECK_ARG(d->n_lev == 2 || d->n_lev == 4 || d->n_lev == 8, "n_lev=%d must be 2, 4 or 8", d->n_lev);
     VAEQ_CHECK_ARG(d->B > 2 * (d->M / 2), "batch_len=%d must exceed M_est-1=%d (the loss's valid region is empty)", d->B, 2 * (d->M / 2));
-    VAEQ_CHECK_ARG(d->rx && d->amp && d->P && d->var && d->W && d->h && d->q && d->out, "NULL tensor pointer");
-    VAEQ_CHECK_ARG(d->ld_rx >= (int64_t)d->B * d->sps && d->ld_q >= d->B && d->ld_out >= d->B, "row stride smaller than the row");
+    // batch-split calls may pass q = out = NULL together with q_keep / out_keep: only the kept section of the window is wanted then
+    const bool no_q = cols_qout >= 0 && !d->q && !d->out && (cols_qout == 0 || (d->q_keep && d->out_keep));   // cols 0: the call touches neither
+    VAEQ_CHECK_ARG(d->rx && d->amp && d->P && d->var && d->W && d->h && ((d->q && d->out) || no_q), "NULL tensor pointer");
+    const int64_t need_cols = no_q ? 0 : cols_qout >= 0 ? cols_qout : (int64_t)d->B;
+    VAEQ_CHECK_ARG(d->ld_rx >= (int64_t)d->B * d->sps && d->ld_q >= need_cols && d->ld_out >= need_cols, "row stride smaller than the row");
     VAEQ_CHECK_ARG(!need_grads || need_adam || (d->gW && d->gh), "gW/gh must be given");
     VAEQ_CHECK_ARG(!need_adam || d->adam, "adam state is NULL");
     VAEQ_CHECK_ARG(d->workspace != nullptr, "workspace is NULL");
@@ -1034,6 +1038,94 @@ __global__ void k_dp_reduce_gpart(DpK p, int nparts, float *grads) {
     a = warp_sum(a);
     if (lane == 0) grads[i] = (float)a;
 }
+// ---- one-shot peer reductions over NVLink (vaeq_dp_split_step_peer) --------------------------------------------------------------
+// PUSH model: every rank owns a slot in symmetric memory with one COMPARTMENT per sender.  A reduction is: store my partial into
+// compartment `rank` of EVERY peer's slot (remote stores pipeline over NVLink; nobody reads remote memory), fence, store the epoch word
+// of that compartment in every slot; then poll the epoch words of MY OWN slot (local memory) and add the compartments in rank order, so
+// all ranks compute bit-identical sums (the replicated Adam step depends on it).  Cost: one NVLink store latency + one fence,
+// independent of the number of ranks.  The two exchanges of a step alternate, which is what makes one buffer per exchange enough:
+// nobody can send exchange k + 1 before everybody has read exchange k (see include/vaeq.h).
+struct PeerK {
+    int rank, world;
+    unsigned char *slot[VAEQ_MAX_PEERS];
+    int *epoch;                                              // local: [0] ELBO-sum exchanges done, [1] gradient exchanges done
+    int comp;                                                // bytes per compartment
+};
+constexpr int PEER_HDR = 256;                                // epoch words of a compartment: [0] sums, [32] gradients (128 bytes apart)
+__host__ __device__ inline size_t peer_stats_bytes(int M) { return (size_t)(8 + 4 * (M / 2)) * sizeof(double); }
+__host__ __device__ inline size_t peer_comp_bytes(int M) { return (PEER_HDR + peer_stats_bytes(M) + (size_t)16 * M * sizeof(float) + 255) / 256 * 256; }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// after every thread has stored its part of the partial into the peers' compartments: make the stores visible, raise the epoch word of
+// my compartment in every slot, then wait until all senders' epoch words in MY slot have reached the same epoch (a sender that never
+// arrives traps after 20 s).  One thread per peer does the flag traffic.
+__device__ __forceinline__ void peer_signal_and_wait(const PeerK &c, int which) {
+    __threadfence_system();
+    __syncthreads();
+    const unsigned e = (unsigned)(*reinterpret_cast<volatile int *>(c.epoch + which) + 1);
+    if ((int)threadIdx.x < c.world) {
+        st_release_sys(reinterpret_cast<unsigned *>(c.slot[threadIdx.x] + (size_t)c.rank * c.comp) + 32 * which, e);
+        const unsigned *flag = reinterpret_cast<const unsigned *>(c.slot[c.rank] + (size_t)threadIdx.x * c.comp) + 32 * which;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(flag) - e) < 0) {
+            if (globaltimer_ns() - t0 > 20000000000ull) __trap();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) c.epoch[which] = (int)e;
+}
+__global__ void __launch_bounds__(256) k_dp_peer_reduce_stats(DpK p, int nparts, PeerK c) {
+    __shared__ double st[8 + 4 * (VAEQ_MAX_TAPS / 2)];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, ns = 8 + 4 * p.mh;
+    if (wid < 5) {
+        double a = 0.0;
+        for (int b = lane; b < nparts; b += 32) a += p.part_fwd[(int64_t)b * 8 + wid];
+        a = warp_sum(a);
+        if (lane == 0) st[wid] = a;
+    }
+    if (threadIdx.x >= 5 && threadIdx.x < 8) st[threadIdx.x] = 0.0;
+    for (int i = threadIdx.x; i < 4 * p.mh; i += blockDim.x) st[8 + i] = (double)p.edge_vs[i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < c.world * ns; idx += blockDim.x) {      // my sums -> compartment `rank` of every slot
+        const int r = idx / ns, i = idx - r * ns;
+        reinterpret_cast<double *>(c.slot[r] + (size_t)c.rank * c.comp + PEER_HDR)[i] = st[i];
+    }
+    peer_signal_and_wait(c, 0);
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        double a = 0.0;
+        for (int r = 0; r < c.world; ++r) a += *reinterpret_cast<const volatile double *>(c.slot[c.rank] + (size_t)r * c.comp + PEER_HDR + 8 * i);
+        if (i < 8) p.part_fwd[i] = a;
+        else p.edge_vs[i - 8] = (float)a;
+    }
+}
+// gradients: p.gfinal holds this rank's partial (k_dp_reduce_gpart); the sum over the ranks lands in row 0 of p.gpart, where Adam reads it
+__global__ void __launch_bounds__(1024) k_dp_peer_reduce_grads(DpK p, PeerK c) {
+    const size_t off = PEER_HDR + peer_stats_bytes(p.M);
+    const int n = 16 * p.M;
+    for (int idx = threadIdx.x; idx < c.world * n; idx += blockDim.x) {
+        const int r = idx / n, i = idx - r * n;
+        reinterpret_cast<float *>(c.slot[r] + (size_t)c.rank * c.comp + off)[i] = p.gfinal[i];
+    }
+    peer_signal_and_wait(c, 1);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = 0.0;
+        for (int r = 0; r < c.world; ++r) a += (double)*reinterpret_cast<const volatile float *>(c.slot[c.rank] + (size_t)r * c.comp + off + 4 * i);
+        p.gpart[i] = (float)a;
+    }
+}
+static int64_t split_cols(const vaeq_dp_desc *d, int32_t lo, int32_t hi) {      // columns a rank writes: its range widened by DP_SPLIT_EXT
+    if (d == nullptr || lo < 0 || hi > d->B || lo >= hi) return -1;                // (bad ranges are reported by split_check)
+    return (int64_t)min(d->B, hi + DP_SPLIT_EXT) - max(0, lo - DP_SPLIT_EXT);
+}
 static int split_check(const vaeq_dp_desc *d, int32_t lo, int32_t hi) {
     VAEQ_CHECK_ARG(lo >= 0 && hi <= d->B && lo < hi && lo % 4 == 0 && hi % 4 == 0, "bad symbol range [%d,%d) (multiples of 4 inside [0,B))", lo, hi);
     return VAEQ_OK;
@@ -1043,7 +1135,7 @@ static int split_check(const vaeq_dp_desc *d, int32_t lo, int32_t hi) {
 extern "C" size_t vaeq_dp_split_stats_doubles(int32_t M) { return (size_t)8 + 4 * (M / 2); }
 
 extern "C" int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, double *stats_out, void *stream) {
-    int rc = dp_validate(d, false, false);
+    int rc = dp_validate(d, false, false, split_cols(d, sym_lo, sym_hi));
     if (rc) return rc;
     if ((rc = split_check(d, sym_lo, sym_hi))) return rc;
     VAEQ_CHECK_ARG(stats_out != nullptr, "stats_out is NULL");
@@ -1068,7 +1160,7 @@ extern "C" int vaeq_dp_split_forward(const vaeq_dp_desc *d, int32_t sym_lo, int3
 
 extern "C" int vaeq_dp_split_backward(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, const double *stats_in,
                                       float *grads_out, void *stream) {
-    int rc = dp_validate(d, false, false);
+    int rc = dp_validate(d, false, false, 0);                // the backward kernels read the scratch rows, not q / out
     if (rc) return rc;
     if ((rc = split_check(d, sym_lo, sym_hi))) return rc;
     VAEQ_CHECK_ARG(stats_in && grads_out, "stats_in / grads_out is NULL");
@@ -1093,12 +1185,57 @@ extern "C" int vaeq_dp_split_backward(const vaeq_dp_desc *d, int32_t sym_lo, int
 }
 
 extern "C" int vaeq_dp_split_update(const vaeq_dp_desc *d, const float *grads_in, float lr_w, float lr_h, void *stream) {
-    int rc = dp_validate(d, true, true);
+    int rc = dp_validate(d, true, true, 0);                  // the update touches neither q nor out
     if (rc) return rc;
     VAEQ_CHECK_ARG(grads_in != nullptr, "grads_in is NULL");
     DpK p = dp_make_params(d);
     p.gpart = const_cast<float *>(grads_in);
     return dp_launch_adam(p, 1, DP_MODE_TRAIN, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0, (cudaStream_t)stream);
+}
+
+extern "C" size_t vaeq_peer_slot_bytes(int32_t M) { return (size_t)VAEQ_MAX_PEERS * peer_comp_bytes(M); }
+
+extern "C" int vaeq_dp_split_step_peer(const vaeq_dp_desc *d, int32_t sym_lo, int32_t sym_hi, const vaeq_peer_comm *comm, float lr_w, float lr_h,
+                                       void *stream) {
+    int rc = dp_validate(d, true, true, split_cols(d, sym_lo, sym_hi));
+    if (rc) return rc;
+    if ((rc = split_check(d, sym_lo, sym_hi))) return rc;
+    VAEQ_CHECK_ARG(comm != nullptr && comm->world >= 1 && comm->world <= VAEQ_MAX_PEERS && comm->rank >= 0 && comm->rank < comm->world && comm->epoch != nullptr,
+                   "bad peer communicator (world 1..%d, rank inside it, epoch counters)", VAEQ_MAX_PEERS);
+    PeerK c;
+    c.rank = comm->rank; c.world = comm->world; c.epoch = comm->epoch; c.comp = (int)peer_comp_bytes(d->M);
+    for (int r = 0; r < VAEQ_MAX_PEERS; ++r) {
+        c.slot[r] = r < comm->world ? static_cast<unsigned char *>(comm->slot[r]) : nullptr;
+        VAEQ_CHECK_ARG(r >= comm->world || (c.slot[r] != nullptr && reinterpret_cast<uintptr_t>(c.slot[r]) % 16 == 0), "peer slot %d is NULL or unaligned", r);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DpK p = dp_make_params(d);
+    p.sym_lo = sym_lo; p.sym_hi = sym_hi;
+    p.clo = max(0, sym_lo - DP_SPLIT_EXT); p.chi = min(d->B, sym_hi + DP_SPLIT_EXT);
+    VAEQ_CUDA(cudaMemsetAsync(p.edge_vs, 0, 4 * (VAEQ_MAX_TAPS / 2 + 1) * sizeof(float), st));
+    if (p.dyn) VAEQ_CUDA(cudaMemsetAsync(p.tile_ctr, 0, 4 * sizeof(int), st));
+    int nparts = 0, rc2 = VAEQ_OK;
+    if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_FWD, st, &nparts, &rc2)) {
+        set_error("batch-split needs the fast path: M_est in {5,9,13,25}, 16-byte aligned rows, B %% 4 == 0, B >= 992");
+        return VAEQ_EINVAL;
+    }
+    if (rc2) return rc2;
+    ktime_begin(VAEQ_K_DP_FIN, st);
+    k_dp_peer_reduce_stats<<<1, 256, 0, st>>>(p, nparts, c);
+    ktime_end(VAEQ_K_DP_FIN, st);
+    VAEQ_LAUNCH_CHECK("k_dp_peer_reduce_stats");
+    if ((rc = dp_launch_fin(p, 1, st))) return rc;
+    if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_BWD, st, &nparts, &rc2)) {
+        set_error("batch-split needs the fast path");
+        return VAEQ_EINVAL;
+    }
+    if (rc2) return rc2;
+    ktime_begin(VAEQ_K_DP_ADAM, st);
+    k_dp_reduce_gpart<<<(16 * p.M + 7) / 8, 256, 0, st>>>(p, nparts, p.gfinal);
+    k_dp_peer_reduce_grads<<<1, 1024, 0, st>>>(p, c);
+    ktime_end(VAEQ_K_DP_ADAM, st);
+    VAEQ_LAUNCH_CHECK("k_dp_peer_reduce_grads");
+    return dp_launch_adam(p, 1, DP_MODE_TRAIN, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0, st);
 }
 
 extern "C" int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,

@@ -73,7 +73,9 @@ class DPEqualizer:
     def step_count(self) -> int:
         return int(self.adam[48 * self.M:48 * self.M + 1].view(torch.int32).item())
 
-    def _desc(self, rx, q, out, B, ld_rx=None, q_keep=None, out_keep=None, keep_lo=0, keep_n=0):
+    def _desc(self, rx, q, out, B, ld_rx=None, q_keep=None, out_keep=None, keep_lo=0, keep_n=0, col0=0):
+        """col0 != 0: q / out hold the columns [col0, col0 + q.shape[-1]) of the minibatch only (batch-split ranks); the descriptor
+        then carries base pointers shifted back by col0 columns -- the library touches no column outside the rank's range."""
         _require_cuda(rx, "rx")
         ws = self._workspace(B)
         d = _lib.DpDesc()
@@ -82,8 +84,9 @@ class DPEqualizer:
         d.rx, d.ld_rx = rx.data_ptr(), int(rx.stride(1) if ld_rx is None else ld_rx)
         d.amp, d.P, d.var = self.amp.data_ptr(), self.P.data_ptr(), self.var.data_ptr()
         d.W, d.h, d.adam = self.W.data_ptr(), self.h.data_ptr(), self.adam.data_ptr()
-        d.q, d.ld_q = q.data_ptr(), int(q.stride(1))
-        d.out, d.ld_out = out.data_ptr(), int(out.stride(1))
+        if q is not None:
+            d.q, d.ld_q = q.data_ptr() - 4 * int(col0), int(q.stride(1))
+            d.out, d.ld_out = out.data_ptr() - 4 * int(col0), int(out.stride(1))
         if q_keep is not None:
             d.q_keep, d.ld_q_keep = q_keep.data_ptr(), int(q_keep.stride(1))
             d.out_keep, d.ld_out_keep = out_keep.data_ptr(), int(out_keep.stride(1))
@@ -173,10 +176,18 @@ class DPEqualizer:
         return loss_steps, var_steps
 
     # -- batch-split phases (vaeq_dp_split_*; the caller all-reduces `stats` and `grads` between them) ---------------
+    def _check_split_cols(self, B, sym_lo, sym_hi, q, out, col0):
+        if q is None and out is None:           # only the kept columns are wanted (frame loops): no per-window q / out at all
+            return
+        clo, chi = max(0, sym_lo - 16), min(B, sym_hi + 16)
+        if col0 % 4 or col0 > clo or col0 + q.shape[-1] < chi or col0 + out.shape[-1] < chi:
+            raise _lib.VaeqError(f"q / out hold columns [{col0}, {col0 + q.shape[-1]}) but the rank writes [{clo}, {chi})")
+
     @_lib.device_guard
-    def split_forward(self, rx, sym_lo, sym_hi, q, out):
+    def split_forward(self, rx, sym_lo, sym_hi, q, out, col0=0, q_keep=None, out_keep=None, keep_lo=0, keep_n=0):
         B = self._check_rx(rx)
-        d = self._desc(rx, q, out, B)
+        self._check_split_cols(B, sym_lo, sym_hi, q, out, col0)
+        d = self._desc(rx, q, out, B, q_keep=q_keep, out_keep=out_keep, keep_lo=keep_lo, keep_n=keep_n, col0=col0)
         if not hasattr(self, "_stats"):
             self._stats = torch.zeros(int(self.lib.vaeq_dp_split_stats_doubles(self.M)), dtype=torch.float64, device=self.device)
             self._grads = torch.zeros(16 * self.M, dtype=_F32, device=self.device)
@@ -185,19 +196,28 @@ class DPEqualizer:
         return self._stats
 
     @_lib.device_guard
-    def split_backward(self, rx, sym_lo, sym_hi, q, out):
+    def split_backward(self, rx, sym_lo, sym_hi, q, out, col0=0):
         B = self._check_rx(rx)
-        d = self._desc(rx, q, out, B)
+        d = self._desc(rx, q, out, B, col0=col0)
         _lib.check(self.lib.vaeq_dp_split_backward(C.byref(d), int(sym_lo), int(sym_hi), self._stats.data_ptr(),
                                                    self._grads.data_ptr(), _lib.current_stream()), "vaeq_dp_split_backward")
         return self._grads
 
     @_lib.device_guard
-    def split_update(self, rx, q, out, lr_w, lr_h):
+    def split_update(self, rx, q, out, lr_w, lr_h, col0=0):
         B = self._check_rx(rx)
-        d = self._desc(rx, q, out, B)
+        d = self._desc(rx, q, out, B, col0=col0)
         _lib.check(self.lib.vaeq_dp_split_update(C.byref(d), self._grads.data_ptr(), float(lr_w), float(lr_h),
                                                  _lib.current_stream()), "vaeq_dp_split_update")
+
+    @_lib.device_guard
+    def split_step_peer(self, rx, sym_lo, sym_hi, q, out, comm, lr_w, lr_h, col0=0, q_keep=None, out_keep=None, keep_lo=0, keep_n=0):
+        """The whole batch-split step in one call, both reductions over NVLink peer memory (vaeq_dp_split_step_peer)."""
+        B = self._check_rx(rx)
+        self._check_split_cols(B, sym_lo, sym_hi, q, out, col0)
+        d = self._desc(rx, q, out, B, q_keep=q_keep, out_keep=out_keep, keep_lo=keep_lo, keep_n=keep_n, col0=col0)
+        _lib.check(self.lib.vaeq_dp_split_step_peer(C.byref(d), int(sym_lo), int(sym_hi), C.byref(comm), float(lr_w), float(lr_h),
+                                                    _lib.current_stream()), "vaeq_dp_split_step_peer")
 
 
 class DPEqualizerRuns:

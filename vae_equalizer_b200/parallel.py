@@ -66,24 +66,176 @@ def allreduce_sum_(t: torch.Tensor, group=None):
     return t
 
 
+def kept_owner_ranges(B: int, world: int, keep_lo: int, keep_n: int):
+    """Per rank: the part [a, b) of the kept section [keep_lo, keep_lo + keep_n) of a window that this rank's symbol range covers, as
+    offsets INSIDE the kept section (empty ranges have a == b).  The ranges of all ranks tile [0, keep_n)."""
+    out = []
+    for lo, hi in split_ranges(B, world):
+        a, b = max(lo, keep_lo), min(hi, keep_lo + keep_n)
+        out.append((a - keep_lo, b - keep_lo) if b > a else (0, 0))
+    return out
+
+
 class BatchSplitDP:
     """One DP VAE-LE/VAE-flex run whose minibatch is split over the ranks of `group` (all ranks call in lockstep).
 
     Every rank keeps the full rx window (an input, replicated once per frame outside the step) and an identical
-    copy of W / h / Adam state; the update is replicated and bit-identical because both all-reduces return the same
-    bits on every rank.  Summation order differs from the single-GPU run, so parity with it is ~1e-6, not bitwise."""
+    copy of W / h / Adam state; the update is replicated and bit-identical because both reductions return the same
+    bits on every rank.  Summation order differs from the single-GPU run, so parity with it is ~1e-6, not bitwise.
 
-    def __init__(self, eq, group=None):
+    transport: "peer" = both reductions inside the library over NVLink peer memory (vaeq_dp_split_step_peer: slots in
+    torch symmetric memory, epoch flags, partials added in rank order; no host-issued collective in the step), "nccl" = two
+    NCCL all-reduces between the three phase calls, "auto" = peer when symmetric memory can be set up for the group."""
+
+    def __init__(self, eq, group=None, transport="auto"):
         self.eq, self.group = eq, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.transport, self.comm, self._graphs, self._local, self._warm = "nccl", None, {}, {}, set()
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError(f"unknown transport {transport!r}")
+        if transport != "nccl" and self.world > 1:
+            try:
+                self._setup_peer()
+                self.transport = "peer"
+            except Exception as e:              # no symmetric memory on this box / build: NCCL carries the two messages
+                if transport == "peer":
+                    raise
+                self.peer_error = repr(e)
+            if transport == "auto":             # every rank must take the same path
+                ok = torch.tensor([1 if self.transport == "peer" else 0], device=eq.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0:
+                    self.transport = "nccl"
 
-    def train_step(self, rx, lr_w, lr_h, q, out):
+    def _setup_peer(self):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        if self.world > 8:
+            raise _lib.VaeqError("peer transport: at most 8 ranks (one NVSwitch domain)")
+        nbytes = int(self.eq.lib.vaeq_peer_slot_bytes(self.eq.M))
+        self._slot = symm.empty(nbytes, dtype=torch.uint8, device=self.eq.device)
+        self._slot.zero_()
+        hdl = symm.rendezvous(self._slot, self.group if self.group is not None else dist.group.WORLD)
+        ptrs = [int(x) for x in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or int(hdl.rank) != self.rank:
+            raise _lib.VaeqError("symmetric-memory rendezvous does not match the process group")
+        self._epoch = torch.zeros(2, dtype=torch.int32, device=self.eq.device)
+        comm = _lib.PeerComm()
+        comm.rank, comm.world, comm.epoch = self.rank, self.world, self._epoch.data_ptr()
+        for r, ptr in enumerate(ptrs):
+            comm.slot[r] = ptr
+        torch.cuda.synchronize(self.eq.device)
+        dist.barrier(group=self.group)          # every slot is zeroed before anyone publishes into it
+        self.comm, self._symm_handle = comm, hdl
+
+    # -- per-rank buffers ------------------------------------------------------------------------------------------------------
+    def local_columns(self, B: int):
+        """(lo, hi, col0, n_cols): this rank's symbol range of a batch_len-B window and the q / out columns it writes."""
+        lo, hi = split_ranges(B, self.world)[self.rank]
+        col0, col1 = max(0, lo - 16), min(B, hi + 16)
+        return lo, hi, col0, col1 - col0
+
+    def alloc_local(self, B: int):
+        """q / out buffers holding only this rank's columns of a window (pass them with col0 = local_columns(B)[2])."""
+        if B not in self._local:
+            lo, hi, col0, n = self.local_columns(B)
+            dev = self.eq.device
+            self._local[B] = (torch.empty(2, 2 * self.eq.n_lev, n, dtype=torch.float32, device=dev),
+                              torch.empty(2, 2, n, dtype=torch.float32, device=dev), col0)
+        return self._local[B]
+
+    # -- one step ----------------------------------------------------------------------------------------------------------------
+    def train_step(self, rx, lr_w, lr_h, q=None, out=None, col0=0, q_keep=None, out_keep=None, keep_lo=0, keep_n=0):
+        """One optimizer step on the window rx (2,2,sps*B).  q / out: full-width (col0 = 0) or this rank's columns only
+        (alloc_local); q_keep / out_keep receive the kept columns this rank counts."""
         B = rx.shape[-1] // self.eq.sps
         lo, hi = split_ranges(B, self.world)[self.rank]
-        stats = self.eq.split_forward(rx, lo, hi, q, out)
-        allreduce_sum_(stats, self.group)
-        grads = self.eq.split_backward(rx, lo, hi, q, out)
-        allreduce_sum_(grads, self.group)
-        self.eq.split_update(rx, q, out, lr_w, lr_h)
+        if q is None and q_keep is None:
+            q, out, col0 = self.alloc_local(B)
+        if self.transport == "peer":
+            self.eq.split_step_peer(rx, lo, hi, q, out, self.comm, lr_w, lr_h, col0, q_keep, out_keep, keep_lo, keep_n)
+        else:
+            stats = self.eq.split_forward(rx, lo, hi, q, out, col0, q_keep, out_keep, keep_lo, keep_n)
+            allreduce_sum_(stats, self.group)
+            grads = self.eq.split_backward(rx, lo, hi, q, out, col0)
+            allreduce_sum_(grads, self.group)
+            self.eq.split_update(rx, q, out, lr_w, lr_h, col0)
         return self.eq.loss, self.eq.var_est, (lo, hi)
+
+    # -- one frame of sliding windows (func_VAEflex_DP_MQAM_shaping.py:59-70) -------------------------------------------------------
+    def train_frame(self, rx_frame, batch_len, stride_sym, n_steps, lr_w, lr_h, out_train, out_const, keep_lo, keep_n, graph=True):
+        """Step m trains on symbols [m*stride_sym, m*stride_sym + batch_len) of the frame, every window split over the ranks; the kept
+        columns of step m that THIS rank counts land at column m*stride_sym + (u - keep_lo) of out_train / out_const (call
+        gather_kept to assemble them on one rank).  graph=True replays the whole frame loop from a CUDA graph (one capture per
+        (buffers, shapes, learning rates)); the rx / out tensors must then be the same objects frame after frame.
+        Returns (loss_steps (n_steps,), var_est_steps (2, n_steps))."""
+        eq, sps, B = self.eq, self.eq.sps, int(batch_len)
+        dev = eq.device
+        q = out = None                           # the frame loop wants the kept section of every window only: no per-window q / out is written
+        col0 = 0
+        key = (rx_frame.data_ptr(), out_train.data_ptr(), out_const.data_ptr(), B, int(stride_sym), int(n_steps), float(lr_w), float(lr_h),
+               int(keep_lo), int(keep_n))
+
+        def run(loss_steps, var_steps):
+            for m in range(n_steps):
+                s0 = m * stride_sym
+                win = rx_frame[:, :, s0 * sps:(s0 + B) * sps]
+                self.train_step(win, lr_w, lr_h, q, out, col0, out_train[:, :, s0:], out_const[:, :, s0:], keep_lo, keep_n)
+                loss_steps[m:m + 1].copy_(eq.loss)
+                var_steps[:, m].copy_(eq.var_est)
+
+        if not graph:
+            loss_steps = torch.empty(n_steps, dtype=torch.float32, device=dev)
+            var_steps = torch.empty(2, n_steps, dtype=torch.float32, device=dev)
+            run(loss_steps, var_steps)
+            return loss_steps, var_steps
+        if key not in self._graphs:
+            loss_steps = torch.empty(n_steps, dtype=torch.float32, device=dev)
+            var_steps = torch.empty(2, n_steps, dtype=torch.float32, device=dev)
+            if B not in self._warm:              # first frame of this batch_len: a plain step allocates the workspaces and sets the kernel
+                saved = (eq.W.clone(), eq.h.clone(), eq.adam.clone())              # attributes; it must not count as training: state restored
+                self.train_step(rx_frame[:, :, :B * sps], lr_w, lr_h, None, None, 0, out_train, out_const, keep_lo, keep_n)
+                eq.W.copy_(saved[0]); eq.h.copy_(saved[1]); eq.adam.copy_(saved[2])
+                self._warm.add(B)                # (the peer epoch counters stay advanced: every rank made the same extra call)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(g):
+                run(loss_steps, var_steps)
+            self._graphs[key] = (g, loss_steps, var_steps, (rx_frame, out_train, out_const))
+        g, loss_steps, var_steps, _ = self._graphs[key]
+        g.replay()
+        return loss_steps, var_steps
+
+    def gather_kept(self, B, stride_sym, n_steps, out_train, out_const, keep_lo, keep_n, dst=0):
+        """Assemble the kept columns of a frame on rank `dst`: every rank sends the columns it counted (its part of the kept section
+        of every step, packed) point to point; nothing is sent for empty parts.  keep_n must equal stride_sym (VAE-flex keeps
+        the middle flex_step symbols of every window, VAEflex_DP:64-65)."""
+        if self.world == 1:
+            return
+        if keep_n != stride_sym:
+            raise ValueError("gather_kept needs keep_n == stride_sym")
+        parts = kept_owner_ranges(B, self.world, keep_lo, keep_n)
+        views = [t[:, :, :n_steps * stride_sym].unflatten(2, (n_steps, stride_sym)) for t in (out_train, out_const)]
+        ops, bufs = [], []
+        if self.rank == dst:
+            for r, (a, b) in enumerate(parts):
+                if r == dst or b <= a:
+                    continue
+                for v in views:
+                    buf = torch.empty(v.shape[:3] + (b - a,), dtype=v.dtype, device=v.device)
+                    ops.append(dist.P2POp(dist.irecv, buf, dist.get_global_rank(self.group, r) if self.group is not None else r, self.group))
+                    bufs.append((v, a, b, buf))
+        else:
+            a, b = parts[self.rank]
+            if b > a:
+                for v in views:
+                    buf = v[:, :, :, a:b].contiguous()
+                    ops.append(dist.P2POp(dist.isend, buf, dist.get_global_rank(self.group, dst) if self.group is not None else dst, self.group))
+                    bufs.append(buf)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.rank == dst:
+            for v, a, b, buf in bufs:
+                v[:, :, :, a:b].copy_(buf)

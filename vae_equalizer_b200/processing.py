@@ -163,8 +163,18 @@ def processing_vaele_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, b
 
 def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
                           channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, *, device=None, rng=None, verbose=True, datagen="numpy", seed=0,
-                          eval_mode="per_op"):
-    """VAE-flex, sliding window advanced by flex_step (func_VAEflex_DP_MQAM_shaping.py:16-88)."""
+                          eval_mode="per_op", group=None, split_transport="auto"):
+    """VAE-flex, sliding window advanced by flex_step (func_VAEflex_DP_MQAM_shaping.py:16-88).
+
+    group (a torch.distributed process group, or True for the default group; one process per GPU, every rank calls with the same
+    arguments): ONE run whose every window is batch-split over the ranks (BASELINE configs[2]; parallel.BatchSplitDP) -- rank 0
+    generates the frame and broadcasts rx, every rank trains its symbol range of every window (two tiny reductions per step,
+    replicated Adam), the kept columns are gathered on rank 0, which evaluates like the single-GPU driver; the SER / Var_est it returns
+    are broadcast, so every rank returns the same tensors."""
+    if group is not None:
+        return _processing_vaeflex_split(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
+                                         channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, device, rng, verbose, datagen, seed, eval_mode,
+                                         group, split_transport)
     device = _cuda_device(device)
     if verbose:
         print("We are using the following device for learning:", device)
@@ -201,6 +211,61 @@ def processing_vaeflex_dp(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim,
         SER_valid[:, frame], _, (sh, r) = eval_frame_vae(out_train, out_const, data_tensor, amp_levels, nu_sc, var, 0)
         if verbose:
             _print_frame(frame, loss_steps[-1].item(), sh, r, (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
+    return SER_valid, Var_est, var
+
+
+def _processing_vaeflex_split(mod, sps, SNR, nu, M_est, theta_diff, theta, lr_optim, batch_len, N_train_max, num_frames, flex_step,
+                              channel, symb_rate, tau_cd, tau_pmd, phiIQ, N_lrhalf, device, rng, verbose, datagen, seed, eval_mode, group, transport):
+    """processing_vaeflex_dp with every window split over the ranks of `group` (same frame loop: VAEflex_DP:36-86)."""
+    import torch.distributed as dist
+    from .parallel import BatchSplitDP
+    group = None if group is True else group
+    device = _cuda_device(device)
+    rank = dist.get_rank(group)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    verbose = verbose and rank == 0
+    if verbose:
+        print("We are using the following device for learning:", device, f"(batch-split over {dist.get_world_size(group)} ranks)")
+    h_est, h_channel, P, amp_levels, amps, pol, nu_sc, var, pow_mean = sfun.init(channel, mod, device, nu, sps, M_est, SNR)
+    num_lev = amp_levels.shape[0]
+    eq = DPEqualizer(M_est, sps, amp_levels, P, var, nu_sc, device=device)
+    bs = BatchSplitDP(eq, group, transport)
+    SER_valid = torch.zeros(4, num_frames, device=device, dtype=torch.float32)
+    Var_est = torch.empty(pol, num_frames, device=device, dtype=torch.float32)
+    N_frame = (N_train_max // batch_len) * batch_len
+    m_max = (N_frame - batch_len) // flex_step * flex_step          # VAEflex_DP:39
+    n_steps = m_max // flex_step
+    keep_lo, keep_hi = (batch_len - flex_step) // 2, (batch_len + flex_step) // 2     # VAEflex_DP:64-65
+    rx_buf = torch.empty(pol, 2, sps * N_frame, device=device, dtype=torch.float32)   # the same buffers every frame: the frame loop is a CUDA graph
+    out_train = torch.empty(pol, 2 * num_lev, m_max, device=device, dtype=torch.float32)
+    out_const = torch.empty(pol, 2, m_max, device=device, dtype=torch.float32)
+    lr_w = lr_optim
+    for frame in range(num_frames):
+        if frame % N_lrhalf == 0 and frame != 0:
+            lr_w = lr_optim * 0.5
+        data_tensor = None
+        if rank == 0:
+            rx_tensor, data_tensor, _ = _make_frame(datagen, N_frame, amps, SNR, h_channel, P, pol, symb_rate, sps, tau_cd, tau_pmd,
+                                                    phiIQ, theta, device, rng, seed * 100003 + frame)
+            data_tensor = data_tensor[:, :, batch_len // 2:m_max + batch_len // 2]             # VAEflex_DP:51
+            rx_buf.copy_(rx_tensor)
+        dist.broadcast(rx_buf, src=src, group=group)
+        theta += theta_diff
+        out_train.zero_()
+        out_const.zero_()
+        loss_steps, var_est = bs.train_frame(rx_buf, batch_len, flex_step, n_steps, lr_w, lr_optim, out_train, out_const, keep_lo, keep_hi - keep_lo)
+        bs.gather_kept(batch_len, flex_step, n_steps, out_train, out_const, keep_lo, keep_hi - keep_lo, dst=0)
+        SNR_est = pow_mean / torch.mean(var_est)
+        Var_est[:, frame] = torch.mean(var_est, dim=1)
+        if rank == 0:
+            if eval_mode == "fused":
+                SER_valid[:, frame], al = _eval_fused(out_train, out_const, data_tensor, amp_levels, var, nu_sc, 0)
+                sh, r = al.tolist()[1][:2], al.tolist()[1][2]
+            else:
+                SER_valid[:, frame], _, (sh, r) = eval_frame_vae(out_train.clone(), out_const.clone(), data_tensor, amp_levels, nu_sc, var, 0)
+            if verbose:
+                _print_frame(frame, loss_steps[-1].item(), sh, r, (10 * torch.log10(SNR_est)).item(), SER_valid[:, frame].tolist())
+    dist.broadcast(SER_valid, src=src, group=group)
     return SER_valid, Var_est, var
 
 

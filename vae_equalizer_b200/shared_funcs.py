@@ -170,6 +170,8 @@ def _equalizer_node(q):
 def soft_dec(out, var, amp_levels, nu_sc):
     """Soft demapper with the PCS correction term (sf:529-542)."""
     _require_cuda(out, "out")
+    _lib.require_current_device(var, "var")                  # the kernel dereferences all three on out's device
+    _lib.require_current_device(amp_levels, "amp_levels")
     lib = _lib.load()
     n, N = int(amp_levels.numel()), int(out.shape[-1])
     ld = _rows(out, "out")
