@@ -224,7 +224,8 @@ int vaeq_dp_split_update(const vaeq_dp_desc *d, const float *grads_in, float lr_
  * rank allocates a slot of vaeq_peer_slot_bytes(M) bytes, zero-initialised, in memory all peers can address (CUDA IPC / VMM, e.g.
  * torch.distributed._symmetric_memory) and passes the `world` peer-mapped pointers in rank order (slot[rank] = its own) plus two
  * zero-initialised int32 counters in its own device memory.  One call = forward, exchange of the ELBO sums, loss / kappa, backward,
- * exchange of the 16 M gradient floats, replicated Adam: 8 launches, no host synchronisation, graph-capturable.  An exchange is a PUSH:
+ * exchange of the 16 M gradient floats, replicated Adam: 6 launches (the exchanges are fused with the loss assembly and with Adam), no
+ * host synchronisation, graph-capturable.  An exchange is a PUSH:
  * a rank stores its partial into its own compartment of EVERY peer's slot, fences, raises that compartment's epoch word in every slot,
  * then polls the epoch words of its own slot (local memory) and adds the compartments in rank order -- bit-identical on every rank, one
  * NVLink store latency whatever the number of ranks.  All ranks must make the same sequence of calls; a peer that does not show up

@@ -1106,9 +1106,12 @@ __global__ void __launch_bounds__(256) k_dp_peer_reduce_stats(DpK p, int nparts,
         if (i < 8) p.part_fwd[i] = a;
         else p.edge_vs[i - 8] = (float)a;
     }
+    __syncthreads();                                         // the block's own global writes are visible to the block after the barrier
+    dp_fin_body(p, 1);                                       // C, loss, var_est, kappa, S_nu(j) from the reduced sums (k_dp_fin's body)
 }
 // gradients: p.gfinal holds this rank's partial (k_dp_reduce_gpart); the sum over the ranks lands in row 0 of p.gpart, where Adam reads it
-__global__ void __launch_bounds__(1024) k_dp_peer_reduce_grads(DpK p, PeerK c) {
+__global__ void __launch_bounds__(1024) k_dp_peer_reduce_grads_adam(DpK p, PeerK c, float lr_w, float lr_h, int amsgrad) {
+    __shared__ float sum_sh[16 * VAEQ_MAX_TAPS];
     const size_t off = PEER_HDR + peer_stats_bytes(p.M);
     const int n = 16 * p.M;
     for (int idx = threadIdx.x; idx < c.world * n; idx += blockDim.x) {
@@ -1119,8 +1122,18 @@ __global__ void __launch_bounds__(1024) k_dp_peer_reduce_grads(DpK p, PeerK c) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double a = 0.0;
         for (int r = 0; r < c.world; ++r) a += (double)*reinterpret_cast<const volatile float *>(c.slot[c.rank] + (size_t)r * c.comp + off + 4 * i);
-        p.gpart[i] = (float)a;
+        sum_sh[i] = (float)a;                                // a float, like the all-reduced gradient of the NCCL transport
     }
+    // ---- replicated Adam on the reduced gradient (k_dp_adam's finish for one "partial"), step counter bumped by this single CTA ----
+    __shared__ double bc1_sh;
+    __shared__ float bc2s_sh;
+    int *step_ptr = reinterpret_cast<int *>(p.adam + 48 * p.M);
+    const int step = *step_ptr + 1;
+    if (threadIdx.x == blockDim.x - 1) adam_bias(step, &bc1_sh, &bc2s_sh);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dp_adam_finish(p, i, (double)sum_sh[i], 1, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
+    __syncthreads();
+    if (threadIdx.x == 0) *step_ptr = step;
 }
 static int64_t split_cols(const vaeq_dp_desc *d, int32_t lo, int32_t hi) {      // columns a rank writes: its range widened by DP_SPLIT_EXT
     if (d == nullptr || lo < 0 || hi > d->B || lo >= hi) return -1;                // (bad ranges are reported by split_check)
@@ -1221,10 +1234,9 @@ extern "C" int vaeq_dp_split_step_peer(const vaeq_dp_desc *d, int32_t sym_lo, in
     }
     if (rc2) return rc2;
     ktime_begin(VAEQ_K_DP_FIN, st);
-    k_dp_peer_reduce_stats<<<1, 256, 0, st>>>(p, nparts, c);
+    k_dp_peer_reduce_stats<<<1, 256, 0, st>>>(p, nparts, c);               // exchange of the ELBO sums + C, loss, var_est, kappa, S_nu(j)
     ktime_end(VAEQ_K_DP_FIN, st);
     VAEQ_LAUNCH_CHECK("k_dp_peer_reduce_stats");
-    if ((rc = dp_launch_fin(p, 1, st))) return rc;
     if (!dp_try_fast(p, d->n_lev, DP_MODE_SPLIT_BWD, st, &nparts, &rc2)) {
         set_error("batch-split needs the fast path");
         return VAEQ_EINVAL;
@@ -1232,10 +1244,10 @@ extern "C" int vaeq_dp_split_step_peer(const vaeq_dp_desc *d, int32_t sym_lo, in
     if (rc2) return rc2;
     ktime_begin(VAEQ_K_DP_ADAM, st);
     k_dp_reduce_gpart<<<(16 * p.M + 7) / 8, 256, 0, st>>>(p, nparts, p.gfinal);
-    k_dp_peer_reduce_grads<<<1, 1024, 0, st>>>(p, c);
+    k_dp_peer_reduce_grads_adam<<<1, 1024, 0, st>>>(p, c, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0);   // exchange of the gradients + Adam
     ktime_end(VAEQ_K_DP_ADAM, st);
-    VAEQ_LAUNCH_CHECK("k_dp_peer_reduce_grads");
-    return dp_launch_adam(p, 1, DP_MODE_TRAIN, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0, st);
+    VAEQ_LAUNCH_CHECK("k_dp_peer_reduce_grads_adam");
+    return VAEQ_OK;
 }
 
 extern "C" int vaeq_adam_update(float *param, const float *grad, float *state, int32_t n, float lr, int32_t amsgrad,
