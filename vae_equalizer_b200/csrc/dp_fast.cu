@@ -140,6 +140,94 @@ __device__ __forceinline__ void tile_fetch_next(const DpK &p, int k, int cur, in
     if (threadIdx.x == 0) *s_next = p.dyn ? atomicAdd(p.tile_ctr + k, 1) + (int)gridDim.x : cur + (int)gridDim.x;
 }
 
+// point-wise stage of the forward kernel for a thread's FT_R symbols: soft demapper, posterior moments, entropy, backward
+// coefficients, row stores.  Rolled over the polarisation (code size); y rotates by two components per pass.  Posterior means go
+// straight to the shared E_q window (float2 half per polarisation pass): they are not held in registers across the stage, which
+// sits at the 128-register cap.  MOM = moment form of the demapper (demap_mom), else the per-level sums (demap_fast).
+template <int NL, int MH, bool MOM>
+__device__ __forceinline__ void fwd_pointwise(const DpK &p, const FastConst &c, float (&y)[FT_R][4], float4 *m1s, int tid, int u0, bool owned,
+                                              bool counted, float &accEnt, float &accV0, float &accV1) {
+#pragma unroll 1
+    for (int pol = 0; pol < 2; ++pol) {
+        float vs[FT_R];
+#pragma unroll
+        for (int cq = 0; cq < 2; ++cq) {
+            const int cc = 2 * pol + cq;
+            float qv[FT_R][NL], m1v[FT_R], s1v[FT_R], t2v[FT_R], s3v[FT_R];
+#pragma unroll
+            for (int r = 0; r < FT_R; ++r) {
+                float v, ent;
+                if (MOM) {
+                    demap_mom<NL>(y[r][cq], c.ct[pol], c.eps[pol], c.inv_var[pol], c, qv[r], m1v[r], v, ent, s1v[r], t2v[r], s3v[r]);
+                } else {
+                    float m2, S2;
+                    demap_fast<NL, true>(y[r][cq], c.c2[pol], c.inv_var[pol], c, qv[r], m1v[r], m2, ent, s1v[r], S2, s3v[r]);
+                    t2v[r] = fmaf(-2.f * m1v[r], s1v[r], S2);
+                    v = m2 - m1v[r] * m1v[r];                                             // sf:113
+                }
+                const int u = u0 + r;
+                if (counted && u >= MH && u < p.B - MH) accEnt += ent;                    // sf:132
+                vs[r] = cq ? vs[r] + v : v;
+                reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1v[r];
+            }
+            if (owned) {
+                if (p.q != nullptr) {                // NULL in the frame loops that only keep a section of every window
+#pragma unroll
+                    for (int l = 0; l < NL; ++l)
+                        st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
+                    st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
+                }
+                st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
+                if (p.need_bwd) {
+                    st_row4(p.srows, p.B, cc, u0, make_float4(s1v[0], s1v[1], s1v[2], s1v[3]));
+                    st_row4(p.srows, p.B, 4 + cc, u0, make_float4(t2v[0], t2v[1], t2v[2], t2v[3]));
+                    st_row4(p.srows, p.B, 8 + cc, u0, make_float4(s3v[0], s3v[1], s3v[2], s3v[3]));
+                }
+                if (p.qk != nullptr && counted) {    // batch-split: the rank that counts a symbol keeps it
+                    const int k0 = u0 - p.keep_lo;
+                    if (p.keep_vec && k0 >= 0 && k0 + FT_R <= p.keep_n) {            // all four symbols kept, 16-byte aligned destination
+                        const int64_t col = p.keep_base + k0;
+#pragma unroll
+                        for (int l = 0; l < NL; ++l)
+                            *reinterpret_cast<float4 *>(p.qk + (int64_t)(cc * NL + l) * p.ld_qk + col) = make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]);
+                        *reinterpret_cast<float4 *>(p.outk + (int64_t)cc * p.ld_outk + col) = make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]);
+                    } else if (k0 > -FT_R && k0 < p.keep_n) {
+#pragma unroll 1
+                        for (int r = 0; r < FT_R; ++r) {
+                            const int u = u0 + r;
+                            if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
+                                const int64_t col = p.keep_base + (u - p.keep_lo);
+                                for (int l = 0; l < NL; ++l)
+                                    p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
+                                p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (counted) {
+            const float vsum = (vs[0] + vs[1]) + (vs[2] + vs[3]);
+            accV0 += pol ? 0.f : vsum;
+            accV1 += pol ? vsum : 0.f;
+#pragma unroll
+            for (int r = 0; r < FT_R; ++r) {
+                const int u = u0 + r;
+                if (u < MH || u >= p.B - MH) {
+                    const int slot = (u < MH) ? u : MH + (u - (p.B - MH));
+                    p.edge_vs[2 * MH * pol + slot] = vs[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < FT_R; ++r) {             // rotate: the next pass finds its components in slots 0,1
+            float t;
+            t = y[r][0]; y[r][0] = y[r][2]; y[r][2] = t;
+            t = y[r][1]; y[r][1] = y[r][3]; y[r][3] = t;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -193,8 +281,6 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.chi);
         const bool counted = owned && (u0 >= p.sym_lo) && (u0 < p.sym_hi);   // sums only over this rank's symbols
-        // posterior means go straight to the shared E_q window (float2 half per polarisation pass): they are not held in
-        // registers across the point-wise stage, which sits at the 128-register cap
         if (!in_seq) {
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) m1s[5 * tid + r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -209,81 +295,10 @@ __global__ void __launch_bounds__(FT_NT, FT_MINB_PW) k_dp_fwd_fast(DpK p) {
             for (int ph = 0; ph < 2; ++ph)
                 fir4(ph ? xo : xe, i0 + FT_XOFF - HF, tapF + (ph ? FT_TAPV * NE : 0), ph ? NO : NE, y);
             PT(2)
-            // point-wise stage, rolled over the polarisation (code size); y rotates by two components per pass
-#pragma unroll 1
-            for (int pol = 0; pol < 2; ++pol) {
-                float vs[FT_R];
-#pragma unroll
-                for (int cq = 0; cq < 2; ++cq) {
-                    const int cc = 2 * pol + cq;
-                    float qv[FT_R][NL], m1v[FT_R], s1v[FT_R], t2v[FT_R], s3v[FT_R];
-#pragma unroll
-                    for (int r = 0; r < FT_R; ++r) {
-                        float m2, ent, S2;
-                        demap_fast<NL, true>(y[r][cq], c.c2[pol], c.inv_var[pol], c, qv[r], m1v[r], m2, ent, s1v[r], S2, s3v[r]);
-                        t2v[r] = fmaf(-2.f * m1v[r], s1v[r], S2);
-                        const int u = u0 + r;
-                        if (counted && u >= MH && u < p.B - MH) accEnt += ent;                // sf:132
-                        const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
-                        vs[r] = cq ? vs[r] + v : v;
-                        reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1v[r];
-                    }
-                    if (owned) {
-                        if (p.q != nullptr) {                // NULL in the frame loops that only keep a section of every window
-#pragma unroll
-                            for (int l = 0; l < NL; ++l)
-                                st_row4(p.q, p.ld_q, cc * NL + l, u0, make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]));
-                            st_row4(p.out, p.ld_out, cc, u0, make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]));
-                        }
-                        st_row4(p.m1rows, p.B, cc, u0, make_float4(m1v[0], m1v[1], m1v[2], m1v[3]));
-                        if (p.need_bwd) {
-                            st_row4(p.srows, p.B, cc, u0, make_float4(s1v[0], s1v[1], s1v[2], s1v[3]));
-                            st_row4(p.srows, p.B, 4 + cc, u0, make_float4(t2v[0], t2v[1], t2v[2], t2v[3]));
-                            st_row4(p.srows, p.B, 8 + cc, u0, make_float4(s3v[0], s3v[1], s3v[2], s3v[3]));
-                        }
-                        if (p.qk != nullptr && counted) {    // batch-split: the rank that counts a symbol keeps it
-                            const int k0 = u0 - p.keep_lo;
-                            if (p.keep_vec && k0 >= 0 && k0 + FT_R <= p.keep_n) {            // all four symbols kept, 16-byte aligned destination
-                                const int64_t col = p.keep_base + k0;
-#pragma unroll
-                                for (int l = 0; l < NL; ++l)
-                                    *reinterpret_cast<float4 *>(p.qk + (int64_t)(cc * NL + l) * p.ld_qk + col) = make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]);
-                                *reinterpret_cast<float4 *>(p.outk + (int64_t)cc * p.ld_outk + col) = make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]);
-                            } else if (k0 > -FT_R && k0 < p.keep_n) {
-#pragma unroll 1
-                                for (int r = 0; r < FT_R; ++r) {
-                                    const int u = u0 + r;
-                                    if (u >= p.keep_lo && u < p.keep_lo + p.keep_n) {
-                                        const int64_t col = p.keep_base + (u - p.keep_lo);
-                                        for (int l = 0; l < NL; ++l)
-                                            p.qk[(int64_t)(cc * NL + l) * p.ld_qk + col] = f4c(make_float4(qv[0][l], qv[1][l], qv[2][l], qv[3][l]), r);
-                                        p.outk[(int64_t)cc * p.ld_outk + col] = f4c(make_float4(y[0][cq], y[1][cq], y[2][cq], y[3][cq]), r);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                if (counted) {
-                    const float vsum = (vs[0] + vs[1]) + (vs[2] + vs[3]);
-                    accV0 += pol ? 0.f : vsum;
-                    accV1 += pol ? vsum : 0.f;
-#pragma unroll
-                    for (int r = 0; r < FT_R; ++r) {
-                        const int u = u0 + r;
-                        if (u < MH || u >= p.B - MH) {
-                            const int slot = (u < MH) ? u : MH + (u - (p.B - MH));
-                            p.edge_vs[2 * MH * pol + slot] = vs[r];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < FT_R; ++r) {             // rotate: the next pass finds its components in slots 0,1
-                    float t;
-                    t = y[r][0]; y[r][0] = y[r][2]; y[r][2] = t;
-                    t = y[r][1]; y[r][1] = y[r][3]; y[r][3] = t;
-                }
-            }
+            // point-wise stage: moment form when the prior is of the Maxwell-Boltzmann family (every reference constellation), else the
+            // per-level sums (CTA-uniform branch: one of the two code paths runs for the whole launch)
+            if (c.quad) fwd_pointwise<NL, MH, true>(p, c, y, m1s, tid, u0, owned, counted, accEnt, accV0, accV1);
+            else fwd_pointwise<NL, MH, false>(p, c, y, m1s, tid, u0, owned, counted, accEnt, accV0, accV1);
         }
         PT(3)
         __syncthreads();
