@@ -154,21 +154,37 @@ __device__ __forceinline__ void fwd_pointwise(const DpK &p, const FastConst &c, 
         for (int cq = 0; cq < 2; ++cq) {
             const int cc = 2 * pol + cq;
             float qv[FT_R][NL], m1v[FT_R], s1v[FT_R], t2v[FT_R], s3v[FT_R];
+            if (MOM) {
 #pragma unroll
-            for (int r = 0; r < FT_R; ++r) {
-                float v, ent;
-                if (MOM) {
-                    demap_mom<NL>(y[r][cq], c.ct[pol], c.eps[pol], c.inv_var[pol], c, qv[r], m1v[r], v, ent, s1v[r], t2v[r], s3v[r]);
-                } else {
-                    float m2, S2;
+                for (int r = 0; r < FT_R; r += 2) {                                       // a symbol pair per packed instruction
+                    float2 q2[NL], m1p, vp, entp, s1p, t2p, s3p;
+                    demap_mom2<NL>(make_float2(y[r][cq], y[r + 1][cq]), c.ct[pol], c.eps[pol], c.inv_var[pol], c, q2, m1p, vp, entp, s1p, t2p, s3p);
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) { qv[r][l] = q2[l].x; qv[r + 1][l] = q2[l].y; }
+                    m1v[r] = m1p.x; m1v[r + 1] = m1p.y;
+                    s1v[r] = s1p.x; s1v[r + 1] = s1p.y;
+                    t2v[r] = t2p.x; t2v[r + 1] = t2p.y;
+                    s3v[r] = s3p.x; s3v[r + 1] = s3p.y;
+                    const int u = u0 + r;
+                    if (counted && u >= MH && u < p.B - MH) accEnt += entp.x;             // sf:132
+                    if (counted && u + 1 >= MH && u + 1 < p.B - MH) accEnt += entp.y;
+                    vs[r] = cq ? vs[r] + vp.x : vp.x;
+                    vs[r + 1] = cq ? vs[r + 1] + vp.y : vp.y;
+                    reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1p.x;
+                    reinterpret_cast<float *>(&m1s[5 * tid + r + 1])[2 * pol + cq] = m1p.y;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < FT_R; ++r) {
+                    float v, ent, m2, S2;
                     demap_fast<NL, true>(y[r][cq], c.c2[pol], c.inv_var[pol], c, qv[r], m1v[r], m2, ent, s1v[r], S2, s3v[r]);
                     t2v[r] = fmaf(-2.f * m1v[r], s1v[r], S2);
                     v = m2 - m1v[r] * m1v[r];                                             // sf:113
+                    const int u = u0 + r;
+                    if (counted && u >= MH && u < p.B - MH) accEnt += ent;                // sf:132
+                    vs[r] = cq ? vs[r] + v : v;
+                    reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1v[r];
                 }
-                const int u = u0 + r;
-                if (counted && u >= MH && u < p.B - MH) accEnt += ent;                    // sf:132
-                vs[r] = cq ? vs[r] + v : v;
-                reinterpret_cast<float *>(&m1s[5 * tid + r])[2 * pol + cq] = m1v[r];
             }
             if (owned) {
                 if (p.q != nullptr) {                // NULL in the frame loops that only keep a section of every window
