@@ -36,9 +36,9 @@ N_LEV = 8
 ALG_BYTES_PER_SYMBOL = 4 * 2 * (2 * SPS + 2 * N_LEV + 2)        # read rx once, write q and out once = 176 B
 ALG_FLOP_PER_SYMBOL = 5 * 32 * M_EST + 1000                      # 5 tap contractions + point-wise work
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (k_dp_fwd_fast<8,12>) at batch_len 2^22 from the
-# `ncu --set full` capture summarised in profiles/r01d_ncu_full_summary.json: 134.3 MB read + 948.1 MB written = 258.1 B/symbol
-FWD_DRAM_BYTES_PER_SYMBOL = (134.274e6 + 948.072e6) / (1 << 22)
-TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_dp_fwd_fast<8,12>, profiles/r01d_ncu_full_summary.json, scaled to this batch_len"
+# `ncu --set full` capture summarised in profiles/r02b_ncu_full_summary.json (entry fwd_moment_form_packed): 134.3 MB read + 948.8 MB written = 258.2 B/symbol
+FWD_DRAM_BYTES_PER_SYMBOL = (134.298e6 + 948.839e6) / (1 << 22)
+TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_dp_fwd_fast<8,12>, profiles/r02b_ncu_full_summary.json, scaled to this batch_len"
 CPU_SAMPLE_LOG2 = 17
 
 
