@@ -26,6 +26,27 @@ def test_split_ranges_cover_and_align():
         par.split_ranges(992, 8)
 
 
+def test_split_ranges_balance_the_cost_of_the_kept_section():
+    """Frame loops write q / out for the kept middle section only (VAEflex_DP:64-65): ranges of equal COST, still a tiling of [0, B) in whole tiles."""
+    for B, world in ((8 << 22, 8), (4 << 22, 4), (2 << 22, 2), (496 * 64, 3)):
+        keep = (B // 4, B // 2)
+        r, e = par.split_ranges(B, world, keep=keep), par.split_ranges(B, world)
+
+        def cost(lo, hi):
+            return (hi - lo) + par.KEEP_COST * max(0, min(hi, keep[0] + keep[1]) - max(lo, keep[0]))
+
+        assert r[0][0] == 0 and r[-1][1] == B and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(lo % 4 == 0 and (hi - lo) % par.TILE == 0 for lo, hi in r[:-1])
+        spread = max(cost(*x) for x in r) / min(cost(*x) for x in r)
+        assert spread <= max(cost(*x) for x in e) / min(cost(*x) for x in e) + 1e-9
+        if B >= 1 << 22:
+            assert spread < 1.001
+        parts = par.kept_owner_ranges(B, world, keep[0], keep[1], weighted=True)
+        assert sum(b - a for a, b in parts) == keep[1]
+        assert [p for p in parts if p[1] > p[0]][0][0] == 0
+    assert par.split_ranges(1 << 22, 4, keep=None) == par.split_ranges(1 << 22, 4, keep=(0, 1 << 22), keep_cost=0.0)
+
+
 def test_sweep_cells_order_matches_reference_loops():
     cells = par.sweep_cells(nu=[0, 0.027], lr=[2.5e-3, 2e-3, 3e-3], SNR=[20, 23], it=list(range(5)))
     assert len(cells) == 60 and cells[0] == dict(nu=0, lr=2.5e-3, SNR=20, it=0) and cells[1]["it"] == 1 and cells[5]["SNR"] == 23
@@ -93,7 +114,7 @@ def _gather_worker(rank, world, port, q):
         bs = par.BatchSplitDP(_FakeEq(), None, "nccl")             # host logic only: ranges, kept-column exchange
         lo, hi, col0, n = bs.local_columns(B)
         ot, oc = torch.zeros(2, 16, n_steps * stride), torch.zeros(2, 2, n_steps * stride)
-        a, b = par.kept_owner_ranges(B, world, keep_lo, stride)[rank]
+        a, b = par.kept_owner_ranges(B, world, keep_lo, stride, weighted=True)[rank]
         for m in range(n_steps):                                   # what the forward kernel leaves: this rank's part of every kept section
             cols = torch.arange(m * stride + a, m * stride + b, dtype=torch.float32)
             ot[:, :, m * stride + a:m * stride + b] = cols

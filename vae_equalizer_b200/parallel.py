@@ -20,15 +20,53 @@ import torch.distributed as dist
 TILE = 496                      # owned symbols per tile of the fast kernels (csrc/dp_fast.cu FT_T = 4 * 128 - 16)
 
 
-def split_ranges(B: int, world: int, align: int = TILE):
-    """Contiguous symbol ranges [lo, hi) covering [0, B), multiples of 4, sized in whole tiles where possible."""
+KEEP_COST = 0.04                # extra cost of a tile whose q / out columns are WRITTEN, relative to the whole step of a tile that writes none
+                                # (forward 279 vs 259 us of a ~500 us step at N = 8, profiles/r02_batch_split.txt)
+
+
+def split_ranges(B: int, world: int, align: int = TILE, keep=None, keep_cost: float = KEEP_COST):
+    """Contiguous symbol ranges [lo, hi) covering [0, B), multiples of 4, sized in whole tiles where possible.
+
+    keep = (keep_lo, keep_n): the window is stepped by a frame loop that writes q / out for the kept section only (VAEflex_DP:64-65), so a
+    tile inside it costs 1 + keep_cost and one outside 1; the ranges then carry equal COST instead of equal length (the ranks inside
+    the kept section get ~keep_cost/2 fewer symbols), which removes the wait of the other ranks at the first exchange of every step."""
     if B % 4:
         raise ValueError("batch-split needs batch_len % 4 == 0")
     units = (B + align - 1) // align
+    if units < world:
+        raise ValueError(f"batch_len={B} is too short to split {world} ways in tiles of {align} symbols")
+    if keep is None or keep_cost <= 0.0 or world == 1:
+        counts = [units // world + (1 if r < units % world else 0) for r in range(world)]
+    else:
+        klo, khi = int(keep[0]), int(keep[0]) + int(keep[1])
+
+        def cost_upto(u):                                   # cost of tiles [0, u): u + keep_cost * (kept symbols below u * align) / align
+            kept = max(0, min(u * align, khi, B) - klo)
+            return u + keep_cost * kept / align
+
+        total, bounds = cost_upto(units), [0]
+        for r in range(1, world):
+            target, lo_u, hi_u = total * r / world, bounds[-1] + 1, units - (world - r)
+            a, b = lo_u, hi_u                                # smallest u in [lo_u, hi_u] with cost_upto(u) >= target (cost_upto is monotone)
+            while a < b:
+                mid = (a + b) // 2
+                if cost_upto(mid) >= target:
+                    b = mid
+                else:
+                    a = mid + 1
+            if a > lo_u and target - cost_upto(a - 1) < cost_upto(a) - target:
+                a -= 1
+            bounds.append(a)
+        bounds.append(units)
+        counts = [bounds[r + 1] - bounds[r] for r in range(world)]
+        equal, eb = [units // world + (1 if r < units % world else 0) for r in range(world)], [0]
+        for n in equal:
+            eb.append(eb[-1] + n)
+        if max(cost_upto(eb[r + 1]) - cost_upto(eb[r]) for r in range(world)) <= max(cost_upto(bounds[r + 1]) - cost_upto(bounds[r]) for r in range(world)):
+            counts = equal                                   # tile granularity: the equal split is at least as good (short windows)
     out, lo = [], 0
     for r in range(world):
-        n = units // world + (1 if r < units % world else 0)
-        hi = min(B, lo + n * align)
+        hi = min(B, lo + counts[r] * align)
         if r == world - 1:
             hi = B
         out.append((lo, hi))
@@ -66,11 +104,12 @@ def allreduce_sum_(t: torch.Tensor, group=None):
     return t
 
 
-def kept_owner_ranges(B: int, world: int, keep_lo: int, keep_n: int):
+def kept_owner_ranges(B: int, world: int, keep_lo: int, keep_n: int, weighted: bool = False):
     """Per rank: the part [a, b) of the kept section [keep_lo, keep_lo + keep_n) of a window that this rank's symbol range covers, as
-    offsets INSIDE the kept section (empty ranges have a == b).  The ranges of all ranks tile [0, keep_n)."""
+    offsets INSIDE the kept section (empty ranges have a == b).  The ranges of all ranks tile [0, keep_n).  weighted: the cost-balanced
+    ranges of a frame loop that writes the kept section only (split_ranges(keep=...))."""
     out = []
-    for lo, hi in split_ranges(B, world):
+    for lo, hi in split_ranges(B, world, keep=(keep_lo, keep_n) if weighted else None):
         a, b = max(lo, keep_lo), min(hi, keep_lo + keep_n)
         out.append((a - keep_lo, b - keep_lo) if b > a else (0, 0))
     return out
@@ -87,8 +126,9 @@ class BatchSplitDP:
     torch symmetric memory, epoch flags, partials added in rank order; no host-issued collective in the step), "nccl" = two
     NCCL all-reduces between the three phase calls, "auto" = peer when symmetric memory can be set up for the group."""
 
-    def __init__(self, eq, group=None, transport="auto"):
+    def __init__(self, eq, group=None, transport="auto", balance_keep=True):
         self.eq, self.group = eq, group
+        self.balance_keep = bool(balance_keep)   # steps that write the kept section only split the window by cost, not by length
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.transport, self.comm, self._graphs, self._local, self._warm = "nccl", None, {}, {}, set()
@@ -150,9 +190,10 @@ class BatchSplitDP:
         """One optimizer step on the window rx (2,2,sps*B).  q / out: full-width (col0 = 0) or this rank's columns only
         (alloc_local); q_keep / out_keep receive the kept columns this rank counts."""
         B = rx.shape[-1] // self.eq.sps
-        lo, hi = split_ranges(B, self.world)[self.rank]
         if q is None and q_keep is None:
             q, out, col0 = self.alloc_local(B)
+        keep_only = self.balance_keep and q is None and q_keep is not None and keep_n > 0
+        lo, hi = split_ranges(B, self.world, keep=(keep_lo, keep_n) if keep_only else None)[self.rank]
         if self.transport == "peer":
             self.eq.split_step_peer(rx, lo, hi, q, out, self.comm, lr_w, lr_h, col0, q_keep, out_keep, keep_lo, keep_n)
         else:
@@ -215,7 +256,7 @@ class BatchSplitDP:
             return
         if keep_n != stride_sym:
             raise ValueError("gather_kept needs keep_n == stride_sym")
-        parts = kept_owner_ranges(B, self.world, keep_lo, keep_n)
+        parts = kept_owner_ranges(B, self.world, keep_lo, keep_n, weighted=self.balance_keep)
         views = [t[:, :, :n_steps * stride_sym].unflatten(2, (n_steps, stride_sym)) for t in (out_train, out_const)]
         ops, bufs = [], []
         if self.rank == dst:
