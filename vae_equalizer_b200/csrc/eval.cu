@@ -47,7 +47,7 @@ static bool ev_vec_ok(const void *a, int64_t ld_a, const void *tx, int64_t ld_tx
 // grid (chunks): CTA c scans its contiguous range of t once for ALL shifts (shift_corr.cuh) and writes part[c][i][k],
 //   S[comp][b][a] = sum_t tx[a][comp][t] * E[b][(t - (i - half)) mod N]          (sf:300-304, circular roll), k = comp*4 + b*2 + a
 template <bool FROM_Q, int NPASS>
-__global__ void __launch_bounds__(SC_NT, FROM_Q ? 2 : SC_MINB) k_shift_corr(const float *q, int64_t ld_q, const float *out, int64_t ld_out,
+__global__ void __launch_bounds__(SC_NT, (FROM_Q || NPASS == 0) ? 2 : SC_MINB) k_shift_corr(const float *q, int64_t ld_q, const float *out, int64_t ld_out,
                                                       const uint16_t *tx, int64_t ld_tx, const float *amp, int n_lev,
                                                       int N, int n_shift, int64_t per, double *part) {
     __shared__ ShiftSmem sm;
@@ -395,7 +395,9 @@ extern "C" int vaeq_find_shift(const float *q, int64_t ld_q, const float *out, i
     double *part = static_cast<double *>(scratch);
     const bool one = n_shift <= 32;
     ktime_begin(VAEQ_K_EVAL, st);
-    if (q && one) k_shift_corr<true, 1><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
+    if (q && n_shift <= 8 * SC_J) k_shift_corr<true, 0><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
+    else if (n_shift <= 8 * SC_J) k_shift_corr<false, 0><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);
+    else if (q && one) k_shift_corr<true, 1><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
     else if (q) k_shift_corr<true, 2><<<grid, SC_NT, 0, st>>>(q, ld_q, nullptr, 0, tx, ld_tx, amp, n_lev, N, n_shift, per, part);
     else if (one) k_shift_corr<false, 1><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);
     else k_shift_corr<false, 2><<<grid, SC_NT, 0, st>>>(nullptr, 0, out, ld_out, tx, ld_tx, nullptr, 0, N, n_shift, per, part);

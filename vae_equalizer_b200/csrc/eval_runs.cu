@@ -53,7 +53,7 @@ __device__ __forceinline__ int er_wrap(int t, int N) {
 
 // ---- shift search, both estimators, all runs: grid (ER_CHUNKS, 2 R); a CTA scans its range of t once for all shifts ------------
 template <int NPASS>
-__global__ void __launch_bounds__(SC_NT, SC_MINB) k_er_shift_corr(EvalRunsK p) {
+__global__ void __launch_bounds__(SC_NT, NPASS == 0 ? 2 : SC_MINB) k_er_shift_corr(EvalRunsK p) {
     __shared__ ShiftSmem sm;
     const int chunk = blockIdx.x, run = blockIdx.y >> 1, est = blockIdx.y & 1, N = p.N;
     if (!((p.which >> est) & 1)) return;
@@ -362,7 +362,8 @@ extern "C" int vaeq_frame_eval_runs_ex(const float *q, int64_t ld_q, int64_t rs_
     __VA_ARGS__;                                \
     ktime_end(VAEQ_K_EVAL, st);                 \
     VAEQ_LAUNCH_CHECK(name);
-    if (n_shift <= 32) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<1><<<dim3(p.chunks, 2 * n_runs), SC_NT, 0, st>>>(p)) }
+    if (n_shift <= 8 * SC_J) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<0><<<dim3(p.chunks, 2 * n_runs), SC_NT, 0, st>>>(p)) }
+    else if (n_shift <= 32) { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<1><<<dim3(p.chunks, 2 * n_runs), SC_NT, 0, st>>>(p)) }
     else { ER_LAUNCH("k_er_shift_corr", k_er_shift_corr<2><<<dim3(p.chunks, 2 * n_runs), SC_NT, 0, st>>>(p)) }
     ER_LAUNCH("k_er_shift_decide", k_er_shift_decide<<<(2 * n_runs + ER_DEC_NT / 32 - 1) / (ER_DEC_NT / 32), ER_DEC_NT, 0, st>>>(p))
     if (which & 1) {
