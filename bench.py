@@ -342,7 +342,7 @@ def ours_arm(args, rank, local_rank, world):
         _sweep.sweep_vae_dp(cells, MOD, SPS, M_EST, Bs, Bs * ns, 1, kind="VAE", datagen="gpu_batched", device=dev)   # warm-up at full size (allocator, cuFFT plans)
         torch.cuda.synchronize()
         tw = time.perf_counter()
-        n_fr = 8
+        n_fr = 24
         ser_s, _, _ = _sweep.sweep_vae_dp(cells, MOD, SPS, M_EST, Bs, Bs * ns, n_fr, kind="VAE", datagen="gpu_batched", device=dev)
         torch.cuda.synchronize()
         tw = time.perf_counter() - tw

@@ -47,7 +47,7 @@ static bool ev_vec_ok(const void *a, int64_t ld_a, const void *tx, int64_t ld_tx
 // grid (chunks): CTA c scans its contiguous range of t once for ALL shifts (shift_corr.cuh) and writes part[c][i][k],
 //   S[comp][b][a] = sum_t tx[a][comp][t] * E[b][(t - (i - half)) mod N]          (sf:300-304, circular roll), k = comp*4 + b*2 + a
 template <bool FROM_Q, int NPASS>
-__global__ void __launch_bounds__(SC_NT, (FROM_Q || NPASS == 0) ? 2 : SC_MINB) k_shift_corr(const float *q, int64_t ld_q, const float *out, int64_t ld_out,
+__global__ void __launch_bounds__(SC_NT, (FROM_Q || NPASS == 0) ? 4 : SC_MINB) k_shift_corr(const float *q, int64_t ld_q, const float *out, int64_t ld_out,
                                                       const uint16_t *tx, int64_t ld_tx, const float *amp, int n_lev,
                                                       int N, int n_shift, int64_t per, double *part) {
     __shared__ ShiftSmem sm;
@@ -66,8 +66,15 @@ __global__ void __launch_bounds__(1024) k_shift_decide(const double *part, int n
     const int il = threadIdx.x % lanes, gq = threadIdx.x / lanes;
     double s = 0.0;
     if (gq < ng && il < nidx) {
-#pragma unroll 4
-        for (int c = gq; c < chunks; c += ng) s += part[(int64_t)c * nidx + il];
+        int c = gq;
+        for (; c + 15 * ng < chunks; c += 16 * ng) {        // 16 independent loads in flight (the kernel is one CTA of pure L2 latency); same order of additions
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = part[(int64_t)(c + k * ng) * nidx + il];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s += v[k];
+        }
+        for (; c < chunks; c += ng) s += part[(int64_t)c * nidx + il];
     }
     ps[threadIdx.x] = s;
     __syncthreads();

@@ -53,7 +53,7 @@ __device__ __forceinline__ int er_wrap(int t, int N) {
 
 // ---- shift search, both estimators, all runs: grid (ER_CHUNKS, 2 R); a CTA scans its range of t once for all shifts ------------
 template <int NPASS>
-__global__ void __launch_bounds__(SC_NT, NPASS == 0 ? 2 : SC_MINB) k_er_shift_corr(EvalRunsK p) {
+__global__ void __launch_bounds__(SC_NT, NPASS == 0 ? 4 : SC_MINB) k_er_shift_corr(EvalRunsK p) {
     __shared__ ShiftSmem sm;
     const int chunk = blockIdx.x, run = blockIdx.y >> 1, est = blockIdx.y & 1, N = p.N;
     if (!((p.which >> est) & 1)) return;

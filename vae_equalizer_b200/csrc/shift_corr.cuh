@@ -20,12 +20,12 @@
 
 namespace vaeq {
 
-constexpr int SC_NT = 256, SC_NW = SC_NT / 32;
-constexpr int SC_T = 768;                      // symbols per tile
+constexpr int SC_NT = 128, SC_NW = SC_NT / 32;
+constexpr int SC_T = 384;                      // symbols per tile
 constexpr int SC_SLICE = SC_T / SC_NW;         // symbols per warp and tile
 constexpr int SC_MAXSHIFT = 64;
 #ifndef SC_MINB_DEF
-#define SC_MINB_DEF 3
+#define SC_MINB_DEF 6
 #endif
 constexpr int SC_MINB = SC_MINB_DEF;            // CTAs per SM: the tile loop is load -> barrier -> correlate -> barrier, other CTAs hide the waits
 

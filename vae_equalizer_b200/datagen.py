@@ -142,6 +142,11 @@ def _generate_frames_cuda(N, amps, SNR, P, theta, dev, seed, symb_rate, tau_cd, 
     terms = _cached_channel_terms(n_up, symb_rate, sps, tau_cd, tau_pmd, dev)
     n_pulse, Pcd, Picd, pulse = terms[5], terms[6], terms[7], terms[8]
     n = 2 * n_conv - n_pulse
+    skey = ("jones_terms_over_n", n_up, float(symb_rate), float(tau_cd), float(tau_pmd), str(dev))
+    scaled = _GPU_CACHE.get(skey)
+    if scaled is None:                                        # the 1/n of the inverse DFT folded into the per-bin terms: the Jones kernel's output is
+        scaled = _GPU_CACHE[skey] = ((Pcd / n).contiguous(), (Picd / n).contiguous())      # linear in them, and ifft(norm="forward") skips its scaling pass
+    Pcd, Picd = scaled
     st = _lib.current_stream()
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     lev = torch.empty(R, 4, n_conv, dtype=f32, device=dev)
@@ -155,7 +160,7 @@ def _generate_frames_cuda(N, amps, SNR, P, theta, dev, seed, symb_rate, tau_cd, 
     ph = np.asarray(phiIQ)
     phi0, phi1 = float(np.real(ph[0])), float(np.real(ph[1]))
     _lib.check(lib.vaeq_gen_jones(X.data_ptr(), Pcd.data_ptr(), Picd.data_ptr(), th.data_ptr(), phi0, phi1, n, R, st), "vaeq_gen_jones")
-    sig = torch.fft.ifft(X, dim=-1)
+    sig = torch.fft.ifft(X, dim=-1, norm="forward")
     power = torch.linalg.vector_norm(torch.view_as_real(sig).reshape(R, -1), dim=1).square() / (2 * n)       # mean |sig|^2 over both pols  (sf:83)
     sigma_n = torch.sqrt(power * sps / 2 / 10 ** (snr / 10))
     rx = torch.empty(R, 2, 2, sps * N, dtype=f32, device=dev)
