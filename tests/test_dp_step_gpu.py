@@ -150,8 +150,12 @@ def test_bad_arguments_raise():
         DPEqualizer(9, 2, g["amp"], g["P"], g["var"], 0.0).forward(torch.zeros(2, 2, 12, device="cuda"))    # B <= Mh
 
 
-def test_fast_path_matches_generic_kernels_and_trains():
-    """Same inputs through the register-blocked kernels (dp_fast.cu) and the generic ones (dp_step.cu)."""
+@pytest.mark.parametrize("prior", ["reference", "mb_other_nu", "arbitrary"])
+def test_fast_path_matches_generic_kernels_and_trains(prior):
+    """Same inputs through the register-blocked kernels (dp_fast.cu) and the generic ones (dp_step.cu).  prior: "reference" = sf:572
+    (Maxwell-Boltzmann with the demapper's own nu: moment form of the demapper, beta = -nu_sc log2 e), "mb_other_nu" = a Maxwell-Boltzmann
+    pmf whose nu differs from the demapper's PCS term (moment form with beta != -nu_sc log2 e), "arbitrary" = a pmf outside the family (the
+    forward kernel must detect it and take the per-level sums)."""
     from vae_equalizer_b200 import _lib
     from vae_equalizer_b200.dp import DPEqualizer
     lib = _lib.load()
@@ -160,6 +164,11 @@ def test_fast_path_matches_generic_kernels_and_trains():
     rx, tx, _ = O.generate_data_shaping(B, amps, 23, h_ch, P, 2, 90e9, 2, -26e-24, 0.1e-12 * np.sqrt(1000),
                                         np.array([0.0314, 0.0314], dtype=np.complex64), np.pi / 10, "cpu", rng=np.random.default_rng(2))
     Pt = torch.tensor(P, dtype=torch.float32)
+    if prior == "mb_other_nu":
+        Pt = torch.exp(-2.5 * nu_sc * amp.double() ** 2)
+        Pt = (Pt / Pt.sum()).float()
+    elif prior == "arbitrary":
+        Pt = torch.tensor([0.05, 0.2, 0.1, 0.15, 0.15, 0.1, 0.2, 0.05], dtype=torch.float32)
     res = {}
     for tag, force in (("fast", 0), ("generic", 1)):
         lib.vaeq_dp_force_generic(force)
