@@ -377,12 +377,16 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
             const int fam = wid >> 2, ft = tid & 127;
             // dW: an item = a tap pair, BOTH input polarisations at once (the window element {I0, I1, Q0, Q1} is the packed operand);
             // dh: an item = (tx pol, tap pair), both rx polarisations chi at once (window element {re0, re1, im0, im1})
-            const int items = fam == 0 ? nps : 2 * nps, parts = max(1, 128 / items), chunk = (B + parts - 1) / parts;
+            // Lane mapping: lanes 2i, 2i + 1 share an item and take NEIGHBOURING parts, and the chunk length is odd.  The window positions a
+            // quarter-warp's LDS.128 touches are then 2 q + {0, chunk} for four consecutive tap pairs q: eight distinct residues mod 8, i.e.
+            // no bank conflict (with lanes = consecutive items the positions 0, 2, ..., 14 collided two by two: 2.7 x the ideal wavefronts
+            // in this shared-memory-bound kernel, profiles/r02b_frame_kernel.txt).
+            const int items = fam == 0 ? nps : 2 * nps, parts = max(2, 2 * (64 / items)), chunk = ((B + parts - 1) / parts) | 1;
             float4 *pbase = part4 + (fam == 0 ? 0 : 4 * 128);
-            if (ft < items * parts) {
-                const int item = ft % items, part = ft / items;
+            if ((ft >> 1) < items * (parts >> 1)) {
+                const int item = (ft >> 1) % items, part = 2 * ((ft >> 1) / items) + (ft & 1);
                 const int sel = fam == 0 ? 0 : item / nps, q = item - sel * nps, ph = q >= np0, kA = (ph ? kf1 : kf0) + 4 * (ph ? q - np0 : q);
-                const int u0 = part * chunk, u1 = min(B, u0 + chunk), off = (kA - mh - ph) >> 1;
+                const int u0 = min(B, part * chunk), u1 = min(B, u0 + chunk), off = (kA - mh - ph) >> 1;
                 const float2 z2 = make_float2(0.f, 0.f);
                 if (fam == 0) {                                  // f = dL/dout {o0 re, im, o1 re, im}; window = rx of both input pols
                     float2 a0r = z2, a0i = z2, a1r = z2, a1i = z2, b0r = z2, b0i = z2, b1r = z2, b1i = z2;     // (input pol 0, input pol 1)
@@ -401,11 +405,11 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                         b1r = __ffma2_rn(fz, nI, b1r); b1r = __ffma2_rn(fw, nQ, b1r); b1i = __ffma2_rn(fw, nI, b1i); b1i = __ffma2_rn(nfz, nQ, b1i);
                         wa = wn;
                     }
-                    float4 *dst = pbase + (part * items + item) * 4;         // [tap of the pair][input pol] -> {o0 re, o0 im, o1 re, o1 im}
-                    dst[0] = make_float4(a0r.x, a0i.x, a1r.x, a1i.x);
-                    dst[1] = make_float4(a0r.y, a0i.y, a1r.y, a1i.y);
-                    dst[2] = make_float4(b0r.x, b0i.x, b1r.x, b1i.x);
-                    dst[3] = make_float4(b0r.y, b0i.y, b1r.y, b1i.y);
+                    float4 *dst = pbase + ft;                                // [slot = tap of the pair x input pol][thread] -> {o0 re, o0 im, o1 re, o1 im}
+                    dst[0] = make_float4(a0r.x, a0i.x, a1r.x, a1i.x);        // (slot-major: consecutive lanes store consecutive float4)
+                    dst[128] = make_float4(a0r.y, a0i.y, a1r.y, a1i.y);
+                    dst[256] = make_float4(b0r.x, b0i.x, b1r.x, b1i.x);
+                    dst[384] = make_float4(b0r.y, b0i.y, b1r.y, b1i.y);
                 } else {                                         // window = residual e {chi0 re, chi1 re, chi0 im, chi1 im}; f = E_q of tx pol sel
                     float2 ar = z2, ai = z2, br = z2, bi = z2;                  // (chi 0, chi 1)
                     const float4 *wb = eph + ph * SA + SO + off;
@@ -421,8 +425,8 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                         br = __ffma2_rn(nR, fi2, br); br = __ffma2_rn(nI, fq2, br); bi = __ffma2_rn(nI, fi2, bi); bi = __ffma2_rn(nR, nq2, bi);
                         wa = wn;
                     }
-                    pbase[(part * items + item) * 2] = make_float4(ar.x, ai.x, ar.y, ai.y);          // {chi0 re, chi0 im, chi1 re, chi1 im}
-                    pbase[(part * items + item) * 2 + 1] = make_float4(br.x, bi.x, br.y, bi.y);
+                    pbase[ft] = make_float4(ar.x, ai.x, ar.y, ai.y);          // [slot = tap of the pair][thread] -> {chi0 re, chi0 im, chi1 re, chi1 im}
+                    pbase[128 + ft] = make_float4(br.x, bi.x, br.y, bi.y);
                 }
             }
             __syncthreads();
@@ -433,10 +437,11 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                 const int kk = kA + 2 * tb;
                 if (kk < M) {
                     // fixed-order sum of the chunk partials (deterministic)
-                    const int per = fam == 0 ? 4 : 2, item = fam == 0 ? q : sel * nps + q, slot = fam == 0 ? tb * 2 + sel : tb;
-                    float4 sacc = pbase[item * per + slot];
+                    const int item = fam == 0 ? q : sel * nps + q, slot = fam == 0 ? tb * 2 + sel : tb;
+                    const float4 *src = pbase + slot * 128 + 2 * item;       // thread of (item, part) = 2 ((part >> 1) items + item) + (part & 1)
+                    float4 sacc = src[0];
                     for (int part = 1; part < parts; ++part) {
-                        const float4 t4 = pbase[(part * items + item) * per + slot];
+                        const float4 t4 = src[2 * (part >> 1) * items + (part & 1)];
                         sacc.x += t4.x; sacc.y += t4.y; sacc.z += t4.z; sacc.w += t4.w;
                     }
                     if (fam == 0) {
