@@ -18,6 +18,8 @@
 
 namespace vaeq {
 
+__device__ __forceinline__ float fneg(float v) { return __uint_as_float(__float_as_uint(v) ^ 0x80000000u); }   // sign flip as an integer op
+
 #ifdef VAEQ_SMALL_TIMING
 __device__ unsigned long long g_small_cyc[16];
 #define ST_DECL long long _st = clock64(); unsigned long long _sa[16] = {0};
@@ -34,7 +36,7 @@ constexpr int SM_NT = 256;
 // shared-memory plan (offsets in floats); doubles first (8-byte aligned), then float4 arrays, then floats
 struct SmallLayout {
     int XA, XO, SA, SO;                     // phase-array lengths (float4) and zero margins of x and e
-    int dsc, xph, m1s, eph, gys, Wt, hD, hG, Wn, hDn, hGn, part4, cst, srow, vsc, PS, Asum, edge, Wf, hf, adam, gfin, hsq, red, scal, total;
+    int dsc, xph, m1s, eph, gys, Wt, hD, hG, part4, cst, srow, vsc, PS, Asum, edge, Wf, hf, adam, gfin, hsq, red, scal, total;
 };
 __host__ __device__ inline SmallLayout small_layout(int B, int M) {
     SmallLayout l;
@@ -57,9 +59,6 @@ __host__ __device__ inline SmallLayout small_layout(int B, int M) {
     l.Wt = take(4 * 2 * M);
     l.hD = take(4 * 2 * M);
     l.hG = take(4 * 2 * M);
-    l.Wn = take(2 * 2 * M);                 // negated imaginary-part pairs of the three tap tables (operands of the packed FMAs)
-    l.hDn = take(2 * 2 * M);
-    l.hGn = take(2 * 2 * M);
     l.part4 = take(4 * 3 * SM_NT);          // chunk partials of the tap gradients: dW 128 x 4 float4, dh 128 x 2 float4
     l.cst = take((int)(sizeof(FastConst) / 4));
     l.srow = take(12 * B);
@@ -108,7 +107,6 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
     float4 *Wt = reinterpret_cast<float4 *>(sm + lay.Wt);        // [o][k]   {wr<-p0, wr<-p1, wi<-p0, wi<-p1}
     float4 *hD = reinterpret_cast<float4 *>(sm + lay.hD);        // [chi][j] {h_chi,0 re, h_chi,1 re, h_chi,0 im, h_chi,1 im}
     float4 *hG = reinterpret_cast<float4 *>(sm + lay.hG);        // [nu][j]  {h_0,nu re, h_1,nu re, h_0,nu im, h_1,nu im}   (kappa applied at use)
-    float2 *Wn = reinterpret_cast<float2 *>(sm + lay.Wn), *hDn = reinterpret_cast<float2 *>(sm + lay.hDn), *hGn = reinterpret_cast<float2 *>(sm + lay.hGn);   // -im pairs
     float4 *part4 = reinterpret_cast<float4 *>(sm + lay.part4);
     FastConst *cst = reinterpret_cast<FastConst *>(sm + lay.cst);
     float *srow = sm + lay.srow, *vsc = sm + lay.vsc, *PS = sm + lay.PS, *Asum = sm + lay.Asum, *edge = sm + lay.edge;
@@ -168,13 +166,10 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
         for (int idx = tid; idx < 2 * M; idx += SM_NT) {
             const int o = idx / M, k = idx - o * M;
             Wt[idx] = make_float4(Wf[(o * 4 + 0) * M + k], Wf[(o * 4 + 1) * M + k], Wf[(o * 4 + 2) * M + k], Wf[(o * 4 + 3) * M + k]);
-            Wn[idx] = make_float2(-Wf[(o * 4 + 2) * M + k], -Wf[(o * 4 + 3) * M + k]);
             hD[idx] = make_float4(hf[((o * 2 + 0) * 2 + 0) * M + k], hf[((o * 2 + 1) * 2 + 0) * M + k],
                                   hf[((o * 2 + 0) * 2 + 1) * M + k], hf[((o * 2 + 1) * 2 + 1) * M + k]);
-            hDn[idx] = make_float2(-hf[((o * 2 + 0) * 2 + 1) * M + k], -hf[((o * 2 + 1) * 2 + 1) * M + k]);
             hG[idx] = make_float4(hf[((0 * 2 + o) * 2 + 0) * M + k], hf[((1 * 2 + o) * 2 + 0) * M + k],
                                   hf[((0 * 2 + o) * 2 + 1) * M + k], hf[((1 * 2 + o) * 2 + 1) * M + k]);
-            hGn[idx] = make_float2(-hf[((0 * 2 + o) * 2 + 1) * M + k], -hf[((1 * 2 + o) * 2 + 1) * M + k]);
         }
         if (wid >= 4) {                                      // warp 4 + cn: PS[cn][j] = sum_{j' < j} |h_cn,j'|^2, cn = chi * 2 + nu
             const int cn = wid - 4;
@@ -221,13 +216,13 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                 const int k0 = (mh + ph) & 1;                    // taps k = k0, k0+2, ... read samples of phase ph
                 const float4 *xb = xph + ph * XA + u + XO + ((k0 - mh - ph) >> 1);
                 const float4 *wb = Wt + o * M + k0;
-                const float2 *nb = Wn + o * M + k0;
                 const int n = (M - k0 + 1) >> 1;
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
                     const float4 x = xb[i], w = wb[2 * i];
-                    const float2 wn = nb[2 * i], wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w), xI = make_float2(x.x, x.y), xQ = make_float2(x.z, x.w);
-                    re2 = __ffma2_rn(wr, xI, re2); re2 = __ffma2_rn(wn, xQ, re2);
+                    const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w), xI = make_float2(x.x, x.y), xQ = make_float2(x.z, x.w);
+                    const float2 nxQ = make_float2(fneg(x.z), fneg(x.w));      // (-wi) xQ = wi (-xQ) bit for bit: a sign flip on the ALU pipe instead of a third
+                    re2 = __ffma2_rn(wr, xI, re2); re2 = __ffma2_rn(wi, nxQ, re2);                  // shared-memory load per lag (the kernel is LSU-bound)
                     im2 = __ffma2_rn(wr, xQ, im2); im2 = __ffma2_rn(wi, xI, im2);
                 }
             }
@@ -270,14 +265,14 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                 float2 dr2 = make_float2(0.f, 0.f), di2 = dr2;   // (contribution of tx pol 0, of tx pol 1)
                 const int par = (s + mh) & 1;
                 const float4 *hb = hD + chi * M + par;
-                const float2 *nb = hDn + chi * M + par;
                 const float4 *mb = m1s + ((s + mh - par) >> 1);                       // E_q[(s + mh - j)/2], j = par + 2i
                 const int n = (M - par + 1) >> 1;
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
                     const float4 hh = hb[2 * i], mm = mb[-i];
-                    const float2 hn = nb[2 * i], hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), mI = make_float2(mm.x, mm.y), mQ = make_float2(mm.z, mm.w);
-                    dr2 = __ffma2_rn(hr, mI, dr2); dr2 = __ffma2_rn(hn, mQ, dr2);
+                    const float2 hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), mI = make_float2(mm.x, mm.y), mQ = make_float2(mm.z, mm.w);
+                    const float2 nmQ = make_float2(fneg(mm.z), fneg(mm.w));
+                    dr2 = __ffma2_rn(hr, mI, dr2); dr2 = __ffma2_rn(hi, nmQ, dr2);
                     di2 = __ffma2_rn(hi, mI, di2); di2 = __ffma2_rn(hr, mQ, di2);
                 }
                 const float4 x = xph[(s & 1) * XA + (s >> 1) + XO];
@@ -341,14 +336,14 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                 const int j0 = (mh + ph) & 1;                    // gD sample 2u - mh + j has phase ph for j = j0, j0+2, ...
                 const float4 *eb = eph + ph * SA + u + SO + ((j0 - mh - ph) >> 1);
                 const float4 *hb = hG + nu * M + j0;
-                const float2 *nb = hGn + nu * M + j0;
                 const int n = (M - j0 + 1) >> 1;
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
                     const float4 e = eb[i], hh = hb[2 * i];
-                    const float2 hn = nb[2 * i], hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), eR = make_float2(e.x, e.y), eI = make_float2(e.z, e.w);
+                    const float2 hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), eR = make_float2(e.x, e.y), eI = make_float2(e.z, e.w);
+                    const float2 neR = make_float2(fneg(e.x), fneg(e.y));
                     gr2 = __ffma2_rn(hr, eR, gr2); gr2 = __ffma2_rn(hi, eI, gr2);
-                    gi2 = __ffma2_rn(hr, eI, gi2); gi2 = __ffma2_rn(hn, eR, gi2);
+                    gi2 = __ffma2_rn(hr, eI, gi2); gi2 = __ffma2_rn(hi, neR, gi2);
                 }
             }
             const float grA = gr2.x, grB = gr2.y, giA = gi2.x, giB = gi2.y;
