@@ -258,34 +258,34 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
         // ---- P3: D = h * E_q on the valid samples, residual e = D - rx (sf:115-134), one (sample, rx pol) item per thread;
         //      then the edge sums of S_nu(j) = V_nu - edge_nu(j) (Var over source symbols outside Mh <= 2u+j < L, sf:128) --------
         float accC0 = 0.f, accC1 = 0.f;
-        for (int it = tid; it < 2 * L; it += SM_NT) {
-            const int chi = it >= L, s = it - chi * L;
-            float er = 0.f, ei = 0.f;
+        for (int s = tid; s < L; s += SM_NT) {                   // one SAMPLE per item, both rx polarisations: the E_q window element of a lag is
+            float er0 = 0.f, ei0 = 0.f, er1 = 0.f, ei1 = 0.f;    // loaded once for the two of them (the kernel is shared-memory-bandwidth bound)
             if (s >= mh && s < L - mh) {                                             // sf:120 "valid", in SAMPLES
-                float2 dr2 = make_float2(0.f, 0.f), di2 = dr2;   // (contribution of tx pol 0, of tx pol 1)
+                const float2 z2 = make_float2(0.f, 0.f);
+                float2 dr0 = z2, di0 = z2, dr1 = z2, di1 = z2;   // (contribution of tx pol 0, of tx pol 1) for chi = 0 / 1
                 const int par = (s + mh) & 1;
-                const float4 *hb = hD + chi * M + par;
+                const float4 *hb0 = hD + par, *hb1 = hD + M + par;
                 const float4 *mb = m1s + ((s + mh - par) >> 1);                       // E_q[(s + mh - j)/2], j = par + 2i
                 const int n = (M - par + 1) >> 1;
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
-                    const float4 hh = hb[2 * i], mm = mb[-i];
-                    const float2 hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), mI = make_float2(mm.x, mm.y), mQ = make_float2(mm.z, mm.w);
-                    const float2 nmQ = make_float2(fneg(mm.z), fneg(mm.w));
-                    dr2 = __ffma2_rn(hr, mI, dr2); dr2 = __ffma2_rn(hi, nmQ, dr2);
-                    di2 = __ffma2_rn(hi, mI, di2); di2 = __ffma2_rn(hr, mQ, di2);
+                    const float4 mm = mb[-i], ha = hb0[2 * i], hc = hb1[2 * i];
+                    const float2 mI = make_float2(mm.x, mm.y), mQ = make_float2(mm.z, mm.w), nmQ = make_float2(fneg(mm.z), fneg(mm.w));
+                    const float2 ar = make_float2(ha.x, ha.y), ai = make_float2(ha.z, ha.w), cr = make_float2(hc.x, hc.y), ci = make_float2(hc.z, hc.w);
+                    dr0 = __ffma2_rn(ar, mI, dr0); dr0 = __ffma2_rn(ai, nmQ, dr0);
+                    di0 = __ffma2_rn(ai, mI, di0); di0 = __ffma2_rn(ar, mQ, di0);
+                    dr1 = __ffma2_rn(cr, mI, dr1); dr1 = __ffma2_rn(ci, nmQ, dr1);
+                    di1 = __ffma2_rn(ci, mI, di1); di1 = __ffma2_rn(cr, mQ, di1);
                 }
                 const float4 x = xph[(s & 1) * XA + (s >> 1) + XO];
-                er = (dr2.x + dr2.y) - (chi ? x.y : x.x);
-                ei = (di2.x + di2.y) - (chi ? x.w : x.z);
+                er0 = (dr0.x + dr0.y) - x.x;
+                ei0 = (di0.x + di0.y) - x.z;
+                er1 = (dr1.x + dr1.y) - x.y;
+                ei1 = (di1.x + di1.y) - x.w;
             }
-            {
-                float *e4 = reinterpret_cast<float *>(eph + (s & 1) * SA + (s >> 1) + SO);
-                e4[chi] = er;
-                e4[2 + chi] = ei;
-            }
-            const float e2 = er * er + ei * ei;
-            if (chi) accC1 += e2; else accC0 += e2;
+            eph[(s & 1) * SA + (s >> 1) + SO] = make_float4(er0, er1, ei0, ei1);      // {chi0 re, chi1 re, chi0 im, chi1 im}
+            accC0 += er0 * er0 + ei0 * ei0;
+            accC1 += er1 * er1 + ei1 * ei1;
         }
         float accB0 = 0.f, accB1 = 0.f;                          // sum_{nu,j} |h_chi,nu,j|^2 edge_nu(j); on the LAST 2M threads,
         for (int idx = tid - (SM_NT - 2 * M); idx >= 0 && idx < 2 * M; idx += SM_NT) {      // which have the fewest D items above
