@@ -327,35 +327,41 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
 
         ST(4)
         // ---- P5: dL/dE_q = conj(h) (*) gD with gD = 2 kappa_chi e, then dL/dout = dL/dE_q S1 + dL/dVar T2 + w S3;
-        //      one (symbol, tx pol) item per thread ----------------------------------------------------------------------------
-        for (int it = tid; it < 2 * B; it += SM_NT) {
-            const int nu = it >= B, u = it - nu * B;
-            float2 gr2 = make_float2(0.f, 0.f), gi2 = gr2;       // (chi = 0 terms, chi = 1 terms)
+        //      one symbol (both tx pols) per thread ----------------------------------------------------------------------------
+        for (int u = tid; u < B; u += SM_NT) {                   // one SYMBOL per item, both tx polarisations: the residual window element of a lag is loaded once
+            const float2 z2 = make_float2(0.f, 0.f);
+            float2 gr0 = z2, gi0 = z2, gr1 = z2, gi1 = z2;       // (chi = 0 terms, chi = 1 terms) for nu = 0 / 1
 #pragma unroll
             for (int ph = 0; ph < 2; ++ph) {
                 const int j0 = (mh + ph) & 1;                    // gD sample 2u - mh + j has phase ph for j = j0, j0+2, ...
                 const float4 *eb = eph + ph * SA + u + SO + ((j0 - mh - ph) >> 1);
-                const float4 *hb = hG + nu * M + j0;
+                const float4 *hb0 = hG + j0, *hb1 = hG + M + j0;
                 const int n = (M - j0 + 1) >> 1;
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
-                    const float4 e = eb[i], hh = hb[2 * i];
-                    const float2 hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), eR = make_float2(e.x, e.y), eI = make_float2(e.z, e.w);
-                    const float2 neR = make_float2(fneg(e.x), fneg(e.y));
-                    gr2 = __ffma2_rn(hr, eR, gr2); gr2 = __ffma2_rn(hi, eI, gr2);
-                    gi2 = __ffma2_rn(hr, eI, gi2); gi2 = __ffma2_rn(hi, neR, gi2);
+                    const float4 e = eb[i], ha = hb0[2 * i], hc = hb1[2 * i];
+                    const float2 eR = make_float2(e.x, e.y), eI = make_float2(e.z, e.w), neR = make_float2(fneg(e.x), fneg(e.y));
+                    const float2 ar = make_float2(ha.x, ha.y), ai = make_float2(ha.z, ha.w), cr = make_float2(hc.x, hc.y), ci = make_float2(hc.z, hc.w);
+                    gr0 = __ffma2_rn(ar, eR, gr0); gr0 = __ffma2_rn(ai, eI, gr0);
+                    gi0 = __ffma2_rn(ar, eI, gi0); gi0 = __ffma2_rn(ai, neR, gi0);
+                    gr1 = __ffma2_rn(cr, eR, gr1); gr1 = __ffma2_rn(ci, eI, gr1);
+                    gi1 = __ffma2_rn(cr, eI, gi1); gi1 = __ffma2_rn(ci, neR, gi1);
                 }
             }
-            const float grA = gr2.x, grB = gr2.y, giA = gi2.x, giB = gi2.y;
-            const float gr = 2.f * (kap0 * grA + kap1 * grB), gi = 2.f * (kap0 * giA + kap1 * giB);
             const int jlo = max(0, Mh - 2 * u), jhi = min(M, L - 2 * u);
-            const float gV = kap0 * (PS[(0 * 2 + nu) * (M + 1) + jhi] - PS[(0 * 2 + nu) * (M + 1) + jlo]) +
-                             kap1 * (PS[(1 * 2 + nu) * (M + 1) + jhi] - PS[(1 * 2 + nu) * (M + 1) + jlo]);
             const float entw = (u >= mh && u < B - mh) ? LN2 : 0.f;
-            const int cc = 2 * nu;
-            const float gI = fmaf(gr, srow[cc * B + u], fmaf(gV, srow[(4 + cc) * B + u], entw * srow[(8 + cc) * B + u]));
-            const float gQ = fmaf(gi, srow[(cc + 1) * B + u], fmaf(gV, srow[(5 + cc) * B + u], entw * srow[(9 + cc) * B + u]));
-            reinterpret_cast<float2 *>(gys + u)[nu] = make_float2(gI, gQ);
+            float g4[4];
+#pragma unroll
+            for (int nu = 0; nu < 2; ++nu) {
+                const float2 gr2 = nu ? gr1 : gr0, gi2 = nu ? gi1 : gi0;
+                const float gr = 2.f * (kap0 * gr2.x + kap1 * gr2.y), gi = 2.f * (kap0 * gi2.x + kap1 * gi2.y);
+                const float gV = kap0 * (PS[(0 * 2 + nu) * (M + 1) + jhi] - PS[(0 * 2 + nu) * (M + 1) + jlo]) +
+                                 kap1 * (PS[(1 * 2 + nu) * (M + 1) + jhi] - PS[(1 * 2 + nu) * (M + 1) + jlo]);
+                const int cc = 2 * nu;
+                g4[2 * nu] = fmaf(gr, srow[cc * B + u], fmaf(gV, srow[(4 + cc) * B + u], entw * srow[(8 + cc) * B + u]));
+                g4[2 * nu + 1] = fmaf(gi, srow[(cc + 1) * B + u], fmaf(gV, srow[(5 + cc) * B + u], entw * srow[(9 + cc) * B + u]));
+            }
+            gys[u] = make_float4(g4[0], g4[1], g4[2], g4[3]);
         }
         __syncthreads();
 
