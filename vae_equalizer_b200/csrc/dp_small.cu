@@ -208,26 +208,35 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
         // ---- P1: butterfly FIR (sf:500-518) + soft demapper, moments, entropy, backward coefficients (sf:511-523, 101-113):
         //      one (symbol, output pol) item per thread, its two components demapped right away ------------------------------
         float accEnt = 0.f, accV0 = 0.f, accV1 = 0.f;
-        for (int it = tid; it < 2 * B; it += SM_NT) {
-            const int o = it >= B, u = it - o * B;
-            float2 re2 = make_float2(0.f, 0.f), im2 = re2;       // (contribution of input pol 0, of input pol 1)
+        // FIR: one SYMBOL per item, both output polarisations (the sample-window element of a lag is loaded once for the two of them: the
+        // kernel is shared-memory-bandwidth bound); the four outputs go through the dL/dout buffer (dead until P5) to the demapper items
+        for (int u = tid; u < B; u += SM_NT) {
+            const float2 z2 = make_float2(0.f, 0.f);
+            float2 re0 = z2, im0 = z2, re1 = z2, im1 = z2;       // (contribution of input pol 0, of input pol 1) for o = 0 / 1
 #pragma unroll
             for (int ph = 0; ph < 2; ++ph) {
                 const int k0 = (mh + ph) & 1;                    // taps k = k0, k0+2, ... read samples of phase ph
                 const float4 *xb = xph + ph * XA + u + XO + ((k0 - mh - ph) >> 1);
-                const float4 *wb = Wt + o * M + k0;
+                const float4 *wb0 = Wt + k0, *wb1 = Wt + M + k0;
                 const int n = (M - k0 + 1) >> 1;
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
-                    const float4 x = xb[i], w = wb[2 * i];
-                    const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w), xI = make_float2(x.x, x.y), xQ = make_float2(x.z, x.w);
-                    const float2 nxQ = make_float2(fneg(x.z), fneg(x.w));      // (-wi) xQ = wi (-xQ) bit for bit: a sign flip on the ALU pipe instead of a third
-                    re2 = __ffma2_rn(wr, xI, re2); re2 = __ffma2_rn(wi, nxQ, re2);                  // shared-memory load per lag (the kernel is LSU-bound)
-                    im2 = __ffma2_rn(wr, xQ, im2); im2 = __ffma2_rn(wi, xI, im2);
+                    const float4 x = xb[i], wa = wb0[2 * i], wc = wb1[2 * i];
+                    const float2 xI = make_float2(x.x, x.y), xQ = make_float2(x.z, x.w), nxQ = make_float2(fneg(x.z), fneg(x.w));   // (-wi) xQ = wi (-xQ) bit for bit:
+                    const float2 ar = make_float2(wa.x, wa.y), ai = make_float2(wa.z, wa.w), cr = make_float2(wc.x, wc.y), ci = make_float2(wc.z, wc.w);   // FFMA2 negates for free
+                    re0 = __ffma2_rn(ar, xI, re0); re0 = __ffma2_rn(ai, nxQ, re0);
+                    im0 = __ffma2_rn(ar, xQ, im0); im0 = __ffma2_rn(ai, xI, im0);
+                    re1 = __ffma2_rn(cr, xI, re1); re1 = __ffma2_rn(ci, nxQ, re1);
+                    im1 = __ffma2_rn(cr, xQ, im1); im1 = __ffma2_rn(ci, xI, im1);
                 }
             }
-            const float reA = re2.x, reB = re2.y, imA = im2.x, imB = im2.y;
-            const float yc[2] = {reA + reB, imA + imB};
+            gys[u] = make_float4(re0.x + re0.y, im0.x + im0.y, re1.x + re1.y, im1.x + im1.y);
+        }
+        __syncthreads();
+        for (int it = tid; it < 2 * B; it += SM_NT) {
+            const int o = it >= B, u = it - o * B;
+            const float2 y2 = reinterpret_cast<const float2 *>(gys + u)[o];
+            const float yc[2] = {y2.x, y2.y};
             const bool keep = qk != nullptr && u >= p.keep_lo && u < p.keep_lo + p.keep_n;      // VAELE_DP:61-62 / VAEflex_DP:64-65
             const int64_t col = keep_base + (u - p.keep_lo);
             float vsum = 0.f;
