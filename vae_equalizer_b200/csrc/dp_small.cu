@@ -18,6 +18,27 @@
 
 namespace vaeq {
 
+// block_sum (common.cuh) with the final reduction on the LAST warp of the CTA: totals valid in all its lanes
+template <int NV>
+__device__ __forceinline__ void block_sum_last(float (&v)[NV], float *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[i * 32 + wid] = v[i];
+    }
+    __syncthreads();
+    if (wid == nw - 1) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float x = lane < nw ? scratch[i * 32 + lane] : 0.f;
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
 __device__ __forceinline__ float fneg(float v) { return __uint_as_float(__float_as_uint(v) ^ 0x80000000u); }   // sign flip as an integer op
 
 #ifdef VAEQ_SMALL_TIMING
@@ -312,9 +333,9 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
         // ---- P4: ELBO scalars (sf:131-137): C = sum|e|^2 + sum_nu V_nu A_chi,nu - B_chi, loss, var_est, kappa = (L-Mh)/C ---------
         {
             float v[7] = {accC0, accC1, accEnt, accV0, accV1, accB0, accB1};
-            block_sum<7>(v, red);                                // its barriers also publish eph and edge; totals in ALL lanes of warp 0
-            if (tid < 2) {
-                const int chi = tid;
+            block_sum_last<7>(v, red);                           // its barriers also publish eph and edge; totals in ALL lanes of the LAST warp, which has
+            if (wid == SM_NT / 32 - 1 && lane < 2) {             // no P5 item at the reference's batch_len: its two double-precision logs overlap the contraction below
+                const int chi = lane;
                 const double C = (double)v[chi] + ((double)v[3] * (double)Asum[chi * 2] + (double)v[4] * (double)Asum[chi * 2 + 1]) -
                                  (double)v[5 + chi];                                 // sf:133-134
                 const double term = width * log(C);                                  // sf:136
@@ -331,15 +352,14 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                 }
             }
         }
-        __syncthreads();
-        const float kap0 = scal[0], kap1 = scal[1];
-
-        ST(4)
         // ---- P5: dL/dE_q = conj(h) (*) gD with gD = 2 kappa_chi e, then dL/dout = dL/dE_q S1 + dL/dVar T2 + w S3;
-        //      one symbol (both tx pols) per thread ----------------------------------------------------------------------------
-        for (int u = tid; u < B; u += SM_NT) {                   // one SYMBOL per item, both tx polarisations: the residual window element of a lag is loaded once
-            const float2 z2 = make_float2(0.f, 0.f);
-            float2 gr0 = z2, gi0 = z2, gr1 = z2, gi1 = z2;       // (chi = 0 terms, chi = 1 terms) for nu = 0 / 1
+        //      one symbol (both tx pols) per thread.  The contraction over e does not need kappa (it is linear in kappa_chi, applied after the
+        //      sum), so with one item per thread (batch_len <= 256) it runs BEFORE the barrier that publishes kappa, while the last warp
+        //      is still at the logs of the ELBO scalars -----------------------------------------------------------------------
+        const float2 z2 = make_float2(0.f, 0.f);
+        float2 gr0 = z2, gi0 = z2, gr1 = z2, gi1 = z2;           // (chi = 0 terms, chi = 1 terms) for nu = 0 / 1
+        auto contract = [&](int u) {
+            gr0 = gi0 = gr1 = gi1 = z2;
 #pragma unroll
             for (int ph = 0; ph < 2; ++ph) {
                 const int j0 = (mh + ph) & 1;                    // gD sample 2u - mh + j has phase ph for j = j0, j0+2, ...
@@ -357,6 +377,15 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
                     gi1 = __ffma2_rn(cr, eI, gi1); gi1 = __ffma2_rn(ci, neR, gi1);
                 }
             }
+        };
+        const bool one_item = B <= SM_NT;
+        if (one_item && tid < B) contract(tid);
+        __syncthreads();
+        const float kap0 = scal[0], kap1 = scal[1];
+
+        ST(4)
+        for (int u = tid; u < B; u += SM_NT) {
+            if (!one_item) contract(u);
             const int jlo = max(0, Mh - 2 * u), jhi = min(M, L - 2 * u);
             const float entw = (u >= mh && u < B - mh) ? LN2 : 0.f;
             float g4[4];
