@@ -265,9 +265,40 @@ __global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys
                 }
                 __syncthreads();
             }
+            if (STAGED) {
+                // item = (o, i, m), BOTH components c of the tap increment at once: they share all five shared-memory operands of a symbol.
+                // The valid symbols of the window form ONE range (kap >= 0 and 0 <= s < N, s = (kap + off) sps - mh + m ascending in kap): bounds
+                // hoisted, pointers stepped: 5 shared loads + 6 FP operations per symbol (the generic loop below was 35 instructions per symbol and
+                // component, 68 % of the kernel's instruction stream); same expressions in the same order per accumulator: bit-identical sums
+                for (int it = tid; it < 4 * M; it += CMA_NT) {
+                    const int m = it % M, oi = it / M, i = oi & 1, o = oi >> 1;
+                    float acc0 = 0.f, acc1 = 0.f;
+                    const int t0s = mh - m - off * sps;                              // s >= 0  <=>  kap * sps >= t0s
+                    const int lo_s = t0s <= 0 ? 0 : (t0s + sps - 1) / sps;
+                    const int hi_s = (N - 1 + t0s) >= 0 ? (N - 1 + t0s) / sps : -1;  // s <= N - 1  <=>  kap * sps <= N - 1 + t0s
+                    const int ka = max(max(kap0, 0), lo_s), kb = min(k_fire, hi_s + 1);
+                    if (ka < kb) {
+                        const int w0 = ka - kap0, s0 = (ka + off) * sps - mh + m - sw_base;
+                        const float *ya = ybuf + (2 * i) * ycap + s0, *yb = ybuf + (2 * i + 1) * ycap + s0;
+                        const float *pI = obuf + (2 * o) * batchlen + w0, *pQ = obuf + (2 * o + 1) * batchlen + w0, *pe = ebuf + 2 * w0 + o;
+                        const int cnt = kb - ka;
+#pragma unroll 4
+                        for (int n = 0; n < cnt; ++n) {
+                            const float a = ya[n * sps], b = yb[n * sps], vI = pI[n], vQ = pQ[n], ev = pe[2 * n];
+                            const float inc0 = (vI * a + vQ * b);                    // sf:414-422
+                            const float inc1 = (vQ * a - vI * b);
+                            acc0 += ev * inc0;
+                            acc1 += ev * inc1;
+                        }
+                    }
+                    hs[((o * 2 + i) * 2 + 0) * M + m] += lr2 * acc0;                 // sf:425-433
+                    hs[((o * 2 + i) * 2 + 1) * M + m] += lr2 * acc1;
+                }
+            } else {
             for (int idx = tid; idx < 8 * M; idx += CMA_NT) {
                 const int m = idx % M, oic = idx / M, c = oic & 1, oi = oic >> 1, i = oi & 1, o = oi >> 1;
                 float acc = 0.f;
+                {
                 for (int kap = kap0; kap < k_fire; ++kap) {
                     const int ks = kap + off, s = ks * sps - mh + m;
                     if (kap < 0 || s < 0 || s >= N) continue;                    // kap < 0 would read torch.empty garbage in the reference
@@ -279,7 +310,9 @@ __global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys
                     const float inc = c ? (vQ * a - vI * b) : (vI * a + vQ * b);     // sf:414-422
                     acc += (STAGED ? ebuf[2 * w + o] : r.e[2 * kap + o]) * inc;
                 }
+                }
                 hs[idx] += lr2 * acc;                                            // sf:425-433
+            }
             }
             __syncthreads();
         }
