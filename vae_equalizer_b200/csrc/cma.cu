@@ -220,9 +220,10 @@ __global__ void __launch_bounds__(CMA_NT) k_cma_block(const float *Rx, float *ys
             if (k <= kc_hi) {
                 const int ks = k + off;
                 float oI[2] = {0.f, 0.f}, oQ[2] = {0.f, 0.f};
-                for (int m = 0; m < M; ++m) {
-                    const int s = ks * sps - mh + m;
-                    if (s < 0 || s >= N) continue;
+                const int sm0 = ks * sps - mh, m_lo = max(0, -sm0), m_hi = min(M, N - sm0);      // taps whose sample lies inside [0, N): one range
+#pragma unroll 2
+                for (int m = m_lo; m < m_hi; ++m) {
+                    const int s = sm0 + m;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const float a = STAGED ? ybuf[(2 * i) * ycap + (s - s_base)] : r.y[(int64_t)(2 * i) * N + s];
