@@ -85,18 +85,20 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
     // the window of symbol ks + 1 does not depend on the tap recurrence: it is loaded one iteration ahead, so that the
     // L2 latency of the loads is not part of the per-symbol dependency chain (one warp per run has nothing else to hide it)
     float nI[NSLOT][2], nQ[NSLOT][2];                                                   // [slot][in pol]
-    auto load_window = [&](int ks) {
+    const float *yrow[4] = {r.y, r.y + N, r.y + 2 * (int64_t)N, r.y + 3 * (int64_t)N};   // row bases once: the loop is one warp's dependent chain,
+    auto load_window = [&](int ks) {                                                  // every instruction in it counts
 #pragma unroll
         for (int sl = 0; sl < NSLOT; ++sl) {
             const int k = lane + 32 * sl, s = ks * sps - mh + k;
-            const bool ok = (k < M) && (s >= 0) && (s < N);
+            const bool ok = (k < M) && ((unsigned)s < (unsigned)N);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                nI[sl][i] = ok ? r.y[(int64_t)(2 * i) * N + s] : 0.f;
-                nQ[sl][i] = ok ? r.y[(int64_t)(2 * i + 1) * N + s] : 0.f;
+                nI[sl][i] = ok ? yrow[2 * i][s] : 0.f;
+                nQ[sl][i] = ok ? yrow[2 * i + 1][s] : 0.f;
             }
         }
     };
+    const int koff = mh / sps - mh;                                                   // cma_out_index(ks) = ks + koff: (mh + ks sps) / sps = ks + mh / sps
     load_window(0);
     for (int ks = 0; ks < nsym_loop; ++ks) {
         float yI[NSLOT][2], yQ[NSLOT][2];
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(32) k_cma_sample(const float *Rx, float *ys, f
         float err[2];
 #pragma unroll
         for (int o = 0; o < 2; ++o) err[o] = R - oI[o] * oI[o] - oQ[o] * oQ[o];  // sf:366-367
-        int k = cma_out_index(ks, sps, mh, Nsym);
+        int k = ks + koff;                                                       // sf:357, may be negative: wraps to the end
         if (k < 0) k += Nsym;
         if (lane == 0 && k >= 0 && k < Nsym) {
             r.out[0 * Nsym + k] = oI[0];
