@@ -29,15 +29,14 @@ struct AwK {
 };
 
 __device__ __forceinline__ void adam_apply_awgn(float *param, float g, float *m, float *v, float *vmax, int i, float lr,
-                                                bool amsgrad, int step) {
+                                                bool amsgrad, double bc1, float bc2s) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     float mi = m[i], vi = v[i];
     mi = mi + (g - mi) * (1.f - b1);
     vi = vi * b2 + (1.f - b2) * g * g;
     m[i] = mi;
     v[i] = vi;
-    const double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
-    const float step_size = (float)(-(double)lr / bc1), bc2s = (float)sqrt(bc2);
+    const float step_size = (float)(-(double)lr / bc1);    // bias corrections: two double-precision pow, computed ONCE per step by thread 0
     float vv = vi;
     if (amsgrad) {
         vv = fmaxf(vmax[i], vi);
@@ -211,8 +210,14 @@ __global__ void __launch_bounds__(AW_NT) k_awgn_step(AwK p) {
     __syncthreads();
     // ---- phase 6: tap gradients (one output per thread), then Adam -----------------------------------------
     __shared__ int step_sh;
+    __shared__ double bc1_sh;
+    __shared__ float bc2s_sh;
     int *step_ptr = p.adam ? reinterpret_cast<int *>(p.adam + 12 * M) : nullptr;
-    if (tid == 0 && p.mode == DP_MODE_TRAIN) step_sh = *step_ptr + 1;
+    if (tid == 0 && p.mode == DP_MODE_TRAIN) {
+        step_sh = *step_ptr + 1;
+        bc1_sh = 1.0 - pow(0.9, (double)step_sh);            // (every parameter's thread used to evaluate both pow: FP64 at 1/64 rate)
+        bc2s_sh = (float)sqrt(1.0 - pow(0.999, (double)step_sh));
+    }
     __syncthreads();
     for (int idx = tid; idx < 4 * M; idx += AW_NT) {
         float g = 0.f;
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(AW_NT) k_awgn_step(AwK p) {
             }
             if (p.gW_out) p.gW_out[idx] = g;
             if (p.mode == DP_MODE_TRAIN)
-                adam_apply_awgn(p.W, g, p.adam, p.adam + 2 * M, p.adam + 4 * M, idx, p.lr_w, p.amsgrad != 0, step_sh);
+                adam_apply_awgn(p.W, g, p.adam, p.adam + 2 * M, p.adam + 4 * M, idx, p.lr_w, p.amsgrad != 0, bc1_sh, bc2s_sh);
         } else {                                         // dh[c][j]
             const int r = idx - 2 * M, c = r / M, j = r - c * M;
             for (int s = mh; s < L - mh; ++s) {
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(AW_NT) k_awgn_step(AwK p) {
             g += kap2 * hs[r] * Ssh[j];
             if (p.gh_out) p.gh_out[r] = g;
             if (p.mode == DP_MODE_TRAIN)
-                adam_apply_awgn(p.h, g, p.adam + 6 * M, p.adam + 8 * M, p.adam + 10 * M, r, p.lr_h, p.amsgrad != 0, step_sh);
+                adam_apply_awgn(p.h, g, p.adam + 6 * M, p.adam + 8 * M, p.adam + 10 * M, r, p.lr_h, p.amsgrad != 0, bc1_sh, bc2s_sh);
         }
     }
     __syncthreads();
