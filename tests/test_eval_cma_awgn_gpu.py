@@ -282,7 +282,7 @@ def test_dropin_awgn_runs():
     assert SER.shape == (4,) and torch.isfinite(SER).all() and float(SER[-1]) < float(SER[0]) + 1e-6
 
 
-@pytest.mark.parametrize("N,n_shift", [(64, 21), (516, 21), (1003, 21), (20000, 41), (4100, 64), (300000, 21)])
+@pytest.mark.parametrize("N,n_shift", [(64, 21), (516, 21), (1003, 21), (20000, 41), (4100, 64), (300000, 21), (516, 5), (1003, 24), (2000, 1), (3000, 25)])
 def test_find_shift_one_pass_kernel_against_oracle(N, n_shift):
     """csrc/shift_corr.cuh: tiles, circular wrap at both ends, vector and scalar staging, one and two shift passes."""
     import vae_equalizer_b200.shared_funcs as sfun
