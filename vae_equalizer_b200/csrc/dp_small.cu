@@ -192,6 +192,17 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
             hG[idx] = make_float4(hf[((0 * 2 + o) * 2 + 0) * M + k], hf[((1 * 2 + o) * 2 + 0) * M + k],
                                   hf[((0 * 2 + o) * 2 + 1) * M + k], hf[((1 * 2 + o) * 2 + 1) * M + k]);
         }
+        if (tid == 0) {                                      // Adam bias corrections 1 - beta^t: running products (pow once per frame)
+            b1t *= 0.9;
+            b2t *= 0.999;
+            dsc[0] = 1.0 - b1t;
+            scal[6] = sqrtf((float)(1.0 - b2t));
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // this step's window (issued during the previous step)
+        __syncthreads();
+        if (!last) issue_window(m + 1);                      // lands in the other buffer while this step computes
+        // |h|^2 and its prefix sums (used from P3 / P4 on) by warps 4-7 AFTER the barrier: they run next to the FIR of warps 0-3 instead of
+        // holding every warp at the top of the step
         if (wid >= 4) {                                      // warp 4 + cn: PS[cn][j] = sum_{j' < j} |h_cn,j'|^2, cn = chi * 2 + nu
             const int cn = wid - 4;
             float carry = 0.f;
@@ -215,15 +226,6 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
             }
             if (lane == 0) Asum[cn] = carry;
         }
-        if (tid == 0) {                                      // Adam bias corrections 1 - beta^t: running products (pow once per frame)
-            b1t *= 0.9;
-            b2t *= 0.999;
-            dsc[0] = 1.0 - b1t;
-            scal[6] = sqrtf((float)(1.0 - b2t));
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");      // this step's window (issued during the previous step)
-        __syncthreads();
-        if (!last) issue_window(m + 1);                      // lands in the other buffer while this step computes
 
         ST(0)
         // ---- P1: butterfly FIR (sf:500-518) + soft demapper, moments, entropy, backward coefficients (sf:511-523, 101-113):
