@@ -338,11 +338,12 @@ __global__ void __launch_bounds__(SM_NT, MINB) k_dp_frame_fast(DpK p, DpRunsK rs
             block_sum_last<7>(v, red);                           // its barriers also publish eph and edge; totals in ALL lanes of the LAST warp, which has
             if (wid == SM_NT / 32 - 1 && lane < 2) {             // no P5 item at the reference's batch_len: its two double-precision logs overlap the contraction below
                 const int chi = lane;
-                const double C = (double)v[chi] + ((double)v[3] * (double)Asum[chi * 2] + (double)v[4] * (double)Asum[chi * 2 + 1]) -
-                                 (double)v[5 + chi];                                 // sf:133-134
+                const float vC = chi ? v[1] : v[0], vB = chi ? v[6] : v[5], vV = chi ? v[4] : v[3];   // selects, not v[chi]: a run-time index would put
+                const double C = (double)vC + ((double)v[3] * (double)Asum[chi * 2] + (double)v[4] * (double)Asum[chi * 2 + 1]) -   // the whole array in local memory
+                                 (double)vB;                                         // sf:133-134
                 const double term = width * log(C);                                  // sf:136
                 scal[chi] = (float)(width / C);                                      // kappa
-                scal[2 + chi] = v[3 + chi];                                          // V_nu, for S_nu(j) in the Adam phase
+                scal[2 + chi] = vV;                                                  // V_nu, for S_nu(j) in the Adam phase
                 const float ve = (float)(C / width);                                 // sf:137
                 if (rs.var_steps) rs.var_steps[((int64_t)run * 2 + chi) * n_steps + m] = ve;
                 if (last && rs.var_last) rs.var_last[2 * run + chi] = ve;
