@@ -18,14 +18,14 @@
 
 namespace vaeq {
 
-// block_sum (common.cuh) with the final reduction on the LAST warp of the CTA: totals valid in all its lanes
+// block_sum (common.cuh) with the final reduction on the LAST warp of the CTA: totals valid in all its lanes; ONE barrier (the caller
+// uses the scratch once per step)
 template <int NV>
 __device__ __forceinline__ void block_sum_last(float (&v)[NV], float *scratch) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-    __syncthreads();
-    if (lane == 0) {
+    if (lane == 0) {                                         // no barrier before the stores: the scratch was last read a whole step (ten barriers) ago
 #pragma unroll
         for (int i = 0; i < NV; ++i) scratch[i * 32 + wid] = v[i];
     }
