@@ -134,12 +134,13 @@ int vaeq_dp_fused_backward(int32_t on);
  * departs from the hot path's stated "no tensor cores" design and was adopted on measurement (profiles/r02_tc_taps.txt). */
 int vaeq_dp_tc_taps(int32_t on);
 
-/* Forward kernel of the fast path: != 0 runs the 2x2 butterfly FIR and the channel convolution D = h * E_q on tcgen05 tensor cores
- * (dp_fwd_tc.cu: the sample / E_q windows are Hankel operands read straight from the staged rows, tf32 hi + lo split of both
- * operands, fp32 accumulation in TMEM, the three centre taps in fp32 on the CUDA cores because the tensor core truncates its
- * accumulator); 0 (default) = the CUDA-core kernel k_dp_fwd_fast.  Same outputs within the step tolerances; measured 278 us against
- * 275 us at batch_len 2^22 (252 us with every tap on the tensor core, at 4.5 x the output error), so it stays an experiment
- * (profiles/r02_tc_forward.txt). */
+/* Forward kernel of the fast path: != 0 (default since r02c) runs the 2x2 butterfly FIR and the channel convolution D = h * E_q on
+ * tcgen05 tensor cores (dp_fwd_tc.cu: the sample / E_q windows are Hankel operands read straight from the staged rows, tf32 hi + lo
+ * split of both operands, fp32 accumulation in TMEM; the tensor core truncates its accumulator, so the MMAs are issued by growing
+ * magnitude -- lo parts, outer taps, the K steps with the centre taps last -- and the centre tap itself stays in fp32 on the CUDA
+ * cores); 0 = the CUDA-core kernel k_dp_fwd_fast, which also serves the (n_lev, M_est) the tensor-core kernel is not built for.
+ * Same outputs within the step tolerances; at batch_len 2^22: 244 us against 257 us, out against float64 max 4.4e-7 / rms 5.3e-8
+ * against 6.7e-7 / 6.5e-8 (profiles/r02c_tc_forward.txt). */
 int vaeq_dp_tc_forward(int32_t on);
 
 /* forward only: q, out, loss, var_est  (net(minibatch) + loss_function_shaping, no grad) */

@@ -503,7 +503,7 @@ def test_tensor_core_forward_against_the_cuda_core_forward(M, mod, B):
                 torch.cuda.synchronize()
                 assert all(torch.equal(a.cpu(), b) for a, b in zip(again, res[1]))                         # static tiles: bitwise reproducible
     finally:
-        lib.vaeq_dp_tc_forward(0)
+        lib.vaeq_dp_tc_forward(1)                            # the library default
         lib.vaeq_dp_dynamic_tiles(1)
     (q1, o1, l1, v1, gW1, gh1), (q0, o0, l0, v0, gW0, gh0) = res[1], res[0]
     e_o, e_q = float((o1 - o0).abs().max()), float((q1 - q0).abs().max())
@@ -545,7 +545,7 @@ def test_forward_out_error_against_float64(tc):
         q, out, loss, ve = eq.forward(rx)
         torch.cuda.synchronize()
     finally:
-        lib.vaeq_dp_tc_forward(0)
+        lib.vaeq_dp_tc_forward(1)                            # the library default
     ref = _fir_float64(rx, W0.cuda(), M)
     err = out.double() - ref
     e_max, e_rms, bias = float(err.abs().max()), float(err.pow(2).mean().sqrt()), float((err * ref.sign()).mean())

@@ -16,7 +16,7 @@ NK = 11
 for fused in [int(a) for a in (sys.argv[1:] or ["2", "1", "0"])]:      # 2: tensor-core tap gradients, 1: fused CUDA-core backward, 0: three kernels
     lib.vaeq_dp_fused_backward(1 if fused == 1 else 0)
     lib.vaeq_dp_tc_taps(1 | int(os.environ.get('TC_DEBUG', 0)) if fused == 2 else 0)
-    lib.vaeq_dp_tc_forward(int(os.environ.get('TC_FWD', 0)))
+    lib.vaeq_dp_tc_forward(int(os.environ.get('TC_FWD', 1)))
     eq = DPEqualizer(M, 2, amp, P, var, nu_sc)
     for i in range(4):
         eq.train_step(rxs[i % 3], 2.5e-3, 2.5e-3, q=q, out=out)
@@ -40,4 +40,4 @@ for fused in [int(a) for a in (sys.argv[1:] or ["2", "1", "0"])]:      # 2: tens
           + ", ".join(f"{k}: {v:.1f}" for k, v in per.items()) + f"; loss {float(eq.loss):.6g}")
 lib.vaeq_dp_fused_backward(0)
 lib.vaeq_dp_tc_taps(1)
-lib.vaeq_dp_tc_forward(0)
+lib.vaeq_dp_tc_forward(1)

@@ -727,8 +727,10 @@ static int dp_run_fast_t(DpK p, int mode, cudaStream_t st, int *grid_bwd_out) {
 
 bool g_fused_bwd = false;   // until the fused launch beats the three kernels (profiles/r02_fused_backward.txt)
 
-bool g_tc_fwd = false;      // forward kernel with the FIR and the channel convolution on tcgen05 (dp_fwd_tc.cu): measured, not faster than
-                            // k_dp_fwd_fast at equal accuracy (profiles/r02_tc_forward.txt) -> opt-in through vaeq_dp_tc_forward(1)
+bool g_tc_fwd = true;       // forward kernel with the FIR and the channel convolution on tcgen05 (dp_fwd_tc.cu), default since r02c: with the moment-form
+                            // demapper and the magnitude-ordered MMAs it is faster than k_dp_fwd_fast (244 vs 257 us) at a smaller output error
+                            // (profiles/r02c_tc_forward.txt); vaeq_dp_tc_forward(0) selects k_dp_fwd_fast, which also serves every (n_lev, M_est)
+                            // the tensor-core kernel is not built for
 
 bool g_tc_taps = true;      // both tap-gradient correlations on tcgen05 (dp_taps_tc.cu); false = the two CUDA-core correlation kernels
 

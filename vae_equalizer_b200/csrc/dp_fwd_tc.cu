@@ -17,14 +17,17 @@
 // One CTA of 4 independent 128-thread groups per SM (they share the 32 KB of tap tables; each group runs the tile loop of a
 // k_dp_fwd_fast CTA with named barriers and its own mbarriers / TMEM columns), 174 KB of shared memory.
 // Reference: twoXtwoFIR.forward sf:500-527, loss_function_shaping sf:92-137.
+#include <type_traits>
 #include "dp_fast.cuh"
 #include "tma.cuh"
 
 namespace vaeq {
 
 #ifndef FWDTC_CENTER
-#define FWDTC_CENTER 1                            // 1: the three centre taps of W and h on the CUDA cores (precision, see the kernel); 0: experiment, all taps on tcgen05
+#define FWDTC_CENTER 1                            // number of centre taps of W and of h kept on the CUDA cores in fp32: 0 (all taps on tcgen05), 1 or 3 (precision, see the kernel)
 #endif
+static_assert(FWDTC_CENTER == 0 || FWDTC_CENTER == 1 || FWDTC_CENTER == 3, "FWDTC_CENTER");
+constexpr int FC_CH = (FWDTC_CENTER - 1) / 2;     // half width of the CUDA-core tap range (meaningful for FWDTC_CENTER > 0)
 constexpr int FC_NG = 4;                          // groups per CTA
 constexpr int FC_GT = 128;                        // threads per group = TMEM lanes = 4-symbol blocks per tile
 constexpr int FC_NT = FC_NG * FC_GT;
@@ -86,6 +89,26 @@ struct FwdTcGeom {
     static constexpr int NKD = (MH + 3) / 2 + 1;             // channel-convolution K steps (2 positions): last position used = 3 + MH
     static constexpr int TAPF_FLOATS = 4 * NKF * 256;        // per step: N = 32 ([hi | lo] x 4 symbols x 4 outputs) x K = 8
     static constexpr int TAPD_FLOATS = NKD * 512;            // per step: N = 64 ([hi | lo] x 2 phases x 4 symbols x 4 outputs) x K = 8
+    // issue order of the MMAs (see the FIR issue loop): position t -> K step.  FIR: steps FSL, FSL + 1 of every rx row hold the taps MH - 1 ... MH + 1 of
+    // the four symbols of a block (samples OX - 1 ... OX + 7); convolution: the three steps from CSL on hold positions HF ... HF + 4
+    static constexpr int FSL = (OX - 1) / 8, CSL = HF / 2;
+    static_assert(FSL + 1 < NKF && CSL + 2 < NKD, "centre steps");
+    __host__ __device__ static constexpr int fir_step(int t) {                   // returns row * NKF + step
+        if (t < 4 * NKF) return t;                           // x_lo: any order
+        t -= 4 * NKF;
+        if (t < 4 * (NKF - 2)) {
+            const int c = t / (NKF - 2 > 0 ? NKF - 2 : 1), n = t - c * (NKF - 2);
+            return c * NKF + (n < FSL ? n : n + 2);
+        }
+        t -= 4 * (NKF - 2);
+        return (t >> 1) * NKF + FSL + (t & 1);
+    }
+    __host__ __device__ static constexpr int conv_step(int t) {
+        if (t < NKD) return t;                               // q_lo
+        t -= NKD;
+        if (t < NKD - 3) return t < CSL ? t : t + 3;
+        return CSL + (t - (NKD - 3));
+    }
     static constexpr size_t GROUP0 = 2048 + (size_t)(TAPF_FLOATS + TAPD_FLOATS) * 4;
     static constexpr size_t SMEM = GROUP0 + (size_t)FC_NG * 2 * FC_XB;
     static_assert(8 * 127 + 8 * NKF <= 4 * FC_XCH && 8 * 127 + OX + 8 <= 4 * FC_XCH, "sample window");
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         const int c = step / NKF, s = step - c * NKF, j = 8 * s + k8;
         const int half = n >> 4, i = (n >> 2) & 3, o = n & 3, k = j - 2 * i - SH;
         float v = 0.f;
-        if (k >= 0 && k < M && (!FWDTC_CENTER || k < MH - 1 || k > MH + 1)) {      // the three centre taps stay on the CUDA cores (see below)
+        if (k >= 0 && k < M && (!FWDTC_CENTER || k < MH - FC_CH || k > MH + FC_CH)) {      // the centre taps stay on the CUDA cores (see below)
             const int op = o >> 1, oc = o & 1, ip = c >> 1, ic = c & 1;
             const float tr = p.W[(op * 4 + ip) * M + k], ti = p.W[(op * 4 + 2 + ip) * M + k];
             v = oc == ic ? tr : (oc ? ti : -ti);             // Re = tr xr - ti xi, Im = ti xr + tr xi
@@ -131,7 +154,7 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         const int half = n >> 5, ph = (n >> 4) & 1, i = (n >> 2) & 3, o = n & 3, a = j - i - ph;
         float v = 0.f;
         const int jj = ph ? 2 * MH - 1 - 2 * a : 2 * MH - 2 * a;
-        if (a >= 0 && a < (ph ? MH : MH + 1) && (!FWDTC_CENTER || jj < MH - 1 || jj > MH + 1)) {   // even samples: h[2MH - 2a] E_q[u + a - HF];  odd: h[2MH - 1 - 2b] E_q[u + b - HF + 1]
+        if (a >= 0 && a < (ph ? MH : MH + 1) && (!FWDTC_CENTER || jj < MH - FC_CH || jj > MH + FC_CH)) {   // even samples: h[2MH - 2a] E_q[u + a - HF];  odd: h[2MH - 1 - 2b] E_q[u + b - HF + 1]
             const int chi = o >> 1, oc = o & 1, nu = c >> 1, ic = c & 1;
             const float hr = p.h[((chi * 2 + nu) * 2 + 0) * M + jj], hi_ = p.h[((chi * 2 + nu) * 2 + 1) * M + jj];
             v = oc == ic ? hr : (oc ? hi_ : -hi_);
@@ -205,11 +228,14 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             // 64-bit adds per MMA (a rolled loop with the descriptor arithmetic inside kept the other 127 threads waiting ~3000 cycles)
             const uint64_t dah = umma_desc(smem_u32(xhi), 16, 256, UMMA_SW32), dal = umma_desc(smem_u32(xlo), 16, 256, UMMA_SW32);
             const uint64_t db0 = umma_desc(smem_u32(tapF), 128, 256, UMMA_SW_NONE);
+            // order: the tensor core truncates every group of four products at the ulp of the accumulator (tools/tc_accum_bench.cu), so the
+            // terms go in by growing magnitude -- all x_lo steps, then the x_hi steps without a centre tap, and the K steps that hold the
+            // centre taps (|w| ~ 1) LAST: only those few accumulate at the ulp of the final value
 #pragma unroll
-            for (int st = 0; st < 4 * NKF; ++st) {
+            for (int t = 0; t < 8 * NKF; ++t) {
+                const int st = G::fir_step(t);
                 const uint64_t ao = (uint64_t)(((st / NKF) * FC_XCB + 32 * (st % NKF)) >> 4), bo = (uint64_t)((st * 1024) >> 4);
-                umma_tf32_k(tmem + 128 * g, dah + ao, db0 + bo, umma_idesc_k(32), st != 0);
-                umma_tf32_k(tmem + 128 * g, dal + ao, db0 + bo, umma_idesc_k(32), 1);
+                umma_tf32_k(tmem + 128 * g, (t < 4 * NKF ? dal : dah) + ao, db0 + bo, umma_idesc_k(32), t != 0);
             }
             umma_commit_to(bar_f);
         }
@@ -242,7 +268,7 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
                 const float4 xa = *reinterpret_cast<const float4 *>(row + swz32(16u * ch)), xb = *reinterpret_cast<const float4 *>(row + swz32(16u * (ch + 1)));
                 const float xs[9] = {*reinterpret_cast<const float *>(row + swz32(16u * (ch - 1)) + 12), xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
+                for (int d = 1 - FC_CH; d <= 1 + FC_CH; ++d) {
                     const float4 w = ctrF[d * 4 + ci];
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r) {
@@ -275,7 +301,10 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
                 *reinterpret_cast<float4 *>(qlo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
-            // point-wise stage, rolled over the polarisation (code size); y rotates by two components per pass
+            // point-wise stage, rolled over the polarisation (code size); y rotates by two components per pass.  Moment form when the prior is of the
+            // Maxwell-Boltzmann family (CTA-uniform: one of the two instantiations runs for the whole launch)
+            auto pointwise = [&](auto mom_tag) {
+            constexpr bool MOM = decltype(mom_tag)::value;
 #pragma unroll 1
             for (int pol = 0; pol < 2; ++pol) {
                 float vs[FT_R];
@@ -283,15 +312,37 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
                 for (int cq = 0; cq < 2; ++cq) {
                     const int cc = 2 * pol + cq;
                     float qv[FT_R][NL], m1v[FT_R], s1v[FT_R], t2v[FT_R], s3v[FT_R];
+                    if (MOM) {                               // moment form, a symbol pair per packed instruction (dp_math.cuh, as in k_dp_fwd_fast)
+#pragma unroll
+                        for (int r = 0; r < FT_R; r += 2) {
+                            float2 q2[NL], m1p, vp, entp, s1p, t2p, s3p;
+                            demap_mom2<NL>(make_float2(y[r][cq], y[r + 1][cq]), c.ct[pol], c.eps[pol], c.inv_var[pol], c, q2, m1p, vp, entp, s1p, t2p, s3p);
+#pragma unroll
+                            for (int l = 0; l < NL; ++l) { qv[r][l] = q2[l].x; qv[r + 1][l] = q2[l].y; }
+                            m1v[r] = m1p.x; m1v[r + 1] = m1p.y;
+                            s1v[r] = s1p.x; s1v[r + 1] = s1p.y;
+                            t2v[r] = t2p.x; t2v[r + 1] = t2p.y;
+                            s3v[r] = s3p.x; s3v[r + 1] = s3p.y;
+                            const int u = u0 + r;
+                            if (counted && u >= MH && u < p.B - MH) accEnt += entp.x;         // sf:132
+                            if (counted && u + 1 >= MH && u + 1 < p.B - MH) accEnt += entp.y;
+                            vs[r] = cq ? vs[r] + vp.x : vp.x;
+                            vs[r + 1] = cq ? vs[r + 1] + vp.y : vp.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < FT_R; ++r) {
+                            float m2, ent, S2;
+                            demap_fast<NL, true>(y[r][cq], c.c2[pol], c.inv_var[pol], c, qv[r], m1v[r], m2, ent, s1v[r], S2, s3v[r]);
+                            t2v[r] = fmaf(-2.f * m1v[r], s1v[r], S2);
+                            const int u = u0 + r;
+                            if (counted && u >= MH && u < p.B - MH) accEnt += ent;            // sf:132
+                            const float v = m2 - m1v[r] * m1v[r];                             // sf:113
+                            vs[r] = cq ? vs[r] + v : v;
+                        }
+                    }
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r) {
-                        float m2, ent, S2;
-                        demap_fast<NL, true>(y[r][cq], c.c2[pol], c.inv_var[pol], c, qv[r], m1v[r], m2, ent, s1v[r], S2, s3v[r]);
-                        t2v[r] = fmaf(-2.f * m1v[r], s1v[r], S2);
-                        const int u = u0 + r;
-                        if (counted && u >= MH && u < p.B - MH) accEnt += ent;                // sf:132
-                        const float v = m2 - m1v[r] * m1v[r];                                 // sf:113
-                        vs[r] = cq ? vs[r] + v : v;
                         const uint32_t off = swz64(qoff0 + 16u * r) + 4u * cc;
                         *reinterpret_cast<float *>(qhi + off) = m1v[r];
                         *reinterpret_cast<float *>(qlo + off) = tf32_lo_part(m1v[r]);
@@ -352,6 +403,9 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
                     t = y[r][1]; y[r][1] = y[r][3]; y[r][3] = t;
                 }
             }
+            };
+            if (c.quad) pointwise(std::true_type{});
+            else pointwise(std::false_type{});
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -362,10 +416,10 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             const uint64_t dqh = umma_desc(smem_u32(qhi), 16, 512, UMMA_SW64), dql = umma_desc(smem_u32(qlo), 16, 512, UMMA_SW64);
             const uint64_t db0 = umma_desc(smem_u32(tapD), 128, 256, UMMA_SW_NONE);
 #pragma unroll
-            for (int st = 0; st < NKD; ++st) {
+            for (int t = 0; t < 2 * NKD; ++t) {              // same order as the FIR: lo parts, outer taps, centre taps
+                const int st = G::conv_step(t);
                 const uint64_t ao = (uint64_t)((32 * st) >> 4), bo = (uint64_t)((st * 2048) >> 4);
-                umma_tf32_k(tmem + 128 * g + 32, dqh + ao, db0 + bo, umma_idesc_k(64), st != 0);
-                umma_tf32_k(tmem + 128 * g + 32, dql + ao, db0 + bo, umma_idesc_k(64), 1);
+                umma_tf32_k(tmem + 128 * g + 32, (t < NKD ? dql : dqh) + ao, db0 + bo, umma_idesc_k(64), t != 0);
             }
             umma_commit_to(bar_d);
         }
@@ -385,10 +439,12 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
                     const float q0 = f4c(eq[r], ci), q1 = f4c(eq[r + 1], ci);
                     a0 = __ffma2_rn(make_float2(w0.x, w0.y), make_float2(q0, q0), a0);
                     a1 = __ffma2_rn(make_float2(w0.z, w0.w), make_float2(q0, q0), a1);
-                    b0 = __ffma2_rn(make_float2(wp.x, wp.y), make_float2(q0, q0), b0);
-                    b1 = __ffma2_rn(make_float2(wp.z, wp.w), make_float2(q0, q0), b1);
-                    b0 = __ffma2_rn(make_float2(wm.x, wm.y), make_float2(q1, q1), b0);
-                    b1 = __ffma2_rn(make_float2(wm.z, wm.w), make_float2(q1, q1), b1);
+                    if (FWDTC_CENTER == 3) {
+                        b0 = __ffma2_rn(make_float2(wp.x, wp.y), make_float2(q0, q0), b0);
+                        b1 = __ffma2_rn(make_float2(wp.z, wp.w), make_float2(q0, q0), b1);
+                        b0 = __ffma2_rn(make_float2(wm.x, wm.y), make_float2(q1, q1), b0);
+                        b1 = __ffma2_rn(make_float2(wm.z, wm.w), make_float2(q1, q1), b1);
+                    }
                 }
                 dc[0][r][0] = a0; dc[0][r][1] = a1; dc[1][r][0] = b0; dc[1][r][1] = b1;
             }
