@@ -72,6 +72,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {       // the caller issues tcgen05.wait::st
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+                 "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+                 "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async16_zfill(void *dst_smem, const void *src_gmem, bool ok) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     const int n = ok ? 16 : 0;                               // src-size 0: the 16 bytes are zero-filled, the source is not read
@@ -185,19 +193,14 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
     const FastConst &c = *cst;
 
     uint64_t *bar_f = bars + g, *bar_d = bars + FC_NG + g;
-    const uint32_t tm_y = tmem + 128 * g + ((uint32_t)(32 * wq) << 16), tm_d = tm_y + 32;       // this warp's TMEM lanes, this group's columns
+    const uint32_t tm_y = tmem + 128 * g + ((uint32_t)(32 * wq) << 16), tm_d = tm_y + 32, tm_x = tm_y + 96;       // this warp's TMEM lanes, this group's columns: y 32, D 64, parked rx 32
     const int nv = (int)gridDim.x * FC_NG, vcta = (int)blockIdx.x * FC_NG + g;                  // a group is a virtual CTA of the tile loop
     const int i0 = FT_R * gt;
     float accC[2] = {0.f, 0.f}, accEnt = 0.f, accV0 = 0.f, accV1 = 0.f;
     uint32_t par = 0;
-
-#pragma unroll 1
-    for (int tile = vcta; tile < p.ntiles; par ^= 1) {
-        const int t0 = p.clo + tile * FT_T;
-        if (gt == 0) s_next[g] = p.dyn ? atomicAdd(p.tile_ctr, 1) + nv : tile + nv;
-        // ---- stage the tile's rx window: every rx row as it lies in HBM, 16-byte chunks, SWIZZLE_32B by absolute address; a chunk lies
-        // entirely inside or outside [0, L).  Then the thread derives the lo parts of ITS OWN chunks (no barrier in between).
-        const int64_t o_smp = 2 * (int64_t)(t0 - FT_HP) - OX;            // global sample index of window sample 0
+    // cp.async of a tile's rx window into x_hi; a chunk lies entirely inside or outside [0, L) (zero-filled outside)
+    auto stage_rx = [&](int tile_s) {
+        const int64_t o_smp = 2 * (int64_t)(p.clo + tile_s * FT_T - FT_HP) - OX;            // global sample index of window sample 0
 #pragma unroll 1
         for (int ch = gt; ch < FC_XCH; ch += FC_GT) {
             const int64_t s0 = o_smp + 4 * ch;
@@ -208,6 +211,15 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             for (int r = 0; r < 4; ++r) cp_async16_zfill(xhi + r * FC_XCB + off, src + (int64_t)r * p.ld_rx, ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (vcta < p.ntiles) stage_rx(vcta);
+
+#pragma unroll 1
+    for (int tile = vcta; tile < p.ntiles; par ^= 1) {
+        const int t0 = p.clo + tile * FT_T;
+        if (gt == 0) s_next[g] = p.dyn ? atomicAdd(p.tile_ctr, 1) + nv : tile + nv;
+        // ---- the tile's rx window (every rx row as it lies in HBM, 16-byte chunks, SWIZZLE_32B by absolute address) was requested by cp.async
+        // during the previous tile (see stage_rx below); the thread derives the lo parts of ITS OWN chunks (no barrier in between).
         asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 1
         for (int ch = gt; ch < FC_XCH; ch += FC_GT) {
@@ -240,15 +252,6 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             umma_commit_to(bar_f);
         }
         __syncwarp();
-        {   // the next tile's rx rows -> L2 while this one is computed
-            const int64_t first = 2 * (int64_t)(p.clo + tile_next * FT_T - FT_HP) - OX;
-            if (tile_next < p.ntiles && gt < 4 * 33) {
-                const int r = gt / 33, ln = gt - r * 33;
-                const int64_t off = first + 32 * (int64_t)ln;
-                if (off >= 0 && off < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rx + (int64_t)r * p.ld_rx + off));
-            }
-        }
-
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.chi);
@@ -262,22 +265,32 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) yc[r][0] = yc[r][1] = make_float2(0.f, 0.f);
             const uint32_t ch = 2u * gt + OX / 4;
+            float rxs[2][16];                                // this thread's own samples [phase][4 component + symbol]: parked in TMEM for the residual
 #pragma unroll
-            for (int ci = 0; ci < (FWDTC_CENTER ? 4 : 0); ++ci) {
+            for (int ci = 0; ci < 4; ++ci) {
                 const unsigned char *row = xhi + ci * FC_XCB;
                 const float4 xa = *reinterpret_cast<const float4 *>(row + swz32(16u * ch)), xb = *reinterpret_cast<const float4 *>(row + swz32(16u * (ch + 1)));
-                const float xs[9] = {*reinterpret_cast<const float *>(row + swz32(16u * (ch - 1)) + 12), xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                rxs[0][4 * ci + 0] = xa.x; rxs[0][4 * ci + 1] = xa.z; rxs[0][4 * ci + 2] = xb.x; rxs[0][4 * ci + 3] = xb.z;
+                rxs[1][4 * ci + 0] = xa.y; rxs[1][4 * ci + 1] = xa.w; rxs[1][4 * ci + 2] = xb.y; rxs[1][4 * ci + 3] = xb.w;
+                if (FWDTC_CENTER) {
+                    const float xs[9] = {FWDTC_CENTER == 3 ? *reinterpret_cast<const float *>(row + swz32(16u * (ch - 1)) + 12) : 0.f, xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                for (int d = 1 - FC_CH; d <= 1 + FC_CH; ++d) {
-                    const float4 w = ctrF[d * 4 + ci];
+                    for (int d = 1 - FC_CH; d <= 1 + FC_CH; ++d) {
+                        const float4 w = ctrF[d * 4 + ci];
 #pragma unroll
-                    for (int r = 0; r < FT_R; ++r) {
-                        const float2 xx = make_float2(xs[2 * r + d], xs[2 * r + d]);
-                        yc[r][0] = __ffma2_rn(make_float2(w.x, w.y), xx, yc[r][0]);
-                        yc[r][1] = __ffma2_rn(make_float2(w.z, w.w), xx, yc[r][1]);
+                        for (int r = 0; r < FT_R; ++r) {
+                            const float2 xx = make_float2(xs[2 * r + d], xs[2 * r + d]);
+                            yc[r][0] = __ffma2_rn(make_float2(w.x, w.y), xx, yc[r][0]);
+                            yc[r][1] = __ffma2_rn(make_float2(w.z, w.w), xx, yc[r][1]);
+                        }
                     }
                 }
             }
+            // x_hi is not read again after this point (the FIR MMAs are waited for just below): the samples the residual e = D - rx needs go to
+            // the group's 32 spare TMEM columns (lane = thread), so that the NEXT tile's rows can land in x_hi during the rest of this tile
+            tmem_st16(tm_x, rxs[0]);
+            tmem_st16(tm_x + 16, rxs[1]);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             mbar_wait(bar_f, par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float vh[16], vl[16];
@@ -410,6 +423,7 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         named_bar_sync(1 + g, FC_GT);
+        if (tile_next < p.ntiles) stage_rx(tile_next);       // every thread of the group is past its last read of x_hi: lands during the D MMAs and the residual
         if (gt == 0) {
             // ---- D (128 x 64: [hi | lo] x even / odd sample x 4 symbols x 4 components) = sum over NKD K steps of (q_hi + q_lo) [h_hi | h_lo] ----
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -458,20 +472,18 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             float dh[16], dl[16];
             tmem_ld16(tm_d + 16 * ph, dh);
             tmem_ld16(tm_d + 32 + 16 * ph, dl);
+            float xs[16];
+            tmem_ld16(tm_x + 16 * ph, xs);
             if (owned) {
                 float ev[4][FT_R];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t ch = 2u * gt + OX / 4;
-                    const float4 xa = *reinterpret_cast<const float4 *>(xhi + k * FC_XCB + swz32(16u * ch));
-                    const float4 xb = *reinterpret_cast<const float4 *>(xhi + k * FC_XCB + swz32(16u * (ch + 1)));
-                    const float xs[FT_R] = {ph ? xa.y : xa.x, ph ? xa.w : xa.z, ph ? xb.y : xb.x, ph ? xb.w : xb.z};
 #pragma unroll
                     for (int r = 0; r < FT_R; ++r) {
                         const int s = 2 * (u0 + r) + ph;
                         const bool valid = (s >= MH) && (s < p.L - MH);                     // sf:120 "valid" region
                         const float2 dcv = dc[ph][r][k >> 1];
-                        ev[k][r] = valid ? ((dh[4 * r + k] + dl[4 * r + k]) + ((k & 1) ? dcv.y : dcv.x)) - xs[r] : 0.f;
+                        ev[k][r] = valid ? ((dh[4 * r + k] + dl[4 * r + k]) + ((k & 1) ? dcv.y : dcv.x)) - xs[4 * k + r] : 0.f;
                     }
                 }
                 if (counted) {
