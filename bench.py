@@ -35,10 +35,11 @@ MOD, NU, SNR, M_EST, SPS, LR = "64-QAM", 0.0270955, 23, 25, 2, 2.5e-3
 N_LEV = 8
 ALG_BYTES_PER_SYMBOL = 4 * 2 * (2 * SPS + 2 * N_LEV + 2)        # read rx once, write q and out once = 176 B
 ALG_FLOP_PER_SYMBOL = 5 * 32 * M_EST + 1000                      # 5 tap contractions + point-wise work
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (k_dp_fwd_fast<8,12>) at batch_len 2^22 from the
-# `ncu --set full` capture summarised in profiles/r02b_ncu_full_summary.json (entry fwd_moment_form_packed): 134.3 MB read + 948.8 MB written = 258.2 B/symbol
-FWD_DRAM_BYTES_PER_SYMBOL = (134.298e6 + 948.839e6) / (1 << 22)
-TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_dp_fwd_fast<8,12>, profiles/r02b_ncu_full_summary.json, scaled to this batch_len"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (k_dp_fwd_tc<8,12>, the default forward kernel since r02c) at
+# batch_len 2^22 from the `ncu --set full` capture summarised in profiles/r02c_ncu_full_summary.json (entry early_staging): 134.3 MB read + 949.7 MB
+# written = 258.5 B/symbol
+FWD_DRAM_BYTES_PER_SYMBOL = (134.307e6 + 949.731e6) / (1 << 22)
+TRAFFIC_SOURCE = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_dp_fwd_tc<8,12>, profiles/r02c_ncu_full_summary.json, scaled to this batch_len"
 CPU_SAMPLE_LOG2 = 17
 
 
@@ -425,7 +426,9 @@ def ours_arm(args, rank, local_rank, world):
     peak, peak_src = load_peaks()
     achieved = B * ALG_BYTES_PER_SYMBOL / (dom_ms * 1e-3) / 1e9
     step_gbs = B * ALG_BYTES_PER_SYMBOL * K / (ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    symbols = {"k_dp_fwd": "vaeq::k_dp_fwd_tc<8,12> (FIR and channel convolution on tcgen05, point-wise stage on the CUDA cores; csrc/dp_fwd_tc.cu)",
+               "k_dp_taps<W>": "vaeq::k_dp_taps_tc (both tap-gradient correlations in one tcgen05 launch; csrc/dp_taps_tc.cu)"}
+    roofline = {"bound": "hbm", "kernel": names[dom], "kernel_symbol": symbols.get(names[dom], names[dom]), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (FWD_DRAM_BYTES_PER_SYMBOL * B if names[dom] == "k_dp_fwd" and M_EST == 25 else None),
                 "traffic_unit": "bytes per launch", "traffic_source": TRAFFIC_SOURCE + " -- taken from that ncu capture, NOT measured in this run",
                 "peak_source": peak_src, "alg_bytes_per_symbol": ALG_BYTES_PER_SYMBOL,
