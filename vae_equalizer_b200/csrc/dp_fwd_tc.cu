@@ -212,6 +212,48 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // ---- residual e = D - rx of the tile whose D MMAs were waited for last (t0_res): deferred, so that it runs while the FIR MMAs of the NEXT tile
+    // execute (every thread used to wait ~0.7 us per tile for them with nothing to do).  D accumulator and parked rx come from TMEM, the centre-tap part
+    // dc from registers; nothing here touches shared memory.
+    float2 dc[2][FT_R][2];
+    int t0_res = 0;
+    bool have_res = false;
+    auto residual = [&]() {
+        const int u0 = t0_res - FT_HP + i0;
+        const bool in_seq = (u0 >= 0) && (u0 < p.B);
+        const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.chi);
+        const bool counted = owned && (u0 >= p.sym_lo) && (u0 < p.sym_hi);
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            float dh[16], dl[16];
+            tmem_ld16(tm_d + 16 * ph, dh);
+            tmem_ld16(tm_d + 32 + 16 * ph, dl);
+            float xs[16];
+            tmem_ld16(tm_x + 16 * ph, xs);
+            if (owned) {
+                float ev[4][FT_R];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int r = 0; r < FT_R; ++r) {
+                        const int s = 2 * (u0 + r) + ph;
+                        const bool valid = (s >= MH) && (s < p.L - MH);                     // sf:120 "valid" region
+                        const float2 dcv = dc[ph][r][k >> 1];
+                        ev[k][r] = valid ? ((dh[4 * r + k] + dl[4 * r + k]) + ((k & 1) ? dcv.y : dcv.x)) - xs[4 * k + r] : 0.f;
+                    }
+                }
+                if (counted) {
+#pragma unroll
+                    for (int r = 0; r < FT_R; ++r) {
+                        accC[0] += ev[0][r] * ev[0][r] + ev[1][r] * ev[1][r];
+                        accC[1] += ev[2][r] * ev[2][r] + ev[3][r] * ev[3][r];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st_row4(p.erows, p.B, 4 * ph + k, u0, make_float4(ev[k][0], ev[k][1], ev[k][2], ev[k][3]));
+            }
+        }
+    };
     if (vcta < p.ntiles) stage_rx(vcta);
 
 #pragma unroll 1
@@ -252,6 +294,7 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             umma_commit_to(bar_f);
         }
         __syncwarp();
+        if (have_res) residual();                            // previous tile: behind this tile's FIR MMAs
         const int u0 = t0 - FT_HP + i0;
         const bool in_seq = (u0 >= 0) && (u0 < p.B);         // B % 4 == 0: all four symbols in or out together
         const bool owned = in_seq && (i0 >= FT_HP) && (i0 < FT_HP + FT_T) && (u0 < p.chi);
@@ -439,7 +482,6 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         }
         __syncwarp();
         // centre taps of h (j = MH - 1, MH, MH + 1) on the CUDA cores while the MMAs run: even sample h[MH] E_q[u], odd h[MH+1] E_q[u] + h[MH-1] E_q[u+1]
-        float2 dc[2][FT_R][2];
         {
             float4 eq[FT_R + 1];
 #pragma unroll
@@ -466,41 +508,14 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         mbar_wait(bar_d, par);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- residual e = D - rx for the owned samples (rx from the staged rows: window samples 8 gt + OX + 2 r + ph) ----
-#pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {
-            float dh[16], dl[16];
-            tmem_ld16(tm_d + 16 * ph, dh);
-            tmem_ld16(tm_d + 32 + 16 * ph, dl);
-            float xs[16];
-            tmem_ld16(tm_x + 16 * ph, xs);
-            if (owned) {
-                float ev[4][FT_R];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                    for (int r = 0; r < FT_R; ++r) {
-                        const int s = 2 * (u0 + r) + ph;
-                        const bool valid = (s >= MH) && (s < p.L - MH);                     // sf:120 "valid" region
-                        const float2 dcv = dc[ph][r][k >> 1];
-                        ev[k][r] = valid ? ((dh[4 * r + k] + dl[4 * r + k]) + ((k & 1) ? dcv.y : dcv.x)) - xs[4 * k + r] : 0.f;
-                    }
-                }
-                if (counted) {
-#pragma unroll
-                    for (int r = 0; r < FT_R; ++r) {
-                        accC[0] += ev[0][r] * ev[0][r] + ev[1][r] * ev[1][r];
-                        accC[1] += ev[2][r] * ev[2][r] + ev[3][r] * ev[3][r];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) st_row4(p.erows, p.B, 4 * ph + k, u0, make_float4(ev[k][0], ev[k][1], ev[k][2], ev[k][3]));
-            }
-        }
+        t0_res = t0;                                         // the residual of this tile runs behind the FIR MMAs of the next one (or after the loop)
+        have_res = true;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         named_bar_sync(1 + g, FC_GT);                        // x_hi, the E_q arrays and both accumulators are free for the next tile
         tile = tile_next;
     }
+
+    if (have_res) residual();                                // last tile
 
     // ---- this group's partial sums (fixed order) ----
     {
