@@ -226,11 +226,11 @@ int vaeq_dp_split_update(const vaeq_dp_desc *d, const float *grads_in, float lr_
  * torch.distributed._symmetric_memory) and passes the `world` peer-mapped pointers in rank order (slot[rank] = its own) plus two
  * zero-initialised int32 counters in its own device memory.  One call = forward, exchange of the ELBO sums, loss / kappa, backward,
  * exchange of the 16 M gradient floats, replicated Adam: 6 launches (the exchanges are fused with the loss assembly and with Adam), no
- * host synchronisation, graph-capturable.  An exchange is a PUSH:
- * a rank stores its partial into its own compartment of EVERY peer's slot, fences, raises that compartment's epoch word in every slot,
- * then polls the epoch words of its own slot (local memory) and adds the compartments in rank order -- bit-identical on every rank, one
- * NVLink store latency whatever the number of ranks.  All ranks must make the same sequence of calls; a peer that does not show up
- * within 20 s traps the kernel. */
+ * host synchronisation, graph-capturable.  An exchange is a PUSH with the flag inside every word:
+ * a rank stores its partial into its own compartment of EVERY peer's slot as aligned 8-byte words {payload32, epoch32}, then polls the
+ * words of its own slot (local memory) until each carries the epoch of this exchange and adds the payloads in rank order -- bit-identical
+ * on every rank, no fence, one NVLink store latency whatever the number of ranks.  All ranks must make the same sequence of calls; a peer
+ * that does not show up within 20 s traps the kernel. */
 #define VAEQ_MAX_PEERS 8
 typedef struct vaeq_peer_comm {
     int32_t rank, world;

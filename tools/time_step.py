@@ -8,7 +8,7 @@ from vae_equalizer_b200.datagen import generate_data_gpu
 from vae_equalizer_b200.dp import DPEqualizer
 lib = _lib.load()
 M = int(os.environ.get("M_EST", 25))
-B = 1 << int(os.environ.get("LOG2B", 22))
+B = int(os.environ["B_SYMS"]) if "B_SYMS" in os.environ else 1 << int(os.environ.get("LOG2B", 22))
 h_est, h_ch, P, amp, amps, pol, nu_sc, var, pow_mean = init("h0", "64-QAM", "cpu", 0.0270955, 2, M, 23)
 rxs = [generate_data_gpu(B, amps, 23, P, 2, np.pi / 10, "cuda", 1 + i)[0] for i in range(3)]
 q = torch.empty(2, 16, B, device="cuda"); out = torch.empty(2, 2, B, device="cuda")

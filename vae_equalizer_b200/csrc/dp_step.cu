@@ -1039,53 +1039,49 @@ __global__ void k_dp_reduce_gpart(DpK p, int nparts, float *grads) {
     if (lane == 0) grads[i] = (float)a;
 }
 // ---- one-shot peer reductions over NVLink (vaeq_dp_split_step_peer) --------------------------------------------------------------
-// PUSH model: every rank owns a slot in symmetric memory with one COMPARTMENT per sender.  A reduction is: store my partial into
-// compartment `rank` of EVERY peer's slot (remote stores pipeline over NVLink; nobody reads remote memory), fence, store the epoch word
-// of that compartment in every slot; then poll the epoch words of MY OWN slot (local memory) and add the compartments in rank order, so
-// all ranks compute bit-identical sums (the replicated Adam step depends on it).  Cost: one NVLink store latency + one fence,
-// independent of the number of ranks.  The two exchanges of a step alternate, which is what makes one buffer per exchange enough:
-// nobody can send exchange k + 1 before everybody has read exchange k (see include/vaeq.h).
+// PUSH model, flag-in-word ("LL") protocol: every rank owns a slot in symmetric memory with one COMPARTMENT per sender.  A reduction is:
+// store my partial into compartment `rank` of EVERY peer's slot as 8-byte words {payload32, epoch32} (remote stores pipeline over NVLink;
+// nobody reads remote memory; an aligned 8-byte store arrives whole), then poll the words of MY OWN slot (local memory) until each carries
+// the epoch of this exchange and add the payloads in rank order, so all ranks compute bit-identical sums (the replicated Adam step depends
+// on it).  No fence and no separate flag: one NVLink store latency per exchange, independent of the number of ranks (the fence + epoch-word
+// version this replaces cost two more NVLink round trips: fin 10.6 -> 24 us, Adam 10 -> 27 us at N = 4, profiles/r02c_batch_split.txt).
+// The two exchanges of a step alternate, which is what makes one buffer per exchange enough: nobody can send exchange k + 1 before
+// everybody has read exchange k (see include/vaeq.h).
 struct PeerK {
     int rank, world;
     unsigned char *slot[VAEQ_MAX_PEERS];
     int *epoch;                                              // local: [0] ELBO-sum exchanges done, [1] gradient exchanges done
     int comp;                                                // bytes per compartment
 };
-constexpr int PEER_HDR = 256;                                // epoch words of a compartment: [0] sums, [32] gradients (128 bytes apart)
-__host__ __device__ inline size_t peer_stats_bytes(int M) { return (size_t)(8 + 4 * (M / 2)) * sizeof(double); }
-__host__ __device__ inline size_t peer_comp_bytes(int M) { return (PEER_HDR + peer_stats_bytes(M) + (size_t)16 * M * sizeof(float) + 255) / 256 * 256; }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+constexpr int PEER_HDR = 256;                                // reserved
+__host__ __device__ inline size_t peer_stats_bytes(int M) { return (size_t)(8 + 4 * (M / 2)) * 2 * sizeof(unsigned long long); }   // a double = two words
+__host__ __device__ inline size_t peer_comp_bytes(int M) { return (PEER_HDR + peer_stats_bytes(M) + (size_t)16 * M * sizeof(unsigned long long) + 255) / 256 * 256; }
+__device__ __forceinline__ void st_word_sys(unsigned long long *p, unsigned payload, unsigned epoch) {
+    const unsigned long long v = ((unsigned long long)epoch << 32) | payload;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// after every thread has stored its part of the partial into the peers' compartments: make the stores visible, raise the epoch word of
-// my compartment in every slot, then wait until all senders' epoch words in MY slot have reached the same epoch (a sender that never
-// arrives traps after 20 s).  One thread per peer does the flag traffic.
-__device__ __forceinline__ void peer_signal_and_wait(const PeerK &c, int which) {
-    __threadfence_system();
-    __syncthreads();
-    const unsigned e = (unsigned)(*reinterpret_cast<volatile int *>(c.epoch + which) + 1);
-    if ((int)threadIdx.x < c.world) {
-        st_release_sys(reinterpret_cast<unsigned *>(c.slot[threadIdx.x] + (size_t)c.rank * c.comp) + 32 * which, e);
-        const unsigned *flag = reinterpret_cast<const unsigned *>(c.slot[c.rank] + (size_t)threadIdx.x * c.comp) + 32 * which;
+// spin on a word of my own slot until its epoch half is `epoch` (a sender that never arrives traps after 20 s); returns the payload
+__device__ __forceinline__ unsigned ld_word_wait(const unsigned long long *p, unsigned epoch) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if ((unsigned)(v >> 32) != epoch) {
         const unsigned long long t0 = globaltimer_ns();
-        while ((int)(ld_acquire_sys(flag) - e) < 0) {
+        do {
             if (globaltimer_ns() - t0 > 20000000000ull) __trap();
-        }
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        } while ((unsigned)(v >> 32) != epoch);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) c.epoch[which] = (int)e;
+    return (unsigned)v;
 }
 __global__ void __launch_bounds__(256) k_dp_peer_reduce_stats(DpK p, int nparts, PeerK c) {
     __shared__ double st[8 + 4 * (VAEQ_MAX_TAPS / 2)];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, ns = 8 + 4 * p.mh;
+    const unsigned e = (unsigned)(*reinterpret_cast<volatile int *>(c.epoch) + 1);
     if (wid < 5) {
         double a = 0.0;
         for (int b = lane; b < nparts; b += 32) a += p.part_fwd[(int64_t)b * 8 + wid];
@@ -1095,33 +1091,49 @@ __global__ void __launch_bounds__(256) k_dp_peer_reduce_stats(DpK p, int nparts,
     if (threadIdx.x >= 5 && threadIdx.x < 8) st[threadIdx.x] = 0.0;
     for (int i = threadIdx.x; i < 4 * p.mh; i += blockDim.x) st[8 + i] = (double)p.edge_vs[i];
     __syncthreads();
-    for (int idx = threadIdx.x; idx < c.world * ns; idx += blockDim.x) {      // my sums -> compartment `rank` of every slot
-        const int r = idx / ns, i = idx - r * ns;
-        reinterpret_cast<double *>(c.slot[r] + (size_t)c.rank * c.comp + PEER_HDR)[i] = st[i];
+    for (int idx = threadIdx.x; idx < c.world * 2 * ns; idx += blockDim.x) {  // my sums -> compartment `rank` of every slot, low / high half of each double
+        const int r = idx / (2 * ns), w = idx - r * (2 * ns);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(st[w >> 1]);
+        st_word_sys(reinterpret_cast<unsigned long long *>(c.slot[r] + (size_t)c.rank * c.comp + PEER_HDR) + w, (unsigned)(bits >> (32 * (w & 1))), e);
     }
-    peer_signal_and_wait(c, 0);
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
         double a = 0.0;
-        for (int r = 0; r < c.world; ++r) a += *reinterpret_cast<const volatile double *>(c.slot[c.rank] + (size_t)r * c.comp + PEER_HDR + 8 * i);
+        for (int r = 0; r < c.world; ++r) {
+            const unsigned long long *w = reinterpret_cast<const unsigned long long *>(c.slot[c.rank] + (size_t)r * c.comp + PEER_HDR) + 2 * i;
+            const unsigned lo = ld_word_wait(w, e), hi = ld_word_wait(w + 1, e);
+            a += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        }
         if (i < 8) p.part_fwd[i] = a;
         else p.edge_vs[i - 8] = (float)a;
     }
     __syncthreads();                                         // the block's own global writes are visible to the block after the barrier
+    if (threadIdx.x == 0) c.epoch[0] = (int)e;
     dp_fin_body(p, 1);                                       // C, loss, var_est, kappa, S_nu(j) from the reduced sums (k_dp_fin's body)
 }
-// gradients: p.gfinal holds this rank's partial (k_dp_reduce_gpart); the sum over the ranks lands in row 0 of p.gpart, where Adam reads it
+// gradients, sender side: a warp sums the per-CTA partials of one gradient entry in the fixed order of k_dp_reduce_gpart (same float) and its
+// first `world` lanes store it straight into compartment `rank` of the peers' slots -- the push leaves from the many-CTA reduction kernel, the
+// single-CTA kernel below only collects
+__global__ void k_dp_reduce_gpart_push(DpK p, int nparts, PeerK c) {
+    const int n = 16 * p.M, lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const unsigned e = (unsigned)(*reinterpret_cast<volatile int *>(c.epoch + 1) + 1);
+    double a = 0.0;
+    for (int b = lane; b < nparts; b += 32) a += (double)p.gpart[(int64_t)b * n + i];
+    a = warp_sum(a);
+    const float g = __shfl_sync(0xffffffffu, (float)a, 0);
+    if (lane < c.world)
+        st_word_sys(reinterpret_cast<unsigned long long *>(c.slot[lane] + (size_t)c.rank * c.comp + PEER_HDR + peer_stats_bytes(p.M)) + i, __float_as_uint(g), e);
+}
+// gradients, receiver side: the sum over the ranks (rank order), then the replicated Adam step
 __global__ void __launch_bounds__(1024) k_dp_peer_reduce_grads_adam(DpK p, PeerK c, float lr_w, float lr_h, int amsgrad) {
     __shared__ float sum_sh[16 * VAEQ_MAX_TAPS];
     const size_t off = PEER_HDR + peer_stats_bytes(p.M);
     const int n = 16 * p.M;
-    for (int idx = threadIdx.x; idx < c.world * n; idx += blockDim.x) {
-        const int r = idx / n, i = idx - r * n;
-        reinterpret_cast<float *>(c.slot[r] + (size_t)c.rank * c.comp + off)[i] = p.gfinal[i];
-    }
-    peer_signal_and_wait(c, 1);
+    const unsigned e = (unsigned)(*reinterpret_cast<volatile int *>(c.epoch + 1) + 1);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double a = 0.0;
-        for (int r = 0; r < c.world; ++r) a += (double)*reinterpret_cast<const volatile float *>(c.slot[c.rank] + (size_t)r * c.comp + off + 4 * i);
+        for (int r = 0; r < c.world; ++r)
+            a += (double)__uint_as_float(ld_word_wait(reinterpret_cast<const unsigned long long *>(c.slot[c.rank] + (size_t)r * c.comp + off) + i, e));
         sum_sh[i] = (float)a;                                // a float, like the all-reduced gradient of the NCCL transport
     }
     // ---- replicated Adam on the reduced gradient (k_dp_adam's finish for one "partial"), step counter bumped by this single CTA ----
@@ -1133,7 +1145,10 @@ __global__ void __launch_bounds__(1024) k_dp_peer_reduce_grads_adam(DpK p, PeerK
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) dp_adam_finish(p, i, (double)sum_sh[i], 1, lr_w, lr_h, amsgrad, bc1_sh, bc2s_sh);
     __syncthreads();
-    if (threadIdx.x == 0) *step_ptr = step;
+    if (threadIdx.x == 0) {
+        *step_ptr = step;
+        c.epoch[1] = (int)e;
+    }
 }
 static int64_t split_cols(const vaeq_dp_desc *d, int32_t lo, int32_t hi) {      // columns a rank writes: its range widened by DP_SPLIT_EXT
     if (d == nullptr || lo < 0 || hi > d->B || lo >= hi) return -1;                // (bad ranges are reported by split_check)
@@ -1243,7 +1258,7 @@ extern "C" int vaeq_dp_split_step_peer(const vaeq_dp_desc *d, int32_t sym_lo, in
     }
     if (rc2) return rc2;
     ktime_begin(VAEQ_K_DP_ADAM, st);
-    k_dp_reduce_gpart<<<(16 * p.M + 7) / 8, 256, 0, st>>>(p, nparts, p.gfinal);
+    k_dp_reduce_gpart_push<<<(16 * p.M + 7) / 8, 256, 0, st>>>(p, nparts, c);
     k_dp_peer_reduce_grads_adam<<<1, 1024, 0, st>>>(p, c, lr_w, lr_h, (d->flags & VAEQ_F_AMSGRAD) ? 1 : 0);   // exchange of the gradients + Adam
     ktime_end(VAEQ_K_DP_ADAM, st);
     VAEQ_LAUNCH_CHECK("k_dp_peer_reduce_grads_adam");
