@@ -117,6 +117,24 @@ struct FwdTcGeom {
         if (t < NKD - 3) return t < CSL ? t : t + 3;
         return CSL + (t - (NKD - 3));
     }
+    // both orders visit every K step exactly twice (once with the lo, once with the hi operand)
+    __host__ __device__ static constexpr bool orders_are_permutations() {
+        for (int st = 0; st < 4 * NKF; ++st) {
+            int lo = 0, hi = 0;
+            for (int t = 0; t < 8 * NKF; ++t) {
+                if (fir_step(t) == st) (t < 4 * NKF ? lo : hi) += 1;
+            }
+            if (lo != 1 || hi != 1) return false;
+        }
+        for (int st = 0; st < NKD; ++st) {
+            int lo = 0, hi = 0;
+            for (int t = 0; t < 2 * NKD; ++t) {
+                if (conv_step(t) == st) (t < NKD ? lo : hi) += 1;
+            }
+            if (lo != 1 || hi != 1) return false;
+        }
+        return true;
+    }
     static constexpr size_t GROUP0 = 2048 + (size_t)(TAPF_FLOATS + TAPD_FLOATS) * 4;
     static constexpr size_t SMEM = GROUP0 + (size_t)FC_NG * 2 * FC_XB;
     static_assert(8 * 127 + 8 * NKF <= 4 * FC_XCH && 8 * 127 + OX + 8 <= 4 * FC_XCH, "sample window");
@@ -127,6 +145,7 @@ struct FwdTcGeom {
 template <int NL, int MH>
 __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
     using G = FwdTcGeom<MH>;
+    static_assert(G::orders_are_permutations(), "MMA issue order");
     constexpr int M = G::M, HF = G::HF, OX = G::OX, SH = G::SH, NKF = G::NKF, NKD = G::NKD;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                 // fir_done[4], conv_done[4]
