@@ -62,15 +62,25 @@ __device__ __forceinline__ float tf32_lo_part(float x) {    // x - trunc_tf32(x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(r));
     return __uint_as_float(o);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t u[16];
+// tcgen05.ld is asynchronous: the destination registers are valid after tcgen05.wait::ld.  tmem_ld16_issue only issues the load; tmem_ld16_wait
+// is the wait, with the 16 registers as read-write operands so that the compiler sees every consumer depend on it (several loads can then be
+// in flight under what is, in time, one wait: the second and third wait of a batch return at once)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
-                   "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+                   "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld16_wait(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
+                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    tmem_ld16_issue(taddr, v);
+    tmem_ld16_wait(v);
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {       // the caller issues tcgen05.wait::st
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -245,10 +255,13 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
             float dh[16], dl[16];
-            tmem_ld16(tm_d + 16 * ph, dh);
-            tmem_ld16(tm_d + 32 + 16 * ph, dl);
             float xs[16];
-            tmem_ld16(tm_x + 16 * ph, xs);
+            tmem_ld16_issue(tm_d + 16 * ph, dh);
+            tmem_ld16_issue(tm_d + 32 + 16 * ph, dl);
+            tmem_ld16_issue(tm_x + 16 * ph, xs);
+            tmem_ld16_wait(dh);
+            tmem_ld16_wait(dl);
+            tmem_ld16_wait(xs);
             if (owned) {
                 float ev[4][FT_R];
 #pragma unroll
@@ -356,8 +369,10 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             mbar_wait(bar_f, par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float vh[16], vl[16];
-            tmem_ld16(tm_y, vh);
-            tmem_ld16(tm_y + 16, vl);
+            tmem_ld16_issue(tm_y, vh);
+            tmem_ld16_issue(tm_y + 16, vl);
+            tmem_ld16_wait(vh);
+            tmem_ld16_wait(vl);
 #pragma unroll
             for (int r = 0; r < FT_R; ++r) {
                 y[r][0] = (vh[4 * r] + vl[4 * r]) + yc[r][0].x;
