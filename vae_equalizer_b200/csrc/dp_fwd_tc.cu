@@ -16,6 +16,14 @@
 // lo = tf32(x - trunc(x)); the tap tables carry [hi | lo] side by side in N, two MMAs per K step give (x_hi + x_lo)(w_hi + w_lo).
 // One CTA of 4 independent 128-thread groups per SM (they share the 32 KB of tap tables; each group runs the tile loop of a
 // k_dp_fwd_fast CTA with named barriers and its own mbarriers / TMEM columns), 174 KB of shared memory.
+// The accumulator TRUNCATES every group of four products at its ulp (tools/tc_accum_bench.cu), so the MMAs are issued by growing magnitude (x_lo
+// steps, outer taps, the K steps with the centre taps last) and the centre tap of each contraction stays in fp32 on the CUDA cores: the output
+// error against float64 is then smaller than k_dp_fwd_fast's (profiles/r02c_tc_forward.txt).
+// Tile pipeline of a group (default forward kernel of the fast path since r02c):
+//   wait for this tile's rx rows (cp.async issued during the previous tile) -> derive x_lo -> barrier -> issue the FIR MMAs
+//   -> residual e = D - rx of the PREVIOUS tile (TMEM + registers only) while they run -> centre tap, park this tile's rx samples in the spare
+//   TMEM columns -> wait, read y -> point-wise stage, E_q hi | lo into the x_lo array -> barrier -> request the NEXT tile's rx rows into x_hi,
+//   issue the D MMAs -> centre tap of D -> wait -> barrier.
 // Reference: twoXtwoFIR.forward sf:500-527, loss_function_shaping sf:92-137.
 #include <type_traits>
 #include "dp_fast.cuh"
