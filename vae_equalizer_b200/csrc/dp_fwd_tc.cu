@@ -508,7 +508,6 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         named_bar_sync(1 + g, FC_GT);
-        if (tile_next < p.ntiles) stage_rx(tile_next);       // every thread of the group is past its last read of x_hi: lands during the D MMAs and the residual
         if (gt == 0) {
             // ---- D (128 x 64: [hi | lo] x even / odd sample x 4 symbols x 4 components) = sum over NKD K steps of (q_hi + q_lo) [h_hi | h_lo] ----
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -523,6 +522,7 @@ __global__ void __launch_bounds__(FC_NT, 1) k_dp_fwd_tc(DpK p) {
             umma_commit_to(bar_d);
         }
         __syncwarp();
+        if (tile_next < p.ntiles) stage_rx(tile_next);       // every thread of the group is past its last read of x_hi (barrier above): the rows land during the D MMAs and the next tile's top
         // centre taps of h (j = MH - 1, MH, MH + 1) on the CUDA cores while the MMAs run: even sample h[MH] E_q[u], odd h[MH+1] E_q[u] + h[MH-1] E_q[u+1]
         {
             float4 eq[FT_R + 1];
